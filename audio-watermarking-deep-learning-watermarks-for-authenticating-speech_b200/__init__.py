@@ -1,0 +1,21 @@
+"""wmb200 — B200-native (sm_100a) embed + detect path of the main16 audio watermark.
+
+Drop-in names of the reference (py/main16.py): Generator, Detector, ResBlock,
+generate_watermarked_audio, detect_watermark, load_state_dict_strip_prefix, the helper
+functions fir_lowpass / clamp_peak / limit_rms and the module constants.  All arithmetic
+runs in libwmb200.so (hand-written CUDA, C ABI in include/wmb200.h); there is no CPU or
+PyTorch fallback — calls fail loudly when the library or the GPU is missing.
+"""
+from . import _lib, ops, packing
+from .api import detect_prob, detect_watermark, generate_watermarked_audio, load_audio, save_audio, segment
+from .functional import (AUDIO_LEN, HF_PENALTY_W, LAMBDA_DEC, LAMBDA_L1, LAMBDA_LOC, LAMBDA_LOUD,
+                         LAMBDA_MSSPEC, MAX_RMS, MESSAGE_BITS, SAMPLE_RATE, bit_targets, clamp_peak,
+                         embed_detect, fir_lowpass, limit_rms, postprocess_delta)
+from .models import Detector, Generator, ResBlock, load_state_dict_strip_prefix
+from .sharding import shard_range
+
+__all__ = ["Generator", "Detector", "ResBlock", "generate_watermarked_audio", "detect_watermark", "detect_prob",
+           "load_state_dict_strip_prefix", "fir_lowpass", "clamp_peak", "limit_rms", "postprocess_delta",
+           "embed_detect", "bit_targets", "shard_range", "load_audio", "save_audio", "segment",
+           "SAMPLE_RATE", "AUDIO_LEN", "MESSAGE_BITS", "MAX_RMS", "LAMBDA_L1", "LAMBDA_MSSPEC", "LAMBDA_LOUD",
+           "LAMBDA_LOC", "LAMBDA_DEC", "HF_PENALTY_W"]

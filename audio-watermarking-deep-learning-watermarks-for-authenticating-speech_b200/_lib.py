@@ -1,0 +1,123 @@
+"""ctypes binding of libwmb200.so — the C ABI declared in include/wmb200.h.
+
+This is the stub a maintainer of the reference would add: every
+function takes raw device pointers, sizes and a CUDA stream handle.  There is no
+fallback: if the library is missing or the device is not sm_100 the import of the
+compute path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libwmb200.so")
+ABI_VERSION = 4
+
+# blob offsets (floats) — mirror of the enums in include/wmb200.h
+RB_W1 = 0
+RB_B1 = RB_W1 + 3 * 64 * 64
+RB_W2 = RB_B1 + 64
+RB_B2 = RB_W2 + 3 * 64 * 64
+RB_SIZE = RB_B2 + 64
+G_IN_W = 0
+G_IN_B = G_IN_W + 7 * 64
+G_RB0 = G_IN_B + 64
+G_RB1 = G_RB0 + RB_SIZE
+G_LSTM_WIH = G_RB1 + RB_SIZE
+G_LSTM_WHH = G_LSTM_WIH + 256 * 64
+G_LSTM_B = G_LSTM_WHH + 256 * 64
+G_CT_W = G_LSTM_B + 256
+G_CT_B = G_CT_W + 7 * 64 * 64
+G_RB2 = G_CT_B + 64
+G_HEAD_W = G_RB2 + RB_SIZE
+G_HEAD_B = G_HEAD_W + 64
+G_SIZE = G_HEAD_B + 4
+D_IN_W = 0
+D_IN_B = D_IN_W + 7 * 64
+D_RB0 = D_IN_B + 64
+D_RB1 = D_RB0 + RB_SIZE
+D_HEAD_W = D_RB1 + RB_SIZE
+D_HEAD_B = D_HEAD_W + 32 * 64
+D_SIZE = D_HEAD_B + 32
+MAX_HEAD = 32
+POST_FIR, POST_CLAMP, POST_RMS, POST_ALL = 1, 2, 4, 7
+MATH_FP32, MATH_BF16X2 = 0, 1
+
+_p = C.c_void_p
+_i = C.c_int
+_f = C.c_float
+_sz = C.c_size_t
+_i64 = C.c_int64
+
+# name -> (restype, argtypes); every entry here must be declared in include/wmb200.h
+SIGNATURES = {
+    "wm_abi_version": (_i, []),
+    "wm_last_error": (C.c_char_p, []),
+    "wm_device_ok": (_i, []),
+    "wm_set_math_mode": (_i, [_i]),
+    "wm_get_math_mode": (_i, []),
+    "wm_launch_count": (C.c_ulonglong, []),
+    "wm_conv_in_k7_fwd": (_i, [_p, _p, _p, _p, _i, _i, _p]),
+    "wm_conv64_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "wm_lstm_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
+    "wm_head_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "wm_postprocess_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _p]),
+    "wm_detect_heads_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "wm_generator_workspace_bytes": (_sz, [_i, _i]),
+    "wm_generator_fwd": (_i, [_p, _p, _i64, _p, _p, _p, _p, _sz, _i, _i, _p]),
+    "wm_detector_workspace_bytes": (_sz, [_i, _i]),
+    "wm_detector_fwd": (_i, [_p, _p, _p, _p, _sz, _i, _i, _i, _p]),
+    "wm_detect_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _p]),
+    "wm_embed_detect_workspace_bytes": (_sz, [_i, _i]),
+    "wm_embed_detect_fwd": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
+                                 _i, _i, _i, _i, _p]),
+    "wm_embed_detect_host_workspace_bytes": (_sz, [_i, _i, _i]),
+    "wm_embed_detect_host": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
+                                  _i, _i, _i, _i, _i, _p]),
+}
+
+
+class WmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load(path: str | None = None) -> C.CDLL:
+    """dlopen libwmb200.so and attach the prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise WmError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU or PyTorch fallback for this path)")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.wm_abi_version()
+    if got != ABI_VERSION:
+        raise WmError(f"libwmb200 ABI {got} != binding ABI {ABI_VERSION}; rebuild the library")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().wm_last_error().decode(errors="replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise WmError(f"{what} failed (rc={rc}): {last_error()}")
+
+
+def ptr(t) -> int | None:
+    """Device (or pinned host) address of a torch tensor, None for None."""
+    if t is None:
+        return None
+    return t.data_ptr()

@@ -1,0 +1,335 @@
+// C ABI of libwmb200 (include/wmb200.h): argument checking, error reporting and the
+// module-level drivers that string the kernels together on the caller's stream.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "wm_common.h"
+
+namespace wm {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<int> g_math_mode{WM_MATH_FP32};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+int require_device() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+      set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+      return -4;
+    }
+    ok = (major == 10) ? 1 : 0;
+  }
+  if (!ok) {
+    set_error("libwmb200 is built for sm_100a only and has no fallback path");
+    return -4;
+  }
+  return 0;
+}
+
+// conv64 in the selected arithmetic
+static int conv64(const float *x, const float *w, const float *bias, const float *residual,
+                  const float *chan_add, float *y, int B, int T, int taps, int relu, cudaStream_t st) {
+  return launch_conv64_fp32(x, w, bias, residual, chan_add, y, B, T, taps, relu, st);
+}
+
+// ResBlock (py/main16.py:112-125): y = relu(x + conv2(relu(conv1(x)))) with BN folded.
+// `tmp` and `y` are distinct from `x`.
+static int resblock(const float *rb, const float *x, float *tmp, float *y, int B, int T, cudaStream_t st) {
+  WM_TRY(conv64(x, rb + WM_RB_W1, rb + WM_RB_B1, nullptr, nullptr, tmp, B, T, 3, 1, st));
+  WM_TRY(conv64(tmp, rb + WM_RB_W2, rb + WM_RB_B2, x, nullptr, y, B, T, 3, 1, st));
+  return 0;
+}
+
+static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+static size_t act_bytes(int B, int T) { return align256((size_t)B * T * 64 * sizeof(float)); }
+
+struct Ws {
+  char *p;
+  size_t left;
+  void *take(size_t n) {
+    n = align256(n);
+    if (n > left) return nullptr;
+    void *r = p;
+    p += n;
+    left -= n;
+    return r;
+  }
+};
+
+static int generator_run(const float *blob, const float *embedding, int64_t emb_rows,
+                         const int64_t *message, const float *s, float *delta_raw, float *a0,
+                         float *a1, float *a2, float *emb, int B, int T, cudaStream_t st) {
+  // encoder: conv k7 -> ResBlock -> ResBlock                 (py/main16.py:133-137)
+  WM_TRY(launch_conv_in_k7(s, blob + WM_G_IN_W, blob + WM_G_IN_B, a0, B, T, st));
+  WM_TRY(resblock(blob + WM_G_RB0, a0, a1, a2, B, T, st));  // -> a2
+  WM_TRY(resblock(blob + WM_G_RB1, a2, a0, a1, B, T, st));  // -> a1
+  // LSTM over time                                             (py/main16.py:152-154)
+  WM_TRY(launch_lstm_fp32(a1, blob + WM_G_LSTM_WIH, blob + WM_G_LSTM_WHH, blob + WM_G_LSTM_B, a0, B, T, st));
+  // + embedding(message)[:, :, None]                           (py/main16.py:156-159)
+  const float *chan_add = nullptr;
+  if (message && embedding) {
+    WM_TRY(launch_gather_rows(embedding, emb_rows, message, emb, B, st));
+    chan_add = emb;
+  }
+  // decoder: ConvTranspose k7 -> ResBlock -> Conv 64->1        (py/main16.py:143-147)
+  WM_TRY(conv64(a0, blob + WM_G_CT_W, blob + WM_G_CT_B, nullptr, chan_add, a2, B, T, 7, 0, st));
+  WM_TRY(resblock(blob + WM_G_RB2, a2, a0, a1, B, T, st));  // -> a1
+  WM_TRY(launch_head(a1, blob + WM_G_HEAD_W, blob + WM_G_HEAD_B, delta_raw, B, T, 1, st));
+  return 0;
+}
+
+// Detector trunk (py/main16.py:176-179): result left in *out (one of the three buffers)
+static int detector_trunk(const float *blob, const float *x, float *a0, float *a1, float *a2,
+                          float **out, int B, int T, cudaStream_t st) {
+  WM_TRY(launch_conv_in_k7(x, blob + WM_D_IN_W, blob + WM_D_IN_B, a0, B, T, st));
+  WM_TRY(resblock(blob + WM_D_RB0, a0, a1, a2, B, T, st));  // -> a2
+  WM_TRY(resblock(blob + WM_D_RB1, a2, a0, a1, B, T, st));  // -> a1
+  *out = a1;
+  return 0;
+}
+
+}  // namespace wm
+
+using namespace wm;
+
+extern "C" {
+
+int wm_abi_version(void) { return WM_ABI_VERSION; }
+const char *wm_last_error(void) { return g_err; }
+int wm_device_ok(void) { return require_device() == 0 ? 1 : 0; }
+int wm_set_math_mode(int mode) {
+  int prev = g_math_mode.load();
+  if (mode == WM_MATH_FP32 || mode == WM_MATH_BF16X2) g_math_mode.store(mode);
+  return prev;
+}
+int wm_get_math_mode(void) { return g_math_mode.load(); }
+unsigned long long wm_launch_count(void) { return g_launches.load(); }
+
+#define WM_ENTRY()                 \
+  do {                             \
+    int rc0_ = require_device();   \
+    if (rc0_ != 0) return rc0_;    \
+  } while (0)
+
+int wm_conv_in_k7_fwd(const float *s, const float *w, const float *b, float *y, int B, int T,
+                      void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "conv_in_k7: negative size");
+  WM_CHECK_ARG(B == 0 || T == 0 || (s && w && b && y), "conv_in_k7: null pointer");
+  return launch_conv_in_k7(s, w, b, y, B, T, as_stream(stream));
+}
+
+int wm_conv64_fwd(const float *x, const float *w, const float *bias, const float *residual,
+                  const float *chan_add, float *y, int B, int T, int taps, int relu, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "conv64: negative size");
+  WM_CHECK_ARG(B == 0 || T == 0 || (x && w && bias && y), "conv64: null pointer");
+  WM_CHECK_ARG(x != y, "conv64: in-place operation is not supported");
+  return conv64(x, w, bias, residual, chan_add, y, B, T, taps, relu, as_stream(stream));
+}
+
+int wm_lstm_fwd(const float *x, const float *w_ih, const float *w_hh, const float *bias, float *h,
+                int B, int T, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "lstm: negative size");
+  WM_CHECK_ARG(B == 0 || T == 0 || (x && w_ih && w_hh && bias && h), "lstm: null pointer");
+  WM_CHECK_ARG(x != h, "lstm: in-place operation is not supported");
+  return launch_lstm_fp32(x, w_ih, w_hh, bias, h, B, T, as_stream(stream));
+}
+
+int wm_head_fwd(const float *x, const float *w, const float *b, float *y, int B, int T, int nout,
+                void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "head: negative size");
+  WM_CHECK_ARG(B == 0 || T == 0 || (x && w && b && y), "head: null pointer");
+  return launch_head(x, w, b, y, B, T, nout, as_stream(stream));
+}
+
+int wm_postprocess_fwd(const float *delta_raw, const float *s, const float *fir, float *delta,
+                       float *s_w, float *rms_out, int B, int T, int mode, float peak,
+                       float max_rms, float eps, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "postprocess: negative size");
+  WM_CHECK_ARG(B == 0 || T == 0 || (delta_raw && (s || !s_w)), "postprocess: null pointer");
+  return launch_postprocess(delta_raw, s, fir, delta, s_w, rms_out, B, T, mode, peak, max_rms, eps,
+                            as_stream(stream));
+}
+
+int wm_detect_heads_fwd(const float *logits, const int *valid_len, float *probs, float *clip_prob,
+                        float *msg_logits, float *vote_frac, int B, int T, int nout, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "detect_heads: negative size");
+  WM_CHECK_ARG(B == 0 || T == 0 || logits, "detect_heads: null pointer");
+  return launch_detect_heads(logits, valid_len, probs, clip_prob, msg_logits, vote_frac, B, T, nout,
+                             as_stream(stream));
+}
+
+size_t wm_generator_workspace_bytes(int B, int T) {
+  if (B <= 0 || T <= 0) return 0;
+  return 3 * act_bytes(B, T) + align256((size_t)B * 64 * sizeof(float));
+}
+
+int wm_generator_fwd(const float *blob, const float *embedding, int64_t emb_rows,
+                     const int64_t *message, const float *s, float *delta_raw, void *workspace,
+                     size_t workspace_bytes, int B, int T, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "generator: negative size");
+  if (B == 0 || T == 0) return 0;
+  WM_CHECK_ARG(blob && s && delta_raw && workspace, "generator: null pointer");
+  WM_CHECK_ARG(workspace_bytes >= wm_generator_workspace_bytes(B, T),
+               "generator: workspace too small (%zu < %zu)", workspace_bytes,
+               wm_generator_workspace_bytes(B, T));
+  Ws ws{(char *)workspace, workspace_bytes};
+  float *a0 = (float *)ws.take(act_bytes(B, T)), *a1 = (float *)ws.take(act_bytes(B, T)),
+        *a2 = (float *)ws.take(act_bytes(B, T)), *emb = (float *)ws.take((size_t)B * 64 * 4);
+  return generator_run(blob, embedding, emb_rows, message, s, delta_raw, a0, a1, a2, emb, B, T,
+                       as_stream(stream));
+}
+
+size_t wm_detector_workspace_bytes(int B, int T) {
+  if (B <= 0 || T <= 0) return 0;
+  return 3 * act_bytes(B, T);
+}
+
+int wm_detector_fwd(const float *blob, const float *x, float *logits, void *workspace,
+                    size_t workspace_bytes, int B, int T, int nout, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "detector: negative size");
+  WM_CHECK_ARG(nout >= 1 && nout <= WM_MAX_HEAD, "detector: nout must be in [1,%d]", WM_MAX_HEAD);
+  if (B == 0 || T == 0) return 0;
+  WM_CHECK_ARG(blob && x && logits && workspace, "detector: null pointer");
+  WM_CHECK_ARG(workspace_bytes >= wm_detector_workspace_bytes(B, T), "detector: workspace too small");
+  Ws ws{(char *)workspace, workspace_bytes};
+  float *a0 = (float *)ws.take(act_bytes(B, T)), *a1 = (float *)ws.take(act_bytes(B, T)),
+        *a2 = (float *)ws.take(act_bytes(B, T)), *out = nullptr;
+  cudaStream_t st = as_stream(stream);
+  WM_TRY(detector_trunk(blob, x, a0, a1, a2, &out, B, T, st));
+  return launch_head(out, blob + WM_D_HEAD_W, blob + WM_D_HEAD_B, logits, B, T, nout, st);
+}
+
+int wm_detect_fwd(const float *blob, const float *x, const int *valid_len, float *probs,
+                  float *clip_prob, float *msg_logits, float *vote_frac, void *workspace,
+                  size_t workspace_bytes, int B, int T, int nout, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "detect: negative size");
+  WM_CHECK_ARG(nout >= 1 && nout <= WM_MAX_HEAD, "detect: nout must be in [1,%d]", WM_MAX_HEAD);
+  if (B == 0 || T == 0) return 0;
+  WM_CHECK_ARG(blob && x && workspace, "detect: null pointer");
+  WM_CHECK_ARG(workspace_bytes >= wm_detector_workspace_bytes(B, T), "detect: workspace too small");
+  Ws ws{(char *)workspace, workspace_bytes};
+  float *a0 = (float *)ws.take(act_bytes(B, T)), *a1 = (float *)ws.take(act_bytes(B, T)),
+        *a2 = (float *)ws.take(act_bytes(B, T)), *out = nullptr;
+  cudaStream_t st = as_stream(stream);
+  WM_TRY(detector_trunk(blob, x, a0, a1, a2, &out, B, T, st));
+  return launch_head_detect(out, blob + WM_D_HEAD_W, blob + WM_D_HEAD_B, valid_len, probs, clip_prob,
+                            msg_logits, vote_frac, B, T, nout, st);
+}
+
+size_t wm_embed_detect_workspace_bytes(int B, int T) {
+  if (B <= 0 || T <= 0) return 0;
+  return 3 * act_bytes(B, T) + align256((size_t)B * 64 * sizeof(float)) +
+         align256((size_t)B * T * sizeof(float));
+}
+
+int wm_embed_detect_fwd(const float *g_blob, const float *embedding, int64_t emb_rows,
+                        const float *d_blob, const float *fir, const int64_t *message,
+                        const float *s, float *delta, float *s_w, float *delta_rms, float *probs,
+                        float *clip_prob, float *msg_logits, float *vote_frac, void *workspace,
+                        size_t workspace_bytes, int B, int T, int nout, int post_mode, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "embed_detect: negative size");
+  WM_CHECK_ARG(nout >= 1 && nout <= WM_MAX_HEAD, "embed_detect: nout must be in [1,%d]", WM_MAX_HEAD);
+  if (B == 0 || T == 0) return 0;
+  WM_CHECK_ARG(g_blob && d_blob && s && s_w && workspace, "embed_detect: null pointer");
+  WM_CHECK_ARG(workspace_bytes >= wm_embed_detect_workspace_bytes(B, T),
+               "embed_detect: workspace too small (%zu < %zu)", workspace_bytes,
+               wm_embed_detect_workspace_bytes(B, T));
+  Ws ws{(char *)workspace, workspace_bytes};
+  float *a0 = (float *)ws.take(act_bytes(B, T)), *a1 = (float *)ws.take(act_bytes(B, T)),
+        *a2 = (float *)ws.take(act_bytes(B, T)), *emb = (float *)ws.take((size_t)B * 64 * 4),
+        *draw = (float *)ws.take((size_t)B * T * 4), *out = nullptr;
+  cudaStream_t st = as_stream(stream);
+  WM_TRY(generator_run(g_blob, embedding, emb_rows, message, s, draw, a0, a1, a2, emb, B, T, st));
+  WM_TRY(launch_postprocess(draw, s, fir, delta, s_w, delta_rms, B, T, post_mode, 0.02f, 0.005f, 1e-8f, st));
+  WM_TRY(detector_trunk(d_blob, s_w, a0, a1, a2, &out, B, T, st));
+  return launch_head_detect(out, d_blob + WM_D_HEAD_W, d_blob + WM_D_HEAD_B, nullptr, probs, clip_prob,
+                            msg_logits, vote_frac, B, T, nout, st);
+}
+
+size_t wm_embed_detect_host_workspace_bytes(int chunk, int T, int nout) {
+  if (chunk <= 0 || T <= 0 || nout < 1) return 0;
+  size_t wave = align256((size_t)chunk * T * sizeof(float));
+  return wm_embed_detect_workspace_bytes(chunk, T) + 3 * wave /* s, s_w, probs */ +
+         align256((size_t)chunk * sizeof(int64_t)) + align256((size_t)chunk * sizeof(float)) +
+         align256((size_t)chunk * (nout - 1 > 0 ? nout - 1 : 1) * sizeof(float));
+}
+
+int wm_embed_detect_host(const float *g_blob, const float *embedding, int64_t emb_rows,
+                         const float *d_blob, const float *fir, const int64_t *host_message,
+                         const float *host_s, float *host_s_w, float *host_probs,
+                         float *host_clip_prob, float *host_msg_logits, void *workspace,
+                         size_t workspace_bytes, int B, int T, int nout, int chunk, int post_mode,
+                         void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0 && chunk > 0, "embed_detect_host: bad size");
+  WM_CHECK_ARG(nout >= 1 && nout <= WM_MAX_HEAD, "embed_detect_host: nout must be in [1,%d]", WM_MAX_HEAD);
+  if (B == 0 || T == 0) return 0;
+  WM_CHECK_ARG(g_blob && d_blob && host_s && host_s_w && workspace, "embed_detect_host: null pointer");
+  WM_CHECK_ARG(workspace_bytes >= wm_embed_detect_host_workspace_bytes(chunk, T, nout),
+               "embed_detect_host: workspace too small");
+  const int nbits = nout - 1;
+  Ws ws{(char *)workspace, workspace_bytes};
+  size_t wave = (size_t)chunk * T * sizeof(float);
+  float *d_s = (float *)ws.take(wave), *d_sw = (float *)ws.take(wave), *d_pr = (float *)ws.take(wave);
+  int64_t *d_msg = (int64_t *)ws.take((size_t)chunk * sizeof(int64_t));
+  float *d_cp = (float *)ws.take((size_t)chunk * sizeof(float));
+  float *d_ml = (float *)ws.take((size_t)chunk * (nbits > 0 ? nbits : 1) * sizeof(float));
+  void *inner = ws.p;
+  size_t inner_bytes = ws.left;
+  cudaStream_t st = as_stream(stream);
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    int nb = B - b0 < chunk ? B - b0 : chunk;
+    WM_CHECK_CUDA(cudaMemcpyAsync(d_s, host_s + (size_t)b0 * T, (size_t)nb * T * 4, cudaMemcpyHostToDevice, st));
+    if (host_message)
+      WM_CHECK_CUDA(cudaMemcpyAsync(d_msg, host_message + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, st));
+    WM_TRY(wm_embed_detect_fwd(g_blob, embedding, emb_rows, d_blob, fir, host_message ? d_msg : nullptr, d_s,
+                               nullptr, d_sw, nullptr, host_probs ? d_pr : nullptr, d_cp,
+                               nbits > 0 ? d_ml : nullptr, nullptr, inner, inner_bytes, nb, T, nout,
+                               post_mode, stream));
+    WM_CHECK_CUDA(cudaMemcpyAsync(host_s_w + (size_t)b0 * T, d_sw, (size_t)nb * T * 4, cudaMemcpyDeviceToHost, st));
+    if (host_probs)
+      WM_CHECK_CUDA(cudaMemcpyAsync(host_probs + (size_t)b0 * T, d_pr, (size_t)nb * T * 4, cudaMemcpyDeviceToHost, st));
+    if (host_clip_prob)
+      WM_CHECK_CUDA(cudaMemcpyAsync(host_clip_prob + b0, d_cp, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    if (host_msg_logits && nbits > 0)
+      WM_CHECK_CUDA(cudaMemcpyAsync(host_msg_logits + (size_t)b0 * nbits, d_ml, (size_t)nb * nbits * 4,
+                                    cudaMemcpyDeviceToHost, st));
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+// Shared helpers for the wmb200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/wmb200.h"
+
+namespace wm {
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define WM_CHECK_ARG(cond, ...)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      wm::set_error(__VA_ARGS__);        \
+      return -1;                         \
+    }                                    \
+  } while (0)
+
+#define WM_CHECK_LAUNCH(name)                                                        \
+  do {                                                                               \
+    cudaError_t e_ = cudaGetLastError();                                             \
+    if (e_ != cudaSuccess) {                                                         \
+      wm::set_error("%s launch failed: %s", name, cudaGetErrorString(e_));           \
+      return -2;                                                                     \
+    }                                                                                \
+    wm::count_launch();                                                              \
+  } while (0)
+
+#define WM_CHECK_CUDA(expr)                                                          \
+  do {                                                                               \
+    cudaError_t e_ = (expr);                                                         \
+    if (e_ != cudaSuccess) {                                                         \
+      wm::set_error("%s failed: %s", #expr, cudaGetErrorString(e_));                 \
+      return -3;                                                                     \
+    }                                                                                \
+  } while (0)
+
+#define WM_TRY(expr)        \
+  do {                      \
+    int rc_ = (expr);       \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+int sm_count();
+int require_device();   // 0 when the current device is sm_10x, else sets the error and returns <0
+
+__device__ __forceinline__ float sigmoid_acc(float x) {
+  return __fdividef(1.0f, 1.0f + __expf(-x));
+}
+__device__ __forceinline__ float tanh_acc(float x) {
+  // 2*sigmoid(2x) - 1 ; saturates cleanly for |x| large
+  return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f;
+}
+
+// internal launchers shared between translation units (all async on `st`)
+int launch_conv_in_k7(const float *s, const float *w, const float *b, float *y, int B, int T,
+                      cudaStream_t st);
+int launch_conv64_fp32(const float *x, const float *w, const float *bias, const float *residual,
+                       const float *chan_add, float *y, int B, int T, int taps, int relu,
+                       cudaStream_t st);
+int launch_lstm_fp32(const float *x, const float *w_ih, const float *w_hh, const float *bias,
+                     float *h, int B, int T, cudaStream_t st);
+int launch_head(const float *x, const float *w, const float *b, float *y, int B, int T, int nout,
+                cudaStream_t st);
+int launch_gather_rows(const float *table, int64_t rows, const int64_t *idx, float *out, int B,
+                       cudaStream_t st);
+int launch_postprocess(const float *delta_raw, const float *s, const float *fir, float *delta,
+                       float *s_w, float *rms_out, int B, int T, int mode, float peak,
+                       float max_rms, float eps, cudaStream_t st);
+int launch_detect_heads(const float *logits, const int *valid_len, float *probs, float *clip_prob,
+                        float *msg_logits, float *vote_frac, int B, int T, int nout,
+                        cudaStream_t st);
+// head (64 -> nout) + sigmoid + per-clip reductions straight from the last activation
+int launch_head_detect(const float *x, const float *w, const float *b, const int *valid_len,
+                       float *probs, float *clip_prob, float *msg_logits, float *vote_frac, int B,
+                       int T, int nout, cudaStream_t st);
+
+}  // namespace wm

@@ -1,0 +1,254 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of
+include/wmb200.h).  torch is used for device memory and the current stream only;
+all arithmetic happens inside libwmb200.so.  Nothing here falls back to PyTorch ops.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+PEAK = 0.02        # clamp_peak default, py/main16.py:66
+MAX_RMS = 0.005    # py/main16.py:29
+RMS_EPS = 1e-8     # limit_rms default, py/main16.py:69
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name}: wmb200 runs on a B200 (sm_100a) only — got a {t.device.type} tensor; "
+            "there is no CPU fallback for this path")
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def set_math_mode(mode: int) -> int:
+    return L.load().wm_set_math_mode(mode)
+
+
+def get_math_mode() -> int:
+    return L.load().wm_get_math_mode()
+
+
+def launch_count() -> int:
+    return int(L.load().wm_launch_count())
+
+
+def max_chunk() -> int:
+    """Clips per device pass (workspace ~12.4 MB per clip in the fp32 layout)."""
+    return int(os.environ.get("WMB200_MAX_CLIPS", "2368"))
+
+
+# ---- single operators ------------------------------------------------------
+def conv_in_k7(s: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """s (B,T) -> (B,T,64) channels-last.  py/main16.py:134,177."""
+    s = _req(s, "s")
+    B, T = s.shape
+    y = torch.empty(B, T, 64, device=s.device, dtype=torch.float32)
+    L.check(L.load().wm_conv_in_k7_fwd(L.ptr(s), L.ptr(_req(w, "w")), L.ptr(_req(b, "b")), L.ptr(y),
+                                       B, T, _stream()), "wm_conv_in_k7_fwd")
+    return y
+
+
+def conv64(x, w, bias, residual=None, chan_add=None, taps: int = 3, relu: bool = False):
+    """x (B,T,64) channels-last, w [taps][64][64] -> (B,T,64).  py/main16.py:116-121,144."""
+    x = _req(x, "x")
+    B, T, Cc = x.shape
+    assert Cc == 64
+    y = torch.empty_like(x)
+    res = _req(residual, "residual") if residual is not None else None
+    ca = _req(chan_add, "chan_add") if chan_add is not None else None
+    L.check(L.load().wm_conv64_fwd(L.ptr(x), L.ptr(_req(w, "w")), L.ptr(_req(bias, "bias")), L.ptr(res),
+                                   L.ptr(ca), L.ptr(y), B, T, taps, int(relu), _stream()), "wm_conv64_fwd")
+    return y
+
+
+def lstm(x, w_ih, w_hh, bias):
+    """x (B,T,64) -> all hidden states (B,T,64).  py/main16.py:138,153."""
+    x = _req(x, "x")
+    B, T, _ = x.shape
+    h = torch.empty_like(x)
+    L.check(L.load().wm_lstm_fwd(L.ptr(x), L.ptr(_req(w_ih, "w_ih")), L.ptr(_req(w_hh, "w_hh")),
+                                 L.ptr(_req(bias, "bias")), L.ptr(h), B, T, _stream()), "wm_lstm_fwd")
+    return h
+
+
+def head(x, w, b):
+    """x (B,T,64), w (nout,64) -> (B,T,nout).  py/main16.py:146,180."""
+    x = _req(x, "x")
+    B, T, _ = x.shape
+    nout = w.shape[0]
+    y = torch.empty(B, T, nout, device=x.device, dtype=torch.float32)
+    L.check(L.load().wm_head_fwd(L.ptr(x), L.ptr(_req(w, "w")), L.ptr(_req(b, "b")), L.ptr(y), B, T, nout,
+                                 _stream()), "wm_head_fwd")
+    return y
+
+
+def postprocess(delta_raw, s=None, fir=None, mode: int = L.POST_ALL, want_delta=True, want_sw=True,
+                want_rms=False, peak=PEAK, max_rms=MAX_RMS, eps=RMS_EPS):
+    """delta_raw, s: (B,T) -> (delta, s_w, rms) (None where not requested).  py/main16.py:245-248."""
+    d = _req(delta_raw, "delta_raw")
+    B, T = d.shape
+    sc = _req(s, "s") if s is not None else None
+    want_sw = want_sw and sc is not None
+    delta = torch.empty_like(d) if want_delta else None
+    s_w = torch.empty_like(d) if want_sw else None
+    rms = torch.empty(B, device=d.device, dtype=torch.float32) if want_rms else None
+    f = _req(fir, "fir") if fir is not None else None
+    L.check(L.load().wm_postprocess_fwd(L.ptr(d), L.ptr(sc), L.ptr(f), L.ptr(delta), L.ptr(s_w), L.ptr(rms),
+                                        B, T, mode, peak, max_rms, eps, _stream()), "wm_postprocess_fwd")
+    return delta, s_w, rms
+
+
+def detect_heads(logits, valid_len=None, want_probs=True, want_votes=True):
+    """logits (B,T,nout) contiguous -> dict(probs, clip_prob, msg_logits, vote_frac)."""
+    lg = _req(logits, "logits")
+    B, T, nout = lg.shape
+    dev = lg.device
+    probs = torch.empty(B, T, device=dev) if want_probs else None
+    clip = torch.empty(B, device=dev)
+    ml = torch.empty(B, max(nout - 1, 0), device=dev)
+    vf = torch.empty(B, max(nout - 1, 0), device=dev) if want_votes else None
+    vl = _req(valid_len, "valid_len", torch.int32) if valid_len is not None else None
+    L.check(L.load().wm_detect_heads_fwd(L.ptr(lg), L.ptr(vl), L.ptr(probs), L.ptr(clip), L.ptr(ml), L.ptr(vf),
+                                         B, T, nout, _stream()), "wm_detect_heads_fwd")
+    return {"probs": probs, "clip_prob": clip, "msg_logits": ml, "vote_frac": vf}
+
+
+# ---- module-level drivers ---------------------------------------------------
+def generator_fwd(blob, embedding, message, s):
+    """Generator.forward on s (B,T) -> delta_raw (B,T).  py/main16.py:149-162."""
+    lib = L.load()
+    s = _req(s, "s")
+    B, T = s.shape
+    out = torch.empty_like(s)
+    msg = _req(message, "message", torch.int64) if message is not None else None
+    emb = _req(embedding, "embedding") if embedding is not None else None
+    step = max_chunk()
+    for b0 in range(0, B, step):
+        nb = min(step, B - b0)
+        nbytes = lib.wm_generator_workspace_bytes(nb, T)
+        ws = _ws(nbytes, s.device)
+        L.check(lib.wm_generator_fwd(L.ptr(blob), L.ptr(emb), emb.shape[0] if emb is not None else 0,
+                                     L.ptr(msg[b0:b0 + nb]) if msg is not None else None,
+                                     L.ptr(s[b0:b0 + nb]), L.ptr(out[b0:b0 + nb]), L.ptr(ws), nbytes, nb, T,
+                                     _stream()), "wm_generator_fwd")
+    return out
+
+
+def detector_fwd(blob, x, nout: int):
+    """Detector.forward on x (B,T) -> logits (B,T,nout).  py/main16.py:183-186."""
+    lib = L.load()
+    x = _req(x, "x")
+    B, T = x.shape
+    out = torch.empty(B, T, nout, device=x.device, dtype=torch.float32)
+    step = max_chunk()
+    for b0 in range(0, B, step):
+        nb = min(step, B - b0)
+        nbytes = lib.wm_detector_workspace_bytes(nb, T)
+        ws = _ws(nbytes, x.device)
+        L.check(lib.wm_detector_fwd(L.ptr(blob), L.ptr(x[b0:b0 + nb]), L.ptr(out[b0:b0 + nb]), L.ptr(ws),
+                                    nbytes, nb, T, nout, _stream()), "wm_detector_fwd")
+    return out
+
+
+def detect_fwd(blob, x, nout: int, valid_len=None, want_probs=True, want_votes=True):
+    """Detector + heads, no logits tensor.  py/main16.py:1140-1146, :392-398."""
+    lib = L.load()
+    x = _req(x, "x")
+    B, T = x.shape
+    dev = x.device
+    nbits = max(nout - 1, 0)
+    probs = torch.empty(B, T, device=dev) if want_probs else None
+    clip = torch.empty(B, device=dev)
+    ml = torch.empty(B, nbits, device=dev)
+    vf = torch.empty(B, nbits, device=dev) if want_votes else None
+    vl = _req(valid_len, "valid_len", torch.int32) if valid_len is not None else None
+    step = max_chunk()
+    for b0 in range(0, B, step):
+        nb = min(step, B - b0)
+        nbytes = lib.wm_detector_workspace_bytes(nb, T)
+        ws = _ws(nbytes, dev)
+        sl = slice(b0, b0 + nb)
+        L.check(lib.wm_detect_fwd(L.ptr(blob), L.ptr(x[sl]), L.ptr(vl[sl]) if vl is not None else None,
+                                  L.ptr(probs[sl]) if probs is not None else None, L.ptr(clip[sl]),
+                                  L.ptr(ml[sl]) if nbits else None, L.ptr(vf[sl]) if vf is not None and nbits else None,
+                                  L.ptr(ws), nbytes, nb, T, nout, _stream()), "wm_detect_fwd")
+    return {"probs": probs, "clip_prob": clip, "msg_logits": ml, "vote_frac": vf}
+
+
+def embed_detect_fwd(g_blob, embedding, d_blob, fir, message, s, nout: int, post_mode: int = L.POST_ALL,
+                     want_delta=True, want_probs=True, want_votes=False, want_rms=False):
+    """The benchmark unit on device tensors: s (B,T), message (B,) -> dict."""
+    lib = L.load()
+    s = _req(s, "s")
+    B, T = s.shape
+    dev = s.device
+    nbits = max(nout - 1, 0)
+    msg = _req(message, "message", torch.int64) if message is not None else None
+    emb = _req(embedding, "embedding") if embedding is not None else None
+    f = _req(fir, "fir") if fir is not None else None
+    delta = torch.empty_like(s) if want_delta else None
+    s_w = torch.empty_like(s)
+    rms = torch.empty(B, device=dev) if want_rms else None
+    probs = torch.empty(B, T, device=dev) if want_probs else None
+    clip = torch.empty(B, device=dev)
+    ml = torch.empty(B, nbits, device=dev)
+    vf = torch.empty(B, nbits, device=dev) if want_votes else None
+    step = max_chunk()
+    for b0 in range(0, B, step):
+        nb = min(step, B - b0)
+        sl = slice(b0, b0 + nb)
+        nbytes = lib.wm_embed_detect_workspace_bytes(nb, T)
+        ws = _ws(nbytes, dev)
+        opt = lambda t: L.ptr(t[sl]) if t is not None else None
+        L.check(lib.wm_embed_detect_fwd(L.ptr(g_blob), L.ptr(emb), emb.shape[0] if emb is not None else 0,
+                                        L.ptr(d_blob), L.ptr(f), opt(msg), L.ptr(s[sl]), opt(delta), L.ptr(s_w[sl]),
+                                        opt(rms), opt(probs), L.ptr(clip[sl]), opt(ml) if nbits else None,
+                                        opt(vf) if nbits else None, L.ptr(ws), nbytes, nb, T, nout, post_mode,
+                                        _stream()), "wm_embed_detect_fwd")
+    return {"delta": delta, "s_w": s_w, "delta_rms": rms, "probs": probs, "clip_prob": clip,
+            "msg_logits": ml, "vote_frac": vf}
+
+
+class HostPipeline:
+    """embed+detect with HOST (pinned) buffers through wm_embed_detect_host: H2D, the device
+    pipeline in micro-batches of `chunk` clips and D2H all on the current stream."""
+
+    def __init__(self, g_blob, embedding, d_blob, fir, nout: int, T: int = 16000, chunk: Optional[int] = None,
+                 post_mode: int = L.POST_ALL, device=None):
+        self.lib = L.load()
+        self.g_blob, self.embedding, self.d_blob, self.fir = g_blob, embedding, d_blob, fir
+        self.nout, self.T, self.post_mode = nout, T, post_mode
+        self.chunk = int(chunk or max_chunk())
+        self.device = device or g_blob.device
+        self.nbytes = self.lib.wm_embed_detect_host_workspace_bytes(self.chunk, T, nout)
+        self.ws = _ws(self.nbytes, self.device)
+
+    def __call__(self, host_s, host_message, host_s_w, host_probs=None, host_clip_prob=None,
+                 host_msg_logits=None):
+        for name, t in (("host_s", host_s), ("host_s_w", host_s_w), ("host_probs", host_probs)):
+            if t is not None and (t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32):
+                raise ValueError(f"{name}: expected a contiguous fp32 host tensor")
+        B, T = host_s.shape
+        assert T == self.T
+        emb = self.embedding
+        L.check(self.lib.wm_embed_detect_host(
+            L.ptr(self.g_blob), L.ptr(emb), emb.shape[0] if emb is not None else 0, L.ptr(self.d_blob),
+            L.ptr(self.fir), L.ptr(host_message), L.ptr(host_s), L.ptr(host_s_w), L.ptr(host_probs),
+            L.ptr(host_clip_prob), L.ptr(host_msg_logits), L.ptr(self.ws), self.nbytes, B, T, self.nout,
+            self.chunk, self.post_mode, _stream()), "wm_embed_detect_host")

@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py — clip-seconds/sec of embed+detect (1 s @ 16 kHz) on N B200s.
+
+One "step" = one pass of the hot path over one batch of synthetic clips:
+    G -> fir/clamp/rms -> s + delta -> D -> sigmoid(ch 0), clip mean, message-logit means
+(the forward of the reference's evaluate_model, py/main16.py:378-398).
+Workload = BASELINE.json configs[1]: main16 embed+detect, batch 4096 clips, 16-bit message,
+per GPU (weak scaling: every rank owns its own 4096 clips, no data-path collective).
+
+  value   device-resident inputs, CUDA events, max over ranks
+  e2e     the same through wm_embed_detect_host with pinned HOST buffers (H2D + D2H inside)
+  roofline   the dominant kernel (64->64 convolution) timed alone with CUDA events
+  cpu_baseline  the oracle (torch CPU fp32 restatement of the reference) on a bounded sample
+
+`--impl reference` times the reference's own CPU implementation of the path (the oracle port;
+the reference's notebook export cannot be imported — SURVEY.md §8c) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+T = 16000
+FLOP_PER_CLIP = 5.964e9          # G 4.342 + D 1.622 GFLOP
+CONV64_K3_FLOP_PER_CLIP = 2 * 64 * 64 * 3 * T      # one 64->64 k3 convolution, 786.4 MFLOP / 2 per ResBlock
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) == 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for i, name in ((2, "hw_slowdown"), (3, "hw_thermal_slowdown"), (4, "sw_thermal_slowdown"), (5, "sw_power_cap")):
+            if any(r[i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def build_models(device):
+    import torch
+
+    import wmb200
+    torch.manual_seed(1234)
+    gen = wmb200.Generator(16)                      # random init: models/generator_best.pth is not in the mount
+    det = wmb200.Detector(16)
+    det.load_state_dict(torch.load(os.path.join(ROOT, "tests", "golden", "detector_best.pth")))
+    return gen.to(device).eval(), det.to(device).eval()
+
+
+def synth(B, seed, device, pin=False):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    s = (0.1 * torch.randn(B, T, generator=g)).clamp_(-0.99, 0.99)
+    m = torch.randint(0, 65536, (B,), generator=g)
+    if pin:
+        return s.pin_memory(), m.pin_memory()
+    return s.to(device), m.to(device)
+
+
+def cpu_reference_rate(sample_B, steps, warmup, threads=None):
+    """Oracle (port of the reference's CPU path) on `sample_B` clips per step."""
+    import torch
+
+    from oracle import wm_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    gen, det = build_models("cpu")
+    gsd = {k: v.detach() for k, v in gen.state_dict().items()}
+    dsd = {k: v.detach() for k, v in det.state_dict().items()}
+    s, m = synth(sample_B, 1234, "cpu")
+    s = s.unsqueeze(1)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.embed_detect(gsd, dsd, s, m)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return sample_B * len(times) / sum(times), cores, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_B = 16
+    rate, cores, times = cpu_reference_rate(sample_B, args.steps, args.warmup)
+    sample = f"{sample_B} clips per step (BASELINE configs[0]) of the {args.batch}-clip workload, torch CPU fp32"
+    line = {"impl": "reference", "metric": "clip-seconds/sec embed+detect (1 s@16 kHz)", "value": rate,
+            "unit": "clip-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"main16 embed+detect, batch {args.batch} clips x 1 s @ 16 kHz, 16-bit message",
+                       "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": "clip-s/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "clip-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import wmb200
+    from wmb200 import _lib as L
+    from wmb200 import ops
+    from wmb200.functional import fir_taps_on
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    B = args.batch
+    gen, det = build_models(dev)
+    fir = fir_taps_on(dev)
+    s, m = synth(B, 1234 + rank, dev)
+    g_blob, d_blob, emb = gen.packed(), det.packed(), gen.embedding_table()
+
+    def step():
+        return ops.embed_detect_fwd(g_blob, emb, d_blob, fir, m, s, det.nout, L.POST_ALL, want_delta=False,
+                                    want_probs=True, want_votes=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        n0 = ops.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), ops.launch_count() - n0
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, launches = timed(step, args.steps, args.warmup)
+    sampler.stop_flag.set()
+    sampler.join()
+    value = world * B * args.steps / (ms_dev / 1e3)
+
+    # ---- end to end: pinned host buffers through the C-ABI host entry point -------------
+    hs, hm = synth(B, 4321 + rank, dev, pin=True)
+    h_sw = torch.empty(B, T).pin_memory()
+    h_pr = torch.empty(B, T).pin_memory()
+    h_cp = torch.empty(B).pin_memory()
+    h_ml = torch.empty(B, 16).pin_memory()
+    pipe = ops.HostPipeline(g_blob, emb, d_blob, fir, det.nout, T, chunk=min(B, ops.max_chunk()))
+
+    def step_e2e():
+        pipe(hs, hm, h_sw, h_pr, h_cp, h_ml)
+        torch.cuda.current_stream().synchronize()     # the user's result is on the host
+
+    ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+    h2d = B * T * 4 + B * 8
+    d2h = 2 * B * T * 4 + B * 4 + B * 16 * 4
+
+    # ---- roofline of the dominant kernel: one 64->64 k3 convolution, timed alone ----------
+    Br = min(B, 1024)
+    x = torch.randn(Br, T, 64, device=dev)
+    y = torch.empty_like(x)
+    wk = g_blob[L.G_RB0 + L.RB_W1:L.G_RB0 + L.RB_W1 + 3 * 4096]
+    bk = g_blob[L.G_RB0 + L.RB_B1:L.G_RB0 + L.RB_B1 + 64]
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+
+    def conv_once():
+        L.check(lib.wm_conv64_fwd(x.data_ptr(), wk.data_ptr(), bk.data_ptr(), None, None, y.data_ptr(), Br, T, 3, 1,
+                                  st), "wm_conv64_fwd")
+
+    reps = 10
+    ms_conv, _ = timed(conv_once, reps, 3)
+    conv_tflops = CONV64_K3_FLOP_PER_CLIP * Br * reps / (ms_conv / 1e3) / 1e12
+    del x, y
+    mode = ops.get_math_mode()
+    roofline = {"bound": "tensor", "kernel": "conv64 k3 (%s)" % ("fp32 FMA" if mode == L.MATH_FP32 else "tcgen05 bf16x2"),
+                "achieved": conv_tflops, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                "frac": conv_tflops / peaks["bf16_burst"], "traffic": None, "peak_source": peaks["src"] + " burst",
+                "launch_ms": ms_conv / reps, "clips_per_launch": Br,
+                "path_frac_of_sustained": value / world * FLOP_PER_CLIP / (peaks["bf16_sustained"] * 1e12)}
+
+    if rank == 0:
+        cpu_rate, cores, _ = cpu_reference_rate(16, 3, 1)
+        clocks = sampler.summary()
+        line = {"metric": "clip-seconds/sec embed+detect (1 s@16 kHz)", "value": value, "unit": "clip-s/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if mode == L.MATH_FP32 else "bf16x2 (fp32 accumulate)", "data": "synthetic",
+                "config": {"workload": f"main16 embed+detect, batch {B} clips x 1 s @ 16 kHz per GPU, 16-bit message "
+                                       "(BASELINE configs[1])",
+                           "weights": "Generator random init seed 1234 (checkpoint absent), shipped detector_best.pth",
+                           "l2": "inputs (262 MB/step) and activations larger than L2",
+                           "math_mode": mode, "chunk": ops.max_chunk()},
+                "e2e": {"value": e2e, "unit": "clip-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": {"value": cpu_rate, "unit": "clip-s/s", "cores": cores, "kind": "port",
+                                 "sample": "16 clips per pass (BASELINE configs[0]), best-effort torch CPU fp32, 3 passes"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4096, help="clips per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500), __file__,
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
+               "--batch", str(args.batch)]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,195 @@
+/*
+ * wmb200 — C ABI of the B200-native main16 embed+detect path.
+ *
+ * The reference (Spandan7724/Audio-Watermarking-...) is pure Python and has no
+ * FFI; every entry point below replaces the arithmetic of one Python call site
+ * of the reference (file:line given per function, relative to the reference
+ * root).  A maintainer of the reference binds this library with ctypes exactly
+ * as `audio-watermarking-..._b200/_lib.py` does.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name says `host`;
+ *   - waveforms are fp32 [b][t]; hidden activations of the single-operator
+ *     entry points are fp32 channels-last x[b][t][c], c = 0..63 contiguous;
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as
+ *     void*), never allocates, never synchronises;
+ *   - return value 0 = success, negative = error; wm_last_error() returns the
+ *     message of the last failure on the calling thread;
+ *   - weights arrive as one packed fp32 blob per module (layout below), built
+ *     on the host side from the reference state dict (eval BatchNorm folded).
+ *   - the library only runs on compute capability 10.x; there is no fallback.
+ */
+#ifndef WMB200_H
+#define WMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
+#define WM_FIR_TAPS 101    /* py/main16.py:53 */
+#define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
+#define WM_ABI_VERSION 4
+#define WM_POST_FIR 1
+#define WM_POST_CLAMP 2
+#define WM_POST_RMS 4
+#define WM_POST_ALL 7
+
+/* ---- packed fp32 weight blobs (offsets in floats) ------------------------
+ * conv weights are stored tap-major:  w[j][ci][co]  (co contiguous), i.e. the
+ * reference's Conv1d weight (co,ci,j) permuted to (j,ci,co) with the eval-mode
+ * BatchNorm scale folded in; ConvTranspose1d (ci,co,j) is flipped along j and
+ * stored in the same (j,ci,co) form.  Biases have BatchNorm folded in.       */
+enum {
+  WM_RB_W1 = 0,                          /* [3][64][64] */
+  WM_RB_B1 = WM_RB_W1 + 3 * 64 * 64,     /* [64]        */
+  WM_RB_W2 = WM_RB_B1 + 64,              /* [3][64][64] */
+  WM_RB_B2 = WM_RB_W2 + 3 * 64 * 64,     /* [64]        */
+  WM_RB_SIZE = WM_RB_B2 + 64
+};
+enum {                                   /* Generator, py/main16.py:128-162 */
+  WM_G_IN_W = 0,                         /* encoder.0  [7][64]       */
+  WM_G_IN_B = WM_G_IN_W + 7 * 64,        /* [64]                     */
+  WM_G_RB0 = WM_G_IN_B + 64,             /* encoder.1                */
+  WM_G_RB1 = WM_G_RB0 + WM_RB_SIZE,      /* encoder.2                */
+  WM_G_LSTM_WIH = WM_G_RB1 + WM_RB_SIZE, /* [256][64] rows i,f,g,o   */
+  WM_G_LSTM_WHH = WM_G_LSTM_WIH + 256 * 64,
+  WM_G_LSTM_B = WM_G_LSTM_WHH + 256 * 64,/* [256] = b_ih + b_hh      */
+  WM_G_CT_W = WM_G_LSTM_B + 256,         /* decoder.0 as conv [7][64][64] */
+  WM_G_CT_B = WM_G_CT_W + 7 * 64 * 64,   /* [64]                     */
+  WM_G_RB2 = WM_G_CT_B + 64,             /* decoder.1                */
+  WM_G_HEAD_W = WM_G_RB2 + WM_RB_SIZE,   /* decoder.2 [64]           */
+  WM_G_HEAD_B = WM_G_HEAD_W + 64,        /* [1] (+3 pad)             */
+  WM_G_SIZE = WM_G_HEAD_B + 4
+};
+enum {                                   /* Detector, py/main16.py:170-186 */
+  WM_D_IN_W = 0,                         /* model.0 [7][64]          */
+  WM_D_IN_B = WM_D_IN_W + 7 * 64,
+  WM_D_RB0 = WM_D_IN_B + 64,             /* model.1                  */
+  WM_D_RB1 = WM_D_RB0 + WM_RB_SIZE,      /* model.2                  */
+  WM_D_HEAD_W = WM_D_RB1 + WM_RB_SIZE,   /* model.3 [nout<=32][64]   */
+  WM_D_HEAD_B = WM_D_HEAD_W + 32 * 64,   /* [32]                     */
+  WM_D_SIZE = WM_D_HEAD_B + 32
+};
+
+/* Arithmetic of the 64->64 convolutions (the tensor-pipe part of the path).
+ *   WM_MATH_FP32   CUDA-core fp32 FMA (bit-for-bit the reference's operation order
+ *                  up to summation order; the on-GPU cross-check for the other mode)
+ *   WM_MATH_BF16X2 tcgen05 kind::f16 with every operand split into bf16 hi+lo and
+ *                  all four partial products accumulated in fp32 TMEM              */
+enum { WM_MATH_FP32 = 0, WM_MATH_BF16X2 = 1 };
+
+int wm_abi_version(void);
+const char *wm_last_error(void);
+/* 1 when the current device is compute capability 10.x; the library refuses
+ * to launch anywhere else (there is no fallback path). */
+int wm_device_ok(void);
+/* Select the conv arithmetic for subsequent calls of this process (default
+ * WM_MATH_BF16X2 once available).  Returns the previous mode. */
+int wm_set_math_mode(int mode);
+int wm_get_math_mode(void);
+/* Number of kernels this library has launched since load (bench.py gpu_launches). */
+unsigned long long wm_launch_count(void);
+
+/* ---- single operators ---------------------------------------------------*/
+
+/* nn.Conv1d(1,64,7,padding=3)  — py/main16.py:134 (Generator) and :177 (Detector).
+ * s[B][T] -> y[B][T][64];  w[7][64], b[64]. */
+int wm_conv_in_k7_fwd(const float *s, const float *w, const float *b, float *y,
+                      int B, int T, void *stream);
+
+/* One 64->64 convolution with fused epilogue — the Conv1d(64,64,3,p=1)+BatchNorm
+ * (+ReLU) halves of ResBlock, py/main16.py:116-121, and ConvTranspose1d(64,64,7,
+ * p=3), py/main16.py:144 (taps = 7, weights pre-flipped).
+ *   y = act( conv(x + chan_add) + bias + residual )
+ * chan_add (nullable) is a per-clip [B][64] vector added to every in-range time
+ * step of x before the convolution (the message embedding, py/main16.py:156-159);
+ * residual (nullable) is [B][T][64]; relu != 0 applies max(.,0). */
+int wm_conv64_fwd(const float *x, const float *w, const float *bias, const float *residual,
+                  const float *chan_add, float *y, int B, int T, int taps, int relu,
+                  void *stream);
+
+/* nn.LSTM(64,64,batch_first=True) with zero initial state, all hidden states
+ * returned — py/main16.py:138,153.  x[B][T][64] -> h[B][T][64].
+ * w_ih, w_hh [256][64] (rows i,f,g,o), bias[256] = b_ih + b_hh. */
+int wm_lstm_fwd(const float *x, const float *w_ih, const float *w_hh, const float *bias,
+                float *h, int B, int T, void *stream);
+
+/* Conv1d(64,nout,1): py/main16.py:146 (nout = 1) and :180 (nout = 1+bits <= 32).
+ * x[B][T][64] -> y[B][T][nout] (this IS the permute(0,2,1) view of :186). */
+int wm_head_fwd(const float *x, const float *w, const float *b, float *y,
+                int B, int T, int nout, void *stream);
+
+/* Delta post-processing + mix, py/main16.py:245-248 (fir_lowpass :53-64,
+ * clamp_peak :66-67, limit_rms :69-72, s + delta :248).
+ * mode is a bit mask: WM_POST_FIR | WM_POST_CLAMP | WM_POST_RMS.
+ *   mode 7: delta = limit_rms(clamp_peak(fir(delta_raw)));  s_w = s + delta   (:245-248)
+ *   mode 0: delta = delta_raw;  s_w = s + delta   (generate_watermarked_audio, :1006)
+ * fir[101] are the taps (device, nullable unless WM_POST_FIR); delta / s_w nullable;
+ * rms_out (nullable) [B] receives sqrt(mean(delta^2)) of the final delta
+ * (evaluate_model, py/main16.py:403). */
+int wm_postprocess_fwd(const float *delta_raw, const float *s, const float *fir,
+                       float *delta, float *s_w, float *rms_out, int B, int T, int mode,
+                       float peak, float max_rms, float eps, void *stream);
+
+/* Detection heads on logits[B][T][nout] — py/main16.py:1142-1146, :393-398.
+ *   probs[B][T]          sigmoid(logits[:,:,0])                    (nullable)
+ *   clip_prob[B]         mean over the first valid_len[b] samples
+ *   msg_logits[B][nout-1] mean over valid samples of logits[:,:,1:]
+ *   vote_frac[B][nout-1]  fraction of valid samples with logit > 0 (nullable)
+ * valid_len (nullable, int32 [B]) defaults to T (tail segments, :1159-1164). */
+int wm_detect_heads_fwd(const float *logits, const int *valid_len, float *probs,
+                        float *clip_prob, float *msg_logits, float *vote_frac,
+                        int B, int T, int nout, void *stream);
+
+/* ---- module-level drivers ----------------------------------------------*/
+
+size_t wm_generator_workspace_bytes(int B, int T);
+/* Generator.forward, py/main16.py:149-162.  s[B][T], message (nullable, int64 [B]),
+ * embedding (nullable) [emb_rows][64] -> delta_raw[B][T]. */
+int wm_generator_fwd(const float *blob, const float *embedding, int64_t emb_rows,
+                     const int64_t *message, const float *s, float *delta_raw,
+                     void *workspace, size_t workspace_bytes, int B, int T, void *stream);
+
+size_t wm_detector_workspace_bytes(int B, int T);
+/* Detector.forward, py/main16.py:183-186.  x[B][T] -> logits[B][T][nout]. */
+int wm_detector_fwd(const float *blob, const float *x, float *logits, void *workspace,
+                    size_t workspace_bytes, int B, int T, int nout, void *stream);
+
+/* Detector + heads without materialising the logits: the per-segment body of
+ * detect_watermark, py/main16.py:1140-1146 (and evaluate_model :392-398).
+ * Outputs as wm_detect_heads_fwd. */
+int wm_detect_fwd(const float *blob, const float *x, const int *valid_len, float *probs,
+                  float *clip_prob, float *msg_logits, float *vote_frac, void *workspace,
+                  size_t workspace_bytes, int B, int T, int nout, void *stream);
+
+/* The benchmark unit: one batch of clips through
+ *   G -> fir/clamp/rms (post_mode WM_POST_ALL) or raw (post_mode 0) -> s + delta -> D -> heads,
+ * i.e. the forward of py/main16.py:378-398.  All outputs nullable except s_w. */
+size_t wm_embed_detect_workspace_bytes(int B, int T);
+int wm_embed_detect_fwd(const float *g_blob, const float *embedding, int64_t emb_rows,
+                        const float *d_blob, const float *fir, const int64_t *message,
+                        const float *s, float *delta, float *s_w, float *delta_rms,
+                        float *probs, float *clip_prob, float *msg_logits, float *vote_frac,
+                        void *workspace, size_t workspace_bytes, int B, int T, int nout,
+                        int post_mode, void *stream);
+
+/* Same unit with HOST (pinned) buffers: H2D of s and message, the device pipeline in
+ * micro-batches of `chunk` clips, D2H of s_w, probs, clip_prob and msg_logits, all on
+ * `stream`.  This is what the file-level API and bench.py's e2e leg call.  The device
+ * staging area lives in the caller's workspace (wm_embed_detect_host_workspace_bytes). */
+size_t wm_embed_detect_host_workspace_bytes(int chunk, int T, int nout);
+int wm_embed_detect_host(const float *g_blob, const float *embedding, int64_t emb_rows,
+                         const float *d_blob, const float *fir,
+                         const int64_t *host_message, const float *host_s,
+                         float *host_s_w, float *host_probs, float *host_clip_prob,
+                         float *host_msg_logits, void *workspace, size_t workspace_bytes,
+                         int B, int T, int nout, int chunk, int post_mode, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WMB200_H */

@@ -1,0 +1,309 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the golden fixtures
+generated from the reference.  Tolerances are the north star's: watermark delta max-abs
+<= 1e-3 of full scale, per-sample probabilities within 1e-3, decoded bits exact (asserted
+where |mean logit| exceeds the measured error bound)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import wmb200
+from oracle import wm_oracle as O
+from tests import helpers as H
+from wmb200 import _lib as L
+from wmb200 import ops, packing
+
+pytestmark = pytest.mark.gpu
+
+DELTA_TOL = 1e-3      # north star: delta max-abs error of full scale (1.0)
+PROB_TOL = 1e-3       # north star: per-sample probabilities
+TIGHT = 2e-5          # fp32 kernels vs fp32 oracle (summation order only)
+W = H.weights()
+IO = H.io()
+DEV = "cuda"
+
+
+def maxerr(a, b):
+    a = a.detach().float().cpu() if isinstance(a, torch.Tensor) else torch.as_tensor(a)
+    b = b.detach().float().cpu() if isinstance(b, torch.Tensor) else torch.as_tensor(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max()) if a.numel() else 0.0
+
+
+def tol_tight():
+    return TIGHT if ops.get_math_mode() == L.MATH_FP32 else 2e-4
+
+
+@pytest.fixture(scope="module")
+def gen_B():
+    gsd, rows = H.gen_sd(W, "B")
+    g = wmb200.Generator(16)
+    gsd = dict(gsd, **{"embedding.weight": H.full_embedding(IO, rows)})
+    g.load_state_dict(gsd)
+    return g.to(DEV).eval()
+
+
+@pytest.fixture(scope="module")
+def gen_A():
+    gsd, rows = H.gen_sd(W, "A")
+    g = wmb200.Generator(16)
+    g.load_state_dict(dict(gsd, **{"embedding.weight": H.full_embedding(IO, rows)}))
+    return g.to(DEV).eval()
+
+
+@pytest.fixture(scope="module")
+def det():
+    d = wmb200.Detector(16)
+    d.load_state_dict(torch.load(os.path.join(H.GOLDEN, "detector_best.pth")))   # shipped file, prefixed keys
+    return d.to(DEV).eval()
+
+
+# ---------------------------------------------------------------- single operators
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 127), (2, 128), (2, 1000), (1, 16000)])
+def test_conv_in_k7(B, T):
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    s = torch.randn(B, T, generator=g)
+    w = torch.randn(64, 1, 7, generator=g) * 0.3
+    b = torch.randn(64, generator=g)
+    ref = F.conv1d(s.unsqueeze(1), w, b, padding=3).permute(0, 2, 1)
+    y = ops.conv_in_k7(s.to(DEV), w[:, 0, :].t().contiguous().to(DEV), b.to(DEV))
+    assert maxerr(y, ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,T,taps", [(1, 1, 3), (2, 5, 7), (3, 129, 3), (2, 300, 7), (2, 16000, 3), (1, 1000, 1)])
+@pytest.mark.parametrize("variant", ["plain", "relu_res", "chan_add"])
+def test_conv64(B, T, taps, variant):
+    g = torch.Generator().manual_seed(B * 100 + T + taps)
+    x = torch.randn(B, 64, T, generator=g)
+    w = torch.randn(64, 64, taps, generator=g) / (8.0 * taps ** 0.5)
+    b = torch.randn(64, generator=g)
+    res = torch.randn(B, 64, T, generator=g) if variant == "relu_res" else None
+    ca = torch.randn(B, 64, generator=g) if variant == "chan_add" else None
+    xin = x + ca.unsqueeze(-1) if ca is not None else x
+    ref = F.conv1d(xin, w, b, padding=taps // 2)
+    if res is not None:
+        ref = F.relu(ref + res)
+    wp = w.permute(2, 1, 0).contiguous()
+    cl = lambda t: t.permute(0, 2, 1).contiguous().to(DEV)
+    y = ops.conv64(cl(x), wp.to(DEV), b.to(DEV), residual=cl(res) if res is not None else None,
+                   chan_add=ca.to(DEV) if ca is not None else None, taps=taps, relu=res is not None)
+    assert maxerr(y.permute(0, 2, 1), ref) < tol_tight() * max(1.0, float(ref.abs().max()))
+
+
+def test_conv_transpose_equivalence():
+    """ConvTranspose1d(64,64,7,p=3) == conv with flipped taps (py/main16.py:144)."""
+    gsd, _ = H.gen_sd(W, "A")
+    x = torch.randn(2, 64, 700, generator=torch.Generator().manual_seed(11))
+    ref = F.conv_transpose1d(x, gsd["decoder.0.weight"], gsd["decoder.0.bias"], padding=3)
+    blob = packing.pack_generator(gsd).to(DEV)
+    y = ops.conv64(x.permute(0, 2, 1).contiguous().to(DEV), blob[L.G_CT_W:L.G_CT_W + 7 * 4096],
+                   blob[L.G_CT_B:L.G_CT_B + 64], taps=7)
+    assert maxerr(y.permute(0, 2, 1), ref) < tol_tight()
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 50), (9, 333), (20, 64), (300, 40), (1190, 17)])
+def test_lstm_vs_oracle(B, T):
+    gsd, _ = H.gen_sd(W, "A")
+    x = torch.randn(B, T, 64, generator=torch.Generator().manual_seed(B + T))
+    ref = O.lstm(x, gsd)
+    h = ops.lstm(x.to(DEV), gsd["lstm.weight_ih_l0"].to(DEV), gsd["lstm.weight_hh_l0"].to(DEV),
+                 (gsd["lstm.bias_ih_l0"] + gsd["lstm.bias_hh_l0"]).to(DEV))
+    assert maxerr(h, ref) < 1e-5
+
+
+def test_lstm_full_length_large_weights():
+    """16 000 dependent steps with weights scaled up so the gates saturate and the state carries."""
+    g = torch.Generator().manual_seed(5)
+    sd = {"lstm.weight_ih_l0": torch.randn(256, 64, generator=g) * 0.4,
+          "lstm.weight_hh_l0": torch.randn(256, 64, generator=g) * 0.4,
+          "lstm.bias_ih_l0": torch.randn(256, generator=g) * 0.2, "lstm.bias_hh_l0": torch.zeros(256)}
+    x = torch.randn(3, 16000, 64, generator=g)
+    ref = O.lstm(x, sd)
+    h = ops.lstm(x.to(DEV), sd["lstm.weight_ih_l0"].to(DEV), sd["lstm.weight_hh_l0"].to(DEV),
+                 sd["lstm.bias_ih_l0"].to(DEV))
+    assert maxerr(h, ref) < 2e-4            # chaotic regime: fp32 rounding differences get amplified
+
+
+@pytest.mark.parametrize("nout", [1, 17, 32])
+def test_head(nout):
+    g = torch.Generator().manual_seed(nout)
+    x = torch.randn(3, 777, 64, generator=g)
+    w = torch.randn(nout, 64, generator=g) * 0.2
+    b = torch.randn(nout, generator=g)
+    ref = x @ w.t() + b
+    assert maxerr(ops.head(x.to(DEV), w.to(DEV), b.to(DEV)), ref) < 1e-5
+
+
+@pytest.mark.parametrize("scale", [0.001, 0.05, 1.0])
+@pytest.mark.parametrize("T", [16000, 1000, 101, 7])
+def test_postprocess_vs_oracle(scale, T):
+    g = torch.Generator().manual_seed(int(scale * 1000) + T)
+    d = torch.randn(4, 1, T, generator=g) * scale
+    s = torch.randn(4, 1, T, generator=g) * 0.1
+    ref = O.postprocess(d)
+    fir = packing.fir_taps().to(DEV)
+    delta, s_w, rms = ops.postprocess(d[:, 0].to(DEV), s[:, 0].to(DEV), fir, L.POST_ALL, want_rms=True)
+    assert maxerr(delta, ref[:, 0]) < 1e-7
+    assert maxerr(s_w, (s + ref)[:, 0]) < 1e-7
+    assert maxerr(rms, ref[:, 0].pow(2).mean(1).sqrt()) < 1e-7
+    # the helpers by name
+    assert maxerr(wmb200.fir_lowpass(d.to(DEV)), O.fir_lowpass(d)) < 1e-6 * max(1.0, scale)
+    assert maxerr(wmb200.clamp_peak(d.to(DEV)), O.clamp_peak(d)) == 0.0
+    assert maxerr(wmb200.limit_rms(d.to(DEV)), O.limit_rms(d)) < 1e-7 * max(1.0, scale)
+    raw, sw0, _ = ops.postprocess(d[:, 0].to(DEV), s[:, 0].to(DEV), None, 0)
+    assert maxerr(raw, d[:, 0]) == 0.0 and maxerr(sw0, (s + d)[:, 0]) == 0.0
+
+
+def test_detect_heads_with_ragged_valid_lengths():
+    g = torch.Generator().manual_seed(2)
+    lg = torch.randn(5, 16000, 17, generator=g) * 2
+    valid = torch.tensor([16000, 1, 4800, 15999, 0], dtype=torch.int32)
+    r = ops.detect_heads(lg.to(DEV), valid.to(DEV))
+    assert maxerr(r["probs"], torch.sigmoid(lg[:, :, 0])) < 1e-6
+    for b in range(5):
+        n = int(valid[b])
+        if n == 0:
+            assert float(r["clip_prob"][b]) == 0.0
+            continue
+        assert abs(float(r["clip_prob"][b]) - float(torch.sigmoid(lg[b, :n, 0]).mean())) < 1e-6
+        assert maxerr(r["msg_logits"][b], lg[b, :n, 1:].mean(0)) < 1e-6
+        assert maxerr(r["vote_frac"][b], (lg[b, :n, 1:] > 0).float().mean(0)) < 1e-6
+
+
+# ---------------------------------------------------------------- modules vs golden fixtures
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_generator_matches_reference_goldens(tag, gen_A, gen_B):
+    gen = gen_A if tag == "A" else gen_B
+    s = torch.from_numpy(IO["s"]).to(DEV)
+    msg = torch.from_numpy(IO["messages"]).to(DEV)
+    d = gen(s, msg)
+    assert d.shape == (5, 1, 16000)
+    assert maxerr(d, IO[f"{tag}/delta_raw"]) < DELTA_TOL
+    assert maxerr(gen(s[:1]), IO[f"{tag}/delta_nomsg0"]) < DELTA_TOL      # message=None branch (:156)
+    delta, s_w = wmb200.postprocess_delta(d, s)
+    assert maxerr(delta, IO[f"{tag}/delta"]) < DELTA_TOL
+    assert maxerr(s_w, IO[f"{tag}/s_w"]) < DELTA_TOL
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_detector_matches_reference_goldens(tag, det):
+    x = torch.cat([torch.from_numpy(IO[f"{tag}/s_w"]), torch.from_numpy(IO["s"])], 0).to(DEV)
+    lg = det(x)
+    assert lg.shape == (10, 16000, 17)
+    assert maxerr(lg[0], IO[f"{tag}/logits_clip0"]) < 4e-3              # logit error giving <= 1e-3 in probability
+    assert maxerr(torch.sigmoid(lg[:, :, 0]), IO[f"{tag}/probs"]) < PROB_TOL
+    r = det.detect(x)
+    assert maxerr(r["probs"], IO[f"{tag}/probs"]) < PROB_TOL
+    ml_ref = IO[f"{tag}/msg_logits"]
+    err = maxerr(r["msg_logits"], ml_ref)
+    assert err < 1e-3
+    safe = np.abs(ml_ref) > 4 * max(err, 1e-6)                           # bit-exact where the sign is decidable
+    assert np.array_equal((r["msg_logits"].cpu().numpy() > 0)[safe], (ml_ref > 0)[safe])
+    assert safe.mean() > 0.9
+    vote = (r["vote_frac"] > 0.5).cpu().numpy()
+    assert (vote != IO[f"{tag}/bits_vote"]).mean() < 0.02
+
+
+def test_embed_detect_unit_vs_oracle(gen_B, det):
+    g = torch.Generator().manual_seed(77)
+    s = (0.1 * torch.randn(3, 1, 16000, generator=g)).clamp(-0.99, 0.99)
+    msg = torch.from_numpy(IO["rng_messages"][:3].astype(np.int64))
+    gsd, rows = H.gen_sd(W, "B")
+    ref = O.embed_detect(gsd, H.det_sd(W), s, msg, emb_rows=H.emb_for(IO, rows, msg))
+    r = wmb200.embed_detect(gen_B, det, s.to(DEV), msg.to(DEV), want_rms=True)
+    assert maxerr(r["delta"], ref["delta"]) < DELTA_TOL
+    assert maxerr(r["s_w"], ref["s_w"]) < DELTA_TOL
+    assert maxerr(r["probs"], ref["probs"]) < PROB_TOL
+    assert maxerr(r["clip_prob"], ref["clip_prob"]) < PROB_TOL
+    assert maxerr(r["msg_logits"], ref["msg_logits"]) < 1e-3
+    assert maxerr(r["delta_rms"], ref["delta"][:, 0].pow(2).mean(1).sqrt()) < 1e-6
+    raw = wmb200.embed_detect(gen_B, det, s.to(DEV), msg.to(DEV), postprocess=False)
+    assert maxerr(raw["delta"], ref["delta_raw"]) < DELTA_TOL
+
+
+def test_file_api_matches_reference(tmp_path, gen_B, det):
+    fa = H.load_npz("main16_file_api.npz")
+    import wave
+    p = str(tmp_path / "in.wav")
+    with wave.open(p, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+        w.writeframes(fa["waveform_pcm16"].tobytes())
+    res = wmb200.generate_watermarked_audio(p, gen_B, str(tmp_path / "out" / "wm.wav"), 16, DEV,
+                                            messages=fa["messages"].tolist())
+    assert res["watermarked_waveform"].shape == fa["watermarked"].shape == (1, 36800)
+    assert maxerr(res["delta_waveform"], fa["delta"]) < DELTA_TOL
+    assert maxerr(res["watermarked_waveform"], fa["watermarked"]) < DELTA_TOL
+    m = res["metrics"]
+    got = np.array([m["watermark_rms"], m["si_snr_db"], m["power_ratio_db"]])
+    assert np.allclose(got, fa["metrics"], rtol=2e-3, atol=1e-5), (got, fa["metrics"])
+    assert os.path.exists(str(tmp_path / "out" / "wm.wav"))
+    # detect on the clean file and on a 16-bit re-quantised watermarked file (as make_golden.py did)
+    r0 = wmb200.detect_watermark(p, det, 0.5, False, DEV)
+    assert abs(r0["mean_probability"] - float(fa["clean_mean_probability"])) < PROB_TOL
+    assert r0["temporal_probs"].shape == (36800,) and r0["temporal_probs"].dtype == np.float32
+    conf_err = np.abs(np.array(r0["message_confidence"]) - fa["clean_message_confidence"]).max()
+    assert conf_err < 1e-3
+    pw = str(tmp_path / "wm16.wav")
+    pcm = (torch.from_numpy(fa["watermarked"][0]).clamp(-1, 1) * 32767.0).round().to(torch.int16).numpy()
+    with wave.open(pw, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+        w.writeframes(pcm.tobytes())
+    r1 = wmb200.detect_watermark(pw, det, 0.5, False, DEV)
+    assert abs(r1["mean_probability"] - float(fa["wm_mean_probability"])) < PROB_TOL
+    assert np.abs(r1["temporal_probs"] - fa["wm_temporal_probs"]).max() < PROB_TOL
+    assert r1["is_watermarked"] == (float(fa["wm_mean_probability"]) > 0.5)
+    assert set(r1) == {"mean_probability", "is_watermarked", "temporal_probs", "decision", "predicted_message",
+                       "message_confidence"}
+    # generator on a tensor with the per-segment RNG path (no explicit messages)
+    torch.manual_seed(1)
+    r2 = wmb200.generate_watermarked_audio(torch.from_numpy(fa["waveform_pcm16"].astype(np.float32) / 32768.0),
+                                           gen_B, None, 16, DEV)
+    assert r2["messages"].shape == (3,) and r2["delta_waveform"].shape == (1, 36800)
+
+
+# ---------------------------------------------------------------- size-independent properties
+def test_properties_at_scale(gen_B, det):
+    """Batch-composition independence, determinism, the RMS cap and the peak clamp on a batch
+    that spans several LSTM waves and conv grid rows."""
+    B = 1300
+    g = torch.Generator().manual_seed(9)
+    s = (0.1 * torch.randn(B, 1, 16000, generator=g)).clamp(-0.99, 0.99).to(DEV)
+    msg = torch.randint(0, 65536, (B,), generator=g)
+    msg[:13] = torch.from_numpy(np.concatenate([IO["messages"], IO["rng_messages"]]))
+    msg[13:] = msg[13:] % 13
+    msg[13:] = msg[:13][msg[13:]]                  # only rows present in the fixture embedding
+    msg = msg.to(DEV)
+    r = wmb200.embed_detect(gen_B, det, s, msg, want_rms=True)
+    r2 = wmb200.embed_detect(gen_B, det, s, msg, want_rms=True)
+    for k in ("delta", "s_w", "probs", "clip_prob", "msg_logits"):
+        assert torch.equal(r[k], r2[k]), k                                   # deterministic
+    idx = torch.tensor([0, 7, 591, 592, 1183, 1184, 1299], device=DEV)
+    sub = wmb200.embed_detect(gen_B, det, s[idx], msg[idx])
+    assert maxerr(sub["delta"], r["delta"][idx]) < 1e-6                       # a clip never sees its neighbours
+    assert maxerr(sub["probs"], r["probs"][idx]) < 1e-5
+    d = r["delta"][:, 0]
+    rms = d.pow(2).mean(1).sqrt()
+    assert float(rms.max()) <= 0.005 * (1 + 1e-5)                             # limit_rms (:69-72)
+    assert float(d.abs().max()) <= 0.02                                       # clamp_peak (:66-67)
+    assert maxerr(r["delta_rms"], rms) < 1e-7
+    assert maxerr(r["s_w"], s + r["delta"]) == 0.0
+    assert maxerr(r["clip_prob"], r["probs"].mean(1)) < 1e-5
+    assert bool(((r["probs"] >= 0) & (r["probs"] <= 1)).all())
+
+
+def test_empty_batch_and_bad_arguments(gen_B, det):
+    e = torch.zeros(0, 1, 16000, device=DEV)
+    assert gen_B(e, torch.zeros(0, dtype=torch.int64, device=DEV)).shape == (0, 1, 16000)
+    assert det(e).shape == (0, 16000, 17)
+    with pytest.raises(ValueError):
+        gen_B(torch.zeros(2, 16000, device=DEV))
+    with pytest.raises(ValueError):
+        gen_B(torch.zeros(2, 1, 16000, device=DEV), torch.zeros(3, dtype=torch.int64, device=DEV))
+    with pytest.raises(wmb200._lib.WmError):
+        ops.conv64(torch.zeros(1, 8, 64, device=DEV), torch.zeros(5, 64, 64, device=DEV),
+                   torch.zeros(64, device=DEV), taps=5)
+    # non-1 s lengths work too (T is a runtime argument of every kernel)
+    x = torch.randn(2, 1, 3000, generator=torch.Generator().manual_seed(4)) * 0.1
+    assert maxerr(det(x.to(DEV)), O.detector_forward(H.det_sd(W), x)) < 4e-3
