@@ -19,8 +19,8 @@ __global__ void __launch_bounds__(256) conv_in_k7_kernel(const float *__restrict
                                                           const float *__restrict__ bias,
                                                           float *__restrict__ y, int T) {
   constexpr int TT = 128;  // time steps per block
-  __shared__ float ss[TT + 6];
-  __shared__ float ws[7 * 64 + 64];
+  __shared__ __align__(16) float ss[TT + 8];
+  __shared__ __align__(16) float ws[7 * 64 + 64];
   const int b = blockIdx.y, t0 = blockIdx.x * TT, tid = threadIdx.x;
   const float *sb = s + (size_t)b * T;
   for (int i = tid; i < TT + 6; i += 256) {

@@ -122,7 +122,9 @@ def main():
     ref = extract(os.path.join(REF, "py/main16.py"), WANT, CONSTS)
     msgs = torch.tensor([0, 1, 5, 40000, 65535], dtype=torch.int64)
     rng_msgs = torch.randint(0, 65536, (8,), generator=torch.Generator().manual_seed(7))
-    keep_rows = torch.unique(torch.cat([msgs, rng_msgs]))
+    torch.manual_seed(2024)                      # the draws generate_watermarked_audio makes below (:1001)
+    file_msgs = torch.cat([torch.randint(0, 2 ** 16, (1,)) for _ in range(3)])
+    keep_rows = torch.unique(torch.cat([msgs, rng_msgs, file_msgs]))
 
     # ---- detector: shipped weights -------------------------------------
     dsd = torch.load(os.path.join(REF, "models/detector_best.pth"), map_location="cpu")
@@ -197,8 +199,6 @@ def main():
     gen = gens["B"]
     torch.manual_seed(2024)
     res = ref.generate_watermarked_audio(tmp, gen, None, 16, "cpu")
-    torch.manual_seed(2024)
-    file_msgs = torch.cat([torch.randint(0, 2 ** 16, (1,)) for _ in range(3)])
     tmpw = os.path.join(HERE, "_tmp_wm.wav")
     write_wav(tmpw, res["watermarked_waveform"][0])
     dres = ref.detect_watermark(tmpw, det, 0.5, False, "cpu")
