@@ -12,7 +12,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwmb200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # blob offsets (floats) — mirror of the enums in include/wmb200.h
 RB_W1 = 0
@@ -33,6 +33,12 @@ G_RB2 = G_CT_B + 64
 G_HEAD_W = G_RB2 + RB_SIZE
 G_HEAD_B = G_HEAD_W + 64
 G_SIZE = G_HEAD_B + 4
+TC_IMG3 = 3 * 8 * 128 * 8 // 2
+TC_IMG7 = 7 * 8 * 128 * 8 // 2
+G_TC = (G_SIZE + 63) // 64 * 64
+G_TC_CT = G_TC + 4 * TC_IMG3
+G_TC_RB2 = G_TC_CT + TC_IMG7
+G_BLOB = G_TC_RB2 + 2 * TC_IMG3
 D_IN_W = 0
 D_IN_B = D_IN_W + 7 * 64
 D_RB0 = D_IN_B + 64
@@ -40,6 +46,9 @@ D_RB1 = D_RB0 + RB_SIZE
 D_HEAD_W = D_RB1 + RB_SIZE
 D_HEAD_B = D_HEAD_W + 32 * 64
 D_SIZE = D_HEAD_B + 32
+D_TC = (D_SIZE + 63) // 64 * 64
+D_BLOB = D_TC + 4 * TC_IMG3
+PLANAR_PAD = 4
 MAX_HEAD = 32
 POST_FIR, POST_CLAMP, POST_RMS, POST_ALL = 1, 2, 4, 7
 MATH_FP32, MATH_BF16X2 = 0, 1
@@ -58,6 +67,14 @@ SIGNATURES = {
     "wm_set_math_mode": (_i, [_i]),
     "wm_get_math_mode": (_i, []),
     "wm_launch_count": (C.c_ulonglong, []),
+    "wm_finalize_generator_blob": (_i, [_p, _p]),
+    "wm_finalize_detector_blob": (_i, [_p, _p]),
+    "wm_planar_bytes": (_sz, [_i, _i]),
+    "wm_to_planar": (_i, [_p, _p, _p, _i, _i, _p]),
+    "wm_from_planar": (_i, [_p, _p, _i, _i, _p]),
+    "wm_conv64_tc_weight_bytes": (_sz, [_i]),
+    "wm_pack_conv64_tc": (_i, [_p, _p, _i, _p]),
+    "wm_conv64_tc_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "wm_conv_in_k7_fwd": (_i, [_p, _p, _p, _p, _i, _i, _p]),
     "wm_conv64_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "wm_lstm_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),

@@ -11,7 +11,7 @@ namespace wm {
 
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
-static std::atomic<int> g_math_mode{WM_MATH_FP32};
+static std::atomic<int> g_math_mode{WM_MATH_BF16X2};
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -50,22 +50,13 @@ int require_device() {
   return 0;
 }
 
-// conv64 in the selected arithmetic
-static int conv64(const float *x, const float *w, const float *bias, const float *residual,
-                  const float *chan_add, float *y, int B, int T, int taps, int relu, cudaStream_t st) {
-  return launch_conv64_fp32(x, w, bias, residual, chan_add, y, B, T, taps, relu, st);
-}
-
-// ResBlock (py/main16.py:112-125): y = relu(x + conv2(relu(conv1(x)))) with BN folded.
-// `tmp` and `y` are distinct from `x`.
-static int resblock(const float *rb, const float *x, float *tmp, float *y, int B, int T, cudaStream_t st) {
-  WM_TRY(conv64(x, rb + WM_RB_W1, rb + WM_RB_B1, nullptr, nullptr, tmp, B, T, 3, 1, st));
-  WM_TRY(conv64(tmp, rb + WM_RB_W2, rb + WM_RB_B2, x, nullptr, y, B, T, 3, 1, st));
-  return 0;
-}
-
 static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
-static size_t act_bytes(int B, int T) { return align256((size_t)B * T * 64 * sizeof(float)); }
+static size_t planar_bytes(int B, int T) {
+  // + 4 KB: the bulk copies of a partial last tile read (never use) up to 127 rows past a plane
+  return align256((size_t)B * 16 * ((size_t)T + 2 * WM_PLANAR_PAD) * 16 + 4096);
+}
+// one activation buffer: large enough for either layout (fp32 channels-last or planar bf16 pairs)
+static size_t act_bytes(int B, int T) { return planar_bytes(B, T); }
 
 struct Ws {
   char *p;
@@ -80,36 +71,67 @@ struct Ws {
   }
 };
 
-static int generator_run(const float *blob, const float *embedding, int64_t emb_rows,
-                         const int64_t *message, const float *s, float *delta_raw, float *a0,
-                         float *a1, float *a2, float *emb, int B, int T, cudaStream_t st) {
-  // encoder: conv k7 -> ResBlock -> ResBlock                 (py/main16.py:133-137)
-  WM_TRY(launch_conv_in_k7(s, blob + WM_G_IN_W, blob + WM_G_IN_B, a0, B, T, st));
-  WM_TRY(resblock(blob + WM_G_RB0, a0, a1, a2, B, T, st));  // -> a2
-  WM_TRY(resblock(blob + WM_G_RB1, a2, a0, a1, B, T, st));  // -> a1
-  // LSTM over time                                             (py/main16.py:152-154)
-  WM_TRY(launch_lstm_fp32(a1, blob + WM_G_LSTM_WIH, blob + WM_G_LSTM_WHH, blob + WM_G_LSTM_B, a0, B, T, st));
-  // + embedding(message)[:, :, None]                           (py/main16.py:156-159)
-  const float *chan_add = nullptr;
-  if (message && embedding) {
-    WM_TRY(launch_gather_rows(embedding, emb_rows, message, emb, B, st));
-    chan_add = emb;
-  }
-  // decoder: ConvTranspose k7 -> ResBlock -> Conv 64->1        (py/main16.py:143-147)
-  WM_TRY(conv64(a0, blob + WM_G_CT_W, blob + WM_G_CT_B, nullptr, chan_add, a2, B, T, 7, 0, st));
-  WM_TRY(resblock(blob + WM_G_RB2, a2, a0, a1, B, T, st));  // -> a1
-  WM_TRY(launch_head(a1, blob + WM_G_HEAD_W, blob + WM_G_HEAD_B, delta_raw, B, T, 1, st));
+// ResBlock (py/main16.py:112-125): y = relu(x + conv2(relu(conv1(x)))) with BN folded, fp32 FMA.
+static int resblock_fp32(const float *rb, const float *x, float *tmp, float *y, int B, int T, cudaStream_t st) {
+  WM_TRY(launch_conv64_fp32(x, rb + WM_RB_W1, rb + WM_RB_B1, nullptr, nullptr, tmp, B, T, 3, 1, st));
+  WM_TRY(launch_conv64_fp32(tmp, rb + WM_RB_W2, rb + WM_RB_B2, x, nullptr, y, B, T, 3, 1, st));
+  return 0;
+}
+// the same on planar tensors with the tcgen05 kernel; the second conv writes planar `y` and/or fp32 `y32`
+static int resblock_tc(const float *rb, const float *img /* two 3-tap images */, const void *x, void *tmp, void *y,
+                       float *y32, int B, int T, cudaStream_t st) {
+  WM_TRY(launch_conv64_tc(x, img, rb + WM_RB_B1, nullptr, tmp, nullptr, B, T, 3, 1, st));
+  WM_TRY(launch_conv64_tc(tmp, img + WM_TC_IMG3, rb + WM_RB_B2, x, y, y32, B, T, 3, 1, st));
   return 0;
 }
 
-// Detector trunk (py/main16.py:176-179): result left in *out (one of the three buffers)
-static int detector_trunk(const float *blob, const float *x, float *a0, float *a1, float *a2,
+// r0, r1, r2: three activation buffers of act_bytes(B, T); result: delta_raw[B][T]
+static int generator_run(const float *blob, const float *embedding, int64_t emb_rows,
+                         const int64_t *message, const float *s, float *delta_raw, void *r0, void *r1,
+                         void *r2, float *emb, int B, int T, cudaStream_t st) {
+  const float *chan_add = nullptr;
+  if (message && embedding) {  // embedding(message)  (py/main16.py:156-158)
+    WM_TRY(launch_gather_rows(embedding, emb_rows, message, emb, B, st));
+    chan_add = emb;
+  }
+  float *f0 = (float *)r0, *f1 = (float *)r1, *f2 = (float *)r2;
+  if (g_math_mode.load() == WM_MATH_FP32) {
+    // encoder: conv k7 -> ResBlock -> ResBlock                 (py/main16.py:133-137)
+    WM_TRY(launch_conv_in_k7(s, blob + WM_G_IN_W, blob + WM_G_IN_B, f0, B, T, st));
+    WM_TRY(resblock_fp32(blob + WM_G_RB0, f0, f1, f2, B, T, st));  // -> r2
+    WM_TRY(resblock_fp32(blob + WM_G_RB1, f2, f0, f1, B, T, st));  // -> r1
+    // LSTM over time                                             (py/main16.py:152-154)
+    WM_TRY(launch_lstm_fp32(f1, blob + WM_G_LSTM_WIH, blob + WM_G_LSTM_WHH, blob + WM_G_LSTM_B, f0, B, T, st));
+    // decoder: (+ message) ConvTranspose k7 -> ResBlock -> Conv 64->1   (py/main16.py:143-147,156-159)
+    WM_TRY(launch_conv64_fp32(f0, blob + WM_G_CT_W, blob + WM_G_CT_B, nullptr, chan_add, f2, B, T, 7, 0, st));
+    WM_TRY(resblock_fp32(blob + WM_G_RB2, f2, f0, f1, B, T, st));  // -> r1
+    return launch_head(f1, blob + WM_G_HEAD_W, blob + WM_G_HEAD_B, delta_raw, B, T, 1, st);
+  }
+  const float *tc = blob + WM_G_TC;
+  WM_TRY(launch_conv_in_k7_planar(s, blob + WM_G_IN_W, blob + WM_G_IN_B, r0, B, T, st));
+  WM_TRY(resblock_tc(blob + WM_G_RB0, tc, r0, r1, r2, nullptr, B, T, st));                      // -> r2 planar
+  WM_TRY(resblock_tc(blob + WM_G_RB1, tc + 2 * WM_TC_IMG3, r2, r0, nullptr, f1, B, T, st));     // -> r1 fp32
+  WM_TRY(launch_lstm_fp32(f1, blob + WM_G_LSTM_WIH, blob + WM_G_LSTM_WHH, blob + WM_G_LSTM_B, f0, B, T, st));
+  WM_TRY(launch_to_planar(f0, chan_add, r2, B, T, st));                                          // -> r2 planar
+  WM_TRY(launch_conv64_tc(r2, blob + WM_G_TC_CT, blob + WM_G_CT_B, nullptr, r1, nullptr, B, T, 7, 0, st));
+  WM_TRY(resblock_tc(blob + WM_G_RB2, blob + WM_G_TC_RB2, r1, r0, nullptr, f2, B, T, st));      // -> r2 fp32
+  return launch_head(f2, blob + WM_G_HEAD_W, blob + WM_G_HEAD_B, delta_raw, B, T, 1, st);
+}
+
+// Detector trunk (py/main16.py:176-179): fp32 channels-last result left in *out (one of the buffers)
+static int detector_trunk(const float *blob, const float *x, void *r0, void *r1, void *r2,
                           float **out, int B, int T, cudaStream_t st) {
-  WM_TRY(launch_conv_in_k7(x, blob + WM_D_IN_W, blob + WM_D_IN_B, a0, B, T, st));
-  WM_TRY(resblock(blob + WM_D_RB0, a0, a1, a2, B, T, st));  // -> a2
-  WM_TRY(resblock(blob + WM_D_RB1, a2, a0, a1, B, T, st));  // -> a1
-  *out = a1;
-  return 0;
+  float *f0 = (float *)r0, *f1 = (float *)r1, *f2 = (float *)r2;
+  *out = f1;
+  if (g_math_mode.load() == WM_MATH_FP32) {
+    WM_TRY(launch_conv_in_k7(x, blob + WM_D_IN_W, blob + WM_D_IN_B, f0, B, T, st));
+    WM_TRY(resblock_fp32(blob + WM_D_RB0, f0, f1, f2, B, T, st));  // -> r2
+    return resblock_fp32(blob + WM_D_RB1, f2, f0, f1, B, T, st);   // -> r1
+  }
+  const float *tc = blob + WM_D_TC;
+  WM_TRY(launch_conv_in_k7_planar(x, blob + WM_D_IN_W, blob + WM_D_IN_B, r0, B, T, st));
+  WM_TRY(resblock_tc(blob + WM_D_RB0, tc, r0, r1, r2, nullptr, B, T, st));
+  return resblock_tc(blob + WM_D_RB1, tc + 2 * WM_TC_IMG3, r2, r0, nullptr, f1, B, T, st);
 }
 
 }  // namespace wm
@@ -135,6 +157,64 @@ unsigned long long wm_launch_count(void) { return g_launches.load(); }
     if (rc0_ != 0) return rc0_;    \
   } while (0)
 
+int wm_finalize_generator_blob(float *blob, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(blob, "finalize_generator_blob: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const int rb[3] = {WM_G_RB0, WM_G_RB1, WM_G_RB2};
+  const int img[3] = {WM_G_TC, WM_G_TC + 2 * WM_TC_IMG3, WM_G_TC_RB2};
+  for (int i = 0; i < 3; ++i) {
+    WM_TRY(launch_pack_conv64_tc(blob + rb[i] + WM_RB_W1, blob + img[i], 3, st));
+    WM_TRY(launch_pack_conv64_tc(blob + rb[i] + WM_RB_W2, blob + img[i] + WM_TC_IMG3, 3, st));
+  }
+  return launch_pack_conv64_tc(blob + WM_G_CT_W, blob + WM_G_TC_CT, 7, st);
+}
+
+int wm_finalize_detector_blob(float *blob, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(blob, "finalize_detector_blob: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const int rb[2] = {WM_D_RB0, WM_D_RB1};
+  for (int i = 0; i < 2; ++i) {
+    WM_TRY(launch_pack_conv64_tc(blob + rb[i] + WM_RB_W1, blob + WM_D_TC + (2 * i) * WM_TC_IMG3, 3, st));
+    WM_TRY(launch_pack_conv64_tc(blob + rb[i] + WM_RB_W2, blob + WM_D_TC + (2 * i + 1) * WM_TC_IMG3, 3, st));
+  }
+  return 0;
+}
+
+size_t wm_planar_bytes(int B, int T) { return (B <= 0 || T <= 0) ? 0 : planar_bytes(B, T); }
+size_t wm_conv64_tc_weight_bytes(int taps) { return (size_t)taps * 8 * 128 * 8 * 2; }
+
+int wm_to_planar(const float *x, const float *chan_add, void *y, int B, int T, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "to_planar: negative size");
+  WM_CHECK_ARG(B == 0 || T == 0 || (x && y), "to_planar: null pointer");
+  return launch_to_planar(x, chan_add, y, B, T, as_stream(stream));
+}
+
+int wm_from_planar(const void *x, float *y, int B, int T, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "from_planar: negative size");
+  WM_CHECK_ARG(B == 0 || T == 0 || (x && y), "from_planar: null pointer");
+  return launch_from_planar(x, y, B, T, as_stream(stream));
+}
+
+int wm_pack_conv64_tc(const float *w, void *img, int taps, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(w && img, "pack_conv64_tc: null pointer");
+  WM_CHECK_ARG(taps == 3 || taps == 7, "pack_conv64_tc: taps must be 3 or 7");
+  return launch_pack_conv64_tc(w, img, taps, as_stream(stream));
+}
+
+int wm_conv64_tc_fwd(const void *x, const void *w_img, const float *bias, const void *residual, void *y,
+                     float *y32, int B, int T, int taps, int relu, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "conv64_tc: negative size");
+  WM_CHECK_ARG(B == 0 || T == 0 || (x && w_img && bias && (y || y32)), "conv64_tc: null pointer");
+  WM_CHECK_ARG(x != y, "conv64_tc: in-place operation is not supported");
+  return launch_conv64_tc(x, w_img, bias, residual, y, y32, B, T, taps, relu, as_stream(stream));
+}
+
 int wm_conv_in_k7_fwd(const float *s, const float *w, const float *b, float *y, int B, int T,
                       void *stream) {
   WM_ENTRY();
@@ -149,7 +229,7 @@ int wm_conv64_fwd(const float *x, const float *w, const float *bias, const float
   WM_CHECK_ARG(B >= 0 && T >= 0, "conv64: negative size");
   WM_CHECK_ARG(B == 0 || T == 0 || (x && w && bias && y), "conv64: null pointer");
   WM_CHECK_ARG(x != y, "conv64: in-place operation is not supported");
-  return conv64(x, w, bias, residual, chan_add, y, B, T, taps, relu, as_stream(stream));
+  return launch_conv64_fp32(x, w, bias, residual, chan_add, y, B, T, taps, relu, as_stream(stream));
 }
 
 int wm_lstm_fwd(const float *x, const float *w_ih, const float *w_hh, const float *bias, float *h,
@@ -204,8 +284,8 @@ int wm_generator_fwd(const float *blob, const float *embedding, int64_t emb_rows
                "generator: workspace too small (%zu < %zu)", workspace_bytes,
                wm_generator_workspace_bytes(B, T));
   Ws ws{(char *)workspace, workspace_bytes};
-  float *a0 = (float *)ws.take(act_bytes(B, T)), *a1 = (float *)ws.take(act_bytes(B, T)),
-        *a2 = (float *)ws.take(act_bytes(B, T)), *emb = (float *)ws.take((size_t)B * 64 * 4);
+  void *a0 = ws.take(act_bytes(B, T)), *a1 = ws.take(act_bytes(B, T)), *a2 = ws.take(act_bytes(B, T));
+  float *emb = (float *)ws.take((size_t)B * 64 * 4);
   return generator_run(blob, embedding, emb_rows, message, s, delta_raw, a0, a1, a2, emb, B, T,
                        as_stream(stream));
 }
@@ -224,8 +304,8 @@ int wm_detector_fwd(const float *blob, const float *x, float *logits, void *work
   WM_CHECK_ARG(blob && x && logits && workspace, "detector: null pointer");
   WM_CHECK_ARG(workspace_bytes >= wm_detector_workspace_bytes(B, T), "detector: workspace too small");
   Ws ws{(char *)workspace, workspace_bytes};
-  float *a0 = (float *)ws.take(act_bytes(B, T)), *a1 = (float *)ws.take(act_bytes(B, T)),
-        *a2 = (float *)ws.take(act_bytes(B, T)), *out = nullptr;
+  void *a0 = ws.take(act_bytes(B, T)), *a1 = ws.take(act_bytes(B, T)), *a2 = ws.take(act_bytes(B, T));
+  float *out = nullptr;
   cudaStream_t st = as_stream(stream);
   WM_TRY(detector_trunk(blob, x, a0, a1, a2, &out, B, T, st));
   return launch_head(out, blob + WM_D_HEAD_W, blob + WM_D_HEAD_B, logits, B, T, nout, st);
@@ -241,8 +321,8 @@ int wm_detect_fwd(const float *blob, const float *x, const int *valid_len, float
   WM_CHECK_ARG(blob && x && workspace, "detect: null pointer");
   WM_CHECK_ARG(workspace_bytes >= wm_detector_workspace_bytes(B, T), "detect: workspace too small");
   Ws ws{(char *)workspace, workspace_bytes};
-  float *a0 = (float *)ws.take(act_bytes(B, T)), *a1 = (float *)ws.take(act_bytes(B, T)),
-        *a2 = (float *)ws.take(act_bytes(B, T)), *out = nullptr;
+  void *a0 = ws.take(act_bytes(B, T)), *a1 = ws.take(act_bytes(B, T)), *a2 = ws.take(act_bytes(B, T));
+  float *out = nullptr;
   cudaStream_t st = as_stream(stream);
   WM_TRY(detector_trunk(blob, x, a0, a1, a2, &out, B, T, st));
   return launch_head_detect(out, blob + WM_D_HEAD_W, blob + WM_D_HEAD_B, valid_len, probs, clip_prob,
@@ -269,9 +349,8 @@ int wm_embed_detect_fwd(const float *g_blob, const float *embedding, int64_t emb
                "embed_detect: workspace too small (%zu < %zu)", workspace_bytes,
                wm_embed_detect_workspace_bytes(B, T));
   Ws ws{(char *)workspace, workspace_bytes};
-  float *a0 = (float *)ws.take(act_bytes(B, T)), *a1 = (float *)ws.take(act_bytes(B, T)),
-        *a2 = (float *)ws.take(act_bytes(B, T)), *emb = (float *)ws.take((size_t)B * 64 * 4),
-        *draw = (float *)ws.take((size_t)B * T * 4), *out = nullptr;
+  void *a0 = ws.take(act_bytes(B, T)), *a1 = ws.take(act_bytes(B, T)), *a2 = ws.take(act_bytes(B, T));
+  float *emb = (float *)ws.take((size_t)B * 64 * 4), *draw = (float *)ws.take((size_t)B * T * 4), *out = nullptr;
   cudaStream_t st = as_stream(stream);
   WM_TRY(generator_run(g_blob, embedding, emb_rows, message, s, draw, a0, a1, a2, emb, B, T, st));
   WM_TRY(launch_postprocess(draw, s, fir, delta, s_w, delta_rms, B, T, post_mode, 0.02f, 0.005f, 1e-8f, st));

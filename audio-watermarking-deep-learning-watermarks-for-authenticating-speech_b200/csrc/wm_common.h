@@ -79,4 +79,12 @@ int launch_head_detect(const float *x, const float *w, const float *b, const int
                        float *probs, float *clip_prob, float *msg_logits, float *vote_frac, int B,
                        int T, int nout, cudaStream_t st);
 
+// tcgen05 path (wm_conv_tc.cu); x / residual / y are planar activations, w_img from launch_pack_conv64_tc
+int launch_conv64_tc(const void *x, const void *w_img, const float *bias, const void *residual, void *y, float *y32,
+                     int B, int T, int taps, int relu, cudaStream_t st);
+int launch_pack_conv64_tc(const float *w, void *img, int taps, cudaStream_t st);
+int launch_to_planar(const float *x, const float *chan_add, void *y, int B, int T, cudaStream_t st);
+int launch_from_planar(const void *x, float *y, int B, int T, cudaStream_t st);
+int launch_conv_in_k7_planar(const float *s, const float *w, const float *b, void *y, int B, int T, cudaStream_t st);
+
 }  // namespace wm

@@ -72,7 +72,14 @@ class _Packed(nn.Module):
         key = (str(dev),) + tuple((t.data_ptr(), t._version) for t in tensors)
         if self._blob is None or self._blob_key != key:
             sd = {k: v for k, v in self.state_dict().items() if k != "embedding.weight"}
-            self._blob = self._pack(sd).to(dev)
+            host = self._pack(sd)                      # fp32 part, packed on the host
+            blob = torch.zeros(self._blob_floats, dtype=torch.float32, device=dev)
+            blob[:host.numel()] = host.to(dev)
+            if dev.type == "cuda":                     # tcgen05 weight images, built on the device
+                with torch.cuda.device(dev):
+                    L.check(getattr(L.load(), self._finalize)(blob.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                            self._finalize)
+            self._blob = blob
             self._blob_key = key
         return self._blob
 
@@ -101,6 +108,9 @@ class Generator(_Packed):
             self.embedding = nn.Embedding(2 ** message_bits, HIDDEN)
         self.decoder = nn.Sequential(nn.ConvTranspose1d(HIDDEN, HIDDEN, 7, padding=3), ResBlock(HIDDEN),
                                      nn.Conv1d(HIDDEN, 1, 1))
+
+    _blob_floats = L.G_BLOB
+    _finalize = "wm_finalize_generator_blob"
 
     def _pack(self, sd):
         return packing.pack_generator(sd)
@@ -131,6 +141,9 @@ class Detector(_Packed):
             raise ValueError(f"message_bits must be <= {L.MAX_HEAD - 1}")
         self.model = nn.Sequential(nn.Conv1d(1, HIDDEN, kernel_size=7, padding=3), ResBlock(HIDDEN),
                                    ResBlock(HIDDEN), nn.Conv1d(HIDDEN, 1 + message_bits, kernel_size=1))
+
+    _blob_floats = L.D_BLOB
+    _finalize = "wm_finalize_detector_blob"
 
     def _pack(self, sd):
         return packing.pack_detector(sd)

@@ -77,6 +77,44 @@ def conv64(x, w, bias, residual=None, chan_add=None, taps: int = 3, relu: bool =
     return y
 
 
+def to_planar(x, chan_add=None):
+    """fp32 channels-last (B,T,64) -> planar bf16 hi/lo planes (opaque uint8 buffer)."""
+    lib = L.load()
+    x = _req(x, "x")
+    B, T, _ = x.shape
+    y = torch.empty(max(lib.wm_planar_bytes(B, T), 16), dtype=torch.uint8, device=x.device)
+    ca = _req(chan_add, "chan_add") if chan_add is not None else None
+    L.check(lib.wm_to_planar(L.ptr(x), L.ptr(ca), L.ptr(y), B, T, _stream()), "wm_to_planar")
+    return y
+
+
+def from_planar(p, B: int, T: int):
+    y = torch.empty(B, T, 64, device=p.device, dtype=torch.float32)
+    L.check(L.load().wm_from_planar(L.ptr(p), L.ptr(y), B, T, _stream()), "wm_from_planar")
+    return y
+
+
+def pack_conv64_tc(w):
+    """fp32 w [taps][64][64] -> bf16 tcgen05 weight image."""
+    lib = L.load()
+    w = _req(w, "w")
+    taps = w.shape[0]
+    img = torch.empty(lib.wm_conv64_tc_weight_bytes(taps), dtype=torch.uint8, device=w.device)
+    L.check(lib.wm_pack_conv64_tc(L.ptr(w), L.ptr(img), taps, _stream()), "wm_pack_conv64_tc")
+    return img
+
+
+def conv64_tc(xp, w_img, bias, B: int, T: int, taps: int, residual=None, relu=False, want_planar=True,
+              want_fp32=False):
+    """The tensor-core convolution on planar tensors -> (planar or None, fp32 (B,T,64) or None)."""
+    lib = L.load()
+    y = torch.empty(max(lib.wm_planar_bytes(B, T), 16), dtype=torch.uint8, device=xp.device) if want_planar else None
+    y32 = torch.empty(B, T, 64, device=xp.device, dtype=torch.float32) if want_fp32 else None
+    L.check(lib.wm_conv64_tc_fwd(L.ptr(xp), L.ptr(w_img), L.ptr(_req(bias, "bias")), L.ptr(residual), L.ptr(y),
+                                 L.ptr(y32), B, T, taps, int(relu), _stream()), "wm_conv64_tc_fwd")
+    return y, y32
+
+
 def lstm(x, w_ih, w_hh, bias):
     """x (B,T,64) -> all hidden states (B,T,64).  py/main16.py:138,153."""
     x = _req(x, "x")

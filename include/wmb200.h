@@ -32,7 +32,8 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 4
+#define WM_ABI_VERSION 5
+#define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
 #define WM_POST_RMS 4
@@ -63,7 +64,16 @@ enum {                                   /* Generator, py/main16.py:128-162 */
   WM_G_RB2 = WM_G_CT_B + 64,             /* decoder.1                */
   WM_G_HEAD_W = WM_G_RB2 + WM_RB_SIZE,   /* decoder.2 [64]           */
   WM_G_HEAD_B = WM_G_HEAD_W + 64,        /* [1] (+3 pad)             */
-  WM_G_SIZE = WM_G_HEAD_B + 4
+  WM_G_SIZE = WM_G_HEAD_B + 4,
+  /* tcgen05 weight images (bf16 [tap][ci/8][128][8], see wm_pack_conv64_tc), filled on the
+   * device by wm_finalize_generator_blob: encoder.1 conv1, conv2, encoder.2 conv1, conv2,
+   * decoder.0 (7 taps), decoder.1 conv1, conv2 */
+  WM_G_TC = (WM_G_SIZE + 63) / 64 * 64,
+  WM_TC_IMG3 = 3 * 8 * 128 * 8 / 2,      /* floats occupied by a 3-tap image */
+  WM_TC_IMG7 = 7 * 8 * 128 * 8 / 2,
+  WM_G_TC_CT = WM_G_TC + 4 * WM_TC_IMG3,
+  WM_G_TC_RB2 = WM_G_TC_CT + WM_TC_IMG7,
+  WM_G_BLOB = WM_G_TC_RB2 + 2 * WM_TC_IMG3
 };
 enum {                                   /* Detector, py/main16.py:170-186 */
   WM_D_IN_W = 0,                         /* model.0 [7][64]          */
@@ -72,7 +82,9 @@ enum {                                   /* Detector, py/main16.py:170-186 */
   WM_D_RB1 = WM_D_RB0 + WM_RB_SIZE,      /* model.2                  */
   WM_D_HEAD_W = WM_D_RB1 + WM_RB_SIZE,   /* model.3 [nout<=32][64]   */
   WM_D_HEAD_B = WM_D_HEAD_W + 32 * 64,   /* [32]                     */
-  WM_D_SIZE = WM_D_HEAD_B + 32
+  WM_D_SIZE = WM_D_HEAD_B + 32,
+  WM_D_TC = (WM_D_SIZE + 63) / 64 * 64,  /* model.1 conv1, conv2, model.2 conv1, conv2 */
+  WM_D_BLOB = WM_D_TC + 4 * WM_TC_IMG3
 };
 
 /* Arithmetic of the 64->64 convolutions (the tensor-pipe part of the path).
@@ -94,6 +106,11 @@ int wm_get_math_mode(void);
 /* Number of kernels this library has launched since load (bench.py gpu_launches). */
 unsigned long long wm_launch_count(void);
 
+/* The host packs the first WM_G_SIZE / WM_D_SIZE floats of a WM_G_BLOB / WM_D_BLOB float
+ * device buffer; these fill the tcgen05 weight images behind them (one small kernel per conv). */
+int wm_finalize_generator_blob(float *blob, void *stream);
+int wm_finalize_detector_blob(float *blob, void *stream);
+
 /* ---- single operators ---------------------------------------------------*/
 
 /* nn.Conv1d(1,64,7,padding=3)  — py/main16.py:134 (Generator) and :177 (Detector).
@@ -111,6 +128,23 @@ int wm_conv_in_k7_fwd(const float *s, const float *w, const float *b, float *y,
 int wm_conv64_fwd(const float *x, const float *w, const float *bias, const float *residual,
                   const float *chan_add, float *y, int B, int T, int taps, int relu,
                   void *stream);
+
+/* ---- the tensor-core form of the same convolution -------------------------------------
+ * "planar" activations: per clip 16 planes of (T + 2*WM_PLANAR_PAD) rows x 16 bytes; plane c
+ * (0..7) holds the bf16 high parts of channels 8c..8c+7 of every time step, plane 8+c the bf16
+ * low parts (v = hi + lo), with WM_PLANAR_PAD zero rows before t = 0 and after t = T-1.       */
+size_t wm_planar_bytes(int B, int T);
+/* fp32 channels-last x[B][T][64] (+ chan_add[B][64], nullable) -> planar */
+int wm_to_planar(const float *x, const float *chan_add, void *y, int B, int T, void *stream);
+int wm_from_planar(const void *x, float *y, int B, int T, void *stream);
+/* fp32 w[taps][64][64] (tap-major, as in the blobs) -> bf16 image of wm_conv64_tc_weight_bytes(taps) */
+size_t wm_conv64_tc_weight_bytes(int taps);
+int wm_pack_conv64_tc(const float *w, void *img, int taps, void *stream);
+/* y = act(conv(x) + bias + residual) on planar tensors; taps 3 or 7; y (planar) and y32
+ * (fp32 channels-last [B][T][64]) are both optional outputs.  tcgen05.mma kind::f16, every
+ * operand a bf16 hi+lo pair, all four partial products accumulated in fp32 (TMEM). */
+int wm_conv64_tc_fwd(const void *x, const void *w_img, const float *bias, const void *residual,
+                     void *y, float *y32, int B, int T, int taps, int relu, void *stream);
 
 /* nn.LSTM(64,64,batch_first=True) with zero initial state, all hidden states
  * returned — py/main16.py:138,153.  x[B][T][64] -> h[B][T][64].

@@ -92,6 +92,37 @@ def test_conv64(B, T, taps, variant):
     assert maxerr(y.permute(0, 2, 1), ref) < tol_tight() * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("B,T,taps", [(1, 128, 3), (2, 1, 3), (3, 129, 3), (2, 300, 7), (5, 16000, 3), (2, 16000, 7),
+                                      (160, 1000, 3)])
+@pytest.mark.parametrize("variant", ["plain", "relu_res", "chan_add"])
+def test_conv64_tensor_core(B, T, taps, variant):
+    """tcgen05 implicit GEMM (bf16 hi+lo operand pairs) vs the fp32 reference convolution."""
+    g = torch.Generator().manual_seed(B * 100 + T + taps)
+    x = torch.randn(B, 64, T, generator=g) * 3
+    w = torch.randn(64, 64, taps, generator=g) / (8.0 * taps ** 0.5)
+    b = torch.randn(64, generator=g)
+    res = torch.randn(B, 64, T, generator=g) if variant == "relu_res" else None
+    ca = torch.randn(B, 64, generator=g) if variant == "chan_add" else None
+    xin = x + ca.unsqueeze(-1) if ca is not None else x
+    ref = F.conv1d(xin.double(), w.double(), b.double(), padding=taps // 2)
+    if res is not None:
+        ref = F.relu(ref + res.double())
+    cl = lambda t: t.permute(0, 2, 1).contiguous().to(DEV)
+    xp = ops.to_planar(cl(x), ca.to(DEV) if ca is not None else None)
+    back = ops.from_planar(xp, B, T)
+    assert maxerr(back.permute(0, 2, 1), xin) < 2e-5 * float(xin.abs().max())      # bf16 pair keeps ~16 bits
+    img = ops.pack_conv64_tc(w.permute(2, 1, 0).contiguous().to(DEV))
+    rp = ops.to_planar(cl(res)) if res is not None else None
+    yp, y32 = ops.conv64_tc(xp, img, b.to(DEV), B, T, taps, residual=rp, relu=res is not None, want_fp32=True)
+    scale = max(1.0, float(ref.abs().max()))
+    assert maxerr(y32.permute(0, 2, 1), ref.float()) < 3e-5 * scale
+    assert maxerr(ops.from_planar(yp, B, T).permute(0, 2, 1), ref.float()) < 5e-5 * scale
+    # the planes' zero padding rows survive (the next convolution relies on them)
+    RP = T + 2 * L.PLANAR_PAD
+    planes = yp[:B * 16 * RP * 16].view(B * 16, RP, 16)
+    assert int(planes[:, :L.PLANAR_PAD].max()) == 0 and int(planes[:, T + L.PLANAR_PAD:].max()) == 0
+
+
 def test_conv_transpose_equivalence():
     """ConvTranspose1d(64,64,7,p=3) == conv with flipped taps (py/main16.py:144)."""
     gsd, _ = H.gen_sd(W, "A")
