@@ -12,7 +12,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwmb200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # blob offsets (floats) — mirror of the enums in include/wmb200.h
 RB_W1 = 0
@@ -38,7 +38,9 @@ TC_IMG7 = 7 * 8 * 128 * 8 // 2
 G_TC = (G_SIZE + 63) // 64 * 64
 G_TC_CT = G_TC + 4 * TC_IMG3
 G_TC_RB2 = G_TC_CT + TC_IMG7
-G_BLOB = G_TC_RB2 + 2 * TC_IMG3
+G_TC_LSTM_W = G_TC_RB2 + 2 * TC_IMG3
+G_TC_LSTM_B = G_TC_LSTM_W + 4 * 256 * 64 // 2
+G_BLOB = G_TC_LSTM_B + 256
 D_IN_W = 0
 D_IN_B = D_IN_W + 7 * 64
 D_RB0 = D_IN_B + 64
@@ -75,6 +77,8 @@ SIGNATURES = {
     "wm_conv64_tc_weight_bytes": (_sz, [_i]),
     "wm_pack_conv64_tc": (_i, [_p, _p, _i, _p]),
     "wm_conv64_tc_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "wm_pack_lstm_tc": (_i, [_p, _p, _p, _p, _p, _p]),
+    "wm_lstm_tc_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
     "wm_conv_in_k7_fwd": (_i, [_p, _p, _p, _p, _i, _i, _p]),
     "wm_conv64_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "wm_lstm_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),

@@ -28,9 +28,9 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _digest() -> str:
+def _digest() -> str:  # noqa
     h = hashlib.sha256()
-    files = sources() + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".h")]
+    files = sources() + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".h", ".cuh"))]
     files.append(os.path.join(os.path.dirname(HERE), "include", "wmb200.h"))
     for f in files:
         h.update(f.encode())

@@ -110,12 +110,12 @@ static int generator_run(const float *blob, const float *embedding, int64_t emb_
   const float *tc = blob + WM_G_TC;
   WM_TRY(launch_conv_in_k7_planar(s, blob + WM_G_IN_W, blob + WM_G_IN_B, r0, B, T, st));
   WM_TRY(resblock_tc(blob + WM_G_RB0, tc, r0, r1, r2, nullptr, B, T, st));                      // -> r2 planar
-  WM_TRY(resblock_tc(blob + WM_G_RB1, tc + 2 * WM_TC_IMG3, r2, r0, nullptr, f1, B, T, st));     // -> r1 fp32
-  WM_TRY(launch_lstm_fp32(f1, blob + WM_G_LSTM_WIH, blob + WM_G_LSTM_WHH, blob + WM_G_LSTM_B, f0, B, T, st));
-  WM_TRY(launch_to_planar(f0, chan_add, r2, B, T, st));                                          // -> r2 planar
-  WM_TRY(launch_conv64_tc(r2, blob + WM_G_TC_CT, blob + WM_G_CT_B, nullptr, r1, nullptr, B, T, 7, 0, st));
-  WM_TRY(resblock_tc(blob + WM_G_RB2, blob + WM_G_TC_RB2, r1, r0, nullptr, f2, B, T, st));      // -> r2 fp32
-  return launch_head(f2, blob + WM_G_HEAD_W, blob + WM_G_HEAD_B, delta_raw, B, T, 1, st);
+  WM_TRY(resblock_tc(blob + WM_G_RB1, tc + 2 * WM_TC_IMG3, r2, r0, r1, nullptr, B, T, st));     // -> r1 planar
+  // LSTM (+ message embedding added to its output)            (py/main16.py:152-159)
+  WM_TRY(launch_lstm_tc(r1, blob + WM_G_TC_LSTM_W, blob + WM_G_TC_LSTM_B, chan_add, r0, B, T, st));  // -> r0 planar
+  WM_TRY(launch_conv64_tc(r0, blob + WM_G_TC_CT, blob + WM_G_CT_B, nullptr, r1, nullptr, B, T, 7, 0, st));
+  WM_TRY(resblock_tc(blob + WM_G_RB2, blob + WM_G_TC_RB2, r1, r2, nullptr, f0, B, T, st));      // -> r0 fp32
+  return launch_head(f0, blob + WM_G_HEAD_W, blob + WM_G_HEAD_B, delta_raw, B, T, 1, st);
 }
 
 // Detector trunk (py/main16.py:176-179): fp32 channels-last result left in *out (one of the buffers)
@@ -167,7 +167,9 @@ int wm_finalize_generator_blob(float *blob, void *stream) {
     WM_TRY(launch_pack_conv64_tc(blob + rb[i] + WM_RB_W1, blob + img[i], 3, st));
     WM_TRY(launch_pack_conv64_tc(blob + rb[i] + WM_RB_W2, blob + img[i] + WM_TC_IMG3, 3, st));
   }
-  return launch_pack_conv64_tc(blob + WM_G_CT_W, blob + WM_G_TC_CT, 7, st);
+  WM_TRY(launch_pack_conv64_tc(blob + WM_G_CT_W, blob + WM_G_TC_CT, 7, st));
+  return launch_pack_lstm_tc(blob + WM_G_LSTM_WIH, blob + WM_G_LSTM_WHH, blob + WM_G_LSTM_B,
+                             blob + WM_G_TC_LSTM_W, blob + WM_G_TC_LSTM_B, st);
 }
 
 int wm_finalize_detector_blob(float *blob, void *stream) {
@@ -213,6 +215,22 @@ int wm_conv64_tc_fwd(const void *x, const void *w_img, const float *bias, const 
   WM_CHECK_ARG(B == 0 || T == 0 || (x && w_img && bias && (y || y32)), "conv64_tc: null pointer");
   WM_CHECK_ARG(x != y, "conv64_tc: in-place operation is not supported");
   return launch_conv64_tc(x, w_img, bias, residual, y, y32, B, T, taps, relu, as_stream(stream));
+}
+
+int wm_pack_lstm_tc(const float *w_ih, const float *w_hh, const float *bias, void *wpk, float *bias_p,
+                    void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(w_ih && w_hh && bias && wpk && bias_p, "pack_lstm_tc: null pointer");
+  return launch_pack_lstm_tc(w_ih, w_hh, bias, wpk, bias_p, as_stream(stream));
+}
+
+int wm_lstm_tc_fwd(const void *x, const void *wpk, const float *bias_p, const float *chan_add, void *y, int B,
+                   int T, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "lstm_tc: negative size");
+  WM_CHECK_ARG(B == 0 || T == 0 || (x && wpk && bias_p && y), "lstm_tc: null pointer");
+  WM_CHECK_ARG(x != y, "lstm_tc: in-place operation is not supported");
+  return launch_lstm_tc(x, wpk, bias_p, chan_add, y, B, T, as_stream(stream));
 }
 
 int wm_conv_in_k7_fwd(const float *s, const float *w, const float *b, float *y, int B, int T,

@@ -86,5 +86,9 @@ int launch_pack_conv64_tc(const float *w, void *img, int taps, cudaStream_t st);
 int launch_to_planar(const float *x, const float *chan_add, void *y, int B, int T, cudaStream_t st);
 int launch_from_planar(const void *x, float *y, int B, int T, cudaStream_t st);
 int launch_conv_in_k7_planar(const float *s, const float *w, const float *b, void *y, int B, int T, cudaStream_t st);
+int launch_lstm_tc(const void *x, const void *wpk, const float *bias_p, const float *chan_add, void *y, int B, int T,
+                   cudaStream_t st);
+int launch_pack_lstm_tc(const float *w_ih, const float *w_hh, const float *bias, void *wpk, float *bias_p,
+                        cudaStream_t st);
 
 }  // namespace wm

@@ -115,6 +115,21 @@ def conv64_tc(xp, w_img, bias, B: int, T: int, taps: int, residual=None, relu=Fa
     return y, y32
 
 
+def lstm_tc(xp, w_ih, w_hh, bias, B: int, T: int, chan_add=None):
+    """Tensor-core LSTM on planar tensors -> planar h (+ chan_add on the output)."""
+    lib = L.load()
+    dev = xp.device
+    wpk = torch.empty(4 * 256 * 64 * 2, dtype=torch.uint8, device=dev)
+    bp = torch.empty(256, dtype=torch.float32, device=dev)
+    L.check(lib.wm_pack_lstm_tc(L.ptr(_req(w_ih, "w_ih")), L.ptr(_req(w_hh, "w_hh")), L.ptr(_req(bias, "bias")),
+                                L.ptr(wpk), L.ptr(bp), _stream()), "wm_pack_lstm_tc")
+    y = torch.empty(max(lib.wm_planar_bytes(B, T), 16), dtype=torch.uint8, device=dev)
+    ca = _req(chan_add, "chan_add") if chan_add is not None else None
+    L.check(lib.wm_lstm_tc_fwd(L.ptr(xp), L.ptr(wpk), L.ptr(bp), L.ptr(ca), L.ptr(y), B, T, _stream()),
+            "wm_lstm_tc_fwd")
+    return y
+
+
 def lstm(x, w_ih, w_hh, bias):
     """x (B,T,64) -> all hidden states (B,T,64).  py/main16.py:138,153."""
     x = _req(x, "x")

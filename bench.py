@@ -213,22 +213,31 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel: one 64->64 k3 convolution, timed alone ----------
     Br = min(B, 1024)
+    mode = ops.get_math_mode()
     x = torch.randn(Br, T, 64, device=dev)
-    y = torch.empty_like(x)
     wk = g_blob[L.G_RB0 + L.RB_W1:L.G_RB0 + L.RB_W1 + 3 * 4096]
     bk = g_blob[L.G_RB0 + L.RB_B1:L.G_RB0 + L.RB_B1 + 64]
     lib = L.load()
     st = torch.cuda.current_stream().cuda_stream
+    if mode == L.MATH_FP32:
+        y = torch.empty_like(x)
 
-    def conv_once():
-        L.check(lib.wm_conv64_fwd(x.data_ptr(), wk.data_ptr(), bk.data_ptr(), None, None, y.data_ptr(), Br, T, 3, 1,
-                                  st), "wm_conv64_fwd")
+        def conv_once():
+            L.check(lib.wm_conv64_fwd(x.data_ptr(), wk.data_ptr(), bk.data_ptr(), None, None, y.data_ptr(), Br, T, 3,
+                                      1, st), "wm_conv64_fwd")
+    else:
+        xp = ops.to_planar(x)
+        y = torch.empty_like(xp)
+        img = g_blob[L.G_TC:L.G_TC + L.TC_IMG3]
+
+        def conv_once():
+            L.check(lib.wm_conv64_tc_fwd(xp.data_ptr(), img.data_ptr(), bk.data_ptr(), None, y.data_ptr(), None, Br,
+                                         T, 3, 1, st), "wm_conv64_tc_fwd")
 
     reps = 10
     ms_conv, _ = timed(conv_once, reps, 3)
     conv_tflops = CONV64_K3_FLOP_PER_CLIP * Br * reps / (ms_conv / 1e3) / 1e12
     del x, y
-    mode = ops.get_math_mode()
     roofline = {"bound": "tensor", "kernel": "conv64 k3 (%s)" % ("fp32 FMA" if mode == L.MATH_FP32 else "tcgen05 bf16x2"),
                 "achieved": conv_tflops, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
                 "frac": conv_tflops / peaks["bf16_burst"], "traffic": None, "peak_source": peaks["src"] + " burst",
@@ -236,7 +245,7 @@ def run_ours(args):
                 "path_frac_of_sustained": value / world * FLOP_PER_CLIP / (peaks["bf16_sustained"] * 1e12)}
 
     if rank == 0:
-        cpu_rate, cores, _ = cpu_reference_rate(16, 3, 1)
+        cpu_rate, cores, _ = cpu_reference_rate(16, 3, 1) if not args.no_cpu_baseline else (None, 0, [])
         clocks = sampler.summary()
         line = {"metric": "clip-seconds/sec embed+detect (1 s@16 kHz)", "value": value, "unit": "clip-s/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
@@ -264,6 +273,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096, help="clips per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

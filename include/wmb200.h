@@ -32,7 +32,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 5
+#define WM_ABI_VERSION 6
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -73,7 +73,10 @@ enum {                                   /* Generator, py/main16.py:128-162 */
   WM_TC_IMG7 = 7 * 8 * 128 * 8 / 2,
   WM_G_TC_CT = WM_G_TC + 4 * WM_TC_IMG3,
   WM_G_TC_RB2 = WM_G_TC_CT + WM_TC_IMG7,
-  WM_G_BLOB = WM_G_TC_RB2 + 2 * WM_TC_IMG3
+  /* tensor-core LSTM operands (wm_pack_lstm_tc): bf16 [4][2][128][64] then fp32 bias [2][128] */
+  WM_G_TC_LSTM_W = WM_G_TC_RB2 + 2 * WM_TC_IMG3,
+  WM_G_TC_LSTM_B = WM_G_TC_LSTM_W + 4 * 256 * 64 / 2,
+  WM_G_BLOB = WM_G_TC_LSTM_B + 256
 };
 enum {                                   /* Detector, py/main16.py:170-186 */
   WM_D_IN_W = 0,                         /* model.0 [7][64]          */
@@ -145,6 +148,15 @@ int wm_pack_conv64_tc(const float *w, void *img, int taps, void *stream);
  * operand a bf16 hi+lo pair, all four partial products accumulated in fp32 (TMEM). */
 int wm_conv64_tc_fwd(const void *x, const void *w_img, const float *bias, const void *residual,
                      void *y, float *y32, int B, int T, int taps, int relu, void *stream);
+
+/* The LSTM on tensor cores: planar x -> planar h (+ chan_add[B][64] added to the OUTPUT only, i.e.
+ * the message embedding of py/main16.py:156-159 fused into the store).  Weights resident in TMEM,
+ * bf16 hi+lo operand pairs, fp32 accumulation and fp32 cell state.  wpk / bias_p from wm_pack_lstm_tc
+ * (wpk: 4*256*64 bf16, bias_p: 256 floats). */
+int wm_pack_lstm_tc(const float *w_ih, const float *w_hh, const float *bias, void *wpk, float *bias_p,
+                    void *stream);
+int wm_lstm_tc_fwd(const void *x, const void *wpk, const float *bias_p, const float *chan_add, void *y,
+                   int B, int T, void *stream);
 
 /* nn.LSTM(64,64,batch_first=True) with zero initial state, all hidden states
  * returned — py/main16.py:138,153.  x[B][T][64] -> h[B][T][64].

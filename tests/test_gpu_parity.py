@@ -144,6 +144,41 @@ def test_lstm_vs_oracle(B, T):
     assert maxerr(h, ref) < 1e-5
 
 
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 50), (32, 9), (33, 64), (70, 333), (300, 40)])
+def test_lstm_tensor_core_vs_oracle(B, T):
+    gsd, _ = H.gen_sd(W, "A")
+    g = torch.Generator().manual_seed(B + T)
+    x = torch.randn(B, T, 64, generator=g)
+    emb = torch.randn(B, 64, generator=g)
+    ref = O.lstm(x, gsd)
+    args = (gsd["lstm.weight_ih_l0"].to(DEV), gsd["lstm.weight_hh_l0"].to(DEV),
+            (gsd["lstm.bias_ih_l0"] + gsd["lstm.bias_hh_l0"]).to(DEV))
+    xp = ops.to_planar(x.to(DEV))
+    h = ops.from_planar(ops.lstm_tc(xp, *args, B, T), B, T)
+    assert maxerr(h, ref) < 2e-5
+    h2 = ops.from_planar(ops.lstm_tc(xp, *args, B, T, chan_add=emb.to(DEV)), B, T)
+    assert maxerr(h2, ref + emb.unsqueeze(1)) < 5e-5
+
+
+def test_lstm_tensor_core_full_length():
+    """16 000 dependent steps, weights scaled so gates saturate and the cell state carries."""
+    g = torch.Generator().manual_seed(5)
+    sd = {"lstm.weight_ih_l0": torch.randn(256, 64, generator=g) * 0.4,
+          "lstm.weight_hh_l0": torch.randn(256, 64, generator=g) * 0.4,
+          "lstm.bias_ih_l0": torch.randn(256, generator=g) * 0.2, "lstm.bias_hh_l0": torch.zeros(256)}
+    x = torch.randn(3, 16000, 64, generator=g)
+    ref = O.lstm(x, sd)
+    h = ops.from_planar(ops.lstm_tc(ops.to_planar(x.to(DEV)), sd["lstm.weight_ih_l0"].to(DEV),
+                                    sd["lstm.weight_hh_l0"].to(DEV), sd["lstm.bias_ih_l0"].to(DEV), 3, 16000), 3, 16000)
+    assert maxerr(h, ref) < 5e-4            # chaotic regime: rounding differences get amplified
+    gsd, _ = H.gen_sd(W, "B")
+    x = torch.randn(2, 16000, 64, generator=g).abs()
+    h = ops.from_planar(ops.lstm_tc(ops.to_planar(x.to(DEV)), gsd["lstm.weight_ih_l0"].to(DEV),
+                                    gsd["lstm.weight_hh_l0"].to(DEV),
+                                    (gsd["lstm.bias_ih_l0"] + gsd["lstm.bias_hh_l0"]).to(DEV), 2, 16000), 2, 16000)
+    assert maxerr(h, O.lstm(x, gsd)) < 2e-5
+
+
 def test_lstm_full_length_large_weights():
     """16 000 dependent steps with weights scaled up so the gates saturate and the state carries."""
     g = torch.Generator().manual_seed(5)
