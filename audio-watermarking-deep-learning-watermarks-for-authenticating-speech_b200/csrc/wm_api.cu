@@ -80,9 +80,8 @@ static int resblock_fp32(const float *rb, const float *x, float *tmp, float *y, 
 // the same on planar tensors with the tcgen05 kernel; the second conv writes planar `y` and/or fp32 `y32`
 static int resblock_tc(const float *rb, const float *img /* two 3-tap images */, const void *x, void *tmp, void *y,
                        float *y32, int B, int T, cudaStream_t st) {
-  WM_TRY(launch_conv64_tc(x, img, rb + WM_RB_B1, nullptr, tmp, nullptr, B, T, 3, 1, st));
-  WM_TRY(launch_conv64_tc(tmp, img + WM_TC_IMG3, rb + WM_RB_B2, x, y, y32, B, T, 3, 1, st));
-  return 0;
+  (void)tmp;
+  return launch_resblock_tc(x, img, rb + WM_RB_B1, rb + WM_RB_B2, y, y32, B, T, st);
 }
 
 // r0, r1, r2: three activation buffers of act_bytes(B, T); result: delta_raw[B][T]
@@ -215,6 +214,21 @@ int wm_conv64_tc_fwd(const void *x, const void *w_img, const float *bias, const 
   WM_CHECK_ARG(B == 0 || T == 0 || (x && w_img && bias && (y || y32)), "conv64_tc: null pointer");
   WM_CHECK_ARG(x != y, "conv64_tc: in-place operation is not supported");
   return launch_conv64_tc(x, w_img, bias, residual, y, y32, B, T, taps, relu, as_stream(stream));
+}
+
+/* developer hook (not part of the ABI contract): per-phase cycle counters of the LSTM kernel */
+int wm_debug_lstm_profile(long long *buf16) {
+  set_lstm_profile_buffer(buf16);
+  return 0;
+}
+
+int wm_resblock_tc_fwd(const void *x, const void *w_img, const float *b1, const float *b2, void *y, float *y32,
+                       int B, int T, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "resblock_tc: negative size");
+  WM_CHECK_ARG(B == 0 || T == 0 || (x && w_img && b1 && b2 && (y || y32)), "resblock_tc: null pointer");
+  WM_CHECK_ARG(x != y, "resblock_tc: in-place operation is not supported");
+  return launch_resblock_tc(x, w_img, b1, b2, y, y32, B, T, as_stream(stream));
 }
 
 int wm_pack_lstm_tc(const float *w_ih, const float *w_hh, const float *bias, void *wpk, float *bias_p,

@@ -88,6 +88,9 @@ int launch_from_planar(const void *x, float *y, int B, int T, cudaStream_t st);
 int launch_conv_in_k7_planar(const float *s, const float *w, const float *b, void *y, int B, int T, cudaStream_t st);
 int launch_lstm_tc(const void *x, const void *wpk, const float *bias_p, const float *chan_add, void *y, int B, int T,
                    cudaStream_t st);
+int launch_resblock_tc(const void *x, const void *w_img, const float *b1, const float *b2, void *y, float *y32, int B,
+                       int T, cudaStream_t st);
+void set_lstm_profile_buffer(long long *p);
 int launch_pack_lstm_tc(const float *w_ih, const float *w_hh, const float *bias, void *wpk, float *bias_p,
                         cudaStream_t st);
 

@@ -57,7 +57,8 @@ constexpr float kLog2e = 1.4426950408889634f;
 // wpk: bf16 [mat: Whh_hi, Whh_lo, Wih_hi, Wih_lo][tile 2][lane 128][64]; bias_p: fp32 [tile 2][lane 128]
 __global__ void __launch_bounds__(THREADS, 1)
     lstm_tc_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ wpk, const float *__restrict__ bias_p,
-                   const float *__restrict__ chan_add, uint4 *__restrict__ y, int B, int T) {
+                   const float *__restrict__ chan_add, uint4 *__restrict__ y, int B, int T,
+                   long long *__restrict__ prof) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bars = s_base + OFF_BAR;
@@ -140,11 +141,15 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
     uint4 *h_hi = reinterpret_cast<uint4 *>(smem + OFF_H + c8 * (2 * NCL * 16) + n * 16);
     uint4 *h_lo = h_hi + NCL;
+    const bool pf = prof != nullptr && blockIdx.x == 0 && tid == 0;
+    long long pa[7] = {0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
+      long long c0 = pf ? clock64() : 0;
       mbar_wait(acc_full0 + 8 * buf, (t >> 1) & 1);
       tc_fence_after();
+      long long c1 = pf ? clock64() : 0;
       uint32_t r[64];
       const uint32_t ta = tmem + TM_ACC + buf * 128 + m * 64 + ((uint32_t)(q * 32) << 16);
       tmem_ld32(ta, r);
@@ -152,13 +157,16 @@ __global__ void __launch_bounds__(THREADS, 1)
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(acc_empty0 + 8 * buf);
+      long long c2 = pf ? clock64() : 0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float v = __uint_as_float(r[j]) + __uint_as_float(r[32 + j]) + bias;
         v = fminf(fmaxf(v, -vmax), vmax);
         e_row[j] = ex2_approx(v * escale);
       }
+      long long c3 = pf ? clock64() : 0;
       named_bar_sync(1, N_EPI);
+      long long c4 = pf ? clock64() : 0;
       float hv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -175,8 +183,10 @@ __global__ void __launch_bounds__(THREADS, 1)
       split8(hv, hi, lo);
       *h_hi = hi;
       *h_lo = lo;
+      long long c5 = pf ? clock64() : 0;
       fence_async_smem();
       mbar_arrive(h_ready);
+      long long c6 = pf ? clock64() : 0;
       if (live) {
         if (chan_add != nullptr) {
 #pragma unroll
@@ -186,6 +196,14 @@ __global__ void __launch_bounds__(THREADS, 1)
         y_hi[t] = hi;
         y_lo[t] = lo;
       }
+      if (pf) {
+        long long c7 = clock64();
+        pa[0] += c1 - c0; pa[1] += c2 - c1; pa[2] += c3 - c2; pa[3] += c4 - c3; pa[4] += c5 - c4; pa[5] += c6 - c5;
+        pa[6] += c7 - c6;
+      }
+    }
+    if (pf) {
+      for (int i = 0; i < 7; ++i) prof[i] = pa[i];
     }
   } else if (warp < 12) {
     // ===================== x loader =====================
@@ -236,15 +254,20 @@ __global__ void __launch_bounds__(THREADS, 1)
     mbar_wait(x_full0, 0);
     tc_fence_after();
     issue(s_base + OFF_X, 2, 0, 0);
+    const bool pf = prof != nullptr && blockIdx.x == 0;
+    long long pm[3] = {0, 0, 0};
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
+      long long m0 = pf ? clock64() : 0;
       if (t > 0) {
         mbar_wait(h_ready, (t - 1) & 1);
         tc_fence_after();
       }
+      long long m1 = pf ? clock64() : 0;
       issue(h_tile, 0, buf, 1);                 // + W_hh . h_{t-1}
       tc_commit(acc_full0 + 8 * buf);
+      long long m2 = pf ? clock64() : 0;
       const int t1 = t + 1;
       if (t1 < T) {
         const int ch = t1 / TC_STEPS, tt = t1 % TC_STEPS, st = ch & 1;
@@ -254,6 +277,10 @@ __global__ void __launch_bounds__(THREADS, 1)
         issue(s_base + OFF_X + st * XSTAGE + tt * XSTEP, 2, buf ^ 1, 0);   // W_ih . x_{t+1}
         if (tt == TC_STEPS - 1) tc_commit(x_empty0 + 8 * st);
       }
+      if (pf) { long long m3 = clock64(); pm[0] += m1 - m0; pm[1] += m2 - m1; pm[2] += m3 - m2; }
+    }
+    if (pf) {
+      for (int i = 0; i < 3; ++i) prof[8 + i] = pm[i];
     }
   }
   __syncwarp();
@@ -265,6 +292,10 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
 }
 
+// optional device buffer of 16 int64 receiving per-phase cycle sums of block 0 (tools/lstm_profile.py)
+static long long *g_lstm_prof = nullptr;
+void set_lstm_profile_buffer(long long *p) { g_lstm_prof = p; }
+
 int launch_lstm_tc(const void *x, const void *wpk, const float *bias_p, const float *chan_add, void *y, int B, int T,
                    cudaStream_t st) {
   if (B == 0 || T == 0) return 0;
@@ -275,7 +306,7 @@ int launch_lstm_tc(const void *x, const void *wpk, const float *bias_p, const fl
   }
   lstm_tc_kernel<<<(B + NCL - 1) / NCL, THREADS, LSTM_SMEM, st>>>(
       reinterpret_cast<const uint4 *>(x), reinterpret_cast<const uint4 *>(wpk), bias_p, chan_add,
-      reinterpret_cast<uint4 *>(y), B, T);
+      reinterpret_cast<uint4 *>(y), B, T, g_lstm_prof);
   WM_CHECK_LAUNCH("lstm_tc");
   return 0;
 }

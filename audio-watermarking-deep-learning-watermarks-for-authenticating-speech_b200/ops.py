@@ -50,7 +50,7 @@ def launch_count() -> int:
 
 def max_chunk() -> int:
     """Clips per device pass (workspace ~12.4 MB per clip in the fp32 layout)."""
-    return int(os.environ.get("WMB200_MAX_CLIPS", "2368"))
+    return int(os.environ.get("WMB200_MAX_CLIPS", "4736"))
 
 
 # ---- single operators ------------------------------------------------------
@@ -112,6 +112,18 @@ def conv64_tc(xp, w_img, bias, B: int, T: int, taps: int, residual=None, relu=Fa
     y32 = torch.empty(B, T, 64, device=xp.device, dtype=torch.float32) if want_fp32 else None
     L.check(lib.wm_conv64_tc_fwd(L.ptr(xp), L.ptr(w_img), L.ptr(_req(bias, "bias")), L.ptr(residual), L.ptr(y),
                                  L.ptr(y32), B, T, taps, int(relu), _stream()), "wm_conv64_tc_fwd")
+    return y, y32
+
+
+def resblock_tc(xp, w1, b1, w2, b2, B: int, T: int, want_planar=True, want_fp32=False):
+    """Fused ResBlock on planar x; w1/w2 fp32 [3][64][64] tap-major (BN folded)."""
+    lib = L.load()
+    dev = xp.device
+    img = torch.cat([pack_conv64_tc(w1), pack_conv64_tc(w2)])
+    y = torch.empty(max(lib.wm_planar_bytes(B, T), 16), dtype=torch.uint8, device=dev) if want_planar else None
+    y32 = torch.empty(B, T, 64, device=dev, dtype=torch.float32) if want_fp32 else None
+    L.check(lib.wm_resblock_tc_fwd(L.ptr(xp), L.ptr(img), L.ptr(_req(b1, "b1")), L.ptr(_req(b2, "b2")), L.ptr(y),
+                                   L.ptr(y32), B, T, _stream()), "wm_resblock_tc_fwd")
     return y, y32
 
 

@@ -32,7 +32,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 6
+#define WM_ABI_VERSION 7
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -149,12 +149,21 @@ int wm_pack_conv64_tc(const float *w, void *img, int taps, void *stream);
 int wm_conv64_tc_fwd(const void *x, const void *w_img, const float *bias, const void *residual,
                      void *y, float *y32, int B, int T, int taps, int relu, void *stream);
 
+/* A whole ResBlock (py/main16.py:112-125) in one kernel: y = relu(x + conv2(relu(conv1(x)+b1)) + b2).
+ * w_img: the two 3-tap images (conv1 then conv2) back to back; the intermediate activation stays
+ * in shared memory, the residual is taken from the x tile already on chip. */
+int wm_resblock_tc_fwd(const void *x, const void *w_img, const float *b1, const float *b2, void *y,
+                       float *y32, int B, int T, void *stream);
+
 /* The LSTM on tensor cores: planar x -> planar h (+ chan_add[B][64] added to the OUTPUT only, i.e.
  * the message embedding of py/main16.py:156-159 fused into the store).  Weights resident in TMEM,
  * bf16 hi+lo operand pairs, fp32 accumulation and fp32 cell state.  wpk / bias_p from wm_pack_lstm_tc
  * (wpk: 4*256*64 bf16, bias_p: 256 floats). */
 int wm_pack_lstm_tc(const float *w_ih, const float *w_hh, const float *bias, void *wpk, float *bias_p,
                     void *stream);
+/* developer hook: when buf16 (device, 16 x int64) is non-null the LSTM kernel's block 0 stores
+ * per-phase cycle sums there (tools/lstm_profile.py); pass NULL to switch it off. */
+int wm_debug_lstm_profile(long long *buf16);
 int wm_lstm_tc_fwd(const void *x, const void *wpk, const float *bias_p, const float *chan_add, void *y,
                    int B, int T, void *stream);
 

@@ -123,6 +123,28 @@ def test_conv64_tensor_core(B, T, taps, variant):
     assert int(planes[:, :L.PLANAR_PAD].max()) == 0 and int(planes[:, T + L.PLANAR_PAD:].max()) == 0
 
 
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 125), (1, 126), (3, 127), (2, 253), (4, 16000), (150, 1300)])
+def test_resblock_tensor_core_fused(B, T):
+    """One-kernel ResBlock (intermediate in shared memory) vs the fp64 reference."""
+    g = torch.Generator().manual_seed(B * 7 + T)
+    x = torch.randn(B, 64, T, generator=g) * 2
+    w1 = torch.randn(64, 64, 3, generator=g) / 14
+    w2 = torch.randn(64, 64, 3, generator=g) / 14
+    b1, b2 = torch.randn(64, generator=g), torch.randn(64, generator=g)
+    xd = x.double()
+    u = F.relu(F.conv1d(xd, w1.double(), b1.double(), padding=1))
+    ref = F.relu(xd + F.conv1d(u, w2.double(), b2.double(), padding=1)).float()
+    xp = ops.to_planar(x.permute(0, 2, 1).contiguous().to(DEV))
+    tm = lambda w: w.permute(2, 1, 0).contiguous().to(DEV)
+    yp, y32 = ops.resblock_tc(xp, tm(w1), b1.to(DEV), tm(w2), b2.to(DEV), B, T, want_fp32=True)
+    scale = max(1.0, float(ref.abs().max()))
+    assert maxerr(y32.permute(0, 2, 1), ref) < 3e-5 * scale
+    assert maxerr(ops.from_planar(yp, B, T).permute(0, 2, 1), ref) < 5e-5 * scale
+    RP = T + 2 * L.PLANAR_PAD
+    planes = yp[:B * 16 * RP * 16].view(B * 16, RP, 16)
+    assert int(planes[:, :L.PLANAR_PAD].max()) == 0 and int(planes[:, T + L.PLANAR_PAD:].max()) == 0
+
+
 def test_conv_transpose_equivalence():
     """ConvTranspose1d(64,64,7,p=3) == conv with flipped taps (py/main16.py:144)."""
     gsd, _ = H.gen_sd(W, "A")

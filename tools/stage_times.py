@@ -51,6 +51,12 @@ out["conv64_tc_k3_ms"] = timeit(lambda: lib.wm_conv64_tc_fwd(xp.data_ptr(), img3
 out["conv64_tc_k3_res_ms"] = timeit(lambda: lib.wm_conv64_tc_fwd(xp.data_ptr(), img3.data_ptr(), b3.data_ptr(), rp.data_ptr(), yp.data_ptr(), None, B, T, 3, 1, st))
 out["conv64_tc_k3_res_fp32out_ms"] = timeit(lambda: lib.wm_conv64_tc_fwd(xp.data_ptr(), img3.data_ptr(), b3.data_ptr(), rp.data_ptr(), None, y32.data_ptr(), B, T, 3, 1, st))
 out["conv64_tc_k7_ms"] = timeit(lambda: lib.wm_conv64_tc_fwd(xp.data_ptr(), img7.data_ptr(), b3.data_ptr(), None, yp.data_ptr(), None, B, T, 7, 0, st))
+img33 = blob[L.G_TC:L.G_TC + 2 * L.TC_IMG3]
+b1 = blob[L.G_RB0 + L.RB_B1:]; b2 = blob[L.G_RB0 + L.RB_B2:]
+out["resblock_tc_fused_ms"] = timeit(lambda: lib.wm_resblock_tc_fwd(xp.data_ptr(), img33.data_ptr(), b1.data_ptr(), b2.data_ptr(), yp.data_ptr(), None, B, T, st))
+out["resblock_tc_fused_fp32out_ms"] = timeit(lambda: lib.wm_resblock_tc_fwd(xp.data_ptr(), img33.data_ptr(), b1.data_ptr(), b2.data_ptr(), None, y32.data_ptr(), B, T, st))
+out["resblock_tc_cycles_per_tile_at_1965MHz"] = out["resblock_tc_fused_ms"] * 1e-3 * 1.965e9 * 148 / (B * 127)
+out["resblock_tc_TFLOPs_algorithmic"] = 2 * 2 * 64 * 64 * 3 * T * B / (out["resblock_tc_fused_ms"] * 1e-3) / 1e12
 out["to_planar_ms"] = timeit(lambda: lib.wm_to_planar(x32.data_ptr(), None, yp.data_ptr(), B, T, st))
 wih = blob[L.G_LSTM_WIH:L.G_LSTM_WIH + 16384]
 whh = blob[L.G_LSTM_WHH:L.G_LSTM_WHH + 16384]
