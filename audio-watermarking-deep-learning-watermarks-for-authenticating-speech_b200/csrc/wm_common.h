@@ -91,6 +91,7 @@ int launch_lstm_tc(const void *x, const void *wpk, const float *bias_p, const fl
 int launch_resblock_tc(const void *x, const void *w_img, const float *b1, const float *b2, void *y, float *y32, int B,
                        int T, cudaStream_t st);
 void set_lstm_profile_buffer(long long *p);
+long long *get_profile_buffer();
 int launch_pack_lstm_tc(const float *w_ih, const float *w_hh, const float *bias, void *wpk, float *bias_p,
                         cudaStream_t st);
 

@@ -46,11 +46,11 @@ struct Cfg {
 }  // namespace
 
 // ---------------------------------------------------------------------------
-// The kernel.  192 threads: warp 0 producer (bulk copies), warp 1 MMA issuer and TMEM owner,
-// warps 2..5 epilogue (TMEM lane quadrant = warp_idx % 4).
+// The kernel.  Warps 0..15 epilogue (TMEM lane quadrant = warp % 4, 16-channel slice = warp / 4),
+// warp 16 producer (bulk copies), warp 17 MMA issuer and TMEM owner.
 // ---------------------------------------------------------------------------
 template <int TAPS>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(576, 1)
     conv64_tc_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ w_img, const float *__restrict__ bias,
                      const uint4 *__restrict__ residual, uint4 *__restrict__ y, float *__restrict__ y32, int B, int T,
                      int relu) {
@@ -77,11 +77,11 @@ __global__ void __launch_bounds__(192, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(wbar, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 128) bias_s[threadIdx.x - 64] = bias[threadIdx.x - 64];
-  if (warp == 1) {
+  if (threadIdx.x < 64) bias_s[threadIdx.x] = bias[threadIdx.x];
+  if (warp == 17) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(192, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 16) {
     // ===== producer =====
     if (lane == 0) {
       mbar_arrive_expect_tx(wbar, C::W_BYTES);
@@ -114,44 +114,44 @@ __global__ void __launch_bounds__(192, 1)
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      mbar_wait(wbar, 0);
-      int i = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
-        const int s = i % C::NSTAGE;
-        const uint32_t ph = (i / C::NSTAGE) & 1;
-        const int a = i & 1;
-        const uint32_t aph = (i >> 1) & 1;
-        mbar_wait(tempty_bar(a), aph ^ 1);
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
+  } else if (warp == 17) {
+    // ===== MMA issuer =====  (whole warp walks the pipeline; one elected lane issues)
+    const bool issuer = elect_one();
+    mbar_wait_warp(wbar, 0);
+    const uint64_t b0 = smem_desc(w_smem, 2048, 128);
+    int i = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+      const int s = i % C::NSTAGE;
+      const uint32_t ph = (i / C::NSTAGE) & 1;
+      const int a = i & 1;
+      const uint32_t aph = (i >> 1) & 1;
+      mbar_wait_warp(tempty_bar(a), aph ^ 1);
+      mbar_wait_warp(full_bar(s), ph);
+      tc_fence_after();
+      if (issuer) {
         const uint32_t d_tmem = tmem_base + a * 128;
-        const uint32_t a_stage = a_smem + s * C::A_STAGE_BYTES;
-        uint32_t accum = 0;
-#pragma unroll 1
+        const uint64_t a0 = smem_desc(a_smem + s * C::A_STAGE_BYTES, C::PLANE_BYTES, 128);
+        // descriptors differ only in the 16-byte-granular start address: add compile-time offsets
+#pragma unroll
         for (int j = 0; j < TAPS; ++j) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t bdesc = smem_desc(w_smem + j * C::W_TAP_BYTES + (2 * kk) * 2048, 2048, 128);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-              const uint64_t adesc =
-                  smem_desc(a_stage + (half * 8 + 2 * kk) * C::PLANE_BYTES + j * 16, C::PLANE_BYTES, 128);
-              mma_bf16(d_tmem, adesc, bdesc, kIdesc, accum);
-              accum = 1;
+              mma_bf16(d_tmem, a0 + (uint64_t)(((half * 8 + 2 * kk) * C::PLANE_BYTES + j * 16) >> 4),
+                       b0 + (uint64_t)((j * C::W_TAP_BYTES + (2 * kk) * 2048) >> 4), kIdesc,
+                       (j | kk | half) != 0 ? 1u : 0u);
             }
           }
         }
         tc_commit(empty_bar(s));   // smem stage is free once these MMAs have read it
         tc_commit(tfull_bar(a));   // accumulator complete
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===== epilogue =====
-    const int q = warp & 3;
+    const int q = warp & 3, p = warp >> 2;
     int i = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
       const int a = i & 1;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(192, 1)
       const int t0 = (int)(tile % ntile_t) * TILE;
       const int t = t0 + q * 32 + lane;
       const bool live = t < T;
-      if (y != nullptr && q == 0 && lane < 2 * PAD) {
+      if (y != nullptr && warp == 0 && lane < 2 * PAD) {
         // keep the planes' zero padding rows intact: first / last tile of a clip rewrites them
         const bool head = lane < PAD;
         if (head ? (t0 == 0) : (t0 + TILE >= T)) {
@@ -168,20 +168,17 @@ __global__ void __launch_bounds__(192, 1)
           for (int pl = 0; pl < 16; ++pl) y[((size_t)(b * 16 + pl)) * RP + zr] = make_uint4(0, 0, 0, 0);
         }
       }
-      mbar_wait(tfull_bar(a), aph);
+      mbar_wait_warp(tfull_bar(a), aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + a * 128 + ((uint32_t)(q * 32) << 16);
       const size_t prow = (size_t)t + PAD;
-#pragma unroll 1
-      for (int p = 0; p < 4; ++p) {
+      {
         float v1[16], v2[16];
         tmem_ld16(taddr + p * 16, v1);
         tmem_ld16(taddr + 64 + p * 16, v2);
         tmem_ld_wait();
-        if (p == 3) {  // all of this thread's accumulator has been read: hand the TMEM stage back
-          tc_fence_before();
-          mbar_arrive(tempty_bar(a));
-        }
+        tc_fence_before();
+        mbar_arrive_warp(tempty_bar(a));   // this thread's slice of the accumulator has been read
         float o[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) o[c] = v1[c] + v2[c] + bias_s[p * 16 + c];
@@ -223,7 +220,7 @@ __global__ void __launch_bounds__(192, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 17) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
   }
@@ -241,7 +238,7 @@ static int launch_conv64_tc_t(const void *x, const void *w_img, const float *bia
   }
   long long ntiles = (long long)B * ((T + TILE - 1) / TILE);
   int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-  conv64_tc_kernel<TAPS><<<grid, 192, C::SMEM_BYTES, st>>>(
+  conv64_tc_kernel<TAPS><<<grid, 576, C::SMEM_BYTES, st>>>(
       reinterpret_cast<const uint4 *>(x), reinterpret_cast<const uint4 *>(w_img), bias,
       reinterpret_cast<const uint4 *>(residual), reinterpret_cast<uint4 *>(y), y32, B, T, relu);
   WM_CHECK_LAUNCH("conv64_tc");

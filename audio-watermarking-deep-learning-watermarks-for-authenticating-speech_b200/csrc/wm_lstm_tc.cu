@@ -74,11 +74,11 @@ __global__ void __launch_bounds__(THREADS, 1)
   const int nchunk = (T + TC_STEPS - 1) / TC_STEPS;
 
   if (tid == 0) {
-    mbar_init(h_ready, N_EPI);
+    mbar_init(h_ready, N_EPI / 32);
     for (int i = 0; i < 2; ++i) {
       mbar_init(acc_full0 + 8 * i, 1);
-      mbar_init(acc_empty0 + 8 * i, N_EPI);
-      mbar_init(x_full0 + 8 * i, N_LOAD);
+      mbar_init(acc_empty0 + 8 * i, N_EPI / 32);
+      mbar_init(x_full0 + 8 * i, N_LOAD / 32);
       mbar_init(x_empty0 + 8 * i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       long long c0 = pf ? clock64() : 0;
-      mbar_wait(acc_full0 + 8 * buf, (t >> 1) & 1);
+      mbar_wait_warp(acc_full0 + 8 * buf, (t >> 1) & 1);
       tc_fence_after();
       long long c1 = pf ? clock64() : 0;
       uint32_t r[64];
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       tmem_ld32(ta + 32, r + 32);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(acc_empty0 + 8 * buf);
+      mbar_arrive_warp(acc_empty0 + 8 * buf);
       long long c2 = pf ? clock64() : 0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       *h_lo = lo;
       long long c5 = pf ? clock64() : 0;
       fence_async_smem();
-      mbar_arrive(h_ready);
+      mbar_arrive_warp(h_ready);
       long long c6 = pf ? clock64() : 0;
       if (live) {
         if (chan_add != nullptr) {
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll 1
     for (int ch = 0; ch < nchunk; ++ch) {
       const int st = ch & 1;
-      if (ch >= 2) mbar_wait(x_empty0 + 8 * st, ((ch >> 1) - 1) & 1);
+      if (ch >= 2) mbar_wait_warp(x_empty0 + 8 * st, ((ch >> 1) - 1) & 1);
       const int t = ch * TC_STEPS + tt;
       if (t < T) {
         const uint4 *src = x + ((size_t)b0 * 16 + pl) * RP + PAD + t;
@@ -224,58 +224,63 @@ __global__ void __launch_bounds__(THREADS, 1)
       if (ch >= 1) {  // the previous stage has landed: publish it
         cp_async_wait<1>();
         fence_async_smem();
-        mbar_arrive(x_full0 + 8 * ((ch - 1) & 1));
+        mbar_arrive_warp(x_full0 + 8 * ((ch - 1) & 1));
       }
     }
     cp_async_wait<0>();
     fence_async_smem();
-    mbar_arrive(x_full0 + 8 * ((nchunk - 1) & 1));
-  } else if (lane == 0) {
-    // ===================== MMA issuer =====================
-    const uint32_t h_tile = s_base + OFF_H;
-    auto issue = [&](uint32_t b_tile, uint32_t w_first, int buf, uint32_t accum) {
-      // 2 M-tiles x 4 K steps x {hi, lo} weights; B tile: 64 rows (32 hi + 32 lo clips), chunk pitch 1 KB
+    mbar_arrive_warp(x_full0 + 8 * ((nchunk - 1) & 1));
+  } else {
+    // ===================== MMA issuer (whole warp walks the pipeline; one elected lane issues) =====
+    const bool issuer = elect_one();
+    const uint64_t h_desc = smem_desc(s_base + OFF_H, 2 * NCL * 16, 128);
+    // 2 M-tiles x 4 K steps x {hi, lo} weights; B tile: 64 rows (32 hi + 32 lo clips), chunk pitch 1 KB
+    auto issue = [&](uint64_t b_desc, uint32_t w_first, int buf, uint32_t accum) {
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        const uint32_t d = tmem + TM_ACC + buf * 128 + m * 64;
-        uint32_t acc = accum;
+      for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t bdesc = smem_desc(b_tile + (2 * kk) * (2 * NCL * 16), 2 * NCL * 16, 128);
+        for (int part = 0; part < 2; ++part) {
 #pragma unroll
-          for (int part = 0; part < 2; ++part) {
-            mma_bf16_ts(d, tmem + TM_W + (w_first + part) * 64 + m * 32 + kk * 8, bdesc, kIdescL, acc);
-            acc = 1;
+          for (int m = 0; m < 2; ++m) {
+            mma_bf16_ts(tmem + TM_ACC + buf * 128 + m * 64, tmem + TM_W + (w_first + part) * 64 + m * 32 + kk * 8,
+                        b_desc + (uint64_t)(((2 * kk) * (2 * NCL * 16)) >> 4), kIdescL, (kk | part) != 0 ? 1u : accum);
           }
         }
       }
     };
-    // x part of step 0
-    mbar_wait(x_full0, 0);
-    tc_fence_after();
-    issue(s_base + OFF_X, 2, 0, 0);
-    const bool pf = prof != nullptr && blockIdx.x == 0;
+    const bool pf = prof != nullptr && blockIdx.x == 0 && issuer;
     long long pm[3] = {0, 0, 0};
+    // x part of step 0
+    mbar_wait_warp(x_full0, 0);
+    tc_fence_after();
+    if (issuer) issue(smem_desc(s_base + OFF_X, 2 * NCL * 16, 128), 2, 0, 0);
+    __syncwarp();
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       long long m0 = pf ? clock64() : 0;
       if (t > 0) {
-        mbar_wait(h_ready, (t - 1) & 1);
+        mbar_wait_warp(h_ready, (t - 1) & 1);
         tc_fence_after();
       }
       long long m1 = pf ? clock64() : 0;
-      issue(h_tile, 0, buf, 1);                 // + W_hh . h_{t-1}
-      tc_commit(acc_full0 + 8 * buf);
+      if (issuer) {
+        issue(h_desc, 0, buf, 1);                 // + W_hh . h_{t-1}
+        tc_commit(acc_full0 + 8 * buf);
+      }
+      __syncwarp();
       long long m2 = pf ? clock64() : 0;
       const int t1 = t + 1;
       if (t1 < T) {
         const int ch = t1 / TC_STEPS, tt = t1 % TC_STEPS, st = ch & 1;
-        if (tt == 0) mbar_wait(x_full0 + 8 * st, (ch >> 1) & 1);
-        if (t1 >= 2) mbar_wait(acc_empty0 + 8 * (buf ^ 1), ((t1 >> 1) - 1) & 1);
+        if (tt == 0) mbar_wait_warp(x_full0 + 8 * st, (ch >> 1) & 1);
+        if (t1 >= 2) mbar_wait_warp(acc_empty0 + 8 * (buf ^ 1), ((t1 >> 1) - 1) & 1);
         tc_fence_after();
-        issue(s_base + OFF_X + st * XSTAGE + tt * XSTEP, 2, buf ^ 1, 0);   // W_ih . x_{t+1}
-        if (tt == TC_STEPS - 1) tc_commit(x_empty0 + 8 * st);
+        if (issuer) {
+          issue(smem_desc(s_base + OFF_X + st * XSTAGE + tt * XSTEP, 2 * NCL * 16, 128), 2, buf ^ 1, 0);  // W_ih . x_{t+1}
+          if (tt == TC_STEPS - 1) tc_commit(x_empty0 + 8 * st);
+        }
+        __syncwarp();
       }
       if (pf) { long long m3 = clock64(); pm[0] += m1 - m0; pm[1] += m2 - m1; pm[2] += m3 - m2; }
     }
@@ -292,9 +297,10 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
 }
 
-// optional device buffer of 16 int64 receiving per-phase cycle sums of block 0 (tools/lstm_profile.py)
+// optional device buffer of 32 int64 receiving per-phase cycle sums of block 0 (tools/*_profile.py)
 static long long *g_lstm_prof = nullptr;
 void set_lstm_profile_buffer(long long *p) { g_lstm_prof = p; }
+long long *get_profile_buffer() { return g_lstm_prof; }
 
 int launch_lstm_tc(const void *x, const void *wpk, const float *bias_p, const float *chan_add, void *y, int B, int T,
                    cudaStream_t st) {
