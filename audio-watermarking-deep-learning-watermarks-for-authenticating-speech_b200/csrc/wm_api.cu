@@ -113,8 +113,10 @@ static int generator_run(const float *blob, const float *embedding, int64_t emb_
   // LSTM (+ message embedding added to its output)            (py/main16.py:152-159)
   WM_TRY(launch_lstm_tc(r1, blob + WM_G_TC_LSTM_W, blob + WM_G_TC_LSTM_B, chan_add, r0, B, T, st));  // -> r0 planar
   WM_TRY(launch_conv64_tc(r0, blob + WM_G_TC_CT, blob + WM_G_CT_B, nullptr, r1, nullptr, B, T, 7, 0, st));
-  WM_TRY(resblock_tc(blob + WM_G_RB2, blob + WM_G_TC_RB2, r1, r2, nullptr, f0, B, T, st));      // -> r0 fp32
-  return launch_head(f0, blob + WM_G_HEAD_W, blob + WM_G_HEAD_B, delta_raw, B, T, 1, st);
+  // last ResBlock with the Conv1d(64,1,1) head fused into its epilogue      (py/main16.py:145-146)
+  (void)f0;
+  return launch_resblock_head1_tc(r1, blob + WM_G_TC_RB2, blob + WM_G_RB2 + WM_RB_B1, blob + WM_G_RB2 + WM_RB_B2,
+                                  blob + WM_G_HEAD_W, blob + WM_G_HEAD_B, delta_raw, B, T, st);
 }
 
 // Detector trunk (py/main16.py:176-179): fp32 channels-last result left in *out (one of the buffers)
@@ -131,6 +133,28 @@ static int detector_trunk(const float *blob, const float *x, void *r0, void *r1,
   WM_TRY(launch_conv_in_k7_planar(x, blob + WM_D_IN_W, blob + WM_D_IN_B, r0, B, T, st));
   WM_TRY(resblock_tc(blob + WM_D_RB0, tc, r0, r1, r2, nullptr, B, T, st));
   return resblock_tc(blob + WM_D_RB1, tc + 2 * WM_TC_IMG3, r2, r0, nullptr, f1, B, T, st);
+}
+
+// Detector + heads (py/main16.py:176-180,1142-1146): per-sample probability, clip mean, mean message logits.
+// tcgen05 mode with the shipped 17-output head and no vote request: the 1x1 head, the sigmoid and the
+// per-tile partial sums run in the last ResBlock's epilogue (the (B,T,64) feature map is never stored).
+static int detect_run(const float *blob, const float *x, const int *valid_len, float *probs, float *clip_prob,
+                      float *msg_logits, float *vote_frac, void *r0, void *r1, void *r2, int B, int T, int nout,
+                      cudaStream_t st) {
+  if (g_math_mode.load() == WM_MATH_BF16X2 && nout == 17 && vote_frac == nullptr &&
+      (size_t)B * resblock_tiles_per_clip(T) * 4 * WM_MAX_HEAD * sizeof(float) <= act_bytes(B, T)) {
+    const float *tc = blob + WM_D_TC;
+    float *partials = (float *)r1;
+    WM_TRY(launch_conv_in_k7_planar(x, blob + WM_D_IN_W, blob + WM_D_IN_B, r0, B, T, st));
+    WM_TRY(resblock_tc(blob + WM_D_RB0, tc, r0, r1, r2, nullptr, B, T, st));
+    WM_TRY(launch_resblock_head17_tc(r2, tc + 2 * WM_TC_IMG3, blob + WM_D_RB1 + WM_RB_B1, blob + WM_D_RB1 + WM_RB_B2,
+                                     blob + WM_D_HEAD_W, blob + WM_D_HEAD_B, valid_len, probs, partials, B, T, st));
+    return launch_detect_finalize(partials, valid_len, clip_prob, msg_logits, B, T, nout, st);
+  }
+  float *out = nullptr;
+  WM_TRY(detector_trunk(blob, x, r0, r1, r2, &out, B, T, st));
+  return launch_head_detect(out, blob + WM_D_HEAD_W, blob + WM_D_HEAD_B, valid_len, probs, clip_prob, msg_logits,
+                            vote_frac, B, T, nout, st);
 }
 
 }  // namespace wm
@@ -354,11 +378,8 @@ int wm_detect_fwd(const float *blob, const float *x, const int *valid_len, float
   WM_CHECK_ARG(workspace_bytes >= wm_detector_workspace_bytes(B, T), "detect: workspace too small");
   Ws ws{(char *)workspace, workspace_bytes};
   void *a0 = ws.take(act_bytes(B, T)), *a1 = ws.take(act_bytes(B, T)), *a2 = ws.take(act_bytes(B, T));
-  float *out = nullptr;
-  cudaStream_t st = as_stream(stream);
-  WM_TRY(detector_trunk(blob, x, a0, a1, a2, &out, B, T, st));
-  return launch_head_detect(out, blob + WM_D_HEAD_W, blob + WM_D_HEAD_B, valid_len, probs, clip_prob,
-                            msg_logits, vote_frac, B, T, nout, st);
+  return detect_run(blob, x, valid_len, probs, clip_prob, msg_logits, vote_frac, a0, a1, a2, B, T, nout,
+                    as_stream(stream));
 }
 
 size_t wm_embed_detect_workspace_bytes(int B, int T) {
@@ -382,13 +403,11 @@ int wm_embed_detect_fwd(const float *g_blob, const float *embedding, int64_t emb
                wm_embed_detect_workspace_bytes(B, T));
   Ws ws{(char *)workspace, workspace_bytes};
   void *a0 = ws.take(act_bytes(B, T)), *a1 = ws.take(act_bytes(B, T)), *a2 = ws.take(act_bytes(B, T));
-  float *emb = (float *)ws.take((size_t)B * 64 * 4), *draw = (float *)ws.take((size_t)B * T * 4), *out = nullptr;
+  float *emb = (float *)ws.take((size_t)B * 64 * 4), *draw = (float *)ws.take((size_t)B * T * 4);
   cudaStream_t st = as_stream(stream);
   WM_TRY(generator_run(g_blob, embedding, emb_rows, message, s, draw, a0, a1, a2, emb, B, T, st));
   WM_TRY(launch_postprocess(draw, s, fir, delta, s_w, delta_rms, B, T, post_mode, 0.02f, 0.005f, 1e-8f, st));
-  WM_TRY(detector_trunk(d_blob, s_w, a0, a1, a2, &out, B, T, st));
-  return launch_head_detect(out, d_blob + WM_D_HEAD_W, d_blob + WM_D_HEAD_B, nullptr, probs, clip_prob,
-                            msg_logits, vote_frac, B, T, nout, st);
+  return detect_run(d_blob, s_w, nullptr, probs, clip_prob, msg_logits, vote_frac, a0, a1, a2, B, T, nout, st);
 }
 
 size_t wm_embed_detect_host_workspace_bytes(int chunk, int T, int nout) {

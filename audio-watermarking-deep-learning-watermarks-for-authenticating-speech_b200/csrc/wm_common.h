@@ -90,6 +90,14 @@ int launch_lstm_tc(const void *x, const void *wpk, const float *bias_p, const fl
                    cudaStream_t st);
 int launch_resblock_tc(const void *x, const void *w_img, const float *b1, const float *b2, void *y, float *y32, int B,
                        int T, cudaStream_t st);
+int resblock_tiles_per_clip(int T);
+int launch_resblock_head1_tc(const void *x, const void *w_img, const float *b1, const float *b2, const float *head_w,
+                             const float *head_b, float *delta_raw, int B, int T, cudaStream_t st);
+int launch_resblock_head17_tc(const void *x, const void *w_img, const float *b1, const float *b2, const float *head_w,
+                              const float *head_b, const int *valid_len, float *probs, float *partials, int B, int T,
+                              cudaStream_t st);
+int launch_detect_finalize(const float *partials, const int *valid_len, float *clip_prob, float *msg_logits, int B,
+                           int T, int nout, cudaStream_t st);
 void set_lstm_profile_buffer(long long *p);
 long long *get_profile_buffer();
 int launch_pack_lstm_tc(const float *w_ih, const float *w_hh, const float *bias, void *wpk, float *bias_p,

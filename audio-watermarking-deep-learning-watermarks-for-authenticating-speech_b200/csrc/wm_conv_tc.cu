@@ -27,6 +27,12 @@ using namespace tc;
 namespace {
 
 constexpr uint32_t kIdesc = make_idesc(128, 128);
+// A_lo multiplies W_hi only (first 64 columns of B): the lo x lo product is below the parity budget
+#ifndef WM_FULL_PRODUCTS
+constexpr uint32_t kIdescLo = make_idesc(128, 64);
+#else
+constexpr uint32_t kIdescLo = kIdesc;
+#endif
 constexpr int PAD = WM_PLANAR_PAD;
 constexpr int TILE = 128;
 
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(576, 1)
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               mma_bf16(d_tmem, a0 + (uint64_t)(((half * 8 + 2 * kk) * C::PLANE_BYTES + j * 16) >> 4),
-                       b0 + (uint64_t)((j * C::W_TAP_BYTES + (2 * kk) * 2048) >> 4), kIdesc,
+                       b0 + (uint64_t)((j * C::W_TAP_BYTES + (2 * kk) * 2048) >> 4), half ? kIdescLo : kIdesc,
                        (j | kk | half) != 0 ? 1u : 0u);
             }
           }

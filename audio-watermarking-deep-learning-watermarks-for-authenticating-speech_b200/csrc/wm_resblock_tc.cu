@@ -47,15 +47,29 @@ constexpr int OFF_BIAS = OFF_U + NU * TILE_B;
 constexpr int OFF_BAR = OFF_BIAS + 512;
 constexpr int RB_SMEM = OFF_BAR + 160;
 constexpr uint32_t kIdesc = make_idesc(128, 128);
+// The lo x lo partial product is ~2^-18 of the result, far below the parity budget: the A_lo MMA multiplies
+// only the first 64 columns of B (= W_hi), i.e. 3 products in 1.5 MMAs' worth of tensor time.
+#ifndef WM_FULL_PRODUCTS
+constexpr uint32_t kIdescLo = make_idesc(128, 64);
+#else
+constexpr uint32_t kIdescLo = kIdesc;
+#endif
 constexpr int N_GRP = 256;                  // threads per epilogue group (8 warps: 4 lane quadrants x 2 channel halves)
 constexpr int W_PROD = 2 * N_GRP / 32, W_MMA = W_PROD + 1, RB_THREADS = 2 * N_GRP + 64;
 static_assert(RB_SMEM <= 232448, "shared memory budget");
 
 }  // namespace
 
+// NHEAD = 0: plain ResBlock.  NHEAD = 1: + Conv1d(64,1,1) -> head_out[b][t] (py/main16.py:146).
+// NHEAD = 17: + Conv1d(64,17,1) -> head_out[b][t] = sigmoid(ch 0) and per-(tile, warp) partial sums of the
+// probability and of the 16 message logits over the valid samples -> partials (py/main16.py:180,1142-1146).
+template <int NHEAD>
+// 18 warps = 5 on one SM sub-partition (16 K registers each): 96 registers per thread is the ceiling
 __global__ void __launch_bounds__(RB_THREADS, 1)
     resblock_tc_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ w_img, const float *__restrict__ b1,
                        const float *__restrict__ b2, uint4 *__restrict__ y, float *__restrict__ y32, int B, int T,
+                       const float4 *__restrict__ head_w, const float *__restrict__ head_b,
+                       float *__restrict__ head_out, float *__restrict__ partials, const int *__restrict__ valid_len,
                        long long *__restrict__ prof) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
@@ -77,7 +91,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
     for (int s = 0; s < NST; ++s) { mbar_init(bar(FULL + s), 1); mbar_init(bar(EMPTY + s), 1); }
     mbar_init(bar(WBAR), 1);
     for (int a = 0; a < 2; ++a) {
-      mbar_init(bar(D1_FULL + a), 1); mbar_init(bar(D2_FULL + a), 1); mbar_init(bar(D2_EMPTY + a), N_GRP / 32);
+      mbar_init(bar(D1_FULL + a), 1); mbar_init(bar(D2_FULL + a), 1); mbar_init(bar(D2_EMPTY + a), 4);
       mbar_init(bar(U_FULL + a), N_GRP / 32); mbar_init(bar(U_EMPTY + a), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -125,7 +139,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               mma_bf16(d_tmem, a0 + (uint64_t)(((half * 8 + 2 * kk) * PLANE_B + j * 16) >> 4),
-                       b0 + (uint64_t)((j * W_TAP_B + (2 * kk) * 2048) >> 4), kIdesc, (j | kk | half) != 0 ? 1u : 0u);
+                       b0 + (uint64_t)((j * W_TAP_B + (2 * kk) * 2048) >> 4), half ? kIdescLo : kIdesc,
+                       (j | kk | half) != 0 ? 1u : 0u);
             }
           }
         }
@@ -219,77 +234,123 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
       for (int k = 0; k < 3; ++k) prof[24 + k] = pe[k];
     }
   } else {
-    // ===== group 2: conv2 accumulator + bias + residual -> ReLU -> y =====
+    // ===== group 2: conv2 accumulator + bias + residual -> ReLU -> y (and the fused 1x1 head) =====
+    // two sub-groups of 4 warps (one per TMEM lane quadrant) take alternate tiles, so a thread owns a whole
+    // row (64 channels, four 16-channel passes) and has two tile periods for it; D2[g] belongs to sub-group g
     const int w2 = warp - N_GRP / 32;
-    const int q = w2 & 3, half = w2 >> 2;
+    const int q = w2 & 3, g = w2 >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const bool pfe = prof != nullptr && blockIdx.x == 0 && lane == 0 && w2 == 0;
     long long pe[3] = {0, 0, 0};
-    for (long long i = 0; i < my_tiles; ++i) {
+    for (long long i = g; i < my_tiles; i += 2) {
       const long long tile = blockIdx.x + i * gridDim.x;
       const long long b = tile / ntile_t;
-      const int t0 = (int)(tile % ntile_t) * TO;
-      const int a = (int)(i & 1);
+      const int tt = (int)(tile % ntile_t);
+      const int t0 = tt * TO;
       const int t = t0 + row;
       const bool live = row < TO && t < T;
       const size_t prow = (size_t)t + PAD;
       long long e0 = pfe ? clock64() : 0;
-      if (y != nullptr && w2 == 0 && lane < 2 * PAD) {  // the planes' zero padding rows
+      if (y != nullptr && q == 0 && lane < 2 * PAD) {  // the planes' zero padding rows
         const bool head = lane < PAD;
         if (head ? (t0 == 0) : (t0 + TO >= T)) {
           const size_t zr = head ? (size_t)lane : (size_t)T + lane;
           for (int pl = 0; pl < 16; ++pl) y[((size_t)(b * 16 + pl)) * RP + zr] = make_uint4(0, 0, 0, 0);
         }
       }
-      // residual x[t], this thread's 32 channels: 8 x 16 B from L2 (the tile was fetched a moment ago),
-      // requested before the accumulator wait so the latency hides behind conv2
-      uint4 rres[8];
+      // residual x[t] comes from L2 (the tile was fetched a moment ago), 16 channels (4 x 16 B) per pass,
+      // requested one pass ahead; the first request goes out before the accumulator wait
+      uint4 rres[4];
+      auto fetch = [&](int p) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int ch = half * 4 + k;
-        rres[2 * k] = live ? __ldg(&x[((size_t)(b * 16 + ch)) * RP + prow]) : make_uint4(0, 0, 0, 0);
-        rres[2 * k + 1] = live ? __ldg(&x[((size_t)(b * 16 + 8 + ch)) * RP + prow]) : make_uint4(0, 0, 0, 0);
-      }
-      mbar_wait_warp(bar(D2_FULL + a), (uint32_t)((i >> 1) & 1));
+        for (int h = 0; h < 2; ++h) {
+          const int ch = p * 2 + h;
+          rres[2 * h] = live ? __ldg(&x[((size_t)(b * 16 + ch)) * RP + prow]) : make_uint4(0, 0, 0, 0);
+          rres[2 * h + 1] = live ? __ldg(&x[((size_t)(b * 16 + 8 + ch)) * RP + prow]) : make_uint4(0, 0, 0, 0);
+        }
+      };
+      fetch(0);
+      mbar_wait_warp(bar(D2_FULL + g), (uint32_t)((i >> 1) & 1));
       long long e1 = pfe ? clock64() : 0;
       tc_fence_after();
-      const uint32_t taddr = tmem + 256 + a * 128 + lane_off;
-      float o[32];
+      const uint32_t taddr = tmem + 256 + g * 128 + lane_off;
+      float hacc[NHEAD > 0 ? NHEAD : 1];
 #pragma unroll
-      for (int pp = 0; pp < 2; ++pp) {
-        const int p = half * 2 + pp;
-        float v1[16], v2[16];
+      for (int o = 0; o < (NHEAD > 0 ? NHEAD : 1); ++o) hacc[o] = 0.0f;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float v1[16], v2[16], o[16];
         tmem_ld16(taddr + p * 16, v1);
         tmem_ld16(taddr + 64 + p * 16, v2);
         tmem_ld_wait();
+        if (p == 3) {
+          tc_fence_before();
+          mbar_arrive_warp(bar(D2_EMPTY + g));     // D2[g] may be overwritten by conv2(i+2)
+        }
 #pragma unroll
-        for (int c = 0; c < 16; ++c) o[pp * 16 + c] = v1[c] + v2[c] + bias_s[64 + p * 16 + c];
-      }
-      tc_fence_before();
-      mbar_arrive_warp(bar(D2_EMPTY + a));     // D2[a] may be overwritten by conv2(i+2)
+        for (int h = 0; h < 2; ++h) {
+          float r[8];
+          join8(rres[2 * h], rres[2 * h + 1], r);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float r[8];
-        join8(rres[2 * k], rres[2 * k + 1], r);
+          for (int c = 0; c < 8; ++c)
+            o[h * 8 + c] = fmaxf(v1[h * 8 + c] + v2[h * 8 + c] + bias_s[64 + p * 16 + h * 8 + c] + r[c], 0.0f);
+        }
+        if (p < 3) fetch(p + 1);
+        if (live) {
+          if (y != nullptr) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) o[k * 8 + c] = fmaxf(o[k * 8 + c] + r[c], 0.0f);
-      }
-      if (live) {
-        if (y != nullptr) {
+            for (int h = 0; h < 2; ++h) {
+              const int ch = p * 2 + h;
+              uint4 hi, lo;
+              split8(o + h * 8, hi, lo);
+              y[((size_t)(b * 16 + ch)) * RP + prow] = hi;
+              y[((size_t)(b * 16 + 8 + ch)) * RP + prow] = lo;
+            }
+          }
+          if (y32 != nullptr) {
+            float4 *dst = reinterpret_cast<float4 *>(y32 + ((size_t)b * T + t) * 64 + p * 16);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int ch = half * 4 + k;
-            uint4 hi, lo;
-            split8(o + k * 8, hi, lo);
-            y[((size_t)(b * 16 + ch)) * RP + prow] = hi;
-            y[((size_t)(b * 16 + 8 + ch)) * RP + prow] = lo;
+            for (int c = 0; c < 4; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
           }
         }
-        if (y32 != nullptr) {
-          float4 *dst = reinterpret_cast<float4 *>(y32 + ((size_t)b * T + t) * 64 + half * 32);
+        if constexpr (NHEAD > 0) {
+          // 1x1 head: the weights come through L1 as warp-uniform 16-byte loads (one wavefront each)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+          for (int oo = 0; oo < NHEAD; ++oo) {
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float4 wv = __ldg(head_w + oo * 16 + p * 4 + c4);
+              hacc[oo] = fmaf(o[4 * c4], wv.x, hacc[oo]);
+              hacc[oo] = fmaf(o[4 * c4 + 1], wv.y, hacc[oo]);
+              hacc[oo] = fmaf(o[4 * c4 + 2], wv.z, hacc[oo]);
+              hacc[oo] = fmaf(o[4 * c4 + 3], wv.w, hacc[oo]);
+            }
+          }
+        }
+      }
+      if constexpr (NHEAD == 1) {
+        if (live) head_out[(size_t)b * T + t] = hacc[0] + __ldg(head_b);
+      } else if constexpr (NHEAD > 1) {
+#pragma unroll
+        for (int oo = 0; oo < NHEAD; ++oo) hacc[oo] += __ldg(head_b + oo);
+        const float pr = sigmoid_acc(hacc[0]);
+        if (live && head_out != nullptr) head_out[(size_t)b * T + t] = pr;
+        const int vl = valid_len != nullptr ? min(max(valid_len[b], 0), T) : T;
+        const bool counted = live && t < vl;
+        float red[NHEAD > 0 ? NHEAD : 1];
+        red[0] = counted ? pr : 0.0f;
+#pragma unroll
+        for (int oo = 1; oo < NHEAD; ++oo) red[oo] = counted ? hacc[oo] : 0.0f;
+#pragma unroll
+        for (int oo = 0; oo < NHEAD; ++oo) {
+#pragma unroll
+          for (int sft = 16; sft > 0; sft >>= 1) red[oo] += __shfl_xor_sync(0xffffffffu, red[oo], sft);
+        }
+        if (lane == 0) {
+          float *dst = partials + (((size_t)b * ntile_t + tt) * 4 + q) * WM_MAX_HEAD;
+#pragma unroll
+          for (int oo = 0; oo < NHEAD; ++oo) dst[oo] = red[oo];
         }
       }
       if (pfe) { long long e2 = clock64(); pe[0] += e1 - e0; pe[1] += e2 - e1; }
@@ -306,20 +367,68 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
   }
 }
 
-int launch_resblock_tc(const void *x, const void *w_img, const float *b1, const float *b2, void *y, float *y32, int B,
-                       int T, cudaStream_t st) {
-  if (B == 0 || T == 0) return 0;
+template <int NHEAD>
+static int launch_rb(const void *x, const void *w_img, const float *b1, const float *b2, void *y, float *y32, int B,
+                     int T, const float *head_w, const float *head_b, float *head_out, float *partials,
+                     const int *valid_len, cudaStream_t st) {
+  WM_CHECK_ARG((reinterpret_cast<uintptr_t>(head_w) & 15) == 0, "resblock_tc: head weights must be 16-byte aligned");
   static bool attr_set = false;
   if (!attr_set) {
-    WM_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM));
+    WM_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel<NHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM));
     attr_set = true;
   }
   long long ntiles = (long long)B * ((T + TO - 1) / TO);
   int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-  resblock_tc_kernel<<<grid, RB_THREADS, RB_SMEM, st>>>(reinterpret_cast<const uint4 *>(x),
-                                                 reinterpret_cast<const uint4 *>(w_img), b1, b2,
-                                                 reinterpret_cast<uint4 *>(y), y32, B, T, get_profile_buffer());
+  resblock_tc_kernel<NHEAD><<<grid, RB_THREADS, RB_SMEM, st>>>(
+      reinterpret_cast<const uint4 *>(x), reinterpret_cast<const uint4 *>(w_img), b1, b2, reinterpret_cast<uint4 *>(y),
+      y32, B, T, reinterpret_cast<const float4 *>(head_w), head_b, head_out, partials, valid_len, get_profile_buffer());
   WM_CHECK_LAUNCH("resblock_tc");
+  return 0;
+}
+
+int launch_resblock_tc(const void *x, const void *w_img, const float *b1, const float *b2, void *y, float *y32, int B,
+                       int T, cudaStream_t st) {
+  if (B == 0 || T == 0) return 0;
+  return launch_rb<0>(x, w_img, b1, b2, y, y32, B, T, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+}
+
+int resblock_tiles_per_clip(int T) { return (T + TO - 1) / TO; }
+
+// ResBlock + Conv1d(64,1,1): delta_raw[B][T]   (head_w [64], head_b [1] on the device)
+int launch_resblock_head1_tc(const void *x, const void *w_img, const float *b1, const float *b2, const float *head_w,
+                             const float *head_b, float *delta_raw, int B, int T, cudaStream_t st) {
+  if (B == 0 || T == 0) return 0;
+  return launch_rb<1>(x, w_img, b1, b2, nullptr, nullptr, B, T, head_w, head_b, delta_raw, nullptr, nullptr, st);
+}
+
+// ResBlock + Conv1d(64,17,1) + sigmoid + per-tile partial sums; finish with launch_detect_finalize
+int launch_resblock_head17_tc(const void *x, const void *w_img, const float *b1, const float *b2, const float *head_w,
+                              const float *head_b, const int *valid_len, float *probs, float *partials, int B, int T,
+                              cudaStream_t st) {
+  if (B == 0 || T == 0) return 0;
+  return launch_rb<17>(x, w_img, b1, b2, nullptr, nullptr, B, T, head_w, head_b, probs, partials, valid_len, st);
+}
+
+// clip_prob[b] = sum of the probability partials / valid, msg_logits[b][j] likewise (fixed summation order)
+__global__ void detect_finalize_kernel(const float *__restrict__ partials, const int *__restrict__ valid_len,
+                                       float *__restrict__ clip_prob, float *__restrict__ msg_logits, int nparts, int T,
+                                       int nout) {
+  const int b = blockIdx.x, o = threadIdx.x;
+  if (o >= nout) return;
+  const float *src = partials + (size_t)b * nparts * WM_MAX_HEAD + o;
+  float s = 0.0f;
+  for (int i = 0; i < nparts; ++i) s += src[(size_t)i * WM_MAX_HEAD];
+  const int vl = valid_len != nullptr ? min(max(valid_len[b], 0), T) : T;
+  const float r = vl > 0 ? s / (float)vl : 0.0f;
+  if (o == 0) { if (clip_prob) clip_prob[b] = r; }
+  else if (msg_logits) msg_logits[(size_t)b * (nout - 1) + o - 1] = r;
+}
+
+int launch_detect_finalize(const float *partials, const int *valid_len, float *clip_prob, float *msg_logits, int B,
+                           int T, int nout, cudaStream_t st) {
+  if (B == 0) return 0;
+  detect_finalize_kernel<<<B, 32, 0, st>>>(partials, valid_len, clip_prob, msg_logits, 4 * ((T + TO - 1) / TO), T, nout);
+  WM_CHECK_LAUNCH("detect_finalize");
   return 0;
 }
 

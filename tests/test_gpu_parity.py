@@ -294,6 +294,32 @@ def test_detector_matches_reference_goldens(tag, det):
     assert (vote != IO[f"{tag}/bits_vote"]).mean() < 0.02
 
 
+@pytest.mark.parametrize("T", [16000, 1000, 127, 5])
+def test_detect_fused_heads_ragged_valid_lengths(T, det):
+    """The head fused into the last ResBlock's epilogue (no votes requested) against the oracle, with the
+    tail-segment rule of py/main16.py:1152-1168 (means over the first `valid` samples only), and against
+    the un-fused kernels (votes requested)."""
+    g = torch.Generator().manual_seed(21)
+    x = (0.1 * torch.randn(5, 1, T, generator=g)).clamp(-0.99, 0.99)
+    valid = torch.tensor([T, 1, max(T // 3, 1), T - 1, 0], dtype=torch.int32)
+    lg = O.detector_forward(H.det_sd(W), x)
+    r = det.detect(x.to(DEV), valid.to(DEV), want_votes=False)
+    assert r["vote_frac"] is None
+    assert maxerr(r["probs"], torch.sigmoid(lg[:, :, 0])) < PROB_TOL
+    for b in range(5):
+        n = int(valid[b])
+        if n == 0:
+            assert float(r["clip_prob"][b]) == 0.0 and float(r["msg_logits"][b].abs().max()) == 0.0
+            continue
+        assert abs(float(r["clip_prob"][b]) - float(torch.sigmoid(lg[b, :n, 0]).mean())) < PROB_TOL
+        assert maxerr(r["msg_logits"][b], lg[b, :n, 1:].mean(0)) < 2e-3
+    u = det.detect(x.to(DEV), valid.to(DEV), want_votes=True)
+    assert maxerr(r["probs"], u["probs"]) < 1e-5
+    assert maxerr(r["clip_prob"], u["clip_prob"]) < 1e-5 and maxerr(r["msg_logits"], u["msg_logits"]) < 1e-4
+    q = det.detect(x.to(DEV), valid.to(DEV), want_probs=False, want_votes=False)
+    assert q["probs"] is None and torch.equal(q["clip_prob"], r["clip_prob"])
+
+
 def test_embed_detect_unit_vs_oracle(gen_B, det):
     g = torch.Generator().manual_seed(77)
     s = (0.1 * torch.randn(3, 1, 16000, generator=g)).clamp(-0.99, 0.99)
