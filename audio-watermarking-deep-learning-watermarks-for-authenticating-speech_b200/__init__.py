@@ -11,6 +11,7 @@ from .api import detect_prob, detect_watermark, generate_watermarked_audio, load
 from .functional import (AUDIO_LEN, HF_PENALTY_W, LAMBDA_DEC, LAMBDA_L1, LAMBDA_LOC, LAMBDA_LOUD,
                          LAMBDA_MSSPEC, MAX_RMS, MESSAGE_BITS, SAMPLE_RATE, bit_targets, clamp_peak,
                          embed_detect, fir_lowpass, limit_rms, postprocess_delta)
+from .losses import MultiScaleMelLoss, TFLoudnessLoss, high_freq_penalty, step_losses, stft_magnitude
 from .models import Detector, Generator, ResBlock, load_state_dict_strip_prefix
 from .sharding import shard_range
 
@@ -18,4 +19,5 @@ __all__ = ["Generator", "Detector", "ResBlock", "generate_watermarked_audio", "d
            "load_state_dict_strip_prefix", "fir_lowpass", "clamp_peak", "limit_rms", "postprocess_delta",
            "embed_detect", "bit_targets", "shard_range", "load_audio", "save_audio", "segment",
            "SAMPLE_RATE", "AUDIO_LEN", "MESSAGE_BITS", "MAX_RMS", "LAMBDA_L1", "LAMBDA_MSSPEC", "LAMBDA_LOUD",
-           "LAMBDA_LOC", "LAMBDA_DEC", "HF_PENALTY_W"]
+           "LAMBDA_LOC", "LAMBDA_DEC", "HF_PENALTY_W", "MultiScaleMelLoss", "TFLoudnessLoss", "high_freq_penalty",
+           "step_losses", "stft_magnitude"]

@@ -12,7 +12,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwmb200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # blob offsets (floats) — mirror of the enums in include/wmb200.h
 RB_W1 = 0
@@ -95,6 +95,14 @@ SIGNATURES = {
     "wm_embed_detect_workspace_bytes": (_sz, [_i, _i]),
     "wm_embed_detect_fwd": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
                                  _i, _i, _i, _i, _p]),
+    "wm_loss_workspace_bytes": (_sz, [_i, _i]),
+    "wm_stft_frames": (_i, [_i, _i]),
+    "wm_stft_mag_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "wm_hf_penalty_fwd": (_i, [_p, _p, _p, _sz, _i, _i, _i, _i, _p]),
+    "wm_loud_fwd": (_i, [_p, _p, _p, _p, _sz, _i, _i, _i, _i, _f, _p]),
+    "wm_mel_log_l1_fwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _sz, _i, _i, _i, _i, _p]),
+    "wm_bce_heads_fwd": (_i, [_p, _p, _p, _p, _p, _sz, _i, _i, _i, _i, _p]),
+    "wm_abs_mean_fwd": (_i, [_p, _p, _p, _sz, _i, _i, _p]),
     "wm_embed_detect_host_workspace_bytes": (_sz, [_i, _i, _i]),
     "wm_embed_detect_host": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
                                   _i, _i, _i, _i, _i, _p]),

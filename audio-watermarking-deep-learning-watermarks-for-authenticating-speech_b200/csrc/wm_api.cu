@@ -410,6 +410,67 @@ int wm_embed_detect_fwd(const float *g_blob, const float *embedding, int64_t emb
   return detect_run(d_blob, s_w, nullptr, probs, clip_prob, msg_logits, vote_frac, a0, a1, a2, B, T, nout, st);
 }
 
+/* ---- training-loss forward (py/main16.py:74-81, 192-217, 255-266) ---- */
+size_t wm_loss_workspace_bytes(int B, int T) {
+  if (B <= 0 || T <= 0) return 0;
+  return align256(((size_t)B * (1 + (size_t)T / 64) + 8192) * sizeof(float));
+}
+
+int wm_stft_frames(int T, int hop) { return (T <= 0 || hop <= 0) ? 0 : 1 + T / hop; }
+
+int wm_stft_mag_fwd(const float *x, float *mag, int B, int T, int n_fft, int hop, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0 && hop > 0, "stft_mag: bad size");
+  if (B == 0 || T == 0) return 0;
+  WM_CHECK_ARG(x && mag, "stft_mag: null pointer");
+  return launch_stft_mag(x, mag, B, T, n_fft, hop, as_stream(stream));
+}
+
+#define WM_LOSS_ARGS(name)                                                                        \
+  WM_ENTRY();                                                                                     \
+  WM_CHECK_ARG(B > 0 && T > 0, name ": the mean over an empty batch is undefined");               \
+  WM_CHECK_ARG(out && workspace, name ": null pointer");                                          \
+  WM_CHECK_ARG(workspace_bytes >= wm_loss_workspace_bytes(B, T), name ": workspace too small")
+
+int wm_hf_penalty_fwd(const float *delta, float *out, void *workspace, size_t workspace_bytes, int B, int T, int n_fft,
+                      int first_bin, void *stream) {
+  WM_LOSS_ARGS("hf_penalty");
+  WM_CHECK_ARG(delta, "hf_penalty: null pointer");
+  WM_CHECK_ARG(first_bin >= 0 && first_bin <= n_fft / 2 + 1, "hf_penalty: first_bin out of range");
+  return launch_hf_penalty(delta, out, (float *)workspace, B, T, n_fft, first_bin, as_stream(stream));
+}
+
+int wm_loud_fwd(const float *clean, const float *wmk, float *out, void *workspace, size_t workspace_bytes, int B, int T,
+                int n_fft, int hop, float thresh, void *stream) {
+  WM_LOSS_ARGS("loud");
+  WM_CHECK_ARG(clean && wmk && hop >= 64, "loud: null pointer or hop < 64");
+  return launch_loudness(clean, wmk, out, (float *)workspace, B, T, n_fft, hop, thresh, as_stream(stream));
+}
+
+int wm_mel_log_l1_fwd(const float *clean, const float *wmk, const float *fb, const int *band, int n_mels, float *out,
+                      void *workspace, size_t workspace_bytes, int B, int T, int n_fft, int hop, void *stream) {
+  WM_LOSS_ARGS("mel_log_l1");
+  WM_CHECK_ARG(clean && wmk && fb && band && n_mels > 0 && hop >= 64, "mel_log_l1: null pointer or bad size");
+  return launch_mel_log_l1(clean, wmk, fb, band, n_mels, out, (float *)workspace, B, T, n_fft, hop, as_stream(stream));
+}
+
+int wm_bce_heads_fwd(const float *logits, const int64_t *message, float *loc_out, float *bce_out, void *workspace,
+                     size_t workspace_bytes, int B_wm, int B_total, int T, int nout, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B_total > 0 && T > 0 && B_wm >= 0 && B_wm <= B_total, "bce_heads: bad batch sizes");
+  WM_CHECK_ARG(nout >= 1 && nout <= WM_MAX_HEAD, "bce_heads: nout must be in [1,%d]", WM_MAX_HEAD);
+  WM_CHECK_ARG(logits && loc_out && workspace && (message || nout == 1 || B_wm == 0), "bce_heads: null pointer");
+  WM_CHECK_ARG(workspace_bytes >= wm_loss_workspace_bytes(B_total, T), "bce_heads: workspace too small");
+  return launch_bce_heads(logits, message, loc_out, bce_out, (float *)workspace, B_wm, B_total, T, nout,
+                          as_stream(stream));
+}
+
+int wm_abs_mean_fwd(const float *x, float *out, void *workspace, size_t workspace_bytes, int B, int T, void *stream) {
+  WM_LOSS_ARGS("abs_mean");
+  WM_CHECK_ARG(x, "abs_mean: null pointer");
+  return launch_abs_mean(x, (long long)B * T, out, (float *)workspace, as_stream(stream));
+}
+
 size_t wm_embed_detect_host_workspace_bytes(int chunk, int T, int nout) {
   if (chunk <= 0 || T <= 0 || nout < 1) return 0;
   size_t wave = align256((size_t)chunk * T * sizeof(float));

@@ -98,6 +98,17 @@ int launch_resblock_head17_tc(const void *x, const void *w_img, const float *b1,
                               cudaStream_t st);
 int launch_detect_finalize(const float *partials, const int *valid_len, float *clip_prob, float *msg_logits, int B,
                            int T, int nout, cudaStream_t st);
+// training-loss forward kernels (wm_loss.cu); `partials` is caller workspace (wm_loss_workspace_bytes)
+int launch_stft_mag(const float *x, float *mag, int B, int T, int n_fft, int hop, cudaStream_t st);
+int launch_hf_penalty(const float *delta, float *out, float *partials, int B, int T, int n_fft, int first_bin,
+                      cudaStream_t st);
+int launch_loudness(const float *clean, const float *wmk, float *out, float *partials, int B, int T, int n_fft, int hop,
+                    float thresh, cudaStream_t st);
+int launch_mel_log_l1(const float *clean, const float *wmk, const float *fb, const int *band, int n_mels, float *out,
+                      float *partials, int B, int T, int n_fft, int hop, cudaStream_t st);
+int launch_bce_heads(const float *logits, const int64_t *message, float *loc_out, float *bce_out, float *partials,
+                     int B_wm, int B2, int T, int nout, cudaStream_t st);
+int launch_abs_mean(const float *x, long long n, float *out, float *partials, cudaStream_t st);
 void set_lstm_profile_buffer(long long *p);
 long long *get_profile_buffer();
 int launch_pack_lstm_tc(const float *w_ih, const float *w_hh, const float *bias, void *wpk, float *bias_p,

@@ -317,3 +317,84 @@ class HostPipeline:
             L.ptr(self.fir), L.ptr(host_message), L.ptr(host_s), L.ptr(host_s_w), L.ptr(host_probs),
             L.ptr(host_clip_prob), L.ptr(host_msg_logits), L.ptr(self.ws), self.nbytes, B, T, self.nout,
             self.chunk, self.post_mode, _stream()), "wm_embed_detect_host")
+
+
+# ---- training-loss forward (py/main16.py:74-81, 192-217, 255-266) ----------------------------
+def _loss_ws(lib, B: int, T: int, dev):
+    n = lib.wm_loss_workspace_bytes(B, T)
+    return _ws(n, dev), n
+
+
+def stft_mag(x: torch.Tensor, n_fft: int, hop: int) -> torch.Tensor:
+    """|torch.stft(x, n_fft, hop, window=hann_window(n_fft), return_complex=True)|: (B,T) -> (B, n_fft/2+1, frames)."""
+    lib = L.load()
+    x = _req(x, "x")
+    B, T = x.shape
+    out = torch.empty(B, n_fft // 2 + 1, lib.wm_stft_frames(T, hop), device=x.device)
+    L.check(lib.wm_stft_mag_fwd(L.ptr(x), L.ptr(out), B, T, n_fft, hop, _stream()), "wm_stft_mag_fwd")
+    return out
+
+
+def hf_penalty(delta: torch.Tensor, n_fft: int, first_bin: int) -> torch.Tensor:
+    lib = L.load()
+    d = _req(delta, "delta")
+    B, T = d.shape
+    out = torch.empty(1, device=d.device)
+    ws, n = _loss_ws(lib, B, T, d.device)
+    L.check(lib.wm_hf_penalty_fwd(L.ptr(d), L.ptr(out), L.ptr(ws), n, B, T, n_fft, first_bin, _stream()),
+            "wm_hf_penalty_fwd")
+    return out[0]
+
+
+def loudness(clean: torch.Tensor, wm: torch.Tensor, n_fft: int = 2048, hop: int = 512, thresh: float = 0.01):
+    lib = L.load()
+    c, w = _req(clean, "clean"), _req(wm, "watermarked")
+    if c.shape != w.shape:
+        raise ValueError(f"clean {tuple(c.shape)} and watermarked {tuple(w.shape)} differ in shape")
+    B, T = c.shape
+    out = torch.empty(1, device=c.device)
+    ws, n = _loss_ws(lib, B, T, c.device)
+    L.check(lib.wm_loud_fwd(L.ptr(c), L.ptr(w), L.ptr(out), L.ptr(ws), n, B, T, n_fft, hop, thresh, _stream()),
+            "wm_loud_fwd")
+    return out[0]
+
+
+def mel_log_l1(clean: torch.Tensor, wm: torch.Tensor, fb: torch.Tensor, band: torch.Tensor, n_fft: int = 1024,
+               hop: int = 256):
+    lib = L.load()
+    c, w = _req(clean, "clean"), _req(wm, "watermarked")
+    if c.shape != w.shape:
+        raise ValueError(f"clean {tuple(c.shape)} and watermarked {tuple(w.shape)} differ in shape")
+    fb = _req(fb, "fb")
+    band = _req(band, "band", torch.int32)
+    B, T = c.shape
+    out = torch.empty(1, device=c.device)
+    ws, n = _loss_ws(lib, B, T, c.device)
+    L.check(lib.wm_mel_log_l1_fwd(L.ptr(c), L.ptr(w), L.ptr(fb), L.ptr(band), fb.shape[1], L.ptr(out), L.ptr(ws), n,
+                                  B, T, n_fft, hop, _stream()), "wm_mel_log_l1_fwd")
+    return out[0]
+
+
+def bce_heads(logits: torch.Tensor, message: Optional[torch.Tensor], n_watermarked: int):
+    """logits (B2,T,nout) -> (loc, bce): py/main16.py:255-264."""
+    lib = L.load()
+    lg = _req(logits, "logits")
+    B2, T, nout = lg.shape
+    msg = _req(message, "message", torch.int64) if message is not None else None
+    out = torch.empty(2, device=lg.device)
+    ws, n = _loss_ws(lib, B2, T, lg.device)
+    want_bits = nout > 1 and n_watermarked > 0
+    L.check(lib.wm_bce_heads_fwd(L.ptr(lg), L.ptr(msg), L.ptr(out[0:1]), L.ptr(out[1:2]) if want_bits else None,
+                                 L.ptr(ws), n, n_watermarked, B2, T, nout, _stream()), "wm_bce_heads_fwd")
+    return out[0], (out[1] if want_bits else None)
+
+
+def abs_mean(x: torch.Tensor) -> torch.Tensor:
+    lib = L.load()
+    x = _req(x, "x")
+    x2 = x.reshape(x.shape[0], -1)
+    B, T = x2.shape
+    out = torch.empty(1, device=x.device)
+    ws, n = _loss_ws(lib, B, T, x.device)
+    L.check(lib.wm_abs_mean_fwd(L.ptr(x2), L.ptr(out), L.ptr(ws), n, B, T, _stream()), "wm_abs_mean_fwd")
+    return out[0]

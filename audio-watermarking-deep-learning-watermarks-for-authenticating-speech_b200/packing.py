@@ -7,6 +7,7 @@ convolution with flipped taps, and the two LSTM biases are summed.
 """
 from __future__ import annotations
 
+import math
 from typing import Dict
 
 import torch
@@ -94,3 +95,24 @@ def fir_taps(cutoff: float = 4000.0, taps: int = 101, sample_rate: int = 16000) 
     window = 0.54 - 0.46 * torch.cos(2 * math.pi * (n + (taps - 1) / 2) / (taps - 1))
     k = sinc * window
     return (k / k.sum()).to(torch.float32)
+
+
+def mel_filterbank(n_freqs: int = 513, n_mels: int = 64, sample_rate: int = 16000):
+    """The matrix torchaudio.transforms.MelSpectrogram(16000, 1024, 256, 64) multiplies the power spectrum by
+    (py/main16.py:195-197): HTK mel scale, triangular filters, norm=None, f in [0, sr/2], fp32 throughout.
+    Returns (fb [n_freqs][n_mels] fp32, band [n_mels][2] int32 = half-open non-zero bin range per filter)."""
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_max = 2595.0 * math.log10(1.0 + (sample_rate / 2) / 700.0)
+    m_pts = torch.linspace(0.0, m_max, n_mels + 2)
+    f_pts = 700.0 * (10 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = -slopes[:, :-2] / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    fb = torch.clamp(torch.min(down, up), min=0.0).contiguous()
+    band = torch.zeros(n_mels, 2, dtype=torch.int32)
+    for m in range(n_mels):
+        nz = torch.nonzero(fb[:, m]).flatten()
+        if nz.numel():
+            band[m, 0], band[m, 1] = int(nz[0]), int(nz[-1]) + 1
+    return fb, band

@@ -32,7 +32,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 7
+#define WM_ABI_VERSION 8
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -231,6 +231,36 @@ int wm_embed_detect_fwd(const float *g_blob, const float *embedding, int64_t emb
                         float *probs, float *clip_prob, float *msg_logits, float *vote_frac,
                         void *workspace, size_t workspace_bytes, int B, int T, int nout,
                         int post_mode, void *stream);
+
+/* ---- training-loss forward -------------------------------------------------
+ * Scalars land in device memory (out[0]); `workspace` holds per-CTA partial sums that a
+ * single-block kernel adds in a fixed order, so every loss is deterministic.            */
+size_t wm_loss_workspace_bytes(int B, int T);
+/* frames of torch.stft(centre=True): 1 + T / hop */
+int wm_stft_frames(int T, int hop);
+/* torch.stft(x, n_fft, hop, window=hann_window(n_fft), return_complex=True).abs()
+ * (py/main16.py:77, 212-213): x[B][T] -> mag[B][n_fft/2+1][frames]; n_fft in {512,1024,2048},
+ * reflect padding needs T > n_fft/2. */
+int wm_stft_mag_fwd(const float *x, float *mag, int B, int T, int n_fft, int hop, void *stream);
+/* high_freq_penalty — py/main16.py:74-81: mean over (B, n_fft/2+1, frames) of |STFT(delta)| on bins
+ * >= first_bin (hop = n_fft/4; the reference's cutoff 3500 Hz at n_fft 512 is first_bin 113). */
+int wm_hf_penalty_fwd(const float *delta, float *out, void *workspace, size_t workspace_bytes, int B, int T,
+                      int n_fft, int first_bin, void *stream);
+/* TFLoudnessLoss.forward — py/main16.py:204-217 (n_fft 2048, hop 512, thresh 0.01, strict >). */
+int wm_loud_fwd(const float *clean, const float *watermarked, float *out, void *workspace, size_t workspace_bytes,
+                int B, int T, int n_fft, int hop, float thresh, void *stream);
+/* MultiScaleMelLoss.forward — py/main16.py:192-202: fb[n_fft/2+1][n_mels] is the torchaudio HTK
+ * filterbank, band[2m], band[2m+1] the half-open bin range on which filter m is non-zero. */
+int wm_mel_log_l1_fwd(const float *clean, const float *watermarked, const float *fb, const int *band, int n_mels,
+                      float *out, void *workspace, size_t workspace_bytes, int B, int T, int n_fft, int hop,
+                      void *stream);
+/* F.binary_cross_entropy_with_logits of py/main16.py:255-264 on logits[B_total][T][nout]:
+ * loc_out = mean over all rows of BCE(channel 0, [clip < B_wm]); bce_out (nullable) = mean over the
+ * first B_wm clips of BCE(channel 1+j, bit j of message[b]). */
+int wm_bce_heads_fwd(const float *logits, const int64_t *message, float *loc_out, float *bce_out, void *workspace,
+                     size_t workspace_bytes, int B_wm, int B_total, int T, int nout, void *stream);
+/* F.l1_loss(delta, 0) — py/main16.py:266. */
+int wm_abs_mean_fwd(const float *x, float *out, void *workspace, size_t workspace_bytes, int B, int T, void *stream);
 
 /* Same unit with HOST (pinned) buffers: H2D of s and message, the device pipeline in
  * micro-batches of `chunk` clips, D2H of s_w, probs, clip_prob and msg_logits, all on

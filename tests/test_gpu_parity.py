@@ -421,3 +421,62 @@ def test_empty_batch_and_bad_arguments(gen_B, det):
     # non-1 s lengths work too (T is a runtime argument of every kernel)
     x = torch.randn(2, 1, 3000, generator=torch.Generator().manual_seed(4)) * 0.1
     assert maxerr(det(x.to(DEV)), O.detector_forward(H.det_sd(W), x)) < 4e-3
+
+
+# ---------------------------------------------------------------- training losses, forward (a8-a10)
+@pytest.mark.parametrize("n_fft,hop", [(512, 128), (1024, 256), (2048, 512)])
+@pytest.mark.parametrize("B,T", [(3, 16000), (2, 4099), (1, 1100)])
+def test_stft_magnitude_vs_torch_stft(n_fft, hop, B, T):
+    """|torch.stft| (py/main16.py:77,212-213): centre reflect padding, periodic Hann, onesided."""
+    if T <= n_fft // 2:
+        pytest.skip("reflect padding needs T > n_fft/2")
+    g = torch.Generator().manual_seed(n_fft + T)
+    x = 0.1 * torch.randn(B, T, generator=g)
+    ref = O.stft_mag(x, n_fft, hop)
+    got = wmb200.stft_magnitude(x.to(DEV), n_fft, hop)
+    assert got.shape == ref.shape
+    assert maxerr(got, ref) < 2e-5 * float(ref.max())              # fp32 FFT round-off, relative to the largest bin
+
+
+def test_losses_vs_oracle_random_and_structured():
+    g = torch.Generator().manual_seed(5)
+    s = torch.from_numpy(IO["s"])                                     # noise, quiet noise, zeros, sine, speech-like
+    delta = 0.004 * torch.randn(5, 1, 16000, generator=g)
+    delta[2] = 0.0
+    s_w = s + delta
+    rel = lambda a, b: abs(float(a) - float(b)) / max(abs(float(b)), 1e-12)
+    assert rel(wmb200.high_freq_penalty(delta.to(DEV)), O.high_freq_penalty(delta)) < 1e-4
+    assert rel(wmb200.TFLoudnessLoss()(s.to(DEV), s_w.to(DEV)), O.loudness_loss(s, s_w)) < 1e-3
+    assert rel(wmb200.MultiScaleMelLoss()(s.to(DEV), s_w.to(DEV)), O.mel_loss(s, s_w)) < 1e-3
+    assert rel(ops.abs_mean(delta.to(DEV)), delta.abs().mean()) < 1e-5
+    # identical inputs: zero up to the round-off of separating the two spectra packed into one complex FFT
+    assert float(wmb200.TFLoudnessLoss()(s.to(DEV), s.to(DEV))) < 1e-10
+    assert float(wmb200.MultiScaleMelLoss()(s.to(DEV), s.to(DEV))) < 1e-5
+    # determinism
+    a = wmb200.MultiScaleMelLoss()(s.to(DEV), s_w.to(DEV))
+    assert torch.equal(a, wmb200.MultiScaleMelLoss()(s.to(DEV), s_w.to(DEV)))
+    with pytest.raises(NotImplementedError):
+        wmb200.high_freq_penalty(delta.to(DEV).requires_grad_())
+
+
+def test_bce_heads_vs_torch():
+    g = torch.Generator().manual_seed(6)
+    lg = 3.0 * torch.randn(6, 1000, 17, generator=g)
+    msg = torch.tensor([0, 65535, 40000], dtype=torch.int64)
+    loc, bce = ops.bce_heads(lg.to(DEV), msg.to(DEV), 3)
+    tgt = torch.cat([torch.ones(3, 1000), torch.zeros(3, 1000)])
+    assert abs(float(loc) - float(F.binary_cross_entropy_with_logits(lg[:, :, 0], tgt))) < 1e-5
+    tb = O.bit_targets(msg).unsqueeze(1).expand(-1, 1000, -1)
+    assert abs(float(bce) - float(F.binary_cross_entropy_with_logits(lg[:3, :, 1:], tb))) < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_step_losses_match_reference_goldens(tag, gen_A, gen_B, det):
+    """The loss scalars the reference's own loss definitions produced for the fixtures (make_golden.py)."""
+    gen = gen_A if tag == "A" else gen_B
+    s = torch.from_numpy(IO["s"]).to(DEV)
+    msg = torch.from_numpy(IO["messages"]).to(DEV)
+    r = wmb200.step_losses(gen, det, s, msg)
+    for k, tol in (("l1", 1e-4), ("mel", 2e-3), ("loud", 2e-3), ("loc", 1e-3), ("bce", 1e-3), ("hf", 1e-3)):
+        ref = float(IO[f"{tag}/loss_{k}"])
+        assert abs(float(r[k]) - ref) <= tol * max(abs(ref), 1e-6), (k, float(r[k]), ref)

@@ -185,3 +185,23 @@ def test_two_rank_gloo_shard_and_reduce(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0 and "ok" in out, out
+
+
+def test_mel_filterbank_matches_oracle_and_band_covers_nonzeros():
+    from oracle import wm_oracle as O
+    from wmb200 import packing
+    fb, band = packing.mel_filterbank()
+    assert fb.shape == (513, 64) and torch.equal(fb, O.mel_filterbank())
+    mask = torch.zeros_like(fb, dtype=torch.bool)
+    for m in range(64):
+        mask[band[m, 0]:band[m, 1], m] = True
+    assert int(((fb != 0) & ~mask).sum()) == 0
+    assert int((band[:, 1] - band[:, 0]).max()) <= 41                  # 3-41 bins per filter
+
+
+def test_losses_refuse_cpu_tensors():
+    import wmb200
+    with pytest.raises(RuntimeError):
+        wmb200.high_freq_penalty(torch.zeros(1, 1, 16000))
+    with pytest.raises(RuntimeError):
+        wmb200.TFLoudnessLoss()(torch.zeros(1, 1, 16000), torch.zeros(1, 1, 16000))
