@@ -166,7 +166,7 @@ def test_lstm_vs_oracle(B, T):
     assert maxerr(h, ref) < 1e-5
 
 
-@pytest.mark.parametrize("B,T", [(1, 1), (3, 50), (32, 9), (33, 64), (70, 333), (300, 40)])
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 50), (16, 5), (17, 20), (32, 9), (33, 64), (48, 12), (70, 333), (300, 40)])
 def test_lstm_tensor_core_vs_oracle(B, T):
     gsd, _ = H.gen_sd(W, "A")
     g = torch.Generator().manual_seed(B + T)

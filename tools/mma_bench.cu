@@ -95,6 +95,9 @@ int main() {
     run<64, 2, 1, 0, 0>(out, grid);  run<64, 4, 1, 0, 0>(out, grid);
     run<64, 1, 1, 1, 0>(out, grid);  run<128, 1, 1, 1, 0>(out, grid);
     run<64, 1, 0, 0, 1>(out, grid);  run<128, 1, 0, 0, 1>(out, grid);  run<128, 1, 0, 1, 1>(out, grid);  run<64, 1, 1, 0, 1>(out, grid);
+    // small-N shapes of the LSTM (A = weights in TMEM)
+    run<32, 1, 1, 0, 1>(out, grid);  run<16, 1, 1, 0, 1>(out, grid);  run<32, 2, 1, 0, 1>(out, grid);  run<16, 4, 1, 0, 1>(out, grid);
+    run<32, 1, 0, 0, 1>(out, grid);  run<16, 1, 0, 0, 1>(out, grid);  run<256, 1, 0, 0, 1>(out, grid);  run<256, 1, 1, 0, 1>(out, grid);
   }
   return 0;
 }
