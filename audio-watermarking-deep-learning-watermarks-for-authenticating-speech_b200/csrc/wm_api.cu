@@ -84,6 +84,29 @@ static int resblock_tc(const float *rb, const float *img /* two 3-tap images */,
   return launch_resblock_tc(x, img, rb + WM_RB_B1, rb + WM_RB_B2, y, y32, B, T, st);
 }
 
+// The tcgen05 generator in three phases, so that a host-fed pipeline can run the two convolutional phases
+// per sub-batch (overlapping their neighbours' PCIe copies) around one whole-batch LSTM launch.
+// encoder: conv k7 -> ResBlock -> ResBlock (py/main16.py:133-137); s[B][T] -> r1 planar (r0, r2 scratch)
+static int generator_encoder_tc(const float *blob, const float *s, void *r0, void *r1, void *r2, int B, int T,
+                                cudaStream_t st) {
+  const float *tc = blob + WM_G_TC;
+  WM_TRY(launch_conv_in_k7_planar(s, blob + WM_G_IN_W, blob + WM_G_IN_B, r0, B, T, st));
+  WM_TRY(resblock_tc(blob + WM_G_RB0, tc, r0, r1, r2, nullptr, B, T, st));                      // -> r2 planar
+  return resblock_tc(blob + WM_G_RB1, tc + 2 * WM_TC_IMG3, r2, r0, r1, nullptr, B, T, st);      // -> r1 planar
+}
+// LSTM (+ message embedding added to its output)            (py/main16.py:152-159); x planar -> y planar
+static int generator_lstm_tc(const float *blob, const float *chan_add, const void *x, void *y, int B, int T,
+                             cudaStream_t st) {
+  return launch_lstm_tc(x, blob + WM_G_TC_LSTM_W, blob + WM_G_TC_LSTM_B, chan_add, y, B, T, st);
+}
+// decoder: ConvTranspose k7 -> ResBlock with the Conv1d(64,1,1) head fused into its epilogue (py/main16.py:143-147)
+static int generator_decoder_tc(const float *blob, const void *x, void *tmp, float *delta_raw, int B, int T,
+                                cudaStream_t st) {
+  WM_TRY(launch_conv64_tc(x, blob + WM_G_TC_CT, blob + WM_G_CT_B, nullptr, tmp, nullptr, B, T, 7, 0, st));
+  return launch_resblock_head1_tc(tmp, blob + WM_G_TC_RB2, blob + WM_G_RB2 + WM_RB_B1, blob + WM_G_RB2 + WM_RB_B2,
+                                  blob + WM_G_HEAD_W, blob + WM_G_HEAD_B, delta_raw, B, T, st);
+}
+
 // r0, r1, r2: three activation buffers of act_bytes(B, T); result: delta_raw[B][T]
 static int generator_run(const float *blob, const float *embedding, int64_t emb_rows,
                          const int64_t *message, const float *s, float *delta_raw, void *r0, void *r1,
@@ -106,17 +129,9 @@ static int generator_run(const float *blob, const float *embedding, int64_t emb_
     WM_TRY(resblock_fp32(blob + WM_G_RB2, f2, f0, f1, B, T, st));  // -> r1
     return launch_head(f1, blob + WM_G_HEAD_W, blob + WM_G_HEAD_B, delta_raw, B, T, 1, st);
   }
-  const float *tc = blob + WM_G_TC;
-  WM_TRY(launch_conv_in_k7_planar(s, blob + WM_G_IN_W, blob + WM_G_IN_B, r0, B, T, st));
-  WM_TRY(resblock_tc(blob + WM_G_RB0, tc, r0, r1, r2, nullptr, B, T, st));                      // -> r2 planar
-  WM_TRY(resblock_tc(blob + WM_G_RB1, tc + 2 * WM_TC_IMG3, r2, r0, r1, nullptr, B, T, st));     // -> r1 planar
-  // LSTM (+ message embedding added to its output)            (py/main16.py:152-159)
-  WM_TRY(launch_lstm_tc(r1, blob + WM_G_TC_LSTM_W, blob + WM_G_TC_LSTM_B, chan_add, r0, B, T, st));  // -> r0 planar
-  WM_TRY(launch_conv64_tc(r0, blob + WM_G_TC_CT, blob + WM_G_CT_B, nullptr, r1, nullptr, B, T, 7, 0, st));
-  // last ResBlock with the Conv1d(64,1,1) head fused into its epilogue      (py/main16.py:145-146)
-  (void)f0;
-  return launch_resblock_head1_tc(r1, blob + WM_G_TC_RB2, blob + WM_G_RB2 + WM_RB_B1, blob + WM_G_RB2 + WM_RB_B2,
-                                  blob + WM_G_HEAD_W, blob + WM_G_HEAD_B, delta_raw, B, T, st);
+  WM_TRY(generator_encoder_tc(blob, s, r0, r1, r2, B, T, st));
+  WM_TRY(generator_lstm_tc(blob, chan_add, r1, r0, B, T, st));
+  return generator_decoder_tc(blob, r0, r1, delta_raw, B, T, st);
 }
 
 // Detector trunk (py/main16.py:176-179): fp32 channels-last result left in *out (one of the buffers)
@@ -474,11 +489,52 @@ int wm_abs_mean_fwd(const float *x, float *out, void *workspace, size_t workspac
 size_t wm_embed_detect_host_workspace_bytes(int chunk, int T, int nout) {
   if (chunk <= 0 || T <= 0 || nout < 1) return 0;
   size_t wave = align256((size_t)chunk * T * sizeof(float));
-  return wm_embed_detect_workspace_bytes(chunk, T) + 3 * wave /* s, s_w, probs */ +
-         align256((size_t)chunk * sizeof(int64_t)) + align256((size_t)chunk * sizeof(float)) +
-         align256((size_t)chunk * (nout - 1 > 0 ? nout - 1 : 1) * sizeof(float));
+  // two staging sets (chunk parity): s, s_w, probs, message, clip_prob, msg_logits
+  return wm_embed_detect_workspace_bytes(chunk, T) +
+         2 * (3 * wave + align256((size_t)chunk * sizeof(int64_t)) + align256((size_t)chunk * sizeof(float)) +
+              align256((size_t)chunk * (nout - 1 > 0 ? nout - 1 : 1) * sizeof(float)));
 }
 
+namespace {
+
+// Copy streams and events of the host-fed pipeline, one set per calling host thread (created on first use,
+// kept for the life of the thread) so that concurrent callers on distinct streams never share an event.
+constexpr int HP_NS = 4;   // sub-batches per device pass
+struct HostPipe {
+  int dev = -1;
+  cudaStream_t in = nullptr, out = nullptr;
+  cudaEvent_t start = nullptr, in_done[2][HP_NS], sw_done[2][HP_NS], pr_done[2][HP_NS], s_free[2], out_done[2];
+  int init() {
+    int d = 0;
+    WM_CHECK_CUDA(cudaGetDevice(&d));
+    if (dev == d) return 0;
+    WM_CHECK_CUDA(cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking));
+    WM_CHECK_CUDA(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
+    auto mk = [](cudaEvent_t *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); };
+    WM_CHECK_CUDA(mk(&start));
+    for (int p = 0; p < 2; ++p) {
+      WM_CHECK_CUDA(mk(&s_free[p]));
+      WM_CHECK_CUDA(mk(&out_done[p]));
+      for (int k = 0; k < HP_NS; ++k) {
+        WM_CHECK_CUDA(mk(&in_done[p][k]));
+        WM_CHECK_CUDA(mk(&sw_done[p][k]));
+        WM_CHECK_CUDA(mk(&pr_done[p][k]));
+      }
+    }
+    dev = d;
+    return 0;
+  }
+};
+thread_local HostPipe g_pipe;
+
+}  // namespace
+
+// Host-fed embed+detect.  tcgen05 mode: every device pass of <= chunk clips is cut into HP_NS sub-batches;
+// the convolutional phases (encoder; decoder + post-processing + detector) run per sub-batch so that the
+// H2D copy of sub-batch k+1 and the D2H copies of sub-batch k-1 overlap them on two copy streams, while the
+// latency-bound LSTM runs once over the whole pass.  Staging buffers alternate between passes, so pass c+1's
+// input copy and pass c-1's output copy also overlap pass c.  On return, `stream` has been made to wait for
+// every copy: stream-order semantics are those of a plain sequence of copies and kernels on `stream`.
 int wm_embed_detect_host(const float *g_blob, const float *embedding, int64_t emb_rows,
                          const float *d_blob, const float *fir, const int64_t *host_message,
                          const float *host_s, float *host_s_w, float *host_probs,
@@ -494,32 +550,114 @@ int wm_embed_detect_host(const float *g_blob, const float *embedding, int64_t em
                "embed_detect_host: workspace too small");
   const int nbits = nout - 1;
   Ws ws{(char *)workspace, workspace_bytes};
-  size_t wave = (size_t)chunk * T * sizeof(float);
-  float *d_s = (float *)ws.take(wave), *d_sw = (float *)ws.take(wave), *d_pr = (float *)ws.take(wave);
-  int64_t *d_msg = (int64_t *)ws.take((size_t)chunk * sizeof(int64_t));
-  float *d_cp = (float *)ws.take((size_t)chunk * sizeof(float));
-  float *d_ml = (float *)ws.take((size_t)chunk * (nbits > 0 ? nbits : 1) * sizeof(float));
+  const size_t wave = (size_t)chunk * T * sizeof(float);
+  float *d_s[2], *d_sw[2], *d_pr[2], *d_cp[2], *d_ml[2];
+  int64_t *d_msg[2];
+  for (int p = 0; p < 2; ++p) {
+    d_s[p] = (float *)ws.take(wave); d_sw[p] = (float *)ws.take(wave); d_pr[p] = (float *)ws.take(wave);
+    d_msg[p] = (int64_t *)ws.take((size_t)chunk * sizeof(int64_t));
+    d_cp[p] = (float *)ws.take((size_t)chunk * sizeof(float));
+    d_ml[p] = (float *)ws.take((size_t)chunk * (nbits > 0 ? nbits : 1) * sizeof(float));
+  }
   void *inner = ws.p;
   size_t inner_bytes = ws.left;
   cudaStream_t st = as_stream(stream);
-  for (int b0 = 0; b0 < B; b0 += chunk) {
-    int nb = B - b0 < chunk ? B - b0 : chunk;
-    WM_CHECK_CUDA(cudaMemcpyAsync(d_s, host_s + (size_t)b0 * T, (size_t)nb * T * 4, cudaMemcpyHostToDevice, st));
-    if (host_message)
-      WM_CHECK_CUDA(cudaMemcpyAsync(d_msg, host_message + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, st));
-    WM_TRY(wm_embed_detect_fwd(g_blob, embedding, emb_rows, d_blob, fir, host_message ? d_msg : nullptr, d_s,
-                               nullptr, d_sw, nullptr, host_probs ? d_pr : nullptr, d_cp,
-                               nbits > 0 ? d_ml : nullptr, nullptr, inner, inner_bytes, nb, T, nout,
-                               post_mode, stream));
-    WM_CHECK_CUDA(cudaMemcpyAsync(host_s_w + (size_t)b0 * T, d_sw, (size_t)nb * T * 4, cudaMemcpyDeviceToHost, st));
-    if (host_probs)
-      WM_CHECK_CUDA(cudaMemcpyAsync(host_probs + (size_t)b0 * T, d_pr, (size_t)nb * T * 4, cudaMemcpyDeviceToHost, st));
-    if (host_clip_prob)
-      WM_CHECK_CUDA(cudaMemcpyAsync(host_clip_prob + b0, d_cp, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-    if (host_msg_logits && nbits > 0)
-      WM_CHECK_CUDA(cudaMemcpyAsync(host_msg_logits + (size_t)b0 * nbits, d_ml, (size_t)nb * nbits * 4,
-                                    cudaMemcpyDeviceToHost, st));
+
+  if (g_math_mode.load() != WM_MATH_BF16X2) {   // fp32 cross-check mode: plain sequence on `stream`
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+      int nb = B - b0 < chunk ? B - b0 : chunk;
+      WM_CHECK_CUDA(cudaMemcpyAsync(d_s[0], host_s + (size_t)b0 * T, (size_t)nb * T * 4, cudaMemcpyHostToDevice, st));
+      if (host_message)
+        WM_CHECK_CUDA(cudaMemcpyAsync(d_msg[0], host_message + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, st));
+      WM_TRY(wm_embed_detect_fwd(g_blob, embedding, emb_rows, d_blob, fir, host_message ? d_msg[0] : nullptr, d_s[0],
+                                 nullptr, d_sw[0], nullptr, host_probs ? d_pr[0] : nullptr, d_cp[0],
+                                 nbits > 0 ? d_ml[0] : nullptr, nullptr, inner, inner_bytes, nb, T, nout,
+                                 post_mode, stream));
+      WM_CHECK_CUDA(cudaMemcpyAsync(host_s_w + (size_t)b0 * T, d_sw[0], (size_t)nb * T * 4, cudaMemcpyDeviceToHost, st));
+      if (host_probs)
+        WM_CHECK_CUDA(cudaMemcpyAsync(host_probs + (size_t)b0 * T, d_pr[0], (size_t)nb * T * 4, cudaMemcpyDeviceToHost, st));
+      if (host_clip_prob)
+        WM_CHECK_CUDA(cudaMemcpyAsync(host_clip_prob + b0, d_cp[0], (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+      if (host_msg_logits && nbits > 0)
+        WM_CHECK_CUDA(cudaMemcpyAsync(host_msg_logits + (size_t)b0 * nbits, d_ml[0], (size_t)nb * nbits * 4,
+                                      cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
   }
+
+  HostPipe &hp = g_pipe;
+  WM_TRY(hp.init());
+  Ws iw{(char *)inner, inner_bytes};
+  char *a0 = (char *)iw.take(act_bytes(chunk, T)), *a1 = (char *)iw.take(act_bytes(chunk, T)),
+       *a2 = (char *)iw.take(act_bytes(chunk, T));
+  float *emb = (float *)iw.take((size_t)chunk * 64 * 4), *draw = (float *)iw.take((size_t)chunk * T * 4);
+  WM_CHECK_ARG(a0 && a1 && a2 && emb && draw, "embed_detect_host: workspace too small");
+  const size_t clip_bytes = (size_t)16 * ((size_t)T + 2 * WM_PLANAR_PAD) * 16;   // one clip of a planar buffer
+  const bool use_msg = host_message != nullptr && embedding != nullptr;
+
+  WM_CHECK_CUDA(cudaEventRecord(hp.start, st));
+  WM_CHECK_CUDA(cudaStreamWaitEvent(hp.in, hp.start, 0));
+  WM_CHECK_CUDA(cudaStreamWaitEvent(hp.out, hp.start, 0));
+  int pass = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ++pass) {
+    const int nb = B - b0 < chunk ? B - b0 : chunk;
+    const int p = pass & 1;
+    const int ns = nb >= 128 * HP_NS ? HP_NS : 1;
+    const int sb = (nb + ns - 1) / ns;
+    // ---- input copies (copy-in stream) ----
+    if (pass >= 2) WM_CHECK_CUDA(cudaStreamWaitEvent(hp.in, hp.s_free[p], 0));
+    if (use_msg)
+      WM_CHECK_CUDA(cudaMemcpyAsync(d_msg[p], host_message + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, hp.in));
+    for (int k = 0; k < ns; ++k) {
+      const int k0 = k * sb, kn = nb - k0 < sb ? nb - k0 : sb;
+      if (kn <= 0) { WM_CHECK_CUDA(cudaEventRecord(hp.in_done[p][k], hp.in)); continue; }
+      WM_CHECK_CUDA(cudaMemcpyAsync(d_s[p] + (size_t)k0 * T, host_s + ((size_t)b0 + k0) * T, (size_t)kn * T * 4,
+                                    cudaMemcpyHostToDevice, hp.in));
+      WM_CHECK_CUDA(cudaEventRecord(hp.in_done[p][k], hp.in));
+    }
+    // ---- encoder per sub-batch, LSTM over the pass ----
+    for (int k = 0; k < ns; ++k) {
+      const int k0 = k * sb, kn = nb - k0 < sb ? nb - k0 : sb;
+      WM_CHECK_CUDA(cudaStreamWaitEvent(st, hp.in_done[p][k], 0));
+      if (kn <= 0) continue;
+      WM_TRY(generator_encoder_tc(g_blob, d_s[p] + (size_t)k0 * T, a0 + k0 * clip_bytes, a1 + k0 * clip_bytes,
+                                  a2 + k0 * clip_bytes, kn, T, st));
+    }
+    if (use_msg) WM_TRY(launch_gather_rows(embedding, emb_rows, d_msg[p], emb, nb, st));
+    WM_TRY(generator_lstm_tc(g_blob, use_msg ? emb : nullptr, a1, a0, nb, T, st));
+    // ---- decoder, post-processing, detector per sub-batch; outputs leave on the copy-out stream ----
+    if (pass >= 2) WM_CHECK_CUDA(cudaStreamWaitEvent(st, hp.out_done[p], 0));   // staging set p is being reused
+    for (int k = 0; k < ns; ++k) {
+      const int k0 = k * sb, kn = nb - k0 < sb ? nb - k0 : sb;
+      if (kn <= 0) continue;
+      float *sk = d_s[p] + (size_t)k0 * T, *swk = d_sw[p] + (size_t)k0 * T, *prk = d_pr[p] + (size_t)k0 * T;
+      WM_TRY(generator_decoder_tc(g_blob, a0 + k0 * clip_bytes, a1 + k0 * clip_bytes, draw + (size_t)k0 * T, kn, T, st));
+      WM_TRY(launch_postprocess(draw + (size_t)k0 * T, sk, fir, nullptr, swk, nullptr, kn, T, post_mode, 0.02f, 0.005f,
+                                1e-8f, st));
+      WM_CHECK_CUDA(cudaEventRecord(hp.sw_done[p][k], st));
+      WM_CHECK_CUDA(cudaStreamWaitEvent(hp.out, hp.sw_done[p][k], 0));
+      WM_CHECK_CUDA(cudaMemcpyAsync(host_s_w + ((size_t)b0 + k0) * T, swk, (size_t)kn * T * 4, cudaMemcpyDeviceToHost,
+                                    hp.out));
+      WM_TRY(detect_run(d_blob, swk, nullptr, host_probs ? prk : nullptr, d_cp[p] + k0,
+                        nbits > 0 ? d_ml[p] + (size_t)k0 * nbits : nullptr, nullptr, a0 + k0 * clip_bytes,
+                        a1 + k0 * clip_bytes, a2 + k0 * clip_bytes, kn, T, nout, st));
+      WM_CHECK_CUDA(cudaEventRecord(hp.pr_done[p][k], st));
+      WM_CHECK_CUDA(cudaStreamWaitEvent(hp.out, hp.pr_done[p][k], 0));
+      if (host_probs)
+        WM_CHECK_CUDA(cudaMemcpyAsync(host_probs + ((size_t)b0 + k0) * T, prk, (size_t)kn * T * 4,
+                                      cudaMemcpyDeviceToHost, hp.out));
+    }
+    WM_CHECK_CUDA(cudaEventRecord(hp.s_free[p], st));
+    if (host_clip_prob)
+      WM_CHECK_CUDA(cudaMemcpyAsync(host_clip_prob + b0, d_cp[p], (size_t)nb * 4, cudaMemcpyDeviceToHost, hp.out));
+    if (host_msg_logits && nbits > 0)
+      WM_CHECK_CUDA(cudaMemcpyAsync(host_msg_logits + (size_t)b0 * nbits, d_ml[p], (size_t)nb * nbits * 4,
+                                    cudaMemcpyDeviceToHost, hp.out));
+    WM_CHECK_CUDA(cudaEventRecord(hp.out_done[p], hp.out));
+  }
+  // `stream` completes only after every output has reached the host
+  WM_CHECK_CUDA(cudaStreamWaitEvent(st, hp.out_done[(pass - 1) & 1], 0));
+  if (pass >= 2) WM_CHECK_CUDA(cudaStreamWaitEvent(st, hp.out_done[pass & 1], 0));
   return 0;
 }
 
