@@ -12,7 +12,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwmb200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # blob offsets (floats) — mirror of the enums in include/wmb200.h
 RB_W1 = 0
@@ -20,6 +20,11 @@ RB_B1 = RB_W1 + 3 * 64 * 64
 RB_W2 = RB_B1 + 64
 RB_B2 = RB_W2 + 3 * 64 * 64
 RB_SIZE = RB_B2 + 64
+FIN_W9 = 0
+FIN_B9 = FIN_W9 + 9 * 64
+FIN_WK = FIN_B9 + 64
+FIN_BK = FIN_WK + 3 * 7 * 64
+FIN_SIZE = FIN_BK + 3 * 64
 G_IN_W = 0
 G_IN_B = G_IN_W + 7 * 64
 G_RB0 = G_IN_B + 64
@@ -32,7 +37,8 @@ G_CT_B = G_CT_W + 7 * 64 * 64
 G_RB2 = G_CT_B + 64
 G_HEAD_W = G_RB2 + RB_SIZE
 G_HEAD_B = G_HEAD_W + 64
-G_SIZE = G_HEAD_B + 4
+G_FIN = G_HEAD_B + 4
+G_SIZE = G_FIN + FIN_SIZE
 TC_IMG3 = 3 * 8 * 128 * 8 // 2
 TC_IMG7 = 7 * 8 * 128 * 8 // 2
 G_TC = (G_SIZE + 63) // 64 * 64
@@ -47,7 +53,8 @@ D_RB0 = D_IN_B + 64
 D_RB1 = D_RB0 + RB_SIZE
 D_HEAD_W = D_RB1 + RB_SIZE
 D_HEAD_B = D_HEAD_W + 32 * 64
-D_SIZE = D_HEAD_B + 32
+D_FIN = D_HEAD_B + 32
+D_SIZE = D_FIN + FIN_SIZE
 D_TC = (D_SIZE + 63) // 64 * 64
 D_BLOB = D_TC + 4 * TC_IMG3
 PLANAR_PAD = 4

@@ -4,6 +4,8 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 
 #include "wm_common.h"
 
@@ -50,6 +52,31 @@ int require_device() {
   return 0;
 }
 
+// Host copies of the 1x1 heads of every finalized blob, keyed by the blob's device address.  The fused
+// epilogues take the head weights as a kernel parameter (constant bank), which needs them on the host;
+// wm_finalize_*_blob reads them back once.  A blob must not be modified after it has been finalized.
+struct HeadCopy {
+  float v[17 * 64 + 17];   // 1x1 head: w[n][64] then b[n]
+};
+static std::mutex g_head_mu;
+static std::unordered_map<const float *, HeadCopy> g_heads;
+static int remember_head(const float *blob, int w_off, int b_off, int n, cudaStream_t st) {
+  HeadCopy h;
+  WM_CHECK_CUDA(cudaMemcpyAsync(h.v, blob + w_off, sizeof(float) * n * 64, cudaMemcpyDeviceToHost, st));
+  WM_CHECK_CUDA(cudaMemcpyAsync(h.v + n * 64, blob + b_off, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  WM_CHECK_CUDA(cudaStreamSynchronize(st));
+  std::lock_guard<std::mutex> lk(g_head_mu);
+  g_heads[blob] = h;
+  return 0;
+}
+static bool lookup_head(const float *blob, HeadCopy *out) {
+  std::lock_guard<std::mutex> lk(g_head_mu);
+  auto it = g_heads.find(blob);
+  if (it == g_heads.end()) return false;
+  *out = it->second;
+  return true;
+}
+
 static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 static size_t planar_bytes(int B, int T) {
   // + 4 KB: the bulk copies of a partial last tile read (never use) up to 127 rows past a plane
@@ -90,8 +117,9 @@ static int resblock_tc(const float *rb, const float *img /* two 3-tap images */,
 static int generator_encoder_tc(const float *blob, const float *s, void *r0, void *r1, void *r2, int B, int T,
                                 cudaStream_t st) {
   const float *tc = blob + WM_G_TC;
-  WM_TRY(launch_conv_in_k7_planar(s, blob + WM_G_IN_W, blob + WM_G_IN_B, r0, B, T, st));
-  WM_TRY(resblock_tc(blob + WM_G_RB0, tc, r0, r1, r2, nullptr, B, T, st));                      // -> r2 planar
+  (void)r0;   // input convolution folded into the first ResBlock: s -> r2 planar
+  WM_TRY(launch_resblock_in_tc(s, blob + WM_G_FIN + WM_FIN_W9, blob + WM_G_IN_W, blob + WM_G_FIN, tc + WM_TC_IMG3,
+                               blob + WM_G_RB0 + WM_RB_B2, r2, B, T, st));
   return resblock_tc(blob + WM_G_RB1, tc + 2 * WM_TC_IMG3, r2, r0, r1, nullptr, B, T, st);      // -> r1 planar
 }
 // LSTM (+ message embedding added to its output)            (py/main16.py:152-159); x planar -> y planar
@@ -103,8 +131,15 @@ static int generator_lstm_tc(const float *blob, const float *chan_add, const voi
 static int generator_decoder_tc(const float *blob, const void *x, void *tmp, float *delta_raw, int B, int T,
                                 cudaStream_t st) {
   WM_TRY(launch_conv64_tc(x, blob + WM_G_TC_CT, blob + WM_G_CT_B, nullptr, tmp, nullptr, B, T, 7, 0, st));
-  return launch_resblock_head1_tc(tmp, blob + WM_G_TC_RB2, blob + WM_G_RB2 + WM_RB_B1, blob + WM_G_RB2 + WM_RB_B2,
-                                  blob + WM_G_HEAD_W, blob + WM_G_HEAD_B, delta_raw, B, T, st);
+  HeadCopy h;
+  if (lookup_head(blob, &h))
+    return launch_resblock_head1_tc(tmp, blob + WM_G_TC_RB2, blob + WM_G_RB2 + WM_RB_B1, blob + WM_G_RB2 + WM_RB_B2, h.v,
+                                    delta_raw, B, T, st);
+  // blob never went through wm_finalize_generator_blob on this process: un-fused head (x is dead by now)
+  float *f = (float *)const_cast<void *>(x);
+  WM_TRY(launch_resblock_tc(tmp, blob + WM_G_TC_RB2, blob + WM_G_RB2 + WM_RB_B1, blob + WM_G_RB2 + WM_RB_B2, nullptr, f, B,
+                            T, st));
+  return launch_head(f, blob + WM_G_HEAD_W, blob + WM_G_HEAD_B, delta_raw, B, T, 1, st);
 }
 
 // r0, r1, r2: three activation buffers of act_bytes(B, T); result: delta_raw[B][T]
@@ -145,8 +180,9 @@ static int detector_trunk(const float *blob, const float *x, void *r0, void *r1,
     return resblock_fp32(blob + WM_D_RB1, f2, f0, f1, B, T, st);   // -> r1
   }
   const float *tc = blob + WM_D_TC;
-  WM_TRY(launch_conv_in_k7_planar(x, blob + WM_D_IN_W, blob + WM_D_IN_B, r0, B, T, st));
-  WM_TRY(resblock_tc(blob + WM_D_RB0, tc, r0, r1, r2, nullptr, B, T, st));
+  (void)r0;   // input convolution folded into the first ResBlock: x -> r2 planar
+  WM_TRY(launch_resblock_in_tc(x, blob + WM_D_FIN + WM_FIN_W9, blob + WM_D_IN_W, blob + WM_D_FIN, tc + WM_TC_IMG3,
+                               blob + WM_D_RB0 + WM_RB_B2, r2, B, T, st));
   return resblock_tc(blob + WM_D_RB1, tc + 2 * WM_TC_IMG3, r2, r0, nullptr, f1, B, T, st);
 }
 
@@ -156,14 +192,17 @@ static int detector_trunk(const float *blob, const float *x, void *r0, void *r1,
 static int detect_run(const float *blob, const float *x, const int *valid_len, float *probs, float *clip_prob,
                       float *msg_logits, float *vote_frac, void *r0, void *r1, void *r2, int B, int T, int nout,
                       cudaStream_t st) {
+  HeadCopy h;
   if (g_math_mode.load() == WM_MATH_BF16X2 && nout == 17 && vote_frac == nullptr &&
-      (size_t)B * resblock_tiles_per_clip(T) * 4 * WM_MAX_HEAD * sizeof(float) <= act_bytes(B, T)) {
+      (size_t)B * resblock_tiles_per_clip(T) * 4 * WM_MAX_HEAD * sizeof(float) <= act_bytes(B, T) &&
+      lookup_head(blob, &h)) {
     const float *tc = blob + WM_D_TC;
     float *partials = (float *)r1;
-    WM_TRY(launch_conv_in_k7_planar(x, blob + WM_D_IN_W, blob + WM_D_IN_B, r0, B, T, st));
-    WM_TRY(resblock_tc(blob + WM_D_RB0, tc, r0, r1, r2, nullptr, B, T, st));
-    WM_TRY(launch_resblock_head17_tc(r2, tc + 2 * WM_TC_IMG3, blob + WM_D_RB1 + WM_RB_B1, blob + WM_D_RB1 + WM_RB_B2,
-                                     blob + WM_D_HEAD_W, blob + WM_D_HEAD_B, valid_len, probs, partials, B, T, st));
+    (void)r0;   // input convolution folded into the first ResBlock: x -> r2 planar
+    WM_TRY(launch_resblock_in_tc(x, blob + WM_D_FIN + WM_FIN_W9, blob + WM_D_IN_W, blob + WM_D_FIN, tc + WM_TC_IMG3,
+                                 blob + WM_D_RB0 + WM_RB_B2, r2, B, T, st));
+    WM_TRY(launch_resblock_head17_tc(r2, tc + 2 * WM_TC_IMG3, blob + WM_D_RB1 + WM_RB_B1, blob + WM_D_RB1 + WM_RB_B2, h.v,
+                                     valid_len, probs, partials, B, T, st));
     return launch_detect_finalize(partials, valid_len, clip_prob, msg_logits, B, T, nout, st);
   }
   float *out = nullptr;
@@ -206,8 +245,9 @@ int wm_finalize_generator_blob(float *blob, void *stream) {
     WM_TRY(launch_pack_conv64_tc(blob + rb[i] + WM_RB_W2, blob + img[i] + WM_TC_IMG3, 3, st));
   }
   WM_TRY(launch_pack_conv64_tc(blob + WM_G_CT_W, blob + WM_G_TC_CT, 7, st));
-  return launch_pack_lstm_tc(blob + WM_G_LSTM_WIH, blob + WM_G_LSTM_WHH, blob + WM_G_LSTM_B,
-                             blob + WM_G_TC_LSTM_W, blob + WM_G_TC_LSTM_B, st);
+  WM_TRY(launch_pack_lstm_tc(blob + WM_G_LSTM_WIH, blob + WM_G_LSTM_WHH, blob + WM_G_LSTM_B, blob + WM_G_TC_LSTM_W,
+                             blob + WM_G_TC_LSTM_B, st));
+  return remember_head(blob, WM_G_HEAD_W, WM_G_HEAD_B, 1, st);   // synchronises `stream` (one-time set-up call)
 }
 
 int wm_finalize_detector_blob(float *blob, void *stream) {
@@ -219,7 +259,7 @@ int wm_finalize_detector_blob(float *blob, void *stream) {
     WM_TRY(launch_pack_conv64_tc(blob + rb[i] + WM_RB_W1, blob + WM_D_TC + (2 * i) * WM_TC_IMG3, 3, st));
     WM_TRY(launch_pack_conv64_tc(blob + rb[i] + WM_RB_W2, blob + WM_D_TC + (2 * i + 1) * WM_TC_IMG3, 3, st));
   }
-  return 0;
+  return remember_head(blob, WM_D_HEAD_W, WM_D_HEAD_B, 17, st);  // synchronises `stream` (one-time set-up call)
 }
 
 size_t wm_planar_bytes(int B, int T) { return (B <= 0 || T <= 0) ? 0 : planar_bytes(B, T); }

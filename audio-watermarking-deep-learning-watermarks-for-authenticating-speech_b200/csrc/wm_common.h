@@ -91,10 +91,15 @@ int launch_lstm_tc(const void *x, const void *wpk, const float *bias_p, const fl
 int launch_resblock_tc(const void *x, const void *w_img, const float *b1, const float *b2, void *y, float *y32, int B,
                        int T, cudaStream_t st);
 int resblock_tiles_per_clip(int T);
-int launch_resblock_head1_tc(const void *x, const void *w_img, const float *b1, const float *b2, const float *head_w,
-                             const float *head_b, float *delta_raw, int B, int T, cudaStream_t st);
-int launch_resblock_head17_tc(const void *x, const void *w_img, const float *b1, const float *b2, const float *head_w,
-                              const float *head_b, const int *valid_len, float *probs, float *partials, int B, int T,
+// first ResBlock fused with the input convolution (wm_resblock_in_tc.cu); w9b: device w9[9][64], b9[64];
+// winb: device w_in[7][64], b_in[64]; fin: device WM_FIN_* block; s[B][T] -> y planar
+int launch_resblock_in_tc(const float *s, const float *w9b, const float *winb, const float *fin, const void *w_img2,
+                          const float *b2, void *y, int B, int T, cudaStream_t st);
+// host_head: HOST copy of the 1x1 head (w[n][64] then b[n], n = 1 or 17); it is passed to the kernel by value
+int launch_resblock_head1_tc(const void *x, const void *w_img, const float *b1, const float *b2,
+                             const float *host_head, float *delta_raw, int B, int T, cudaStream_t st);
+int launch_resblock_head17_tc(const void *x, const void *w_img, const float *b1, const float *b2,
+                              const float *host_head, const int *valid_len, float *probs, float *partials, int B, int T,
                               cudaStream_t st);
 int launch_detect_finalize(const float *partials, const int *valid_len, float *clip_prob, float *msg_logits, int B,
                            int T, int nout, cudaStream_t st);

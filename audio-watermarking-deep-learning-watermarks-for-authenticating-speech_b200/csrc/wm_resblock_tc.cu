@@ -21,6 +21,7 @@
 // conv2 of tile i, so the tensor pipe works on the next tile while the epilogue warps turn tile
 // i's conv1 accumulator into conv2's operand.
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "wm_common.h"
 #include "wm_tc.cuh"
@@ -60,6 +61,16 @@ static_assert(RB_SMEM <= 232448, "shared memory budget");
 
 }  // namespace
 
+// 1x1 head weights travel BY VALUE as a kernel parameter: parameters live in the constant bank, so every head
+// FFMA takes its weight as a constant operand (no load instruction, no latency to hide, no state shared
+// between launches).  Measured: with the weights fetched through L1 the 17-output epilogue stalled on every
+// FFMA and the kernel ran 2.4x slower than the plain ResBlock.
+template <int N>
+struct HeadParams {
+  float w[N * 64];   // [out][64]
+  float b[N];
+};
+
 // NHEAD = 0: plain ResBlock.  NHEAD = 1: + Conv1d(64,1,1) -> head_out[b][t] (py/main16.py:146).
 // NHEAD = 17: + Conv1d(64,17,1) -> head_out[b][t] = sigmoid(ch 0) and per-(tile, warp) partial sums of the
 // probability and of the 16 message logits over the valid samples -> partials (py/main16.py:180,1142-1146).
@@ -68,7 +79,7 @@ template <int NHEAD>
 __global__ void __launch_bounds__(RB_THREADS, 1)
     resblock_tc_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ w_img, const float *__restrict__ b1,
                        const float *__restrict__ b2, uint4 *__restrict__ y, float *__restrict__ y32, int B, int T,
-                       const float4 *__restrict__ head_w, const float *__restrict__ head_b,
+                       const __grid_constant__ HeadParams<(NHEAD > 0 ? NHEAD : 1)> hp,
                        float *__restrict__ head_out, float *__restrict__ partials, const int *__restrict__ valid_len,
                        long long *__restrict__ prof) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -315,25 +326,19 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
           }
         }
         if constexpr (NHEAD > 0) {
-          // 1x1 head: the weights come through L1 as warp-uniform 16-byte loads (one wavefront each)
+          // 1x1 head: weights are constant-bank operands of the FFMAs (kernel parameter)
 #pragma unroll
           for (int oo = 0; oo < NHEAD; ++oo) {
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const float4 wv = __ldg(head_w + oo * 16 + p * 4 + c4);
-              hacc[oo] = fmaf(o[4 * c4], wv.x, hacc[oo]);
-              hacc[oo] = fmaf(o[4 * c4 + 1], wv.y, hacc[oo]);
-              hacc[oo] = fmaf(o[4 * c4 + 2], wv.z, hacc[oo]);
-              hacc[oo] = fmaf(o[4 * c4 + 3], wv.w, hacc[oo]);
-            }
+            for (int c = 0; c < 16; ++c) hacc[oo] = fmaf(o[c], hp.w[oo * 64 + p * 16 + c], hacc[oo]);
           }
         }
       }
       if constexpr (NHEAD == 1) {
-        if (live) head_out[(size_t)b * T + t] = hacc[0] + __ldg(head_b);
+        if (live) head_out[(size_t)b * T + t] = hacc[0] + hp.b[0];
       } else if constexpr (NHEAD > 1) {
 #pragma unroll
-        for (int oo = 0; oo < NHEAD; ++oo) hacc[oo] += __ldg(head_b + oo);
+        for (int oo = 0; oo < NHEAD; ++oo) hacc[oo] += hp.b[oo];
         const float pr = sigmoid_acc(hacc[0]);
         if (live && head_out != nullptr) head_out[(size_t)b * T + t] = pr;
         const int vl = valid_len != nullptr ? min(max(valid_len[b], 0), T) : T;
@@ -369,9 +374,16 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
 
 template <int NHEAD>
 static int launch_rb(const void *x, const void *w_img, const float *b1, const float *b2, void *y, float *y32, int B,
-                     int T, const float *head_w, const float *head_b, float *head_out, float *partials,
-                     const int *valid_len, cudaStream_t st) {
-  WM_CHECK_ARG((reinterpret_cast<uintptr_t>(head_w) & 15) == 0, "resblock_tc: head weights must be 16-byte aligned");
+                     int T, const float *host_head, float *head_out, float *partials, const int *valid_len,
+                     cudaStream_t st) {
+  HeadParams<(NHEAD > 0 ? NHEAD : 1)> hp;
+  if (NHEAD > 0) {   // host_head: w[NHEAD][64] then b[NHEAD]
+    memcpy(hp.w, host_head, sizeof(float) * NHEAD * 64);
+    memcpy(hp.b, host_head + NHEAD * 64, sizeof(float) * NHEAD);
+  } else {
+    hp.w[0] = 0.0f;
+    hp.b[0] = 0.0f;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     WM_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel<NHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM));
@@ -381,7 +393,7 @@ static int launch_rb(const void *x, const void *w_img, const float *b1, const fl
   int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
   resblock_tc_kernel<NHEAD><<<grid, RB_THREADS, RB_SMEM, st>>>(
       reinterpret_cast<const uint4 *>(x), reinterpret_cast<const uint4 *>(w_img), b1, b2, reinterpret_cast<uint4 *>(y),
-      y32, B, T, reinterpret_cast<const float4 *>(head_w), head_b, head_out, partials, valid_len, get_profile_buffer());
+      y32, B, T, hp, head_out, partials, valid_len, get_profile_buffer());
   WM_CHECK_LAUNCH("resblock_tc");
   return 0;
 }
@@ -389,24 +401,24 @@ static int launch_rb(const void *x, const void *w_img, const float *b1, const fl
 int launch_resblock_tc(const void *x, const void *w_img, const float *b1, const float *b2, void *y, float *y32, int B,
                        int T, cudaStream_t st) {
   if (B == 0 || T == 0) return 0;
-  return launch_rb<0>(x, w_img, b1, b2, y, y32, B, T, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+  return launch_rb<0>(x, w_img, b1, b2, y, y32, B, T, nullptr, nullptr, nullptr, nullptr, st);
 }
 
 int resblock_tiles_per_clip(int T) { return (T + TO - 1) / TO; }
 
-// ResBlock + Conv1d(64,1,1): delta_raw[B][T]   (head_w [64], head_b [1] on the device)
-int launch_resblock_head1_tc(const void *x, const void *w_img, const float *b1, const float *b2, const float *head_w,
-                             const float *head_b, float *delta_raw, int B, int T, cudaStream_t st) {
+// ResBlock + Conv1d(64,1,1): delta_raw[B][T]   (host_head: HOST copy of w[64], b[1])
+int launch_resblock_head1_tc(const void *x, const void *w_img, const float *b1, const float *b2,
+                             const float *host_head, float *delta_raw, int B, int T, cudaStream_t st) {
   if (B == 0 || T == 0) return 0;
-  return launch_rb<1>(x, w_img, b1, b2, nullptr, nullptr, B, T, head_w, head_b, delta_raw, nullptr, nullptr, st);
+  return launch_rb<1>(x, w_img, b1, b2, nullptr, nullptr, B, T, host_head, delta_raw, nullptr, nullptr, st);
 }
 
 // ResBlock + Conv1d(64,17,1) + sigmoid + per-tile partial sums; finish with launch_detect_finalize
-int launch_resblock_head17_tc(const void *x, const void *w_img, const float *b1, const float *b2, const float *head_w,
-                              const float *head_b, const int *valid_len, float *probs, float *partials, int B, int T,
+int launch_resblock_head17_tc(const void *x, const void *w_img, const float *b1, const float *b2,
+                              const float *host_head, const int *valid_len, float *probs, float *partials, int B, int T,
                               cudaStream_t st) {
   if (B == 0 || T == 0) return 0;
-  return launch_rb<17>(x, w_img, b1, b2, nullptr, nullptr, B, T, head_w, head_b, probs, partials, valid_len, st);
+  return launch_rb<17>(x, w_img, b1, b2, nullptr, nullptr, B, T, host_head, probs, partials, valid_len, st);
 }
 
 // clip_prob[b] = sum of the probability partials / valid, msg_logits[b][j] likewise (fixed summation order)

@@ -49,6 +49,22 @@ def _pack_resblock(blob, off, sd, p):
     _put(blob, off + L.RB_B2, b2)
 
 
+def _pack_fused_input(blob, off, w_in, b_in, w1, b1):
+    """Input Conv1d(1,64,7) composed with the first 64->64 k3 convolution behind it (no non-linearity between
+    them, py/main16.py:134-135 / :177-178), in float64.  w_in [7][64] (tap, channel), b_in [64],
+    w1 [3][ci][co] and b1 [co] with BatchNorm folded.  Layout: WM_FIN_* of include/wmb200.h."""
+    wk = torch.einsum("kio,ji->kjo", w1, w_in)            # [3][7][co]
+    bk = torch.einsum("kio,i->ko", w1, b_in)              # [3][co]
+    w9 = torch.zeros(9, 64, dtype=torch.float64)
+    for k in range(3):
+        for j in range(7):
+            w9[k + j] += wk[k, j]
+    _put(blob, off + L.FIN_W9, w9)
+    _put(blob, off + L.FIN_B9, b1 + bk.sum(0))
+    _put(blob, off + L.FIN_WK, wk)
+    _put(blob, off + L.FIN_BK, bk)
+
+
 def pack_generator(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
     """Everything of Generator (py/main16.py:128-162) except the embedding table."""
     sd = strip_prefix(sd)
@@ -67,6 +83,8 @@ def pack_generator(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
     _pack_resblock(blob, L.G_RB2, sd, "decoder.1")
     _put(blob, L.G_HEAD_W, _f64(sd["decoder.2.weight"])[0, :, 0])
     _put(blob, L.G_HEAD_B, _f64(sd["decoder.2.bias"]))
+    w1, b1 = fold_conv_bn(sd, "encoder.1.block.0", "encoder.1.block.1")
+    _pack_fused_input(blob, L.G_FIN, _f64(sd["encoder.0.weight"])[:, 0, :].t(), _f64(sd["encoder.0.bias"]), w1, b1)
     return blob.to(torch.float32)
 
 
@@ -83,6 +101,8 @@ def pack_detector(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
         raise ValueError(f"detector head has {hw.shape[0]} outputs; this build supports <= {L.MAX_HEAD}")
     _put(blob, L.D_HEAD_W, hw)
     _put(blob, L.D_HEAD_B, _f64(sd["model.3.bias"]))
+    w1, b1 = fold_conv_bn(sd, "model.1.block.0", "model.1.block.1")
+    _pack_fused_input(blob, L.D_FIN, _f64(sd["model.0.weight"])[:, 0, :].t(), _f64(sd["model.0.bias"]), w1, b1)
     return blob.to(torch.float32)
 
 

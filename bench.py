@@ -9,7 +9,7 @@ per GPU (weak scaling: every rank owns its own 4096 clips, no data-path collecti
 
   value   device-resident inputs, CUDA events, max over ranks
   e2e     the same through wm_embed_detect_host with pinned HOST buffers (H2D + D2H inside)
-  roofline   the dominant kernel (64->64 convolution) timed alone with CUDA events
+  roofline   the dominant kernel (the fused ResBlock, 5 launches = ~55 % of a step) timed alone with CUDA events
   cpu_baseline  the oracle (torch CPU fp32 restatement of the reference) on a bounded sample
 
 `--impl reference` times the reference's own CPU implementation of the path (the oracle port;
@@ -31,7 +31,9 @@ if ROOT not in sys.path:
 
 T = 16000
 FLOP_PER_CLIP = 5.964e9          # G 4.342 + D 1.622 GFLOP
-CONV64_K3_FLOP_PER_CLIP = 2 * 64 * 64 * 3 * T      # one 64->64 k3 convolution, 786.4 MFLOP / 2 per ResBlock
+CONV64_K3_FLOP_PER_CLIP = 2 * 64 * 64 * 3 * T      # one 64->64 k3 convolution
+RESBLOCK_FLOP_PER_CLIP = 2 * CONV64_K3_FLOP_PER_CLIP   # 786.4 MFLOP: the two convolutions of a ResBlock
+RESBLOCK_HBM_BYTES_PER_CLIP = 2 * 64 * T * 4       # planar bf16 hi+lo in, same out: 8.19 MB
 
 
 def load_peaks():
@@ -102,8 +104,9 @@ def cpu_reference_rate(sample_B, steps, warmup, threads=None):
     import torch
 
     from oracle import wm_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
+    if threads is None:            # all the host threads we may use (torchrun exports OMP_NUM_THREADS=1)
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, threads))
     cores = torch.get_num_threads()
     gen, det = build_models("cpu")
     gsd = {k: v.detach() for k, v in gen.state_dict().items()}
@@ -211,37 +214,52 @@ def run_ours(args):
     h2d = B * T * 4 + B * 8
     d2h = 2 * B * T * 4 + B * 4 + B * 16 * 4
 
-    # ---- roofline of the dominant kernel: one 64->64 k3 convolution, timed alone ----------
+    # ---- roofline of the dominant kernel: the fused ResBlock (5 of the ~18 launches, ~55 % of a step), timed
+    # alone with CUDA events on the stream it is launched on ---------------------------------------------------
     Br = min(B, 1024)
     mode = ops.get_math_mode()
     x = torch.randn(Br, T, 64, device=dev)
-    wk = g_blob[L.G_RB0 + L.RB_W1:L.G_RB0 + L.RB_W1 + 3 * 4096]
-    bk = g_blob[L.G_RB0 + L.RB_B1:L.G_RB0 + L.RB_B1 + 64]
     lib = L.load()
     st = torch.cuda.current_stream().cuda_stream
+    reps = 10
     if mode == L.MATH_FP32:
         y = torch.empty_like(x)
+        wk = g_blob[L.G_RB0 + L.RB_W1:L.G_RB0 + L.RB_W1 + 3 * 4096]
+        bk = g_blob[L.G_RB0 + L.RB_B1:L.G_RB0 + L.RB_B1 + 64]
 
-        def conv_once():
+        def kernel_once():
             L.check(lib.wm_conv64_fwd(x.data_ptr(), wk.data_ptr(), bk.data_ptr(), None, None, y.data_ptr(), Br, T, 3,
                                       1, st), "wm_conv64_fwd")
+        kname, flop = "conv64_fp32_kernel (64->64 k3, CUDA-core FMA)", CONV64_K3_FLOP_PER_CLIP
     else:
         xp = ops.to_planar(x)
         y = torch.empty_like(xp)
-        img = g_blob[L.G_TC:L.G_TC + L.TC_IMG3]
+        img = g_blob[L.G_TC:L.G_TC + 2 * L.TC_IMG3]
+        b1 = g_blob[L.G_RB0 + L.RB_B1:L.G_RB0 + L.RB_B1 + 64]
+        b2 = g_blob[L.G_RB0 + L.RB_B2:L.G_RB0 + L.RB_B2 + 64]
 
-        def conv_once():
-            L.check(lib.wm_conv64_tc_fwd(xp.data_ptr(), img.data_ptr(), bk.data_ptr(), None, y.data_ptr(), None, Br,
-                                         T, 3, 1, st), "wm_conv64_tc_fwd")
-
-    reps = 10
-    ms_conv, _ = timed(conv_once, reps, 3)
-    conv_tflops = CONV64_K3_FLOP_PER_CLIP * Br * reps / (ms_conv / 1e3) / 1e12
+        def kernel_once():
+            L.check(lib.wm_resblock_tc_fwd(xp.data_ptr(), img.data_ptr(), b1.data_ptr(), b2.data_ptr(), y.data_ptr(),
+                                           None, Br, T, st), "wm_resblock_tc_fwd")
+        kname, flop = "resblock_tc_kernel (fused ResBlock, tcgen05 bf16 pairs)", RESBLOCK_FLOP_PER_CLIP
+    ms_k, _ = timed(kernel_once, reps, 3)
+    k_tflops = flop * Br * reps / (ms_k / 1e3) / 1e12
     del x, y
-    roofline = {"bound": "tensor", "kernel": "conv64 k3 (%s)" % ("fp32 FMA" if mode == L.MATH_FP32 else "tcgen05 bf16x2"),
-                "achieved": conv_tflops, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                "frac": conv_tflops / peaks["bf16_burst"], "traffic": None, "peak_source": peaks["src"] + " burst",
-                "launch_ms": ms_conv / reps, "clips_per_launch": Br,
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_resblock_traffic.json")       # dram bytes of one ncu --set full capture
+    if mode != L.MATH_FP32 and os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj["dram_bytes_per_clip"] * Br, tj["source"]
+    roofline = {"bound": "tensor", "kernel": kname, "achieved": k_tflops, "peak": peaks["bf16_burst"],
+                "unit": "TFLOP/s", "frac": k_tflops / peaks["bf16_burst"], "traffic": traffic,
+                "traffic_source": traffic_src, "peak_source": peaks["src"] + " burst (kernel timed alone)",
+                "launch_ms": ms_k / reps, "clips_per_launch": Br,
+                "algorithmic_flop_per_launch": flop * Br,
+                "algorithmic_hbm_bytes_per_launch": RESBLOCK_HBM_BYTES_PER_CLIP * Br,
+                "hbm_gbs_algorithmic": RESBLOCK_HBM_BYTES_PER_CLIP * Br * reps / (ms_k / 1e3) / 1e9,
+                "issued_flop_factor": 1.0 if mode == L.MATH_FP32 else 1.5,
+                "note": "bf16 hi+lo operands, 3 partial products: the tensor pipe issues 1.5x the algorithmic FLOPs; "
+                        "the kernel sits on the shared-memory operand bandwidth of the 128x128x16 MMA (DESIGN.md §4)",
                 "path_frac_of_sustained": value / world * FLOP_PER_CLIP / (peaks["bf16_sustained"] * 1e12)}
 
     if rank == 0:

@@ -32,7 +32,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 8
+#define WM_ABI_VERSION 9
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -51,6 +51,15 @@ enum {
   WM_RB_B2 = WM_RB_W2 + 3 * 64 * 64,     /* [64]        */
   WM_RB_SIZE = WM_RB_B2 + 64
 };
+/* Input stage fused into the first ResBlock (wm_resblock_in_tc.cu): the input Conv1d(1,64,7) composed with
+ * the ResBlock's first convolution on the host, in float64:  conv1(conv_in(s))[t] = B9 + sum_m W9[m] s[t+m-4]. */
+enum {
+  WM_FIN_W9 = 0,                         /* [9][64]    W9[k+j][co] += sum_ci W1[k][ci][co] w_in[j][ci]            */
+  WM_FIN_B9 = WM_FIN_W9 + 9 * 64,        /* [64]       b1 + sum_k BK[k]                                            */
+  WM_FIN_WK = WM_FIN_B9 + 64,            /* [3][7][64] per conv1 tap k: sum_ci W1[k][ci][co] w_in[j][ci]           */
+  WM_FIN_BK = WM_FIN_WK + 3 * 7 * 64,    /* [3][64]    per conv1 tap k: sum_ci W1[k][ci][co] b_in[ci]              */
+  WM_FIN_SIZE = WM_FIN_BK + 3 * 64
+};
 enum {                                   /* Generator, py/main16.py:128-162 */
   WM_G_IN_W = 0,                         /* encoder.0  [7][64]       */
   WM_G_IN_B = WM_G_IN_W + 7 * 64,        /* [64]                     */
@@ -64,7 +73,8 @@ enum {                                   /* Generator, py/main16.py:128-162 */
   WM_G_RB2 = WM_G_CT_B + 64,             /* decoder.1                */
   WM_G_HEAD_W = WM_G_RB2 + WM_RB_SIZE,   /* decoder.2 [64]           */
   WM_G_HEAD_B = WM_G_HEAD_W + 64,        /* [1] (+3 pad)             */
-  WM_G_SIZE = WM_G_HEAD_B + 4,
+  WM_G_FIN = WM_G_HEAD_B + 4,            /* encoder.0 composed with encoder.1's first convolution */
+  WM_G_SIZE = WM_G_FIN + WM_FIN_SIZE,
   /* tcgen05 weight images (bf16 [tap][ci/8][128][8], see wm_pack_conv64_tc), filled on the
    * device by wm_finalize_generator_blob: encoder.1 conv1, conv2, encoder.2 conv1, conv2,
    * decoder.0 (7 taps), decoder.1 conv1, conv2 */
@@ -85,7 +95,8 @@ enum {                                   /* Detector, py/main16.py:170-186 */
   WM_D_RB1 = WM_D_RB0 + WM_RB_SIZE,      /* model.2                  */
   WM_D_HEAD_W = WM_D_RB1 + WM_RB_SIZE,   /* model.3 [nout<=32][64]   */
   WM_D_HEAD_B = WM_D_HEAD_W + 32 * 64,   /* [32]                     */
-  WM_D_SIZE = WM_D_HEAD_B + 32,
+  WM_D_FIN = WM_D_HEAD_B + 32,           /* model.0 composed with model.1's first convolution */
+  WM_D_SIZE = WM_D_FIN + WM_FIN_SIZE,
   WM_D_TC = (WM_D_SIZE + 63) / 64 * 64,  /* model.1 conv1, conv2, model.2 conv1, conv2 */
   WM_D_BLOB = WM_D_TC + 4 * WM_TC_IMG3
 };

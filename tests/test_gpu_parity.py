@@ -511,3 +511,17 @@ def test_host_pipeline_matches_device_path(B, chunk, gen_B, det):
     pipe(hs, hm, h_sw)
     torch.cuda.current_stream().synchronize()
     assert maxerr(h_sw, ref["s_w"]) < 1e-6
+
+
+@pytest.mark.parametrize("T", [1, 2, 7, 126, 127, 300])
+def test_short_clips_through_the_fused_input_stage(T, gen_A, det):
+    """The input convolution composed with the first ResBlock's conv1 (one 9-tap convolution of the waveform)
+    drops a tap on the first and last sample of a clip: lengths around the 126-row tile and down to 1 sample."""
+    g = torch.Generator().manual_seed(100 + T)
+    s = (0.2 * torch.randn(3, 1, T, generator=g)).clamp(-0.99, 0.99)
+    msg = torch.from_numpy(IO["messages"][:3].astype(np.int64))
+    gsd, rows = H.gen_sd(W, "A")
+    ref = O.generator_forward(gsd, s, msg, emb_rows=H.emb_for(IO, rows, msg))
+    assert maxerr(gen_A(s.to(DEV), msg.to(DEV)), ref) < DELTA_TOL * 0.1
+    lg = O.detector_forward(H.det_sd(W), s)
+    assert maxerr(torch.sigmoid(det(s.to(DEV))[:, :, 0]), torch.sigmoid(lg[:, :, 0])) < PROB_TOL
