@@ -6,18 +6,21 @@
 //     conv1(x0)[t] = B9 + sum_{m<9} W9[m] s[t+m-4],    W9[k+j] += W1[k] . w_in[j],
 // (composed on the host in float64, packing.py) except on the first and last sample of a clip, where
 // conv1's zero padding of x0 drops one of its three taps; those two rows subtract that tap's composed
-// contribution (WK, BK) again.  So this kernel never materialises x0 in HBM (4 MB per clip written and
-// read back), runs conv1 on the CUDA cores in fp32 straight from the waveform and only conv2 on the
-// tensor pipe: half the MMAs and half the shared-memory operand traffic of the general ResBlock kernel,
-// which is what that kernel is bound by.
+// contribution (WK, BK) again.  Both 1->64 convolutions of the waveform are run as ONE small GEMM on the
+// tensor pipe: the A operand is the Toeplitz (im2col) tile of the waveform, built on the fly,
+//     A[r][m] = s[t0 - 5 + r + m]   (128 rows x K = 16, m >= 9 zero),
+// and B = [ W9 | w_in shifted by 2 ] (K = 16 x N = 128), so that accumulator columns 0..63 hold
+// conv1(x0) at time t0 - 1 + r (the rows of conv2's operand tile) and columns 64..127 hold x0 at time
+// t0 + r (the rows of the OUTPUT tile).  With bf16 hi/lo pairs that is 3 MMAs per tile instead of the
+// 24 of a 64-channel conv1, and x0 (4 MB per clip) is never written to or read from HBM.
+// The residual never leaves tensor memory either: the conv1 epilogue stores x0 + b_in + b2 into conv2's
+// accumulator, and conv2 accumulates on top of it.
 //
-// Warps 0..7   group 1 (producers): warp w owns rows 16w..16w+15 of the tile, lane = channel pair, so the
-//              9 + 7 taps of its two channels stay in REGISTERS (packed f32x2) for the whole kernel; per
-//              row 16 FFMA2 give u = conv1(conv_in(s)) and x0 = conv_in(s); relu(u) goes to the
-//              intermediate tile U (bf16 hi/lo planes, conv2's A operand), x0 (fp32) to a side tile
-// warps 8..15  group 2: conv2 accumulator + b2 + x0 (from the side tile) -> ReLU -> planar y; two
-//              sub-groups of 4 warps take alternate tiles
-// warp 16      conv2 weights (bulk copy, once), MMA issue, TMEM owner
+// Warps 0..7   group 1: D1 (u | x0) -> relu(u + B9) as bf16 hi/lo planes in the intermediate tile U (conv2's
+//              A operand); x0 + biases -> D2 (tcgen05.st)
+// warps 8..15  group 2: D2 -> ReLU -> planar y; two sub-groups of 4 warps take alternate tiles
+// warp 16      producer: Toeplitz tiles of the waveform (bf16 hi/lo), conv2 weights (bulk copy, once)
+// warp 17      MMA issue, TMEM owner
 // Tile geometry, operand formats and the 3-partial-product bf16 pair scheme are those of
 // wm_resblock_tc.cu.
 #include <cuda_bf16.h>
@@ -40,39 +43,36 @@ constexpr int TILE_B = 16 * PLANE_B;       // 33 280
 constexpr int W_TAP_B = 8 * 128 * 16;
 constexpr int W_IMG_B = 3 * W_TAP_B;       // 49 152
 constexpr int NU = 2;                      // intermediate tiles in flight
-constexpr int NX = 3;                      // residual side tiles in flight
-constexpr int X0_PITCH = 272;              // bytes per row of the side tile: 64 fp32 + 16 (bank spread for LDS.128)
-constexpr int X0_B = 128 * X0_PITCH;       // 34 816
+constexpr int AT_B = 2 * 128 * 16;         // one Toeplitz operand (hi or lo): [k chunk 2][row 128][8 x bf16]
+constexpr int BT_B = 2 * 128 * 16;         // one B operand (hi or lo):        [k chunk 2][col 128][8 x bf16]
 constexpr int OFF_W = 0;
-constexpr int OFF_U = OFF_W + W_IMG_B;
-constexpr int OFF_X0 = OFF_U + NU * TILE_B;
-constexpr int OFF_BIAS = OFF_X0 + NX * X0_B;
-constexpr int OFF_BAR = OFF_BIAS + 256;
-constexpr int RBI_SMEM = OFF_BAR + 128;
+constexpr int OFF_BT = OFF_W + W_IMG_B;            // B_hi, B_lo
+constexpr int OFF_AT = OFF_BT + 2 * BT_B;          // 2 stages x (A_hi, A_lo)
+constexpr int OFF_U = OFF_AT + 2 * 2 * AT_B;
+constexpr int OFF_BIAS = OFF_U + NU * TILE_B;      // b9[64], (b_in + b2)[64]
+constexpr int OFF_BAR = OFF_BIAS + 512;
+constexpr int RBI_SMEM = OFF_BAR + 160;
 static_assert(RBI_SMEM <= 232448, "shared memory budget");
 constexpr uint32_t kIdesc = make_idesc(128, 128);
 constexpr uint32_t kIdescLo = make_idesc(128, 64);     // A_lo x W_hi only
 constexpr int N_GRP = 256;
-constexpr int W_MMA = 2 * N_GRP / 32, RBI_THREADS = 2 * N_GRP + 32;
+constexpr int W_PROD = 2 * N_GRP / 32, W_MMA = W_PROD + 1, RBI_THREADS = 2 * N_GRP + 64;
 
 }  // namespace
 
-// in: device block  w9[9][64], b9[64], w_in[7][64], b_in[64]  (WM_FIN_W9.. and the input convolution)
-// fin: device pointer to the WM_FIN_* block of the blob (boundary rows read WK / BK from it)
+// w9g: device w9[9][64], b9[64]; wing: device w_in[7][64], b_in[64]; fin: device WM_FIN_* block (edge rows)
 __global__ void __launch_bounds__(RBI_THREADS, 1)
     resblock_in_tc_kernel(const float *__restrict__ s, const float *__restrict__ w9g, const float *__restrict__ wing,
                           const float *__restrict__ fin, const uint4 *__restrict__ w_img2, const float *__restrict__ b2,
                           uint4 *__restrict__ y, int B, int T) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
-  const uint32_t w_smem = s_base + OFF_W, u_smem = s_base + OFF_U;
+  const uint32_t w_smem = s_base + OFF_W, bt_smem = s_base + OFF_BT, at_smem = s_base + OFF_AT, u_smem = s_base + OFF_U;
   const uint32_t bars = s_base + OFF_BAR;
-  enum { WBAR = 0, U_FULL = 1, U_EMPTY = U_FULL + NU, D2_FULL = U_EMPTY + NU, D2_EMPTY = D2_FULL + 2,
-         X_EMPTY = D2_EMPTY + 2, NBAR = X_EMPTY + NX };
-  static_assert(8 * NBAR + 8 <= 128, "barrier block");
+  enum { WBAR = 0, A_FULL = 1, A_EMPTY = 3, D1_FULL = 5, U_FULL = 7, U_EMPTY = 9, D2_FULL = 11, D2_EMPTY = 13, NBAR = 15 };
   auto bar = [&](int i) { return bars + 8 * i; };
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 * NBAR);
-  float *bias_s = reinterpret_cast<float *>(smem + OFF_BIAS);   // b2
+  float *bias_s = reinterpret_cast<float *>(smem + OFF_BIAS);   // [0..63] b9, [64..127] b_in + b2
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntile_t = (T + TO - 1) / TO;
@@ -82,37 +82,90 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
 
   if (threadIdx.x == 0) {
     mbar_init(bar(WBAR), 1);
-    for (int a = 0; a < NU; ++a) { mbar_init(bar(U_FULL + a), N_GRP / 32); mbar_init(bar(U_EMPTY + a), 1); }
-    for (int g = 0; g < 2; ++g) { mbar_init(bar(D2_FULL + g), 1); mbar_init(bar(D2_EMPTY + g), 4); }
-    for (int x = 0; x < NX; ++x) mbar_init(bar(X_EMPTY + x), 4);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar(A_FULL + a), 1); mbar_init(bar(A_EMPTY + a), 1); mbar_init(bar(D1_FULL + a), 1);
+      mbar_init(bar(U_FULL + a), N_GRP / 32); mbar_init(bar(U_EMPTY + a), 1);
+      mbar_init(bar(D2_FULL + a), 1); mbar_init(bar(D2_EMPTY + a), 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < 64) bias_s[threadIdx.x] = b2[threadIdx.x];
+  if (threadIdx.x < 128)
+    bias_s[threadIdx.x] = threadIdx.x < 64 ? w9g[9 * 64 + threadIdx.x]
+                                           : wing[7 * 64 + threadIdx.x - 64] + b2[threadIdx.x - 64];
+  // B operand of the Toeplitz GEMM, bf16 hi and lo: element (k, n), k < 16, n < 128:
+  //   n < 64: W9[k][n] (k < 9);   n >= 64: w_in[k - 2][n - 64] (2 <= k < 9);   else 0
+  for (int e = threadIdx.x; e < 16 * 128; e += RBI_THREADS) {
+    const int k = e >> 7, n = e & 127;
+    float v = 0.0f;
+    if (n < 64) { if (k < 9) v = w9g[k * 64 + n]; }
+    else if (k >= 2 && k < 9) v = wing[(k - 2) * 64 + n - 64];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const int off = (k >> 3) * 2048 + n * 16 + (k & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16 *>(smem + OFF_BT + off) = hi;
+    *reinterpret_cast<__nv_bfloat16 *>(smem + OFF_BT + BT_B + off) = lo;
+  }
   if (warp == W_MMA) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == W_MMA) {
-    // ===== conv2: weights once, then 24 MMAs per tile =====
-    if (elect_one()) {
+  if (warp == W_PROD) {
+    // ===== producer: conv2 weights once; per tile the Toeplitz tile of the waveform (4 rows per lane) =====
+    if (lane == 0) {
       mbar_arrive_expect_tx(bar(WBAR), W_IMG_B);
       for (int j = 0; j < 3; ++j)
         bulk_g2s(w_smem + j * W_TAP_B, reinterpret_cast<const uint8_t *>(w_img2) + (size_t)j * W_TAP_B, W_TAP_B, bar(WBAR));
-      mbar_wait(bar(WBAR), 0);
-      const uint64_t b0 = smem_desc(w_smem, 2048, 128);
-      for (long long i = 0; i < my_tiles; ++i) {
-        const int a = (int)(i % NU), g = (int)(i & 1);
-        mbar_wait(bar(U_FULL + a), (uint32_t)((i / NU) & 1));
-        if (i >= 2) mbar_wait(bar(D2_EMPTY + g), (uint32_t)(((i >> 1) - 1) & 1));
-        tc_fence_after();
-        const uint64_t a0 = smem_desc(u_smem + a * TILE_B, PLANE_B, 128);
-        const uint32_t d_tmem = tmem + g * 128;
+    }
+    for (long long i = 0; i < my_tiles; ++i) {
+      const long long tile = blockIdx.x + i * gridDim.x;
+      const long long b = tile / ntile_t;
+      const int t0 = (int)(tile % ntile_t) * TO;
+      const int st = (int)(i & 1);
+      const float *sb = s + (size_t)b * T;
+      if (i >= 2) mbar_wait_warp(bar(A_EMPTY + st), (uint32_t)(((i >> 1) - 1) & 1));
+      uint8_t *ah = smem + OFF_AT + st * 2 * AT_B, *al = ah + AT_B;
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int r = rr * 32 + lane;
+        float v[10];
+#pragma unroll
+        for (int m = 0; m < 9; ++m) {
+          const int ts = t0 - 5 + r + m;
+          v[m] = (ts >= 0 && ts < T) ? __ldg(sb + ts) : 0.0f;
+        }
+        v[9] = 0.0f;
+        uint32_t h[5], l[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) split2(v[2 * k], v[2 * k + 1], h[k], l[k]);
+        *reinterpret_cast<uint4 *>(ah + r * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(ah + 2048 + r * 16) = make_uint4(h[4], 0, 0, 0);
+        *reinterpret_cast<uint4 *>(al + r * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<uint4 *>(al + 2048 + r * 16) = make_uint4(l[4], 0, 0, 0);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(A_FULL + st));
+    }
+  } else if (warp == W_MMA) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      const uint64_t bt_hi = smem_desc(bt_smem, 2048, 128), bt_lo = smem_desc(bt_smem + BT_B, 2048, 128);
+      auto gemm1 = [&](int st, uint32_t d_tmem) {   // D1 = A_hi B_hi + A_lo B_hi + A_hi B_lo   (K = 16 each)
+        const uint64_t a_hi = smem_desc(at_smem + st * 2 * AT_B, 2048, 128);
+        const uint64_t a_lo = smem_desc(at_smem + st * 2 * AT_B + AT_B, 2048, 128);
+        mma_bf16(d_tmem, a_hi, bt_hi, kIdesc, 0u);
+        mma_bf16(d_tmem, a_lo, bt_hi, kIdesc, 1u);
+        mma_bf16(d_tmem, a_hi, bt_lo, kIdesc, 1u);
+      };
+      auto conv2 = [&](uint32_t a_tile, uint32_t d_tmem) {   // accumulates on the residual stored by group 1
+        const uint64_t a0 = smem_desc(a_tile, PLANE_B, 128), b0 = smem_desc(w_smem, 2048, 128);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
 #pragma unroll
@@ -120,101 +173,107 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               mma_bf16(d_tmem, a0 + (uint64_t)(((half * 8 + 2 * kk) * PLANE_B + j * 16) >> 4),
-                       b0 + (uint64_t)((j * W_TAP_B + (2 * kk) * 2048) >> 4), half ? kIdescLo : kIdesc,
-                       (j | kk | half) != 0 ? 1u : 0u);
+                       b0 + (uint64_t)((j * W_TAP_B + (2 * kk) * 2048) >> 4), half ? kIdescLo : kIdesc, 1u);
             }
           }
         }
-        tc_commit(bar(D2_FULL + g));
+      };
+      mbar_wait(bar(WBAR), 0);
+      if (my_tiles > 0) {
+        mbar_wait(bar(A_FULL), 0);
+        tc_fence_after();
+        gemm1(0, tmem);
+        tc_commit(bar(D1_FULL));
+        tc_commit(bar(A_EMPTY));
+      }
+      for (long long i = 0; i < my_tiles; ++i) {
+        const int a = (int)(i & 1);
+        if (i + 1 < my_tiles) {   // Toeplitz GEMM of the next tile; D1[an] was drained by group 1 of tile i-1 (u_full(i-1))
+          const long long n = i + 1;
+          const int an = (int)(n & 1);
+          mbar_wait(bar(A_FULL + an), (uint32_t)((n >> 1) & 1));
+          tc_fence_after();
+          gemm1(an, tmem + an * 128);
+          tc_commit(bar(D1_FULL + an));
+          tc_commit(bar(A_EMPTY + an));
+        }
+        mbar_wait(bar(U_FULL + a), (uint32_t)((i >> 1) & 1));    // U[a] written and D2[a] initialised with the residual
+        tc_fence_after();
+        conv2(u_smem + a * TILE_B, tmem + 256 + a * 128);
+        tc_commit(bar(D2_FULL + a));
         tc_commit(bar(U_EMPTY + a));
       }
     }
     __syncwarp();
   } else if (warp < N_GRP / 32) {
-    // ===== group 1: rows 16*warp .. +15 of the tile (time t0 - 1 + row), channels 2*lane, 2*lane + 1 =====
-    const int c0 = 2 * lane;
-    f32x2 w9[9], wi[7];
-#pragma unroll
-    for (int m = 0; m < 9; ++m) w9[m] = pk2(__ldg(w9g + m * 64 + c0), __ldg(w9g + m * 64 + c0 + 1));
-#pragma unroll
-    for (int j = 0; j < 7; ++j) wi[j] = pk2(__ldg(wing + j * 64 + c0), __ldg(wing + j * 64 + c0 + 1));
-    const f32x2 b9 = pk2(__ldg(w9g + 9 * 64 + c0), __ldg(w9g + 9 * 64 + c0 + 1));
-    const f32x2 bi = pk2(__ldg(wing + 7 * 64 + c0), __ldg(wing + 7 * 64 + c0 + 1));
-    // this lane's 4 bytes inside the 16-byte row chunk of plane lane / 4 (hi) and 8 + lane / 4 (lo)
-    const int u_off = (lane >> 2) * PLANE_B + (lane & 3) * 4;
+    // ===== group 1: D1 -> U tile (relu(conv1 + B9), bf16 hi/lo) and residual -> D2 =====
+    const int q = warp & 3, half = warp >> 2;          // TMEM lane quadrant, 32-channel half
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     for (long long i = 0; i < my_tiles; ++i) {
       const long long tile = blockIdx.x + i * gridDim.x;
       const long long b = tile / ntile_t;
       const int t0 = (int)(tile % ntile_t) * TO;
-      const int a = (int)(i % NU), xb = (int)(i % NX);
-      const int tu0 = t0 - 1 + 16 * warp;                 // time of this warp's first row
-      const float *sb = s + (size_t)b * T;
-      float sw[24];                                        // s[tu0 - 4 .. tu0 + 19], zero outside the clip
-#pragma unroll
-      for (int k = 0; k < 24; ++k) {
-        const int ts = tu0 - 4 + k;
-        sw[k] = (ts >= 0 && ts < T) ? __ldg(sb + ts) : 0.0f;
+      const int a = (int)(i & 1);
+      const int tu = t0 - 1 + row;
+      const bool inside = tu >= 0 && tu < T;     // conv2 zero-pads the intermediate feature map
+      const bool edge = inside && (tu == 0 || tu == T - 1);
+      uint8_t *us = smem + OFF_U + a * TILE_B + row * 16;
+      mbar_wait_warp(bar(D1_FULL + a), (uint32_t)((i >> 1) & 1));
+      if (i >= 2) {
+        mbar_wait_warp(bar(U_EMPTY + a), (uint32_t)(((i >> 1) - 1) & 1));    // conv2(i-2) has finished reading U[a]
+        mbar_wait_warp(bar(D2_EMPTY + a), (uint32_t)(((i >> 1) - 1) & 1));   // epilogue(i-2) has drained D2[a]
       }
-      if (i >= NU) mbar_wait_warp(bar(U_EMPTY + a), (uint32_t)(((i / NU) - 1) & 1));   // conv2(i-NU) has read U[a]
-      if (i >= NX) mbar_wait_warp(bar(X_EMPTY + xb), (uint32_t)(((i / NX) - 1) & 1));  // epilogue(i-NX) has read X0[xb]
-      uint8_t *us = smem + OFF_U + a * TILE_B + (16 * warp) * 16 + u_off;
-      uint8_t *xs = smem + OFF_X0 + xb * X0_B + (16 * warp) * X0_PITCH + c0 * 4;
+      tc_fence_after();
+      const uint32_t t1 = tmem + a * 128 + lane_off, t2 = tmem + 256 + a * 128 + lane_off;
 #pragma unroll
-      for (int rr = 0; rr < 16; ++rr) {
-        const int tu = tu0 + rr;
-        f32x2 sp[9];
+      for (int pp = 0; pp < 2; ++pp) {
+        const int p = half * 2 + pp;
+        float u[16], xr[16];
+        tmem_ld16(t1 + p * 16, u);
+        tmem_ld16(t1 + 64 + p * 16, xr);
+        tmem_ld_wait();
 #pragma unroll
-        for (int m = 0; m < 9; ++m) sp[m] = pk2(sw[rr + m], sw[rr + m]);
-        f32x2 au = b9, ax = bi;
+        for (int c = 0; c < 16; ++c) { u[c] += bias_s[p * 16 + c]; xr[c] += bias_s[64 + p * 16 + c]; }
+        if (edge) {   // first / last sample of the clip: take back conv1's tap that fell on the zero padding of x0
+          const float *sb = s + (size_t)b * T;
+          const bool drop0 = tu == 0, drop2 = tu == T - 1;
 #pragma unroll
-        for (int m = 0; m < 9; ++m) au = fma2(sp[m], w9[m], au);
-#pragma unroll
-        for (int j = 0; j < 7; ++j) ax = fma2(sp[j + 1], wi[j], ax);
-        float u0, u1;
-        upk2(au, u0, u1);
-        const bool inside = tu >= 0 && tu < T;             // conv2 zero-pads the intermediate feature map
-        u0 = inside ? fmaxf(u0, 0.0f) : 0.0f;
-        u1 = inside ? fmaxf(u1, 0.0f) : 0.0f;
-        uint32_t hi, lo;
-        split2(u0, u1, hi, lo);
-        *reinterpret_cast<uint32_t *>(us + rr * 16) = hi;
-        *reinterpret_cast<uint32_t *>(us + rr * 16 + 8 * PLANE_B) = lo;
-        *reinterpret_cast<f32x2 *>(xs + rr * X0_PITCH) = ax;
-      }
-      // First and last sample of the clip (at most two rows per clip, warp-uniform test): conv1's tap on the zero
-      // padding of x0 is not part of the result; redo that row without it.  Kept out of the row loop so that the
-      // 16 rows' FMA chains interleave freely.
+          for (int c = 0; c < 16; ++c) {      // unrolled: u[] must stay in registers
+            const int co = p * 16 + c;
+            float d = (drop0 ? fin[WM_FIN_BK + co] : 0.0f) + (drop2 ? fin[WM_FIN_BK + 2 * 64 + co] : 0.0f);
 #pragma unroll 1
-      for (int e = 0; e < 2; ++e) {
-        const int te = e == 0 ? 0 : T - 1;
-        const int rr = te - tu0;
-        if (rr < 0 || rr >= 16 || (e == 1 && T == 1)) continue;
-        const bool drop0 = te == 0, drop2 = te == T - 1;
-        float u0 = __ldg(w9g + 9 * 64 + c0), u1 = __ldg(w9g + 9 * 64 + c0 + 1);
-        for (int m = 0; m < 9; ++m) {
-          const int ts = te + m - 4;
-          const float sv = (ts >= 0 && ts < T) ? __ldg(sb + ts) : 0.0f;
-          u0 = fmaf(sv, __ldg(w9g + m * 64 + c0), u0);
-          u1 = fmaf(sv, __ldg(w9g + m * 64 + c0 + 1), u1);
-          for (int k = 0; k < 3; k += 2) {          // conv1 taps 0 and 2: composed tap index m = k + j
-            const int j = m - k;
-            if (j < 0 || j > 6 || !(k == 0 ? drop0 : drop2)) continue;
-            u0 -= sv * fin[WM_FIN_WK + (k * 7 + j) * 64 + c0];
-            u1 -= sv * fin[WM_FIN_WK + (k * 7 + j) * 64 + c0 + 1];
+            for (int j = 0; j < 7; ++j) {
+              const int ts0 = tu + j - 4, ts2 = tu + j - 2;     // sample under composed tap (k = 0, j) / (k = 2, j)
+              if (drop0 && ts0 >= 0 && ts0 < T) d = fmaf(__ldg(sb + ts0), fin[WM_FIN_WK + j * 64 + co], d);
+              if (drop2 && ts2 >= 0 && ts2 < T) d = fmaf(__ldg(sb + ts2), fin[WM_FIN_WK + (14 + j) * 64 + co], d);
+            }
+            u[c] -= d;
           }
         }
-        if (drop0) { u0 -= fin[WM_FIN_BK + c0]; u1 -= fin[WM_FIN_BK + c0 + 1]; }
-        if (drop2) { u0 -= fin[WM_FIN_BK + 2 * 64 + c0]; u1 -= fin[WM_FIN_BK + 2 * 64 + c0 + 1]; }
-        uint32_t hi, lo;
-        split2(fmaxf(u0, 0.0f), fmaxf(u1, 0.0f), hi, lo);
-        *reinterpret_cast<uint32_t *>(us + rr * 16) = hi;
-        *reinterpret_cast<uint32_t *>(us + rr * 16 + 8 * PLANE_B) = lo;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) u[c] = inside ? fmaxf(u[c], 0.0f) : 0.0f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int ch = p * 2 + h;
+          uint4 hi, lo;
+          split8(u + h * 8, hi, lo);
+          *reinterpret_cast<uint4 *>(us + ch * PLANE_B) = hi;
+          *reinterpret_cast<uint4 *>(us + (8 + ch) * PLANE_B) = lo;
+        }
+        // residual x0 + b_in + b2 -> conv2's accumulator (columns of the hi product; the lo-product columns start at 0)
+        tmem_st16(t2 + p * 16, xr);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) xr[c] = 0.0f;
+        tmem_st16(t2 + 64 + p * 16, xr);
       }
+      tmem_st_wait();
+      tc_fence_before();
       fence_async_smem();
       mbar_arrive_warp(bar(U_FULL + a));
     }
   } else {
-    // ===== group 2: conv2 accumulator + b2 + x0 -> ReLU -> y =====
+    // ===== group 2: D2 (residual + conv2, hi and lo products) -> ReLU -> y =====
     const int w2 = warp - N_GRP / 32;
     const int q = w2 & 3, g = w2 >> 2;
     const int row = q * 32 + lane;
@@ -233,35 +292,21 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
           for (int pl = 0; pl < 16; ++pl) y[((size_t)(b * 16 + pl)) * RP + zr] = make_uint4(0, 0, 0, 0);
         }
       }
-      // x0 of output row `row` is row + 1 of the side tile (the tile starts one sample early)
-      const float4 *xr = reinterpret_cast<const float4 *>(smem + OFF_X0 + (int)(i % NX) * X0_B +
-                                                          (row < 127 ? row + 1 : 127) * X0_PITCH);
       mbar_wait_warp(bar(D2_FULL + g), (uint32_t)((i >> 1) & 1));
       tc_fence_after();
-      const uint32_t taddr = tmem + g * 128 + lane_off;
+      const uint32_t taddr = tmem + 256 + g * 128 + lane_off;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         float v1[16], v2[16], o[16];
         tmem_ld16(taddr + p * 16, v1);
         tmem_ld16(taddr + 64 + p * 16, v2);
-        float4 xv[4];
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) xv[c4] = xr[p * 4 + c4];
         tmem_ld_wait();
         if (p == 3) {
           tc_fence_before();
-          mbar_arrive_warp(bar(D2_EMPTY + g));              // D2[g] may be overwritten by conv2(i+2)
-          mbar_arrive_warp(bar(X_EMPTY + (int)(i % NX)));   // and the side tile by the producers of tile i+NX
+          mbar_arrive_warp(bar(D2_EMPTY + g));     // D2[g] may be re-initialised for tile i+2
         }
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const float r4[4] = {xv[c4].x, xv[c4].y, xv[c4].z, xv[c4].w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int c = c4 * 4 + k;
-            o[c] = fmaxf(v1[c] + v2[c] + bias_s[p * 16 + c] + r4[k], 0.0f);
-          }
-        }
+        for (int c = 0; c < 16; ++c) o[c] = fmaxf(v1[c] + v2[c], 0.0f);
         if (live) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -280,7 +325,7 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
   __syncthreads();
   if (warp == W_MMA) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
   }
 }
 
