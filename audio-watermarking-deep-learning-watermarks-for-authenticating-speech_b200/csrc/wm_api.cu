@@ -56,14 +56,14 @@ int require_device() {
 // epilogues take the head weights as a kernel parameter (constant bank), which needs them on the host;
 // wm_finalize_*_blob reads them back once.  A blob must not be modified after it has been finalized.
 struct HeadCopy {
-  float v[17 * 64 + 17];   // 1x1 head: w[n][64] then b[n]
+  float v[64 + 1];   // output 0 of the 1x1 head: w[64] then b
 };
 static std::mutex g_head_mu;
 static std::unordered_map<const float *, HeadCopy> g_heads;
-static int remember_head(const float *blob, int w_off, int b_off, int n, cudaStream_t st) {
+static int remember_head(const float *blob, int w_off, int b_off, cudaStream_t st) {
   HeadCopy h;
-  WM_CHECK_CUDA(cudaMemcpyAsync(h.v, blob + w_off, sizeof(float) * n * 64, cudaMemcpyDeviceToHost, st));
-  WM_CHECK_CUDA(cudaMemcpyAsync(h.v + n * 64, blob + b_off, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  WM_CHECK_CUDA(cudaMemcpyAsync(h.v, blob + w_off, sizeof(float) * 64, cudaMemcpyDeviceToHost, st));
+  WM_CHECK_CUDA(cudaMemcpyAsync(h.v + 64, blob + b_off, sizeof(float), cudaMemcpyDeviceToHost, st));
   WM_CHECK_CUDA(cudaStreamSynchronize(st));
   std::lock_guard<std::mutex> lk(g_head_mu);
   g_heads[blob] = h;
@@ -187,23 +187,25 @@ static int detector_trunk(const float *blob, const float *x, void *r0, void *r1,
 }
 
 // Detector + heads (py/main16.py:176-180,1142-1146): per-sample probability, clip mean, mean message logits.
-// tcgen05 mode with the shipped 17-output head and no vote request: the 1x1 head, the sigmoid and the
-// per-tile partial sums run in the last ResBlock's epilogue (the (B,T,64) feature map is never stored).
+// tcgen05 mode without a vote request: channel 0 of the 1x1 head, the sigmoid and per-tile partial sums of the
+// probability and of the 64 activations run in the last ResBlock's epilogue (the (B,T,64) feature map is never
+// stored); the message head is applied to the per-clip activation means by the finalize kernel.
 static int detect_run(const float *blob, const float *x, const int *valid_len, float *probs, float *clip_prob,
                       float *msg_logits, float *vote_frac, void *r0, void *r1, void *r2, int B, int T, int nout,
                       cudaStream_t st) {
   HeadCopy h;
-  if (g_math_mode.load() == WM_MATH_BF16X2 && nout == 17 && vote_frac == nullptr &&
-      (size_t)B * resblock_tiles_per_clip(T) * 4 * WM_MAX_HEAD * sizeof(float) <= act_bytes(B, T) &&
+  if (g_math_mode.load() == WM_MATH_BF16X2 && vote_frac == nullptr &&
+      (size_t)B * resblock_tiles_per_clip(T) * 4 * WM_DET_PART * sizeof(float) <= act_bytes(B, T) &&
       lookup_head(blob, &h)) {
     const float *tc = blob + WM_D_TC;
     float *partials = (float *)r1;
     (void)r0;   // input convolution folded into the first ResBlock: x -> r2 planar
     WM_TRY(launch_resblock_in_tc(x, blob + WM_D_FIN + WM_FIN_W9, blob + WM_D_IN_W, blob + WM_D_FIN, tc + WM_TC_IMG3,
                                  blob + WM_D_RB0 + WM_RB_B2, r2, B, T, st));
-    WM_TRY(launch_resblock_head17_tc(r2, tc + 2 * WM_TC_IMG3, blob + WM_D_RB1 + WM_RB_B1, blob + WM_D_RB1 + WM_RB_B2, h.v,
+    WM_TRY(launch_resblock_detect_tc(r2, tc + 2 * WM_TC_IMG3, blob + WM_D_RB1 + WM_RB_B1, blob + WM_D_RB1 + WM_RB_B2, h.v,
                                      valid_len, probs, partials, B, T, st));
-    return launch_detect_finalize(partials, valid_len, clip_prob, msg_logits, B, T, nout, st);
+    return launch_detect_finalize(partials, valid_len, blob + WM_D_HEAD_W, blob + WM_D_HEAD_B, clip_prob, msg_logits, B,
+                                  T, nout, st);
   }
   float *out = nullptr;
   WM_TRY(detector_trunk(blob, x, r0, r1, r2, &out, B, T, st));
@@ -247,7 +249,7 @@ int wm_finalize_generator_blob(float *blob, void *stream) {
   WM_TRY(launch_pack_conv64_tc(blob + WM_G_CT_W, blob + WM_G_TC_CT, 7, st));
   WM_TRY(launch_pack_lstm_tc(blob + WM_G_LSTM_WIH, blob + WM_G_LSTM_WHH, blob + WM_G_LSTM_B, blob + WM_G_TC_LSTM_W,
                              blob + WM_G_TC_LSTM_B, st));
-  return remember_head(blob, WM_G_HEAD_W, WM_G_HEAD_B, 1, st);   // synchronises `stream` (one-time set-up call)
+  return remember_head(blob, WM_G_HEAD_W, WM_G_HEAD_B, st);   // synchronises `stream` (one-time set-up call)
 }
 
 int wm_finalize_detector_blob(float *blob, void *stream) {
@@ -259,7 +261,7 @@ int wm_finalize_detector_blob(float *blob, void *stream) {
     WM_TRY(launch_pack_conv64_tc(blob + rb[i] + WM_RB_W1, blob + WM_D_TC + (2 * i) * WM_TC_IMG3, 3, st));
     WM_TRY(launch_pack_conv64_tc(blob + rb[i] + WM_RB_W2, blob + WM_D_TC + (2 * i + 1) * WM_TC_IMG3, 3, st));
   }
-  return remember_head(blob, WM_D_HEAD_W, WM_D_HEAD_B, 17, st);  // synchronises `stream` (one-time set-up call)
+  return remember_head(blob, WM_D_HEAD_W, WM_D_HEAD_B, st);  // synchronises `stream` (one-time set-up call)
 }
 
 size_t wm_planar_bytes(int B, int T) { return (B <= 0 || T <= 0) ? 0 : planar_bytes(B, T); }

@@ -95,14 +95,15 @@ int resblock_tiles_per_clip(int T);
 // winb: device w_in[7][64], b_in[64]; fin: device WM_FIN_* block; s[B][T] -> y planar
 int launch_resblock_in_tc(const float *s, const float *w9b, const float *winb, const float *fin, const void *w_img2,
                           const float *b2, void *y, int B, int T, cudaStream_t st);
-// host_head: HOST copy of the 1x1 head (w[n][64] then b[n], n = 1 or 17); it is passed to the kernel by value
+// host_head: HOST copy of output 0 of the 1x1 head (w[64] then b); it is passed to the kernel by value
 int launch_resblock_head1_tc(const void *x, const void *w_img, const float *b1, const float *b2,
                              const float *host_head, float *delta_raw, int B, int T, cudaStream_t st);
-int launch_resblock_head17_tc(const void *x, const void *w_img, const float *b1, const float *b2,
+#define WM_DET_PART 68   // floats per (tile, warp) partial of the detector epilogue: 64 activation sums, prob sum, pad
+int launch_resblock_detect_tc(const void *x, const void *w_img, const float *b1, const float *b2,
                               const float *host_head, const int *valid_len, float *probs, float *partials, int B, int T,
                               cudaStream_t st);
-int launch_detect_finalize(const float *partials, const int *valid_len, float *clip_prob, float *msg_logits, int B,
-                           int T, int nout, cudaStream_t st);
+int launch_detect_finalize(const float *partials, const int *valid_len, const float *head_w, const float *head_b,
+                           float *clip_prob, float *msg_logits, int B, int T, int nout, cudaStream_t st);
 // training-loss forward kernels (wm_loss.cu); `partials` is caller workspace (wm_loss_workspace_bytes)
 int launch_stft_mag(const float *x, float *mag, int B, int T, int n_fft, int hop, cudaStream_t st);
 int launch_hf_penalty(const float *delta, float *out, float *partials, int B, int T, int n_fft, int first_bin,

@@ -72,14 +72,17 @@ struct HeadParams {
 };
 
 // NHEAD = 0: plain ResBlock.  NHEAD = 1: + Conv1d(64,1,1) -> head_out[b][t] (py/main16.py:146).
-// NHEAD = 17: + Conv1d(64,17,1) -> head_out[b][t] = sigmoid(ch 0) and per-(tile, warp) partial sums of the
-// probability and of the 16 message logits over the valid samples -> partials (py/main16.py:180,1142-1146).
+// NHEAD = 2 (detector): + channel 0 of Conv1d(64,1+bits,1) -> head_out[b][t] = sigmoid(logit 0), and per
+// (tile, warp) partial sums over the valid samples of that probability and of the 64 ACTIVATIONS: the message
+// logits are only ever used as means over time (py/main16.py:1142-1146), and a mean of a linear map is the
+// linear map of the mean, so the 16 x 64 message head is applied once per clip by detect_finalize_kernel
+// instead of 1024 FMAs per sample here.
 template <int NHEAD>
 // 18 warps = 5 on one SM sub-partition (16 K registers each): 96 registers per thread is the ceiling
 __global__ void __launch_bounds__(RB_THREADS, 1)
     resblock_tc_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ w_img, const float *__restrict__ b1,
                        const float *__restrict__ b2, uint4 *__restrict__ y, float *__restrict__ y32, int B, int T,
-                       const __grid_constant__ HeadParams<(NHEAD > 0 ? NHEAD : 1)> hp,
+                       const __grid_constant__ HeadParams<1> hp,
                        float *__restrict__ head_out, float *__restrict__ partials, const int *__restrict__ valid_len,
                        long long *__restrict__ prof) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -286,9 +289,14 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
       long long e1 = pfe ? clock64() : 0;
       tc_fence_after();
       const uint32_t taddr = tmem + 256 + g * 128 + lane_off;
-      float hacc[NHEAD > 0 ? NHEAD : 1];
-#pragma unroll
-      for (int o = 0; o < (NHEAD > 0 ? NHEAD : 1); ++o) hacc[o] = 0.0f;
+      float hacc = 0.0f;
+      [[maybe_unused]] bool counted = false;
+      [[maybe_unused]] float *pdst = nullptr;
+      if constexpr (NHEAD == 2) {
+        const int vl = valid_len != nullptr ? min(max(valid_len[b], 0), T) : T;
+        counted = live && t < vl;
+        pdst = partials + (((size_t)b * ntile_t + tt) * 4 + q) * WM_DET_PART;
+      }
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         float v1[16], v2[16], o[16];
@@ -326,37 +334,38 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
           }
         }
         if constexpr (NHEAD > 0) {
-          // 1x1 head: weights are constant-bank operands of the FFMAs (kernel parameter)
+          // one output of the 1x1 head: weights are constant-bank operands of the FFMAs (kernel parameter)
 #pragma unroll
-          for (int oo = 0; oo < NHEAD; ++oo) {
+          for (int c = 0; c < 16; ++c) hacc = fmaf(o[c], hp.w[p * 16 + c], hacc);
+        }
+        if constexpr (NHEAD == 2) {
+          // sum of these 16 channels over the warp's 32 rows by recursive halving: after the steps 16, 8, 4, 2
+          // lane l holds channel l / 2 summed over 16 lanes, the last exchange folds the lane pair
+          float a8[8], a4[4], a2[2];
+          const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) hacc[oo] = fmaf(o[c], hp.w[oo * 64 + p * 16 + c], hacc[oo]);
+          for (int k = 0; k < 8; ++k) {
+            const float lo_v = counted ? o[k] : 0.0f, hi_v = counted ? o[8 + k] : 0.0f;
+            a8[k] = (b16 ? hi_v : lo_v) + __shfl_xor_sync(0xffffffffu, b16 ? lo_v : hi_v, 16);
           }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) a4[k] = (b8 ? a8[4 + k] : a8[k]) + __shfl_xor_sync(0xffffffffu, b8 ? a8[k] : a8[4 + k], 8);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) a2[k] = (b4 ? a4[2 + k] : a4[k]) + __shfl_xor_sync(0xffffffffu, b4 ? a4[k] : a4[2 + k], 4);
+          float a1 = (b2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? a2[0] : a2[1], 2);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+          if ((lane & 1) == 0) pdst[p * 16 + (lane >> 1)] = a1;
         }
       }
       if constexpr (NHEAD == 1) {
-        if (live) head_out[(size_t)b * T + t] = hacc[0] + hp.b[0];
-      } else if constexpr (NHEAD > 1) {
-#pragma unroll
-        for (int oo = 0; oo < NHEAD; ++oo) hacc[oo] += hp.b[oo];
-        const float pr = sigmoid_acc(hacc[0]);
+        if (live) head_out[(size_t)b * T + t] = hacc + hp.b[0];
+      } else if constexpr (NHEAD == 2) {
+        const float pr = sigmoid_acc(hacc + hp.b[0]);
         if (live && head_out != nullptr) head_out[(size_t)b * T + t] = pr;
-        const int vl = valid_len != nullptr ? min(max(valid_len[b], 0), T) : T;
-        const bool counted = live && t < vl;
-        float red[NHEAD > 0 ? NHEAD : 1];
-        red[0] = counted ? pr : 0.0f;
+        float red = counted ? pr : 0.0f;
 #pragma unroll
-        for (int oo = 1; oo < NHEAD; ++oo) red[oo] = counted ? hacc[oo] : 0.0f;
-#pragma unroll
-        for (int oo = 0; oo < NHEAD; ++oo) {
-#pragma unroll
-          for (int sft = 16; sft > 0; sft >>= 1) red[oo] += __shfl_xor_sync(0xffffffffu, red[oo], sft);
-        }
-        if (lane == 0) {
-          float *dst = partials + (((size_t)b * ntile_t + tt) * 4 + q) * WM_MAX_HEAD;
-#pragma unroll
-          for (int oo = 0; oo < NHEAD; ++oo) dst[oo] = red[oo];
-        }
+        for (int sft = 16; sft > 0; sft >>= 1) red += __shfl_xor_sync(0xffffffffu, red, sft);
+        if (lane == 0) pdst[64] = red;
       }
       if (pfe) { long long e2 = clock64(); pe[0] += e1 - e0; pe[1] += e2 - e1; }
     }
@@ -376,10 +385,10 @@ template <int NHEAD>
 static int launch_rb(const void *x, const void *w_img, const float *b1, const float *b2, void *y, float *y32, int B,
                      int T, const float *host_head, float *head_out, float *partials, const int *valid_len,
                      cudaStream_t st) {
-  HeadParams<(NHEAD > 0 ? NHEAD : 1)> hp;
-  if (NHEAD > 0) {   // host_head: w[NHEAD][64] then b[NHEAD]
-    memcpy(hp.w, host_head, sizeof(float) * NHEAD * 64);
-    memcpy(hp.b, host_head + NHEAD * 64, sizeof(float) * NHEAD);
+  HeadParams<1> hp;
+  if (NHEAD > 0) {   // host_head: w[64] then b[1] (output 0 of the head)
+    memcpy(hp.w, host_head, sizeof(float) * 64);
+    memcpy(hp.b, host_head + 64, sizeof(float));
   } else {
     hp.w[0] = 0.0f;
     hp.b[0] = 0.0f;
@@ -413,33 +422,46 @@ int launch_resblock_head1_tc(const void *x, const void *w_img, const float *b1, 
   return launch_rb<1>(x, w_img, b1, b2, nullptr, nullptr, B, T, host_head, delta_raw, nullptr, nullptr, st);
 }
 
-// ResBlock + Conv1d(64,17,1) + sigmoid + per-tile partial sums; finish with launch_detect_finalize
-int launch_resblock_head17_tc(const void *x, const void *w_img, const float *b1, const float *b2,
+// Detector's last ResBlock + channel 0 of its 1x1 head + sigmoid + per-(tile, warp) partial sums of the
+// probability and of the 64 activations; finish with launch_detect_finalize.  host_head: HOST w0[64], b0.
+// partials: B * tiles_per_clip * 4 * WM_DET_PART floats.
+int launch_resblock_detect_tc(const void *x, const void *w_img, const float *b1, const float *b2,
                               const float *host_head, const int *valid_len, float *probs, float *partials, int B, int T,
                               cudaStream_t st) {
   if (B == 0 || T == 0) return 0;
-  return launch_rb<17>(x, w_img, b1, b2, nullptr, nullptr, B, T, host_head, probs, partials, valid_len, st);
+  return launch_rb<2>(x, w_img, b1, b2, nullptr, nullptr, B, T, host_head, probs, partials, valid_len, st);
 }
 
-// clip_prob[b] = sum of the probability partials / valid, msg_logits[b][j] likewise (fixed summation order)
-__global__ void detect_finalize_kernel(const float *__restrict__ partials, const int *__restrict__ valid_len,
-                                       float *__restrict__ clip_prob, float *__restrict__ msg_logits, int nparts, int T,
-                                       int nout) {
-  const int b = blockIdx.x, o = threadIdx.x;
-  if (o >= nout) return;
-  const float *src = partials + (size_t)b * nparts * WM_MAX_HEAD + o;
-  float s = 0.0f;
-  for (int i = 0; i < nparts; ++i) s += src[(size_t)i * WM_MAX_HEAD];
+// One block per clip: the partial sums are added in a fixed order, then
+//   clip_prob[b] = sum(prob) / valid;  msg_logits[b][j] = head_b[1+j] + head_w[1+j] . (sum(activations) / valid)
+// (the mean over time of the message logits, py/main16.py:1145-1146; 0 when no sample is valid)
+__global__ void __launch_bounds__(128)
+    detect_finalize_kernel(const float *__restrict__ partials, const int *__restrict__ valid_len,
+                           const float *__restrict__ head_w, const float *__restrict__ head_b,
+                           float *__restrict__ clip_prob, float *__restrict__ msg_logits, int nparts, int T, int nout) {
+  __shared__ float mean_s[WM_DET_PART];
+  const int b = blockIdx.x, c = threadIdx.x;
   const int vl = valid_len != nullptr ? min(max(valid_len[b], 0), T) : T;
-  const float r = vl > 0 ? s / (float)vl : 0.0f;
-  if (o == 0) { if (clip_prob) clip_prob[b] = r; }
-  else if (msg_logits) msg_logits[(size_t)b * (nout - 1) + o - 1] = r;
+  if (c <= 64) {
+    const float *src = partials + (size_t)b * nparts * WM_DET_PART + c;
+    float s = 0.0f;
+    for (int i = 0; i < nparts; ++i) s += src[(size_t)i * WM_DET_PART];
+    mean_s[c] = vl > 0 ? s / (float)vl : 0.0f;
+  }
+  __syncthreads();
+  if (c == 0 && clip_prob) clip_prob[b] = mean_s[64];
+  if (c >= 1 && c < nout && msg_logits) {
+    float a = vl > 0 ? head_b[c] : 0.0f;
+    for (int k = 0; k < 64; ++k) a = fmaf(head_w[c * 64 + k], mean_s[k], a);
+    msg_logits[(size_t)b * (nout - 1) + c - 1] = a;
+  }
 }
 
-int launch_detect_finalize(const float *partials, const int *valid_len, float *clip_prob, float *msg_logits, int B,
-                           int T, int nout, cudaStream_t st) {
+int launch_detect_finalize(const float *partials, const int *valid_len, const float *head_w, const float *head_b,
+                           float *clip_prob, float *msg_logits, int B, int T, int nout, cudaStream_t st) {
   if (B == 0) return 0;
-  detect_finalize_kernel<<<B, 32, 0, st>>>(partials, valid_len, clip_prob, msg_logits, 4 * ((T + TO - 1) / TO), T, nout);
+  detect_finalize_kernel<<<B, 128, 0, st>>>(partials, valid_len, head_w, head_b, clip_prob, msg_logits,
+                                            4 * ((T + TO - 1) / TO), T, nout);
   WM_CHECK_LAUNCH("detect_finalize");
   return 0;
 }
