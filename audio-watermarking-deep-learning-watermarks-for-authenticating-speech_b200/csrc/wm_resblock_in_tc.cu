@@ -16,11 +16,11 @@
 // The residual never leaves tensor memory either: the conv1 epilogue stores x0 + b_in + b2 into conv2's
 // accumulator, and conv2 accumulates on top of it.
 //
-// Warps 0..7   group 1: D1 (u | x0) -> relu(u + B9) as bf16 hi/lo planes in the intermediate tile U (conv2's
+// Warps 0..15  group 1: D1 (u | x0) -> relu(u + B9) as bf16 hi/lo planes in the intermediate tile U (conv2's
 //              A operand); x0 + biases -> D2 (tcgen05.st)
-// warps 8..15  group 2: D2 -> ReLU -> planar y; two sub-groups of 4 warps take alternate tiles
-// warp 16      producer: Toeplitz tiles of the waveform (bf16 hi/lo), conv2 weights (bulk copy, once)
-// warp 17      MMA issue, TMEM owner
+// warps 16..23 group 2: D2 -> ReLU -> planar y; two sub-groups of 4 warps take alternate tiles
+// warp 24      producer: Toeplitz tiles of the waveform (bf16 hi/lo), conv2 weights (bulk copy, once)
+// warp 25      MMA issue, TMEM owner
 // Tile geometry, operand formats and the 3-partial-product bf16 pair scheme are those of
 // wm_resblock_tc.cu.
 #include <cuda_bf16.h>
@@ -50,21 +50,27 @@ constexpr int OFF_BT = OFF_W + W_IMG_B;            // B_hi, B_lo
 constexpr int OFF_AT = OFF_BT + 2 * BT_B;          // 2 stages x (A_hi, A_lo)
 constexpr int OFF_U = OFF_AT + 2 * 2 * AT_B;
 constexpr int OFF_BIAS = OFF_U + NU * TILE_B;      // b9[64], (b_in + b2)[64]
-constexpr int OFF_BAR = OFF_BIAS + 512;
+constexpr int OFF_WIN = OFF_BIAS + 512;            // the producer's waveform window (160 floats)
+constexpr int OFF_BAR = OFF_WIN + 640;
 constexpr int RBI_SMEM = OFF_BAR + 160;
 static_assert(RBI_SMEM <= 232448, "shared memory budget");
 constexpr uint32_t kIdesc = make_idesc(128, 128);
 constexpr uint32_t kIdescLo = make_idesc(128, 64);     // A_lo x W_hi only
-constexpr int N_GRP = 256;
-constexpr int W_PROD = 2 * N_GRP / 32, W_MMA = W_PROD + 1, RBI_THREADS = 2 * N_GRP + 64;
+constexpr int N_G1 = 512;                  // group 1: 16 warps = 4 TMEM lane quadrants x 4 slices of 16 channels
+constexpr int N_G2 = 256;                  // group 2: 2 sub-groups of 4 warps
+constexpr int W_PROD = (N_G1 + N_G2) / 32, W_MMA = W_PROD + 1, RBI_THREADS = N_G1 + N_G2 + 64;
 
 }  // namespace
 
 // w9g: device w9[9][64], b9[64]; wing: device w_in[7][64], b_in[64]; fin: device WM_FIN_* block (edge rows)
+template <bool PROF>
 __global__ void __launch_bounds__(RBI_THREADS, 1)
     resblock_in_tc_kernel(const float *__restrict__ s, const float *__restrict__ w9g, const float *__restrict__ wing,
                           const float *__restrict__ fin, const uint4 *__restrict__ w_img2, const float *__restrict__ b2,
-                          uint4 *__restrict__ y, int B, int T) {
+                          uint4 *__restrict__ y, int B, int T, long long *__restrict__ prof) {
+  // PROF: per-phase cycle sums of block 0 (tools/resblock_in_profile.py); the production instantiation has none
+  auto clk = [&]() -> long long { return PROF ? clock64() : 0; };
+  const bool pf0 = PROF && prof != nullptr && blockIdx.x == 0;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
   const uint32_t w_smem = s_base + OFF_W, bt_smem = s_base + OFF_BT, at_smem = s_base + OFF_AT, u_smem = s_base + OFF_U;
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
     mbar_init(bar(WBAR), 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar(A_FULL + a), 1); mbar_init(bar(A_EMPTY + a), 1); mbar_init(bar(D1_FULL + a), 1);
-      mbar_init(bar(U_FULL + a), N_GRP / 32); mbar_init(bar(U_EMPTY + a), 1);
+      mbar_init(bar(U_FULL + a), N_G1 / 32); mbar_init(bar(U_EMPTY + a), 1);
       mbar_init(bar(D2_FULL + a), 1); mbar_init(bar(D2_EMPTY + a), 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -123,23 +129,38 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
       for (int j = 0; j < 3; ++j)
         bulk_g2s(w_smem + j * W_TAP_B, reinterpret_cast<const uint8_t *>(w_img2) + (size_t)j * W_TAP_B, W_TAP_B, bar(WBAR));
     }
-    for (long long i = 0; i < my_tiles; ++i) {
+    // The tile's 136 waveform samples s[t0-5 .. t0+130] are fetched ONCE (coalesced, one tile ahead, so the HBM
+    // latency hides behind the previous build), parked in a private shared-memory window, and the 128 Toeplitz
+    // rows are cut from that window (measured: 36 dependent global loads per lane made this warp pace the kernel).
+    float *swin = reinterpret_cast<float *>(smem + OFF_WIN);
+    float wreg[5];
+    auto fetch_window = [&](long long i) {
       const long long tile = blockIdx.x + i * gridDim.x;
-      const long long b = tile / ntile_t;
-      const int t0 = (int)(tile % ntile_t) * TO;
+      const float *sb = s + (size_t)(tile / ntile_t) * T;
+      const int ts0 = (int)(tile % ntile_t) * TO - 5;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int ts = ts0 + lane + 32 * k;
+        wreg[k] = (ts >= 0 && ts < T) ? __ldg(sb + ts) : 0.0f;
+      }
+    };
+    if (my_tiles > 0) fetch_window(0);
+    for (long long i = 0; i < my_tiles; ++i) {
       const int st = (int)(i & 1);
-      const float *sb = s + (size_t)b * T;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) swin[lane + 32 * k] = wreg[k];
+      __syncwarp();
+      if (i + 1 < my_tiles) fetch_window(i + 1);
+      const long long p0 = clk();
       if (i >= 2) mbar_wait_warp(bar(A_EMPTY + st), (uint32_t)(((i >> 1) - 1) & 1));
+      const long long p1 = clk();
       uint8_t *ah = smem + OFF_AT + st * 2 * AT_B, *al = ah + AT_B;
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
         const int r = rr * 32 + lane;
         float v[10];
 #pragma unroll
-        for (int m = 0; m < 9; ++m) {
-          const int ts = t0 - 5 + r + m;
-          v[m] = (ts >= 0 && ts < T) ? __ldg(sb + ts) : 0.0f;
-        }
+        for (int m = 0; m < 9; ++m) v[m] = swin[r + m];
         v[9] = 0.0f;
         uint32_t h[5], l[5];
 #pragma unroll
@@ -152,6 +173,7 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(A_FULL + st));
+      if (pf0 && lane == 0) { prof[0] += p1 - p0; prof[1] += clk() - p1; }
     }
   } else if (warp == W_MMA) {
     // ===== MMA issuer =====
@@ -188,26 +210,32 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
       }
       for (long long i = 0; i < my_tiles; ++i) {
         const int a = (int)(i & 1);
+        long long m0 = clk(), m1 = m0, m2 = m0;
         if (i + 1 < my_tiles) {   // Toeplitz GEMM of the next tile; D1[an] was drained by group 1 of tile i-1 (u_full(i-1))
           const long long n = i + 1;
           const int an = (int)(n & 1);
           mbar_wait(bar(A_FULL + an), (uint32_t)((n >> 1) & 1));
+          m1 = clk();
           tc_fence_after();
           gemm1(an, tmem + an * 128);
           tc_commit(bar(D1_FULL + an));
           tc_commit(bar(A_EMPTY + an));
+          m2 = clk();
         }
         mbar_wait(bar(U_FULL + a), (uint32_t)((i >> 1) & 1));    // U[a] written and D2[a] initialised with the residual
+        const long long m3 = clk();
         tc_fence_after();
         conv2(u_smem + a * TILE_B, tmem + 256 + a * 128);
         tc_commit(bar(D2_FULL + a));
         tc_commit(bar(U_EMPTY + a));
+        if (pf0) { prof[2] += m1 - m0; prof[3] += m2 - m1; prof[4] += m3 - m2; prof[5] += clk() - m3; prof[15] = my_tiles; }
       }
     }
     __syncwarp();
-  } else if (warp < N_GRP / 32) {
+  } else if (warp < N_G1 / 32) {
     // ===== group 1: D1 -> U tile (relu(conv1 + B9), bf16 hi/lo) and residual -> D2 =====
-    const int q = warp & 3, half = warp >> 2;          // TMEM lane quadrant, 32-channel half
+    // (this stage, not the tensor pipe, paces the kernel: 16 warps, 16 channels of one row per thread)
+    const int q = warp & 3, p = warp >> 2;             // TMEM lane quadrant, 16-channel slice
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     for (long long i = 0; i < my_tiles; ++i) {
@@ -219,16 +247,15 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
       const bool inside = tu >= 0 && tu < T;     // conv2 zero-pads the intermediate feature map
       const bool edge = inside && (tu == 0 || tu == T - 1);
       uint8_t *us = smem + OFF_U + a * TILE_B + row * 16;
+      const long long g0 = clk();
       mbar_wait_warp(bar(D1_FULL + a), (uint32_t)((i >> 1) & 1));
-      if (i >= 2) {
-        mbar_wait_warp(bar(U_EMPTY + a), (uint32_t)(((i >> 1) - 1) & 1));    // conv2(i-2) has finished reading U[a]
-        mbar_wait_warp(bar(D2_EMPTY + a), (uint32_t)(((i >> 1) - 1) & 1));   // epilogue(i-2) has drained D2[a]
-      }
+      const long long g1c = clk();
+      if (i >= 2) mbar_wait_warp(bar(U_EMPTY + a), (uint32_t)(((i >> 1) - 1) & 1));   // conv2(i-2) has finished reading U[a]
+      const long long g2c = clk();
+      long long g3c = g2c, g4c = g2c;
       tc_fence_after();
       const uint32_t t1 = tmem + a * 128 + lane_off, t2 = tmem + 256 + a * 128 + lane_off;
-#pragma unroll
-      for (int pp = 0; pp < 2; ++pp) {
-        const int p = half * 2 + pp;
+      {
         float u[16], xr[16];
         tmem_ld16(t1 + p * 16, u);
         tmem_ld16(t1 + 64 + p * 16, xr);
@@ -261,7 +288,14 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
           *reinterpret_cast<uint4 *>(us + ch * PLANE_B) = hi;
           *reinterpret_cast<uint4 *>(us + (8 + ch) * PLANE_B) = lo;
         }
-        // residual x0 + b_in + b2 -> conv2's accumulator (columns of the hi product; the lo-product columns start at 0)
+        // residual x0 + b_in + b2 -> conv2's accumulator (columns of the hi product; the lo-product columns start at 0);
+        // waited for as late as possible: the epilogue of tile i-2 must have drained D2[a]
+        g3c = clk();
+        if (i >= 2) {
+          mbar_wait_warp(bar(D2_EMPTY + a), (uint32_t)(((i >> 1) - 1) & 1));
+          tc_fence_after();
+        }
+        g4c = clk();
         tmem_st16(t2 + p * 16, xr);
 #pragma unroll
         for (int c = 0; c < 16; ++c) xr[c] = 0.0f;
@@ -271,10 +305,13 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
       tc_fence_before();
       fence_async_smem();
       mbar_arrive_warp(bar(U_FULL + a));
+      if (pf0 && threadIdx.x == 0) {
+        prof[6] += g1c - g0; prof[7] += g2c - g1c; prof[8] += g3c - g2c; prof[9] += g4c - g3c; prof[10] += clk() - g4c;
+      }
     }
   } else {
     // ===== group 2: D2 (residual + conv2, hi and lo products) -> ReLU -> y =====
-    const int w2 = warp - N_GRP / 32;
+    const int w2 = warp - N_G1 / 32;
     const int q = w2 & 3, g = w2 >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -292,7 +329,10 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
           for (int pl = 0; pl < 16; ++pl) y[((size_t)(b * 16 + pl)) * RP + zr] = make_uint4(0, 0, 0, 0);
         }
       }
+      const long long h0 = clk();
       mbar_wait_warp(bar(D2_FULL + g), (uint32_t)((i >> 1) & 1));
+      const long long h1 = clk();
+      long long h2 = h1;
       tc_fence_after();
       const uint32_t taddr = tmem + 256 + g * 128 + lane_off;
 #pragma unroll
@@ -304,6 +344,7 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
         if (p == 3) {
           tc_fence_before();
           mbar_arrive_warp(bar(D2_EMPTY + g));     // D2[g] may be re-initialised for tile i+2
+          h2 = clk();
         }
 #pragma unroll
         for (int c = 0; c < 16; ++c) o[c] = fmaxf(v1[c] + v2[c], 0.0f);
@@ -318,6 +359,7 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
           }
         }
       }
+      if (pf0 && w2 == 0 && lane == 0) { prof[11] += h1 - h0; prof[12] += h2 - h1; prof[13] += clk() - h2; }
     }
   }
   __syncwarp();
@@ -336,13 +378,19 @@ int launch_resblock_in_tc(const float *s, const float *w9b, const float *winb, c
   if (B == 0 || T == 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
-    WM_CHECK_CUDA(cudaFuncSetAttribute(resblock_in_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RBI_SMEM));
+    WM_CHECK_CUDA(cudaFuncSetAttribute(resblock_in_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RBI_SMEM));
+    WM_CHECK_CUDA(cudaFuncSetAttribute(resblock_in_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RBI_SMEM));
     attr_set = true;
   }
   long long ntiles = (long long)B * ((T + TO - 1) / TO);
   int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-  resblock_in_tc_kernel<<<grid, RBI_THREADS, RBI_SMEM, st>>>(s, w9b, winb, fin, reinterpret_cast<const uint4 *>(w_img2), b2,
-                                                            reinterpret_cast<uint4 *>(y), B, T);
+  if (get_profile_buffer() != nullptr)   // developer build with per-phase cycle counters
+    resblock_in_tc_kernel<true><<<grid, RBI_THREADS, RBI_SMEM, st>>>(
+        s, w9b, winb, fin, reinterpret_cast<const uint4 *>(w_img2), b2, reinterpret_cast<uint4 *>(y), B, T,
+        get_profile_buffer());
+  else
+    resblock_in_tc_kernel<false><<<grid, RBI_THREADS, RBI_SMEM, st>>>(
+        s, w9b, winb, fin, reinterpret_cast<const uint4 *>(w_img2), b2, reinterpret_cast<uint4 *>(y), B, T, nullptr);
   WM_CHECK_LAUNCH("resblock_in_tc");
   return 0;
 }
