@@ -14,10 +14,11 @@ from .functional import (AUDIO_LEN, HF_PENALTY_W, LAMBDA_DEC, LAMBDA_L1, LAMBDA_
 from .losses import MultiScaleMelLoss, TFLoudnessLoss, high_freq_penalty, step_losses, stft_magnitude
 from .models import Detector, Generator, ResBlock, load_state_dict_strip_prefix
 from .sharding import shard_range
+from .stream import detect_watermark_folder, embed_detect_stream, process_folder_with_tqdm
 
 __all__ = ["Generator", "Detector", "ResBlock", "generate_watermarked_audio", "detect_watermark", "detect_prob",
            "load_state_dict_strip_prefix", "fir_lowpass", "clamp_peak", "limit_rms", "postprocess_delta",
            "embed_detect", "bit_targets", "shard_range", "load_audio", "save_audio", "segment",
            "SAMPLE_RATE", "AUDIO_LEN", "MESSAGE_BITS", "MAX_RMS", "LAMBDA_L1", "LAMBDA_MSSPEC", "LAMBDA_LOUD",
            "LAMBDA_LOC", "LAMBDA_DEC", "HF_PENALTY_W", "MultiScaleMelLoss", "TFLoudnessLoss", "high_freq_penalty",
-           "step_losses", "stft_magnitude"]
+           "step_losses", "stft_magnitude", "embed_detect_stream", "process_folder_with_tqdm", "detect_watermark_folder"]

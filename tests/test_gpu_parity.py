@@ -525,3 +525,79 @@ def test_short_clips_through_the_fused_input_stage(T, gen_A, det):
     assert maxerr(gen_A(s.to(DEV), msg.to(DEV)), ref) < DELTA_TOL * 0.1
     lg = O.detector_forward(H.det_sd(W), s)
     assert maxerr(torch.sigmoid(det(s.to(DEV))[:, :, 0]), torch.sigmoid(lg[:, :, 0])) < PROB_TOL
+
+
+# ---------------------------------------------------------------- callers at scale: long-form stream, folders
+def test_long_form_stream_sharded_matches_batched(gen_B, det):
+    """BASELINE config 5 in miniature: a 2 min 17.3 s recording cut into 1 s segments, embedded and detected
+    through the host-fed pipeline by 1 rank and by 3 ranks (contiguous segment ranges, no collective); both
+    against the device-resident batched path, with the reference's tail rule (py/main16.py:1011-1026,1152-1168)."""
+    g = torch.Generator().manual_seed(31)
+    N = 137 * 16000 + 4800
+    wav = (0.1 * torch.randn(N, generator=g)).clamp(-0.99, 0.99)
+    ids = torch.from_numpy(np.concatenate([IO["messages"], IO["rng_messages"]]).astype(np.int64))
+    msg = ids[torch.randint(0, len(ids), (138,), generator=g)]
+    full = wmb200.embed_detect_stream(gen_B, det, wav, msg, chunk=64)
+    assert full["segment_range"] == (0, 138) and full["watermarked"].shape == (N,) and full["probs"].shape == (N,)
+    seg, valid = wmb200.segment(wav.unsqueeze(0))
+    ref = wmb200.embed_detect(gen_B, det, seg.to(DEV), msg.to(DEV), want_votes=False)
+    assert maxerr(full["watermarked"], ref["s_w"].reshape(-1)[:N]) < 1e-6
+    assert maxerr(full["probs"][:137 * 16000], ref["probs"].reshape(-1)[:137 * 16000]) < 1e-4
+    assert maxerr(full["msg_logits"][:137], ref["msg_logits"][:137]) < 1e-4
+    # the tail: detection on the cropped, re-padded watermarked segment, means over its 4800 valid samples
+    tail = ref["s_w"][137:138].clone()
+    tail[:, :, 4800:] = 0
+    rt = det.detect(tail, torch.tensor([4800], dtype=torch.int32, device=DEV), want_votes=False)
+    assert maxerr(full["probs"][137 * 16000:], rt["probs"][0, :4800]) < 1e-4
+    assert maxerr(full["msg_logits"][137], rt["msg_logits"][0]) < 1e-4
+    parts = [wmb200.embed_detect_stream(gen_B, det, wav, msg, chunk=64, rank=r, world=3, reduce=False) for r in range(3)]
+    assert [p["segment_range"] for p in parts] == [(0, 46), (46, 92), (92, 138)]
+    assert maxerr(torch.cat([p["watermarked"] for p in parts]), full["watermarked"]) < 1e-6
+    assert maxerr(torch.cat([p["probs"] for p in parts]), full["probs"]) < 1e-4
+    tot = sum(float(p["probs"].double().sum()) for p in parts) / N
+    assert abs(tot - full["mean_probability"]) < 1e-6
+
+
+def test_folder_driver_matches_per_file_api(tmp_path, gen_B, det):
+    """process_folder_with_tqdm (py/main16.py:1409-1446): same output tree, same RNG consumption and the same
+    waveforms as one generate_watermarked_audio call per file, with the segments of several files in one batch."""
+    import wave
+    g = torch.Generator().manual_seed(8)
+    root = tmp_path / "clips"
+    (root / "sub").mkdir(parents=True)
+    lens = {"a.wav": 16000, "b.wav": 40000, "sub/c.wav": 7000, "sub/d.wav": 33000}
+    for name, n in lens.items():
+        pcm = ((0.2 * torch.randn(n, generator=g)).clamp(-0.99, 0.99) * 32767).round().to(torch.int16).numpy()
+        with wave.open(str(root / name), "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+            w.writeframes(pcm.tobytes())
+    ids = [int(v) for v in np.concatenate([IO["messages"], IO["rng_messages"]])]
+
+    class FixedIds:                      # the fixture embedding only has 13 rows: patch the draw, keep its order
+        def __init__(self): self.i = 0
+        def __call__(self, lo, hi, size, device=None):
+            self.i += 1
+            return torch.tensor([ids[self.i % len(ids)]], dtype=torch.int64, device=device)
+    real = torch.randint
+    try:
+        torch.randint = FixedIds()
+        res = wmb200.process_folder_with_tqdm(str(root), gen_B, 16, DEV, max_clips=4, quiet=True)
+        torch.randint = FixedIds()
+        pairs = wmb200.stream.list_audio_files(str(root), res["output_root"])
+        singles = [wmb200.generate_watermarked_audio(i, gen_B, None, 16, DEV) for i, _ in pairs]
+    finally:
+        torch.randint = real
+    assert res["files"] == 4 and os.path.basename(res["output_root"]) == "watermarked_clips"
+    for (inp, outp), one in zip(pairs, singles):
+        assert os.path.exists(outp) and os.path.basename(outp) == "watermarked_" + os.path.basename(inp)
+        got, sr = wmb200.load_audio(outp)
+        assert sr == 16000 and got.shape == one["watermarked_waveform"].shape
+        assert maxerr(got, one["watermarked_waveform"]) < 1e-6
+    assert abs(res["avg_watermark_rms"] - np.mean([o["metrics"]["watermark_rms"] for o in singles])) < 1e-6
+    det_res = wmb200.detect_watermark_folder(res["output_root"], det, 0.5, DEV, max_clips=3)
+    assert len(det_res) == 4
+    for r in det_res:
+        one = wmb200.detect_watermark(r["file"], det, 0.5, False, DEV)
+        assert abs(r["mean_probability"] - one["mean_probability"]) < 1e-4
+        assert r["predicted_message"] == one["predicted_message"] or \
+            np.abs(np.array(r["message_confidence"]) - np.array(one["message_confidence"])).max() < 1e-3

@@ -205,3 +205,20 @@ def test_losses_refuse_cpu_tensors():
         wmb200.high_freq_penalty(torch.zeros(1, 1, 16000))
     with pytest.raises(RuntimeError):
         wmb200.TFLoudnessLoss()(torch.zeros(1, 1, 16000), torch.zeros(1, 1, 16000))
+
+
+def test_folder_driver_planning(tmp_path):
+    from wmb200 import stream
+    assert stream.plan_batches([3, 2, 7, 1, 1], 5) == [(0, 2), (2, 3), (3, 5)]
+    assert stream.plan_batches([9], 4) == [(0, 1)] and stream.plan_batches([], 4) == []
+    assert stream.plan_batches([0, 0, 2], 4) == [(0, 3)]
+    root = tmp_path / "speech"
+    (root / "a").mkdir(parents=True)
+    for name in ("x.wav", "a/y.FLAC", "a/notes.txt"):
+        (root / name).write_bytes(b"")
+    pairs = stream.list_audio_files(str(root), str(tmp_path / "watermarked_speech"))
+    outs = sorted(os.path.relpath(o, str(tmp_path)) for _, o in pairs)
+    assert outs == [os.path.join("watermarked_speech", ".", "watermarked_x.wav"),
+                    os.path.join("watermarked_speech", "a", "watermarked_y.FLAC")] or \
+        sorted(os.path.normpath(o) for o in outs) == [os.path.join("watermarked_speech", "a", "watermarked_y.FLAC"),
+                                                      os.path.join("watermarked_speech", "watermarked_x.wav")]
