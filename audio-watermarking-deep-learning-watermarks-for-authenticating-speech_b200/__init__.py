@@ -6,7 +6,7 @@ functions fir_lowpass / clamp_peak / limit_rms and the module constants.  All ar
 runs in libwmb200.so (hand-written CUDA, C ABI in include/wmb200.h); there is no CPU or
 PyTorch fallback — calls fail loudly when the library or the GPU is missing.
 """
-from . import _lib, ops, packing
+from . import _lib, main14b_2, ops, packing
 from .api import detect_prob, detect_watermark, generate_watermarked_audio, load_audio, save_audio, segment
 from .functional import (AUDIO_LEN, HF_PENALTY_W, LAMBDA_DEC, LAMBDA_L1, LAMBDA_LOC, LAMBDA_LOUD,
                          LAMBDA_MSSPEC, MAX_RMS, MESSAGE_BITS, SAMPLE_RATE, bit_targets, clamp_peak,

@@ -528,6 +528,40 @@ int wm_abs_mean_fwd(const float *x, float *out, void *workspace, size_t workspac
   return launch_abs_mean(x, (long long)B * T, out, (float *)workspace, as_stream(stream));
 }
 
+/* ---- generic operators of the main14b_2 stack (py/main14b_2.py:83-224) ---- */
+int wm_conv1d_out_len(int Tin, int K, int stride, int pad) { return (Tin + 2 * pad - K) / stride + 1; }
+int wm_convtranspose1d_out_len(int Tin, int K, int stride, int pad) { return (Tin - 1) * stride - 2 * pad + K; }
+
+int wm_conv1d_fwd(const float *x, const float *w, const float *bias, const float *chan_add, const float *residual,
+                  float *y, int B, int Cin, int Tin, int Cout, int K, int stride, int pad, int act, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && Cin > 0 && Cout > 0 && Tin >= 0, "conv1d: bad size");
+  WM_CHECK_ARG(act == 0 || act == 1, "conv1d: act must be 0 (none) or 1 (ELU)");
+  if (B == 0 || Tin == 0) return 0;
+  WM_CHECK_ARG(x && w && bias && y, "conv1d: null pointer");
+  WM_CHECK_ARG(x != y && residual != y, "conv1d: in-place operation is not supported");
+  return launch_conv1d_generic(x, w, bias, chan_add, residual, y, B, Cin, Tin, Cout, K, stride, pad, act,
+                               as_stream(stream));
+}
+
+int wm_convtranspose1d_fwd(const float *x, const float *w, const float *bias, float *y, int B, int Cin, int Tin,
+                           int Cout, int K, int stride, int pad, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && Cin > 0 && Cout > 0 && Tin >= 0, "convtranspose1d: bad size");
+  if (B == 0 || Tin == 0) return 0;
+  WM_CHECK_ARG(x && w && bias && y && x != y, "convtranspose1d: null pointer or in-place");
+  return launch_convtranspose1d_generic(x, w, bias, y, B, Cin, Tin, Cout, K, stride, pad, as_stream(stream));
+}
+
+int wm_lstm_small_fwd(const float *x, const float *w_ih, const float *w_hh, const float *bias, float *y, int B, int H,
+                      int T, int layers, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "lstm_small: negative size");
+  if (B == 0 || T == 0) return 0;
+  WM_CHECK_ARG(x && w_ih && w_hh && bias && y && x != y, "lstm_small: null pointer or in-place");
+  return launch_lstm_small(x, w_ih, w_hh, bias, y, B, H, T, layers, as_stream(stream));
+}
+
 size_t wm_embed_detect_host_workspace_bytes(int chunk, int T, int nout) {
   if (chunk <= 0 || T <= 0 || nout < 1) return 0;
   size_t wave = align256((size_t)chunk * T * sizeof(float));

@@ -115,6 +115,14 @@ int launch_mel_log_l1(const float *clean, const float *wmk, const float *fb, con
 int launch_bce_heads(const float *logits, const int64_t *message, float *loc_out, float *bce_out, float *partials,
                      int B_wm, int B2, int T, int nout, cudaStream_t st);
 int launch_abs_mean(const float *x, long long n, float *out, float *partials, cudaStream_t st);
+// generic fp32 operators of the main14b_2 stack (wm_generic.cu); channels-first x[b][c][t]
+int launch_conv1d_generic(const float *x, const float *w, const float *bias, const float *chan_add, const float *res,
+                          float *y, int B, int Cin, int Tin, int Cout, int K, int stride, int pad, int act,
+                          cudaStream_t st);
+int launch_convtranspose1d_generic(const float *x, const float *w, const float *bias, float *y, int B, int Cin, int Tin,
+                                   int Cout, int K, int stride, int pad, cudaStream_t st);
+int launch_lstm_small(const float *x, const float *w_ih, const float *w_hh, const float *bias, float *y, int B, int H,
+                      int T, int L, cudaStream_t st);
 void set_lstm_profile_buffer(long long *p);
 long long *get_profile_buffer();
 int launch_pack_lstm_tc(const float *w_ih, const float *w_hh, const float *bias, void *wpk, float *bias_p,

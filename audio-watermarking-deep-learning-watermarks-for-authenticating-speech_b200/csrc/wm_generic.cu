@@ -1,0 +1,236 @@
+// Generic fp32 operators for the configurable residual stack of main14b_2 (py/main14b_2.py:86-224, BASELINE
+// config 3): strided Conv1d and strided ConvTranspose1d of any channel counts with fused bias / per-clip
+// channel add / residual add / ELU epilogues, and the small 2-layer LSTM(32) bottleneck.  Tensors are
+// channels-first fp32 x[b][c][t] exactly as the reference holds them; weights are the reference's own
+// parameter tensors (Conv1d (co,ci,k), ConvTranspose1d (ci,co,k)), no packing.
+// First correct CUDA path for this model family: CUDA-core FMA with shared-memory tiling (the tcgen05
+// kernels of the main16 path are specialised to 64 channels, stride 1).
+#include "wm_common.h"
+
+namespace wm {
+
+namespace {
+
+constexpr int GT = 64;        // output time steps per block
+constexpr int GCO = 64;       // output channels per block
+constexpr int GCI = 8;        // input channels per shared-memory stage
+constexpr int GTHREADS = 256; // 16 (time) x 16 (channel) threads, 4 x 4 outputs each
+constexpr int GMAXK = 16;     // taps
+constexpr int GMAXS = 8;      // stride
+
+__device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : expm1f(v); }
+
+// y[b][co][t] = act( bias[co] + chan_add[b][co] + sum_ci sum_k w[co][ci][k] x[b][ci][t*stride + k - pad] + res[b][co][t] )
+__global__ void __launch_bounds__(GTHREADS)
+    conv1d_generic_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+                          const float *__restrict__ chan_add, const float *__restrict__ res, float *__restrict__ y,
+                          int Cin, int Tin, int Cout, int Tout, int K, int stride, int pad, int act) {
+  extern __shared__ float sm[];
+  const int span = (GT - 1) * stride + K;            // input samples one stage needs per channel
+  float *xs = sm;                                    // [GCI][span]
+  float *ws = sm + GCI * span;                       // [GCI][K][GCO]  (co contiguous)
+  const int b = blockIdx.z, co0 = blockIdx.y * GCO, t0 = blockIdx.x * GT;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // time group, channel group
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  const float *xb = x + (size_t)b * Cin * Tin;
+  const int in0 = t0 * stride - pad;
+  for (int c0 = 0; c0 < Cin; c0 += GCI) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < GCI * span; e += GTHREADS) {
+      const int ci = e / span, i = e - ci * span, ti = in0 + i;
+      xs[e] = (c0 + ci < Cin && ti >= 0 && ti < Tin) ? xb[(size_t)(c0 + ci) * Tin + ti] : 0.0f;
+    }
+    for (int e = threadIdx.x; e < GCI * K * GCO; e += GTHREADS) {
+      const int co = e % GCO, r = e / GCO, k = r % K, ci = r / K;
+      ws[e] = (c0 + ci < Cin && co0 + co < Cout) ? w[((size_t)(co0 + co) * Cin + c0 + ci) * K + k] : 0.0f;
+    }
+    __syncthreads();
+    for (int ci = 0; ci < GCI; ++ci) {
+      for (int k = 0; k < K; ++k) {
+        const float4 wv = *reinterpret_cast<const float4 *>(&ws[(ci * K + k) * GCO + ty * 4]);
+        const float *xp = &xs[ci * span + k];
+        float xv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xv[j] = xp[(tx + 16 * j) * stride];
+        const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wq[i], xv[j], acc[i][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= Cout) continue;
+    const float add = bias[co] + (chan_add ? chan_add[(size_t)b * Cout + co] : 0.0f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = t0 + tx + 16 * j;
+      if (t >= Tout) continue;
+      const size_t o = ((size_t)b * Cout + co) * Tout + t;
+      float v = acc[i][j] + add;
+      if (res) v += res[o];
+      y[o] = act ? elu1(v) : v;
+    }
+  }
+}
+
+// nn.ConvTranspose1d(Cin, Cout, K, stride, padding):  y[b][co][t] = bias[co] + sum_ci sum_k [ (t + pad - k) % stride == 0 ]
+//   x[b][ci][(t + pad - k) / stride] w[ci][co][k]
+__global__ void __launch_bounds__(GTHREADS)
+    convtranspose1d_generic_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+                                   float *__restrict__ y, int Cin, int Tin, int Cout, int Tout, int K, int stride, int pad) {
+  extern __shared__ float sm[];
+  // inputs that can reach outputs t0 .. t0+GT-1:  i in [ceil((t0 + pad - K + 1) / stride), floor((t0 + GT - 1 + pad) / stride)]
+  const int b = blockIdx.z, co0 = blockIdx.y * GCO, t0 = blockIdx.x * GT;
+  const int nspan = (GT + K - 2) / stride + 2;
+  float *xs = sm;                                    // [GCI][nspan]
+  float *ws = sm + GCI * nspan;                      // [GCI][K][GCO]
+  int ilo = t0 + pad - K + 1;
+  ilo = ilo >= 0 ? (ilo + stride - 1) / stride : -((-ilo) / stride);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  const float *xb = x + (size_t)b * Cin * Tin;
+  for (int c0 = 0; c0 < Cin; c0 += GCI) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < GCI * nspan; e += GTHREADS) {
+      const int ci = e / nspan, i = e - ci * nspan, ti = ilo + i;
+      xs[e] = (c0 + ci < Cin && ti >= 0 && ti < Tin) ? xb[(size_t)(c0 + ci) * Tin + ti] : 0.0f;
+    }
+    for (int e = threadIdx.x; e < GCI * K * GCO; e += GTHREADS) {
+      const int co = e % GCO, r = e / GCO, k = r % K, ci = r / K;
+      ws[e] = (c0 + ci < Cin && co0 + co < Cout) ? w[((size_t)(c0 + ci) * Cout + co0 + co) * K + k] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = t0 + tx + 16 * j;
+      // taps k = (t + pad) % stride, + stride, ... < K
+      for (int k = (t + pad) % stride; k < K; k += stride) {
+        const int i = (t + pad - k) / stride - ilo;   // exact division; may fall outside [0, Tin): staged as zero
+        if (i < 0 || i >= nspan) continue;
+        for (int ci = 0; ci < GCI; ++ci) {
+          const float xv = xs[ci * nspan + i];
+          const float4 wv = *reinterpret_cast<const float4 *>(&ws[(ci * K + k) * GCO + ty * 4]);
+          acc[0][j] = fmaf(wv.x, xv, acc[0][j]);
+          acc[1][j] = fmaf(wv.y, xv, acc[1][j]);
+          acc[2][j] = fmaf(wv.z, xv, acc[2][j]);
+          acc[3][j] = fmaf(wv.w, xv, acc[3][j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = t0 + tx + 16 * j;
+      if (t < Tout) y[((size_t)b * Cout + co) * Tout + t] = acc[i][j] + bias[co];
+    }
+  }
+}
+
+// nn.LSTM(H, H, num_layers = L, batch_first) on channels-first x[b][H][T] -> y[b][H][T] (top layer's hidden states),
+// zero initial state, gate rows i,f,g,o.  One block per clip, 4H threads (thread = gate row); H <= 64, L <= 4.
+// w_ih / w_hh: [L][4H][H], bias: [L][4H] = b_ih + b_hh.
+__global__ void lstm_small_kernel(const float *__restrict__ x, const float *__restrict__ w_ih, const float *__restrict__ w_hh,
+                                  const float *__restrict__ bias, float *__restrict__ y, int H, int T, int L) {
+  extern __shared__ float sm[];
+  float *h = sm;                 // [L][H]
+  float *c = h + L * H;          // [L][H]
+  float *g = c + L * H;          // [4H] gate pre-activations of the current layer
+  float *xin = g + 4 * H;        // [H] input of the current layer
+  const int b = blockIdx.x, r = threadIdx.x;
+  for (int i = r; i < 2 * L * H; i += blockDim.x) h[i] = 0.0f;
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    for (int l = 0; l < L; ++l) {
+      if (r < H) xin[r] = l == 0 ? x[((size_t)b * H + r) * T + t] : h[(l - 1) * H + r];
+      __syncthreads();
+      const float *wi = w_ih + ((size_t)l * 4 * H + r) * H, *wh = w_hh + ((size_t)l * 4 * H + r) * H;
+      float a = bias[l * 4 * H + r];
+      for (int k = 0; k < H; ++k) a = fmaf(wi[k], xin[k], fmaf(wh[k], h[l * H + k], a));
+      g[r] = a;
+      __syncthreads();
+      if (r < H) {
+        const float ig = 1.0f / (1.0f + expf(-g[r])), fg = 1.0f / (1.0f + expf(-g[H + r]));
+        const float gg = tanhf(g[2 * H + r]), og = 1.0f / (1.0f + expf(-g[3 * H + r]));
+        const float cn = fg * c[l * H + r] + ig * gg;
+        c[l * H + r] = cn;
+        h[l * H + r] = og * tanhf(cn);
+      }
+      __syncthreads();
+    }
+    if (r < H) y[((size_t)b * H + r) * T + t] = h[(L - 1) * H + r];
+  }
+}
+
+}  // namespace
+
+int launch_conv1d_generic(const float *x, const float *w, const float *bias, const float *chan_add, const float *res,
+                          float *y, int B, int Cin, int Tin, int Cout, int K, int stride, int pad, int act,
+                          cudaStream_t st) {
+  const int Tout = (Tin + 2 * pad - K) / stride + 1;
+  if (B == 0 || Tout <= 0) return 0;
+  if (K > GMAXK || stride > GMAXS || K < 1 || stride < 1) {
+    set_error("conv1d: kernel size %d / stride %d outside the supported range (<= %d / <= %d)", K, stride, GMAXK, GMAXS);
+    return -1;
+  }
+  const size_t smem = (size_t)(GCI * ((GT - 1) * stride + K) + GCI * K * GCO) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    WM_CHECK_CUDA(cudaFuncSetAttribute(conv1d_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((Tout + GT - 1) / GT, (Cout + GCO - 1) / GCO, B);
+  conv1d_generic_kernel<<<grid, GTHREADS, smem, st>>>(x, w, bias, chan_add, res, y, Cin, Tin, Cout, Tout, K, stride, pad, act);
+  WM_CHECK_LAUNCH("conv1d_generic");
+  return 0;
+}
+
+int launch_convtranspose1d_generic(const float *x, const float *w, const float *bias, float *y, int B, int Cin, int Tin,
+                                   int Cout, int K, int stride, int pad, cudaStream_t st) {
+  const int Tout = (Tin - 1) * stride - 2 * pad + K;
+  if (B == 0 || Tout <= 0) return 0;
+  if (K > 2 * GMAXK || stride > GMAXS || K < 1 || stride < 1) {
+    set_error("convtranspose1d: kernel size %d / stride %d outside the supported range", K, stride);
+    return -1;
+  }
+  const size_t smem = (size_t)(GCI * ((GT + K - 2) / stride + 2) + GCI * K * GCO) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    WM_CHECK_CUDA(cudaFuncSetAttribute(convtranspose1d_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((Tout + GT - 1) / GT, (Cout + GCO - 1) / GCO, B);
+  convtranspose1d_generic_kernel<<<grid, GTHREADS, smem, st>>>(x, w, bias, y, Cin, Tin, Cout, Tout, K, stride, pad);
+  WM_CHECK_LAUNCH("convtranspose1d_generic");
+  return 0;
+}
+
+int launch_lstm_small(const float *x, const float *w_ih, const float *w_hh, const float *bias, float *y, int B, int H,
+                      int T, int L, cudaStream_t st) {
+  if (B == 0 || T == 0) return 0;
+  if (H < 1 || H > 64 || L < 1 || L > 4) {
+    set_error("lstm_small: hidden size %d / layers %d outside the supported range (<= 64 / <= 4)", H, L);
+    return -1;
+  }
+  const size_t smem = (size_t)(2 * L * H + 4 * H + H) * sizeof(float);
+  lstm_small_kernel<<<B, 4 * H, smem, st>>>(x, w_ih, w_hh, bias, y, H, T, L);
+  WM_CHECK_LAUNCH("lstm_small");
+  return 0;
+}
+
+}  // namespace wm

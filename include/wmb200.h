@@ -32,7 +32,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 9
+#define WM_ABI_VERSION 10
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -272,6 +272,23 @@ int wm_bce_heads_fwd(const float *logits, const int64_t *message, float *loc_out
                      size_t workspace_bytes, int B_wm, int B_total, int T, int nout, void *stream);
 /* F.l1_loss(delta, 0) — py/main16.py:266. */
 int wm_abs_mean_fwd(const float *x, float *out, void *workspace, size_t workspace_bytes, int B, int T, void *stream);
+
+/* ---- generic fp32 operators of the main14b_2 residual stack (py/main14b_2.py:83-224, BASELINE config 3) ----
+ * channels-first tensors x[b][c][t] and the reference's own parameter layouts, no packing.           */
+int wm_conv1d_out_len(int Tin, int K, int stride, int pad);
+int wm_convtranspose1d_out_len(int Tin, int K, int stride, int pad);
+/* nn.Conv1d(Cin, Cout, K, stride, padding) (py/main14b_2.py:83-84) with fused epilogue:
+ *   y = act( conv(x) + bias + chan_add[b][co] + residual ),  act 0 = identity, 1 = ELU (py/main14b_2.py:92,99-104);
+ * w (Cout,Cin,K); chan_add and residual nullable.  K <= 16, stride <= 8. */
+int wm_conv1d_fwd(const float *x, const float *w, const float *bias, const float *chan_add, const float *residual,
+                  float *y, int B, int Cin, int Tin, int Cout, int K, int stride, int pad, int act, void *stream);
+/* nn.ConvTranspose1d(Cin, Cout, K, stride, padding, output_padding=0) (py/main14b_2.py:146,201); w (Cin,Cout,K). */
+int wm_convtranspose1d_fwd(const float *x, const float *w, const float *bias, float *y, int B, int Cin, int Tin,
+                           int Cout, int K, int stride, int pad, void *stream);
+/* nn.LSTM(H, H, num_layers, batch_first) on channels-first x[b][H][T] (py/main14b_2.py:137,167); w_ih, w_hh
+ * [layers][4H][H], bias [layers][4H] = b_ih + b_hh; zero initial state; H <= 64, layers <= 4. */
+int wm_lstm_small_fwd(const float *x, const float *w_ih, const float *w_hh, const float *bias, float *y, int B, int H,
+                      int T, int layers, void *stream);
 
 /* Same unit with HOST (pinned) buffers: H2D of s and message, the device pipeline in
  * micro-batches of `chunk` clips, D2H of s_w, probs, clip_prob and msg_logits, all on
