@@ -21,6 +21,7 @@
 // conv2 of tile i, so the tensor pipe works on the next tile while the epilogue warps turn tile
 // i's conv1 accumulator into conv2's operand.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "wm_common.h"
@@ -46,7 +47,7 @@ constexpr int OFF_X = OFF_W + 2 * W_IMG_B;
 constexpr int OFF_U = OFF_X + NST * TILE_B;
 constexpr int OFF_BIAS = OFF_U + NU * TILE_B;
 constexpr int OFF_BAR = OFF_BIAS + 512;
-constexpr int RB_SMEM = OFF_BAR + 160;
+constexpr int RB_SMEM = OFF_BAR + 256;
 constexpr uint32_t kIdesc = make_idesc(128, 128);
 // The lo x lo partial product is ~2^-18 of the result, far below the parity budget: the A_lo MMA multiplies
 // only the first 64 columns of B (= W_hi), i.e. 3 products in 1.5 MMAs' worth of tensor time.
@@ -55,6 +56,11 @@ constexpr uint32_t kIdescLo = make_idesc(128, 64);
 #else
 constexpr uint32_t kIdescLo = kIdesc;
 #endif
+// CTA-pair mode: per (tap, k chunk) a CTA holds its half of [W_hi | W_lo] (64 rows, operand of the A_hi MMA) and its
+// half of W_hi (32 rows, operand of the A_lo MMA)
+constexpr int W2_CHUNK_B = (64 + 32) * 16;             // 1 536
+constexpr int W2_IMG_B = 3 * 8 * W2_CHUNK_B;           // 36 864 per convolution
+constexpr uint32_t kIdesc2 = make_idesc(256, 128), kIdescLo2 = make_idesc(256, 64);
 constexpr int N_GRP = 256;                  // threads per epilogue group (8 warps: 4 lane quadrants x 2 channel halves)
 constexpr int W_PROD = 2 * N_GRP / 32, W_MMA = W_PROD + 1, RB_THREADS = 2 * N_GRP + 64;
 static_assert(RB_SMEM <= 232448, "shared memory budget");
@@ -77,7 +83,12 @@ struct HeadParams {
 // logits are only ever used as means over time (py/main16.py:1142-1146), and a mean of a linear map is the
 // linear map of the mean, so the 16 x 64 message head is applied once per clip by detect_finalize_kernel
 // instead of 1024 FMAs per sample here.
-template <int NHEAD>
+// CTA2: the kernel runs as clusters of two CTAs (one TPC); each CTA owns its own tile (128 rows of M) and all its
+// epilogue work, but the MMAs are issued by the even CTA for both (tcgen05 cta_group::2, M = 256) with every
+// weight operand split between the two shared memories: 21 % fewer operand bytes per CTA, which is what this
+// kernel is bound by.  The odd CTA's MMA warp relays its "tile landed" barriers to the even CTA; its epilogue
+// warps arrive on the even CTA's barriers directly; MMA completions are multicast to both.
+template <int NHEAD, bool CTA2>
 // 18 warps = 5 on one SM sub-partition (16 K registers each): 96 registers per thread is the ceiling
 __global__ void __launch_bounds__(RB_THREADS, 1)
     resblock_tc_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ w_img, const float *__restrict__ b1,
@@ -90,7 +101,9 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
   const uint32_t w_smem = s_base + OFF_W, x_smem = s_base + OFF_X, u_smem = s_base + OFF_U;
   const uint32_t bars = s_base + OFF_BAR;
   // barriers (8 B each), tmem slot behind them
-  enum { FULL = 0, EMPTY = 2, WBAR = 4, D1_FULL = 5, D2_FULL = 7, D2_EMPTY = 9, U_FULL = 11, U_EMPTY = 13, NBAR = 15 };
+  enum { FULL = 0, EMPTY = 2, WBAR = 4, D1_FULL = 5, D2_FULL = 7, D2_EMPTY = 9, U_FULL = 11, U_EMPTY = 13,
+         // CTA-pair mode, even CTA only: the odd CTA's FULL / WBAR / U_FULL / D2_EMPTY events, forwarded by its relay thread
+         PFULL = 15, PWBAR = 17, PU_FULL = 18, PD2_EMPTY = 20, NBAR = 22 };
   auto bar = [&](int i) { return bars + 8 * i; };
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 * NBAR);
   float *bias_s = reinterpret_cast<float *>(smem + OFF_BIAS);   // [0..63] b1, [64..127] b2
@@ -98,8 +111,15 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntile_t = (T + TO - 1) / TO;
   const long long ntiles = (long long)B * ntile_t;
-  const long long my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const size_t RP = (size_t)T + 2 * PAD;
+  // tile of iteration i (clamped; a pair's second tile may not exist) and the number of iterations
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0;
+  const long long stride_t = CTA2 ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+  const long long first_t = CTA2 ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long nunits = CTA2 ? (ntiles + 1) / 2 : ntiles;
+  const long long my_tiles = nunits > first_t ? (nunits - first_t + stride_t - 1) / stride_t : 0;
+  auto tile_raw = [&](long long i) { return CTA2 ? 2 * (first_t + i * stride_t) + rank : first_t + i * stride_t; };
+  auto tile_of = [&](long long i) { const long long t_ = tile_raw(i); return t_ < ntiles ? t_ : ntiles - 1; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(bar(FULL + s), 1); mbar_init(bar(EMPTY + s), 1); }
@@ -107,28 +127,46 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar(D1_FULL + a), 1); mbar_init(bar(D2_FULL + a), 1); mbar_init(bar(D2_EMPTY + a), 4);
       mbar_init(bar(U_FULL + a), N_GRP / 32); mbar_init(bar(U_EMPTY + a), 1);
+      mbar_init(bar(PFULL + a), 1); mbar_init(bar(PU_FULL + a), 1); mbar_init(bar(PD2_EMPTY + a), 1);
     }
+    mbar_init(bar(PWBAR), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 128) bias_s[threadIdx.x] = threadIdx.x < 64 ? b1[threadIdx.x] : b2[threadIdx.x - 64];
   if (warp == W_MMA) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTA2) {   // the same warp of both CTAs, same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();   // both CTAs' barriers exist before anyone arrives on or multicasts to them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
   if (warp == W_PROD) {
     // ===== producer: weights once, then one x tile (16 planes x 130 rows) per stage =====
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar(WBAR), 2 * W_IMG_B);
-      for (int j = 0; j < 6; ++j)
-        bulk_g2s(w_smem + j * W_TAP_B, reinterpret_cast<const uint8_t *>(w_img) + (size_t)j * W_TAP_B, W_TAP_B, bar(WBAR));
+      if constexpr (CTA2) {
+        mbar_arrive_expect_tx(bar(WBAR), 2 * W2_IMG_B);
+        const uint8_t *img = reinterpret_cast<const uint8_t *>(w_img);
+        for (int cj = 0; cj < 2 * 3 * 8; ++cj) {   // (conv, tap, k chunk): image chunk = 128 rows x 16 B
+          bulk_g2s(w_smem + cj * W2_CHUNK_B, img + ((size_t)cj * 128 + 64 * rank) * 16, 64 * 16, bar(WBAR));
+          bulk_g2s(w_smem + cj * W2_CHUNK_B + 64 * 16, img + ((size_t)cj * 128 + 32 * rank) * 16, 32 * 16, bar(WBAR));
+        }
+      } else {
+        mbar_arrive_expect_tx(bar(WBAR), 2 * W_IMG_B);
+        for (int j = 0; j < 6; ++j)
+          bulk_g2s(w_smem + j * W_TAP_B, reinterpret_cast<const uint8_t *>(w_img) + (size_t)j * W_TAP_B, W_TAP_B, bar(WBAR));
+      }
       for (long long i = 0; i < my_tiles; ++i) {
-        const long long tile = blockIdx.x + i * gridDim.x;
+        const long long tile = tile_of(i);
         const int s = (int)(i % NST);
         mbar_wait(bar(EMPTY + s), (uint32_t)(((i / NST) & 1) ^ 1));
         mbar_arrive_expect_tx(bar(FULL + s), TILE_B);
@@ -141,33 +179,81 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
       }
     }
     __syncwarp();
+  } else if (warp == W_MMA && CTA2 && rank == 1) {
+    // ===== odd CTA of a pair: no MMA issue.  One thread forwards this CTA's "operand ready / accumulator drained"
+    // events to the even CTA, in the order its MMA thread waits for them.  The epilogue warps arrive on their own
+    // CTA's barriers as in single-CTA mode: a cluster-scope release from a warp with global stores in flight costs
+    // a full store drain (measured: +70 % epilogue time), from this idle thread it costs nothing.
+    if (elect_one()) {
+      mbar_wait(bar(WBAR), 0);
+      mbar_arrive_cluster(bar(PWBAR), 0);
+      if (my_tiles > 0) {
+        mbar_wait(bar(FULL), 0);
+        mbar_arrive_cluster(bar(PFULL), 0);
+      }
+      for (long long i = 0; i < my_tiles; ++i) {
+        const int a = (int)(i & 1);
+        if (i + 1 < my_tiles) {
+          const long long n = i + 1;
+          const int s = (int)(n % NST);
+          mbar_wait(bar(FULL + s), (uint32_t)((n / NST) & 1));
+          mbar_arrive_cluster(bar(PFULL + s), 0);
+        }
+        mbar_wait(bar(U_FULL + a), (uint32_t)((i >> 1) & 1));
+        mbar_arrive_cluster(bar(PU_FULL + a), 0);
+        if (i >= 2) {
+          mbar_wait(bar(D2_EMPTY + a), (uint32_t)(((i >> 1) - 1) & 1));
+          mbar_arrive_cluster(bar(PD2_EMPTY + a), 0);
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp == W_MMA) {
     // ===== MMA issuer: one elected lane waits, issues and commits; the other lanes idle =====
     if (elect_one()) {
       auto conv = [&](uint32_t a_tile, uint32_t w_img_s, uint32_t d_tmem) {
-        const uint64_t a0 = smem_desc(a_tile, PLANE_B, 128), b0 = smem_desc(w_img_s, 2048, 128);
+        const uint64_t a0 = smem_desc(a_tile, PLANE_B, 128);
+        const uint64_t b0 = CTA2 ? smem_desc(w_img_s, W2_CHUNK_B, 128) : smem_desc(w_img_s, 2048, 128);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-              mma_bf16(d_tmem, a0 + (uint64_t)(((half * 8 + 2 * kk) * PLANE_B + j * 16) >> 4),
-                       b0 + (uint64_t)((j * W_TAP_B + (2 * kk) * 2048) >> 4), half ? kIdescLo : kIdesc,
-                       (j | kk | half) != 0 ? 1u : 0u);
+              const uint64_t ad = a0 + (uint64_t)(((half * 8 + 2 * kk) * PLANE_B + j * 16) >> 4);
+              const uint32_t acc = (j | kk | half) != 0 ? 1u : 0u;
+              if constexpr (CTA2)
+                mma_bf16_cta2(d_tmem, ad, b0 + (uint64_t)(((j * 8 + 2 * kk) * W2_CHUNK_B + half * 64 * 16) >> 4),
+                              half ? kIdescLo2 : kIdesc2, acc);
+              else
+                mma_bf16(d_tmem, ad, b0 + (uint64_t)((j * W_TAP_B + (2 * kk) * 2048) >> 4), half ? kIdescLo : kIdesc, acc);
             }
           }
         }
       };
+      auto commit = [&](uint32_t b_) {
+        if constexpr (CTA2) tc_commit_cta2(b_);
+        else tc_commit(b_);
+      };
+      auto wait_x = [&](int s, uint32_t ph) {   // the x tile of stage s has landed (in both CTAs)
+        mbar_wait(bar(FULL + s), ph);
+        if constexpr (CTA2) mbar_wait_cluster(bar(PFULL + s), ph);
+      };
+      auto wait_both = [&](int local, int peer, uint32_t ph) {   // an event of this CTA's epilogue warps and of the peer's
+        mbar_wait(bar(local), ph);
+        if constexpr (CTA2) mbar_wait_cluster(bar(peer), ph);
+      };
       const bool pf = prof != nullptr && blockIdx.x == 0;
       long long pm[5] = {0, 0, 0, 0, 0};
       mbar_wait(bar(WBAR), 0);
+      if constexpr (CTA2) mbar_wait_cluster(bar(PWBAR), 0);
+      constexpr int W_CONV2 = CTA2 ? W2_IMG_B : W_IMG_B;
       if (my_tiles > 0) {
-        mbar_wait(bar(FULL), 0);
+        wait_x(0, 0);
         tc_fence_after();
         conv(x_smem, w_smem, tmem);
-        tc_commit(bar(D1_FULL));
-        tc_commit(bar(EMPTY));      // conv1 is the x stage's only reader: hand it back to the producer
+        commit(bar(D1_FULL));
+        commit(bar(EMPTY));      // conv1 is the x stage's only reader: hand it back to the producer
       }
       for (long long i = 0; i < my_tiles; ++i) {
         const int a = (int)(i & 1);
@@ -175,22 +261,22 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
         if (i + 1 < my_tiles) {  // conv1 of the next tile; D1[an] was drained by E1(i-1), implied by u_full(i-1)
           const long long n = i + 1;
           const int s = (int)(n % NST), an = (int)(n & 1);
-          mbar_wait(bar(FULL + s), (uint32_t)((n / NST) & 1));
+          wait_x(s, (uint32_t)((n / NST) & 1));
           m1 = pf ? clock64() : 0;
           tc_fence_after();
           conv(x_smem + s * TILE_B, w_smem, tmem + an * 128);
-          tc_commit(bar(D1_FULL + an));
-          tc_commit(bar(EMPTY + s));
+          commit(bar(D1_FULL + an));
+          commit(bar(EMPTY + s));
           m2 = pf ? clock64() : 0;
         }
         // conv2 of this tile
-        mbar_wait(bar(U_FULL + a), (uint32_t)((i >> 1) & 1));
-        if (i >= 2) mbar_wait(bar(D2_EMPTY + a), (uint32_t)(((i >> 1) - 1) & 1));
+        wait_both(U_FULL + a, PU_FULL + a, (uint32_t)((i >> 1) & 1));
+        if (i >= 2) wait_both(D2_EMPTY + a, PD2_EMPTY + a, (uint32_t)(((i >> 1) - 1) & 1));
         long long m3 = pf ? clock64() : 0;
         tc_fence_after();
-        conv(u_smem + a * TILE_B, w_smem + W_IMG_B, tmem + 256 + a * 128);
-        tc_commit(bar(D2_FULL + a));
-        tc_commit(bar(U_EMPTY + a));
+        conv(u_smem + a * TILE_B, w_smem + W_CONV2, tmem + 256 + a * 128);
+        commit(bar(D2_FULL + a));
+        commit(bar(U_EMPTY + a));
         if (pf) { long long m4 = clock64(); pm[0] += m1 - m0; pm[1] += m2 - m1; pm[2] += m3 - m2; pm[3] += m4 - m3; }
       }
       if (pf) {
@@ -207,7 +293,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
     const bool pfe = prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long pe[3] = {0, 0, 0};
     for (long long i = 0; i < my_tiles; ++i) {
-      const long long tile = blockIdx.x + i * gridDim.x;
+      const long long tile = tile_of(i);
       const int t0 = (int)(tile % ntile_t) * TO;
       const int a = (int)(i & 1);
       const int tu = t0 - 1 + row;
@@ -258,15 +344,16 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
     const bool pfe = prof != nullptr && blockIdx.x == 0 && lane == 0 && w2 == 0;
     long long pe[3] = {0, 0, 0};
     for (long long i = g; i < my_tiles; i += 2) {
-      const long long tile = blockIdx.x + i * gridDim.x;
+      const long long tile = tile_of(i);
+      const bool real_tile = tile_raw(i) < ntiles;     // a pair's second tile may not exist: compute, do not store
       const long long b = tile / ntile_t;
       const int tt = (int)(tile % ntile_t);
       const int t0 = tt * TO;
       const int t = t0 + row;
-      const bool live = row < TO && t < T;
+      const bool live = real_tile && row < TO && t < T;
       const size_t prow = (size_t)t + PAD;
       long long e0 = pfe ? clock64() : 0;
-      if (y != nullptr && q == 0 && lane < 2 * PAD) {  // the planes' zero padding rows
+      if (y != nullptr && real_tile && q == 0 && lane < 2 * PAD) {  // the planes' zero padding rows
         const bool head = lane < PAD;
         if (head ? (t0 == 0) : (t0 + TO >= T)) {
           const size_t zr = head ? (size_t)lane : (size_t)T + lane;
@@ -354,7 +441,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
           for (int k = 0; k < 2; ++k) a2[k] = (b4 ? a4[2 + k] : a4[k]) + __shfl_xor_sync(0xffffffffu, b4 ? a4[k] : a4[2 + k], 4);
           float a1 = (b2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? a2[0] : a2[1], 2);
           a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-          if ((lane & 1) == 0) pdst[p * 16 + (lane >> 1)] = a1;
+          if (real_tile && (lane & 1) == 0) pdst[p * 16 + (lane >> 1)] = a1;
         }
       }
       if constexpr (NHEAD == 1) {
@@ -365,7 +452,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
         float red = counted ? pr : 0.0f;
 #pragma unroll
         for (int sft = 16; sft > 0; sft >>= 1) red += __shfl_xor_sync(0xffffffffu, red, sft);
-        if (lane == 0) pdst[64] = red;
+        if (real_tile && lane == 0) pdst[64] = red;
       }
       if (pfe) { long long e2 = clock64(); pe[0] += e1 - e0; pe[1] += e2 - e1; }
     }
@@ -375,10 +462,37 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();   // the peer may still multicast into / arrive on this CTA's barriers
   if (warp == W_MMA) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+    if constexpr (CTA2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
   }
+}
+
+// CTA pairs are OPT-IN (WMB200_CTA2=1): correct (same tests as the single-CTA kernel) but measured slower on B200,
+// 10.8 vs 9.0 ms per launch at 4096 clips: every MMA now needs both SMs' shared memories to be free, the pair
+// advances at the pace of its slower half, and the odd CTA's events reach the issuing thread through a relay hop;
+// that costs more than the 21 % of operand bytes it saves (profiles/r1_resblock_cta2_phases.json).
+static int cta2_clusters(const void *kernel) {
+  static int cached = -2;
+  if (cached != -2) return cached;
+  const char *env = getenv("WMB200_CTA2");
+  if (!(env && env[0] == '1')) return cached = 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * sm_count(), 1, 1);
+  cfg.blockDim = dim3(RB_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = RB_SMEM;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  return cached = n;
 }
 
 template <int NHEAD>
@@ -395,12 +509,32 @@ static int launch_rb(const void *x, const void *w_img, const float *b1, const fl
   }
   static bool attr_set = false;
   if (!attr_set) {
-    WM_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel<NHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM));
+    WM_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel<NHEAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM));
+    WM_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel<NHEAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM));
     attr_set = true;
   }
   long long ntiles = (long long)B * ((T + TO - 1) / TO);
+  const int ncl = cta2_clusters(reinterpret_cast<const void *>(resblock_tc_kernel<NHEAD, true>));
+  if (ncl >= sm_count() / 2 - 2 && ntiles >= 2) {   // CTA pairs (one per TPC)
+    const long long npairs = (ntiles + 1) / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (unsigned)(npairs < ncl ? npairs : ncl), 1, 1);
+    cfg.blockDim = dim3(RB_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = RB_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    WM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, resblock_tc_kernel<NHEAD, true>, reinterpret_cast<const uint4 *>(x),
+                                     reinterpret_cast<const uint4 *>(w_img), b1, b2, reinterpret_cast<uint4 *>(y), y32, B, T,
+                                     hp, head_out, partials, valid_len, get_profile_buffer()));
+    WM_CHECK_LAUNCH("resblock_tc (CTA pairs)");
+    return 0;
+  }
   int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-  resblock_tc_kernel<NHEAD><<<grid, RB_THREADS, RB_SMEM, st>>>(
+  resblock_tc_kernel<NHEAD, false><<<grid, RB_THREADS, RB_SMEM, st>>>(
       reinterpret_cast<const uint4 *>(x), reinterpret_cast<const uint4 *>(w_img), b1, b2, reinterpret_cast<uint4 *>(y),
       y32, B, T, hp, head_out, partials, valid_len, get_profile_buffer());
   WM_CHECK_LAUNCH("resblock_tc");

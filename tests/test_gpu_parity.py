@@ -601,3 +601,15 @@ def test_folder_driver_matches_per_file_api(tmp_path, gen_B, det):
         assert abs(r["mean_probability"] - one["mean_probability"]) < 1e-4
         assert r["predicted_message"] == one["predicted_message"] or \
             np.abs(np.array(r["message_confidence"]) - np.array(one["message_confidence"])).max() < 1e-3
+
+
+def test_resblock_cta_pair_variant_matches():
+    """The opt-in cta_group::2 build of the fused ResBlock (two CTAs share every weight operand) must give the
+    results of the default kernel; the switch is read once per process, so it runs in a child process."""
+    import subprocess, sys
+    env = dict(os.environ, WMB200_CTA2="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-q", "-x", "-m", "gpu", "-k",
+                        "resblock_tensor_core_fused or detector_matches_reference_goldens"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
