@@ -46,36 +46,58 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons while the timed region runs: ONE `nvidia-smi -lms 50` process whose
+    CSV lines are read as they come (spawning nvidia-smi per sample gives only a few samples per second)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.rows, self.stop_flag, self.proc = index, [], threading.Event(), None
+        self.t_first = None
 
     def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                parts = [p.strip() for p in line.strip().split(",")]
                 if len(parts) == 6:
+                    if self.t_first is None:
+                        self.t_first = time.perf_counter()
                     self.rows.append(parts)
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+                if self.stop_flag.is_set():
+                    break
+        except Exception:
+            pass
+        finally:
+            if self.proc is not None:
+                try:
+                    self.proc.kill()        # the exact process this object started
+                except Exception:
+                    pass
 
-    def summary(self):
-        if not self.rows:
+    def wait_ready(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while self.t_first is None and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        """Index of the next sample: samples from here on belong to the timed region."""
+        return len(self.rows)
+
+    def summary(self, first=0, last=None):
+        rows = self.rows[first:last] or self.rows
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
+        sm = sorted(float(r[0]) for r in rows)
         reasons = []
         for i, name in ((2, "hw_slowdown"), (3, "hw_thermal_slowdown"), (4, "sw_thermal_slowdown"), (5, "sw_power_cap")):
-            if any(r[i].lower().startswith("active") for r in self.rows):
+            if any(r[i].lower().startswith("active") for r in rows):
                 reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_mhz_min": sm[0], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "samples": len(rows)}
 
 
 def build_models(device):
@@ -192,9 +214,22 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     sampler.start()
-    ms_dev, launches = timed(step, args.steps, args.warmup)
+    sampler.wait_ready()
+    marks = {}
+
+    def timed_marked(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        marks["first"] = sampler.mark()
+        r = timed(fn, steps, 0)
+        marks["last"] = sampler.mark()
+        return r
+
+    ms_dev, launches = timed_marked(step, args.steps, args.warmup)
+    time.sleep(0.06)                      # let the last in-region sample arrive
+    marks["last"] = max(marks["last"], min(sampler.mark(), marks["last"] + 1))
     sampler.stop_flag.set()
-    sampler.join()
     value = world * B * args.steps / (ms_dev / 1e3)
 
     # ---- end to end: pinned host buffers through the C-ABI host entry point -------------
@@ -264,7 +299,7 @@ def run_ours(args):
 
     if rank == 0:
         cpu_rate, cores, _ = cpu_reference_rate(16, 3, 1) if not args.no_cpu_baseline else (None, 0, [])
-        clocks = sampler.summary()
+        clocks = sampler.summary(marks.get("first", 0), marks.get("last"))
         line = {"metric": "clip-seconds/sec embed+detect (1 s@16 kHz)", "value": value, "unit": "clip-s/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
