@@ -231,7 +231,9 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
       long long c5 = pf ? clock64() : 0;
       fence_async_smem();
-      mbar_arrive_warp(h_ready);
+      // hand h_t to the MMA warp through a hardware named barrier (arrive here, sync there): cheaper than an
+      // mbarrier round trip on the step's critical path
+      asm volatile("bar.arrive %0, %1;" ::"r"(3 + g), "r"(N_EPI + 32) : "memory");
       long long c6 = pf ? clock64() : 0;
       uint4 out;
       if (chan_add != nullptr) {   // warp-uniform
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       const int buf = t & 1;
       long long m0 = pf ? clock64() : 0;
       if (t > 0) {
-        mbar_wait_warp(h_ready, (t - 1) & 1);
+        asm volatile("bar.sync %0, %1;" ::"r"(3 + g), "r"(N_EPI + 32) : "memory");
         tc_fence_after();
       }
       long long m1 = pf ? clock64() : 0;

@@ -613,3 +613,39 @@ def test_resblock_cta_pair_variant_matches():
                         "resblock_tensor_core_fused or detector_matches_reference_goldens"], cwd=root, env=env,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_properties_at_benchmark_size(gen_B, det):
+    """BASELINE configs[1] at full size (4096 clips in one pass): the size-independent contracts of the path —
+    determinism, s_w = s + delta, the RMS cap and peak clamp, clip mean = mean of per-sample probabilities,
+    independence of a clip from its batch, and agreement of the host-fed pipeline with the device-resident one."""
+    B = 4096
+    g = torch.Generator().manual_seed(4096)
+    s_h = (0.1 * torch.randn(B, 16000, generator=g)).clamp(-0.99, 0.99)
+    ids = torch.from_numpy(np.concatenate([IO["messages"], IO["rng_messages"]]).astype(np.int64))
+    msg_h = ids[torch.randint(0, len(ids), (B,), generator=g)]
+    s, msg = s_h.to(DEV).unsqueeze(1), msg_h.to(DEV)
+    r = wmb200.embed_detect(gen_B, det, s, msg, want_votes=False, want_rms=True)
+    r2 = wmb200.embed_detect(gen_B, det, s, msg, want_votes=False, want_rms=True)
+    for k in ("delta", "s_w", "probs", "clip_prob", "msg_logits"):
+        assert torch.equal(r[k], r2[k]), k
+    d = r["delta"][:, 0]
+    assert float(d.pow(2).mean(1).sqrt().max()) <= 0.005 * (1 + 1e-5) and float(d.abs().max()) <= 0.02
+    assert maxerr(r["s_w"], s + r["delta"]) == 0.0
+    assert maxerr(r["clip_prob"], r["probs"].mean(1)) < 1e-5
+    assert bool(torch.isfinite(r["msg_logits"]).all()) and bool(((r["probs"] >= 0) & (r["probs"] <= 1)).all())
+    idx = torch.tensor([0, 31, 32, 2047, 2048, 4095], device=DEV)
+    sub = wmb200.embed_detect(gen_B, det, s[idx], msg[idx], want_votes=False)
+    assert maxerr(sub["delta"], r["delta"][idx]) < 1e-6 and maxerr(sub["probs"], r["probs"][idx]) < 1e-4
+    # bits: decoded message of every clip vs the oracle on a sample of clips
+    gsd, rows = H.gen_sd(W, "B")
+    pick = [0, 777, 4095]
+    ref = O.embed_detect(gsd, H.det_sd(W), s_h[pick].unsqueeze(1), msg_h[pick], emb_rows=H.emb_for(IO, rows, msg_h[pick]))
+    assert maxerr(r["delta"][pick], ref["delta"]) < DELTA_TOL and maxerr(r["probs"][pick], ref["probs"]) < PROB_TOL
+    hs, hm = s_h.pin_memory(), msg_h.pin_memory()
+    h_sw, h_pr = torch.empty(B, 16000).pin_memory(), torch.empty(B, 16000).pin_memory()
+    pipe = ops.HostPipeline(gen_B.packed(), gen_B.embedding_table(), det.packed(), wmb200.functional.fir_taps_on(torch.device(DEV)),
+                            det.nout, 16000, chunk=B)
+    pipe(hs, hm, h_sw, h_pr)
+    torch.cuda.current_stream().synchronize()
+    assert maxerr(h_sw, r["s_w"][:, 0]) < 1e-6 and maxerr(h_pr, r["probs"]) < 1e-4
