@@ -12,7 +12,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwmb200.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # blob offsets (floats) — mirror of the enums in include/wmb200.h
 RB_W1 = 0
@@ -115,6 +115,9 @@ SIGNATURES = {
     "wm_conv1d_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "wm_convtranspose1d_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "wm_lstm_small_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "wm_convtranspose1d_phase_weight_floats": (_sz, [_i, _i, _i]),
+    "wm_convtranspose1d_pack": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "wm_convtranspose1d_phase_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "wm_embed_detect_host_workspace_bytes": (_sz, [_i, _i, _i]),
     "wm_embed_detect_host": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
                                   _i, _i, _i, _i, _i, _p]),

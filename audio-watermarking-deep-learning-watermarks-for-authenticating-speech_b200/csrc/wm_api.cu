@@ -553,6 +553,33 @@ int wm_convtranspose1d_fwd(const float *x, const float *w, const float *bias, fl
   return launch_convtranspose1d_generic(x, w, bias, y, B, Cin, Tin, Cout, K, stride, pad, as_stream(stream));
 }
 
+size_t wm_convtranspose1d_phase_weight_floats(int Cin, int Cout, int stride) {
+  return (Cin <= 0 || Cout <= 0 || stride <= 0) ? 0 : (size_t)Cout * stride * Cin * 3 + (size_t)Cout * stride;
+}
+
+int wm_convtranspose1d_pack(const float *w, const float *bias, float *packed, int Cin, int Cout, int K, int stride,
+                            int pad, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(w && bias && packed, "convtranspose1d_pack: null pointer");
+  WM_CHECK_ARG(K == 2 * stride && pad >= 0 && pad < stride && stride >= 1 && stride <= 8,
+               "convtranspose1d_pack: the phase form needs kernel_size == 2 * stride and padding < stride");
+  return launch_convt_phase_weights(w, bias, packed, packed + (size_t)Cout * stride * Cin * 3, Cin, Cout, stride, pad,
+                                    as_stream(stream));
+}
+
+int wm_convtranspose1d_phase_fwd(const float *x, const float *packed, float *y, int B, int Cin, int Tin, int Cout, int K,
+                                 int stride, int pad, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && Cin > 0 && Cout > 0 && Tin >= 0, "convtranspose1d_phase: bad size");
+  WM_CHECK_ARG(K == 2 * stride && pad >= 0 && pad < stride, "convtranspose1d_phase: needs kernel_size == 2 * stride");
+  if (B == 0 || Tin == 0) return 0;
+  WM_CHECK_ARG(x && packed && y && x != y, "convtranspose1d_phase: null pointer or in-place");
+  const int Tout = (Tin - 1) * stride - 2 * pad + K;
+  const int extra = (Tout + stride - 1) / stride - Tin;       // phase-0 samples beyond the input length
+  return launch_conv1d_generic(x, packed, packed + (size_t)Cout * stride * Cin * 3, nullptr, nullptr, y, B, Cin, Tin,
+                               Cout * stride, 3, 1, 1, 0, as_stream(stream), stride, Tout, extra > 0 ? extra : 0);
+}
+
 int wm_lstm_small_fwd(const float *x, const float *w_ih, const float *w_hh, const float *bias, float *y, int B, int H,
                       int T, int layers, void *stream) {
   WM_ENTRY();

@@ -118,7 +118,9 @@ int launch_abs_mean(const float *x, long long n, float *out, float *partials, cu
 // generic fp32 operators of the main14b_2 stack (wm_generic.cu); channels-first x[b][c][t]
 int launch_conv1d_generic(const float *x, const float *w, const float *bias, const float *chan_add, const float *res,
                           float *y, int B, int Cin, int Tin, int Cout, int K, int stride, int pad, int act,
-                          cudaStream_t st);
+                          cudaStream_t st, int shuffle = 1, int Tstore = 0, int extra_out = 0);
+int launch_convt_phase_weights(const float *w, const float *bias, float *w3, float *b3, int Cin, int Cout, int s, int p,
+                               cudaStream_t st);
 int launch_convtranspose1d_generic(const float *x, const float *w, const float *bias, float *y, int B, int Cin, int Tin,
                                    int Cout, int K, int stride, int pad, cudaStream_t st);
 int launch_lstm_small(const float *x, const float *w_ih, const float *w_hh, const float *bias, float *y, int B, int H,

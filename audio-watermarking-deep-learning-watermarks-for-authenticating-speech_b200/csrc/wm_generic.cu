@@ -24,7 +24,8 @@ __device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : expm1f(v)
 __global__ void __launch_bounds__(GTHREADS)
     conv1d_generic_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
                           const float *__restrict__ chan_add, const float *__restrict__ res, float *__restrict__ y,
-                          int Cin, int Tin, int Cout, int Tout, int K, int stride, int pad, int act) {
+                          int Cin, int Tin, int Cout, int Tout, int K, int stride, int pad, int act, int shuffle,
+                          int Tstore) {
   extern __shared__ float sm[];
   const int span = (GT - 1) * stride + K;            // input samples one stage needs per channel
   float *xs = sm;                                    // [GCI][span]
@@ -73,8 +74,13 @@ __global__ void __launch_bounds__(GTHREADS)
     for (int j = 0; j < 4; ++j) {
       const int t = t0 + tx + 16 * j;
       if (t >= Tout) continue;
-      const size_t o = ((size_t)b * Cout + co) * Tout + t;
       float v = acc[i][j] + add;
+      if (shuffle > 1) {   // channel co = (c, r) is phase r of output channel c: y[b][c][t * shuffle + r]
+        const int ts = t * shuffle + co % shuffle;
+        if (ts < Tstore) y[((size_t)b * (Cout / shuffle) + co / shuffle) * Tstore + ts] = v;
+        continue;
+      }
+      const size_t o = ((size_t)b * Cout + co) * Tout + t;
       if (res) v += res[o];
       y[o] = act ? elu1(v) : v;
     }
@@ -177,12 +183,43 @@ __global__ void lstm_small_kernel(const float *__restrict__ x, const float *__re
   }
 }
 
+// w (Cin, Cout, 2s) of a ConvTranspose1d(stride s, padding p) -> w3 (Cout*s, Cin, 3), b3 (Cout*s):
+// output t = m*s + r takes x[m + a_r] w[.., k_r] + x[m + a_r - 1] w[.., k_r + s], k_r = (r + p) % s, a_r = (r + p) / s
+__global__ void convt_phase_weights_kernel(const float *__restrict__ w, const float *__restrict__ bias, float *__restrict__ w3,
+                                           float *__restrict__ b3, int Cin, int Cout, int s, int p) {
+  const long long n = (long long)Cout * s * Cin;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(e % Cin);
+    const int cr = (int)(e / Cin), co = cr / s, r = cr % s;
+    const int kr = (r + p) % s, ar = (r + p) / s;
+    const float *src = w + ((size_t)ci * Cout + co) * 2 * s;
+    float t3[3] = {0.0f, 0.0f, 0.0f};
+    t3[ar + 1] = src[kr];          // window offset d = a_r      -> tap 1 + d
+    t3[ar] = src[kr + s];          // window offset d = a_r - 1
+    w3[e * 3] = t3[0]; w3[e * 3 + 1] = t3[1]; w3[e * 3 + 2] = t3[2];
+    if (ci == 0) b3[cr] = bias[co];
+  }
+}
+
 }  // namespace
 
+int launch_convt_phase_weights(const float *w, const float *bias, float *w3, float *b3, int Cin, int Cout, int s, int p,
+                               cudaStream_t st) {
+  const long long n = (long long)Cout * s * Cin;
+  const long long nb = (n + 255) / 256;
+  convt_phase_weights_kernel<<<(int)(nb < 4096 ? nb : 4096), 256, 0, st>>>(w, bias, w3, b3, Cin, Cout, s, p);
+  WM_CHECK_LAUNCH("convt_phase_weights");
+  return 0;
+}
+
+// shuffle > 1 (with Tstore): the ConvTranspose1d-as-convolution form.  A stride-s transposed convolution with
+// K = 2s taps is s interleaved 2-tap convolutions of the input (one per output phase), i.e. ONE stride-1 3-tap
+// convolution with Cout*s output channels whose results are written phase-interleaved; `extra_out` computes that
+// many more positions than the input has (the last phase-0 sample of an odd stride).
 int launch_conv1d_generic(const float *x, const float *w, const float *bias, const float *chan_add, const float *res,
                           float *y, int B, int Cin, int Tin, int Cout, int K, int stride, int pad, int act,
-                          cudaStream_t st) {
-  const int Tout = (Tin + 2 * pad - K) / stride + 1;
+                          cudaStream_t st, int shuffle, int Tstore, int extra_out) {
+  const int Tout = (Tin + 2 * pad - K) / stride + 1 + extra_out;
   if (B == 0 || Tout <= 0) return 0;
   if (K > GMAXK || stride > GMAXS || K < 1 || stride < 1) {
     set_error("conv1d: kernel size %d / stride %d outside the supported range (<= %d / <= %d)", K, stride, GMAXK, GMAXS);
@@ -195,7 +232,8 @@ int launch_conv1d_generic(const float *x, const float *w, const float *bias, con
     attr_set = true;
   }
   dim3 grid((Tout + GT - 1) / GT, (Cout + GCO - 1) / GCO, B);
-  conv1d_generic_kernel<<<grid, GTHREADS, smem, st>>>(x, w, bias, chan_add, res, y, Cin, Tin, Cout, Tout, K, stride, pad, act);
+  conv1d_generic_kernel<<<grid, GTHREADS, smem, st>>>(x, w, bias, chan_add, res, y, Cin, Tin, Cout, Tout, K, stride, pad, act,
+                                                      shuffle, Tstore);
   WM_CHECK_LAUNCH("conv1d_generic");
   return 0;
 }

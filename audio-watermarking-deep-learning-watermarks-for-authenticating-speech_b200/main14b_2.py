@@ -43,12 +43,38 @@ def conv1d(x, conv: nn.Conv1d, act: bool = False, residual=None, chan_add=None) 
     return y
 
 
-def conv_transpose1d(x, ct: nn.ConvTranspose1d) -> torch.Tensor:
+_phase_cache = {}
+
+
+def _phase_weights(ct: nn.ConvTranspose1d) -> torch.Tensor:
+    """Per-phase 3-tap convolution weights of a ConvTranspose1d with kernel_size == 2 * stride, built on the device
+    once per parameter version (wm_convtranspose1d_pack)."""
+    lib = L.load()
+    w, b = ct.weight, ct.bias
+    key = (id(ct), w.data_ptr(), w._version, b.data_ptr(), b._version, str(w.device))
+    hit = _phase_cache.get(id(ct))
+    if hit is None or hit[0] != key:
+        Cin, Cout, K = w.shape
+        s, p = ct.stride[0], ct.padding[0]
+        packed = torch.empty(lib.wm_convtranspose1d_phase_weight_floats(Cin, Cout, s), device=w.device)
+        L.check(lib.wm_convtranspose1d_pack(L.ptr(_req(w.detach(), "weight")), L.ptr(_req(b.detach(), "bias")),
+                                            L.ptr(packed), Cin, Cout, K, s, p, _stream()), "wm_convtranspose1d_pack")
+        _phase_cache[id(ct)] = hit = (key, packed)
+    return hit[1]
+
+
+def conv_transpose1d(x, ct: nn.ConvTranspose1d, direct: bool = False) -> torch.Tensor:
+    """nn.ConvTranspose1d forward.  kernel_size == 2 * stride (every layer of this model) runs as one 3-tap
+    convolution over stride-many phase channels (wm_convtranspose1d_phase_fwd); `direct` forces the gather kernel."""
     lib = L.load()
     x = _req(x, "x")
     B, Cin, Tin = x.shape
     Cout, K, s, p = ct.out_channels, ct.kernel_size[0], ct.stride[0], ct.padding[0]
     y = torch.empty(B, Cout, lib.wm_convtranspose1d_out_len(Tin, K, s, p), device=x.device)
+    if not direct and K == 2 * s and 0 <= p < s and ct.output_padding[0] == 0:
+        L.check(lib.wm_convtranspose1d_phase_fwd(L.ptr(x), L.ptr(_phase_weights(ct)), L.ptr(y), B, Cin, Tin, Cout, K, s, p,
+                                                 _stream()), "wm_convtranspose1d_phase_fwd")
+        return y
     L.check(lib.wm_convtranspose1d_fwd(L.ptr(x), L.ptr(_req(ct.weight.detach(), "weight")),
                                        L.ptr(_req(ct.bias.detach(), "bias")), L.ptr(y), B, Cin, Tin, Cout, K, s, p,
                                        _stream()), "wm_convtranspose1d_fwd")

@@ -32,7 +32,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 10
+#define WM_ABI_VERSION 11
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -285,6 +285,14 @@ int wm_conv1d_fwd(const float *x, const float *w, const float *bias, const float
 /* nn.ConvTranspose1d(Cin, Cout, K, stride, padding, output_padding=0) (py/main14b_2.py:146,201); w (Cin,Cout,K). */
 int wm_convtranspose1d_fwd(const float *x, const float *w, const float *bias, float *y, int B, int Cin, int Tin,
                            int Cout, int K, int stride, int pad, void *stream);
+/* The same operator for kernel_size == 2 * stride (every transposed convolution of main14b_2) as ONE stride-1
+ * 3-tap convolution with Cout * stride phase channels written interleaved: `packed` (size from
+ * wm_convtranspose1d_phase_weight_floats) is built once per weight version by wm_convtranspose1d_pack. */
+size_t wm_convtranspose1d_phase_weight_floats(int Cin, int Cout, int stride);
+int wm_convtranspose1d_pack(const float *w, const float *bias, float *packed, int Cin, int Cout, int K, int stride,
+                            int pad, void *stream);
+int wm_convtranspose1d_phase_fwd(const float *x, const float *packed, float *y, int B, int Cin, int Tin, int Cout, int K,
+                                 int stride, int pad, void *stream);
 /* nn.LSTM(H, H, num_layers, batch_first) on channels-first x[b][H][T] (py/main14b_2.py:137,167); w_ih, w_hh
  * [layers][4H][H], bias [layers][4H] = b_ih + b_hh; zero initial state; H <= 64, layers <= 4. */
 int wm_lstm_small_fwd(const float *x, const float *w_ih, const float *w_hh, const float *bias, float *y, int B, int H,

@@ -103,9 +103,11 @@ def test_generic_convtranspose1d_vs_torch(Cin, Cout, stride, T):
     ct = torch.nn.ConvTranspose1d(Cin, Cout, kernel_size=2 * stride, stride=stride, padding=stride // 2)
     x = torch.randn(2, Cin, T, generator=g)
     ref = ct(x).detach()
-    got = M.conv_transpose1d(x.to(DEV), ct.to(DEV))
-    assert got.shape == ref.shape
-    assert maxerr(got, ref) < 2e-5 * (2 * Cin) ** 0.5
+    ctd = ct.to(DEV)
+    for direct in (False, True):             # per-phase convolution form and the gather kernel
+        got = M.conv_transpose1d(x.to(DEV), ctd, direct=direct)
+        assert got.shape == ref.shape
+        assert maxerr(got, ref) < 2e-5 * (2 * Cin) ** 0.5, direct
 
 
 @pytest.mark.gpu
