@@ -6,7 +6,8 @@ functions fir_lowpass / clamp_peak / limit_rms and the module constants.  All ar
 runs in libwmb200.so (hand-written CUDA, C ABI in include/wmb200.h); there is no CPU or
 PyTorch fallback — calls fail loudly when the library or the GPU is missing.
 """
-from . import _lib, main14b_2, ops, packing
+from . import _lib, audio, main14b_2, ops, packing
+from .audio import Resample, file_metrics, from_pcm16, resample, to_pcm16
 from .api import detect_prob, detect_watermark, generate_watermarked_audio, load_audio, save_audio, segment
 from .functional import (AUDIO_LEN, HF_PENALTY_W, LAMBDA_DEC, LAMBDA_L1, LAMBDA_LOC, LAMBDA_LOUD,
                          LAMBDA_MSSPEC, MAX_RMS, MESSAGE_BITS, SAMPLE_RATE, bit_targets, clamp_peak,
@@ -21,4 +22,5 @@ __all__ = ["Generator", "Detector", "ResBlock", "generate_watermarked_audio", "d
            "embed_detect", "bit_targets", "shard_range", "load_audio", "save_audio", "segment",
            "SAMPLE_RATE", "AUDIO_LEN", "MESSAGE_BITS", "MAX_RMS", "LAMBDA_L1", "LAMBDA_MSSPEC", "LAMBDA_LOUD",
            "LAMBDA_LOC", "LAMBDA_DEC", "HF_PENALTY_W", "MultiScaleMelLoss", "TFLoudnessLoss", "high_freq_penalty",
-           "step_losses", "stft_magnitude", "embed_detect_stream", "process_folder_with_tqdm", "detect_watermark_folder"]
+           "step_losses", "stft_magnitude", "embed_detect_stream", "process_folder_with_tqdm", "detect_watermark_folder",
+           "Resample", "resample", "to_pcm16", "from_pcm16", "file_metrics"]

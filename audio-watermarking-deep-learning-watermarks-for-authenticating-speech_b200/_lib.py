@@ -12,7 +12,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwmb200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 # blob offsets (floats) — mirror of the enums in include/wmb200.h
 RB_W1 = 0
@@ -118,6 +118,10 @@ SIGNATURES = {
     "wm_convtranspose1d_phase_weight_floats": (_sz, [_i, _i, _i]),
     "wm_convtranspose1d_pack": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "wm_convtranspose1d_phase_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "wm_resample_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "wm_pcm16_quantize_fwd": (_i, [_p, _p, _sz, _p]),
+    "wm_pcm16_dequantize_fwd": (_i, [_p, _p, _sz, _f, _p]),
+    "wm_file_metrics_fwd": (_i, [_p, _p, _p, _p, _i, _i, _p]),
     "wm_embed_detect_host_workspace_bytes": (_sz, [_i, _i, _i]),
     "wm_embed_detect_host": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
                                   _i, _i, _i, _i, _i, _p]),

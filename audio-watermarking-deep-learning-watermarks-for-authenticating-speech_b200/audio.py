@@ -1,0 +1,77 @@
+"""The data formats either side of the embed+detect path, on the GPU:
+`Resample` / `resample` (torchaudio.transforms.Resample as the reference uses it, py/main16.py:985,1121),
+`to_pcm16` / `from_pcm16` (py/main15.py:859-860) and `file_metrics` (py/main16.py:1030-1049)."""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from . import packing
+from .ops import _req, _stream
+
+_kern_cache = {}
+
+
+def resample(x: torch.Tensor, orig_freq: int, new_freq: int) -> torch.Tensor:
+    """x (..., T) fp32 on the GPU -> (..., ceil(new * T / orig)), torchaudio's default sinc_interp_hann resampler."""
+    if int(orig_freq) == int(new_freq):
+        return x
+    lib = L.load()
+    lead, T = x.shape[:-1], x.shape[-1]
+    x2 = _req(x.reshape(-1, T), "x")
+    key = (int(orig_freq), int(new_freq), str(x2.device))
+    if key not in _kern_cache:
+        kern, down, up, width = packing.resample_kernel(orig_freq, new_freq)
+        _kern_cache[key] = (kern.to(x2.device), down, up, width)
+    kern, down, up, width = _kern_cache[key]
+    Tout = int(math.ceil(up * T / down))
+    y = torch.empty(x2.shape[0], Tout, device=x2.device)
+    L.check(lib.wm_resample_fwd(L.ptr(x2), L.ptr(kern), L.ptr(y), x2.shape[0], T, Tout, down, up, kern.shape[0], width,
+                                _stream()), "wm_resample_fwd")
+    return y.reshape(*lead, Tout)
+
+
+class Resample(torch.nn.Module):
+    """torchaudio.transforms.Resample(orig_freq, new_freq) for CUDA tensors."""
+
+    def __init__(self, orig_freq: int = 16000, new_freq: int = 16000):
+        super().__init__()
+        self.orig_freq, self.new_freq = int(orig_freq), int(new_freq)
+
+    def forward(self, waveform: torch.Tensor) -> torch.Tensor:
+        return resample(waveform, self.orig_freq, self.new_freq)
+
+
+def to_pcm16(x: torch.Tensor) -> torch.Tensor:
+    """(x.clamp(-1, 1) * 32767).to(torch.int16)  — py/main15.py:859-860."""
+    lib = L.load()
+    xc = _req(x, "x")
+    q = torch.empty(xc.shape, dtype=torch.int16, device=xc.device)
+    L.check(lib.wm_pcm16_quantize_fwd(L.ptr(xc), L.ptr(q), xc.numel(), _stream()), "wm_pcm16_quantize_fwd")
+    return q
+
+
+def from_pcm16(q: torch.Tensor, scale: float = 1.0 / 32768.0) -> torch.Tensor:
+    """int16 PCM -> fp32 in [-1, 1) (what a 16-bit WAV loader returns)."""
+    lib = L.load()
+    qc = _req(q, "q", torch.int16)
+    x = torch.empty(qc.shape, dtype=torch.float32, device=qc.device)
+    L.check(lib.wm_pcm16_dequantize_fwd(L.ptr(qc), L.ptr(x), qc.numel(), scale, _stream()), "wm_pcm16_dequantize_fwd")
+    return x
+
+
+def file_metrics(original: torch.Tensor, watermarked: torch.Tensor, valid_len: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Rows of (B,T) waveforms -> (B,3) = watermark RMS, SI-SNR [dB], power ratio [dB]
+    (py/main16.py:1030-1049, compute_si_snr :764-773), reduced on the device in double precision."""
+    lib = L.load()
+    s, w = _req(original, "original"), _req(watermarked, "watermarked")
+    if s.shape != w.shape or s.dim() != 2:
+        raise ValueError(f"file_metrics: expected two (B,T) tensors, got {tuple(s.shape)} and {tuple(w.shape)}")
+    v = _req(valid_len, "valid_len", torch.int32) if valid_len is not None else None
+    out = torch.empty(s.shape[0], 3, device=s.device)
+    L.check(lib.wm_file_metrics_fwd(L.ptr(s), L.ptr(w), L.ptr(v), L.ptr(out), s.shape[0], s.shape[1], _stream()),
+            "wm_file_metrics_fwd")
+    return out

@@ -589,6 +589,37 @@ int wm_lstm_small_fwd(const float *x, const float *w_ih, const float *w_hh, cons
   return launch_lstm_small(x, w_ih, w_hh, bias, y, B, H, T, layers, as_stream(stream));
 }
 
+/* ---- audio formats either side of the path ---- */
+int wm_resample_fwd(const float *x, const float *kern, float *y, int B, int Tin, int Tout, int down, int up, int K,
+                    int width, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && Tin >= 0 && Tout >= 0 && down > 0 && up > 0 && K > 0 && width >= 0, "resample: bad size");
+  if (B == 0 || Tout == 0) return 0;
+  WM_CHECK_ARG(x && kern && y && x != y, "resample: null pointer or in-place");
+  return launch_resample(x, kern, y, B, Tin, Tout, down, up, K, width, as_stream(stream));
+}
+
+int wm_pcm16_quantize_fwd(const float *x, int16_t *q, size_t n, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(n == 0 || (x && q), "pcm16_quantize: null pointer");
+  return launch_pcm16(x, reinterpret_cast<short *>(q), nullptr, (long long)n, 1, 0.0f, as_stream(stream));
+}
+
+int wm_pcm16_dequantize_fwd(const int16_t *q, float *x, size_t n, float scale, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(n == 0 || (x && q), "pcm16_dequantize: null pointer");
+  return launch_pcm16(nullptr, reinterpret_cast<short *>(const_cast<int16_t *>(q)), x, (long long)n, 0, scale,
+                      as_stream(stream));
+}
+
+int wm_file_metrics_fwd(const float *s, const float *s_w, const int *valid_len, float *out, int B, int T, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "file_metrics: negative size");
+  if (B == 0) return 0;
+  WM_CHECK_ARG(s && s_w && out, "file_metrics: null pointer");
+  return launch_file_metrics(s, s_w, valid_len, out, B, T, as_stream(stream));
+}
+
 size_t wm_embed_detect_host_workspace_bytes(int chunk, int T, int nout) {
   if (chunk <= 0 || T <= 0 || nout < 1) return 0;
   size_t wave = align256((size_t)chunk * T * sizeof(float));

@@ -125,6 +125,11 @@ int launch_convtranspose1d_generic(const float *x, const float *w, const float *
                                    int Cout, int K, int stride, int pad, cudaStream_t st);
 int launch_lstm_small(const float *x, const float *w_ih, const float *w_hh, const float *bias, float *y, int B, int H,
                       int T, int L, cudaStream_t st);
+// audio formats either side of the path (wm_audio.cu)
+int launch_resample(const float *x, const float *kern, float *y, int B, int Tin, int Tout, int down, int up, int K,
+                    int width, cudaStream_t st);
+int launch_pcm16(const float *x, short *q, float *xo, long long n, int quantize, float scale, cudaStream_t st);
+int launch_file_metrics(const float *s, const float *sw, const int *valid_len, float *out, int B, int T, cudaStream_t st);
 void set_lstm_profile_buffer(long long *p);
 long long *get_profile_buffer();
 int launch_pack_lstm_tc(const float *w_ih, const float *w_hh, const float *bias, void *wpk, float *bias_p,

@@ -136,3 +136,21 @@ def mel_filterbank(n_freqs: int = 513, n_mels: int = 64, sample_rate: int = 1600
         if nz.numel():
             band[m, 0], band[m, 1] = int(nz[0]), int(nz[-1]) + 1
     return fb, band
+
+
+def resample_kernel(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """The windowed-sinc table torchaudio.transforms.Resample(orig, new) convolves with (sinc_interp_hann, its defaults:
+    torchaudio.functional._get_sinc_resample_kernel), built in float64 and rounded to fp32 like torchaudio does.
+    Returns (kern [K][up] fp32, down, up, width): y[m*up + j] = sum_k kern[k][j] x[m*down + k - width]."""
+    g = math.gcd(int(orig_freq), int(new_freq))
+    down, up = int(orig_freq) // g, int(new_freq) // g
+    base_freq = min(down, up) * rolloff
+    width = math.ceil(lowpass_filter_width * down / base_freq)
+    idx = torch.arange(-width, width + down, dtype=torch.float64)[None, None] / down
+    t = torch.arange(0, -up, -1, dtype=torch.float64)[:, None, None] / up + idx
+    t = (t * base_freq).clamp_(-lowpass_filter_width, lowpass_filter_width)
+    window = torch.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    scale = base_freq / down
+    kern = torch.where(t == 0, torch.tensor(1.0, dtype=torch.float64), t.sin() / t) * window * scale
+    return kern[:, 0, :].to(torch.float32).t().contiguous(), down, up, width

