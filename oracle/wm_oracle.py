@@ -15,8 +15,8 @@ executed in the build container: ``tests/golden/make_golden.py`` AST-extracts
 ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks every function
 here against those files.  The arithmetic itself lives in a third-party,
 un-vendored dependency (PyTorch; README pins "1.9+", this container has
-2.11.0), whose operator semantics are restated explicitly in
-``oracle/ops_numpy.py`` and cross-checked there.
+2.11.0); ``lstm_steps`` restates the one operator whose semantics are not obvious
+from its call (gate order, zero state) step by step and is checked against the library call.
 
 All functions take a *state dict* (name -> tensor, reference key names with or
 without the ``_orig_mod.`` prefix) instead of nn.Modules.
