@@ -121,25 +121,35 @@ def synth(B, seed, device, pin=False):
     return s.to(device), m.to(device)
 
 
-def cpu_reference_rate(sample_B, steps, warmup, threads=None):
-    """Oracle (port of the reference's CPU path) on `sample_B` clips per step."""
+def cpu_reference_rate(sample_B, steps, warmup, threads=None, device="cpu", tf32=False):
+    """Oracle (port of the reference's CPU path) on `sample_B` clips per step.  device="cuda" (informational only,
+    `--ref-device cuda`) runs the same stock-PyTorch eager definitions on the GPU."""
     import torch
 
     from oracle import wm_oracle as O
+    if device != "cpu":
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
     if threads is None:            # all the host threads we may use (torchrun exports OMP_NUM_THREADS=1)
         threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     torch.set_num_threads(max(1, threads))
     cores = torch.get_num_threads()
     gen, det = build_models("cpu")
-    gsd = {k: v.detach() for k, v in gen.state_dict().items()}
-    dsd = {k: v.detach() for k, v in det.state_dict().items()}
-    s, m = synth(sample_B, 1234, "cpu")
+    gsd = {k: v.detach().to(device) for k, v in gen.state_dict().items()}
+    dsd = {k: v.detach().to(device) for k, v in det.state_dict().items()}
+    s, m = synth(sample_B, 1234, device)
     s = s.unsqueeze(1)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
+            if device != "cpu":
+                torch.cuda.synchronize()
             t0 = time.perf_counter()
-            O.embed_detect(gsd, dsd, s, m)
+            r = O.embed_detect(gsd, dsd, s, m)
+            if device != "cpu":
+                float(r["clip_prob"][0])         # device -> host read of a result
+                torch.cuda.synchronize()
+            del r
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     return sample_B * len(times) / sum(times), cores, times
@@ -149,9 +159,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_B = 16
-    rate, cores, times = cpu_reference_rate(sample_B, args.steps, args.warmup)
-    sample = f"{sample_B} clips per step (BASELINE configs[0]) of the {args.batch}-clip workload, torch CPU fp32"
+    sample_B = 16 if args.ref_device == "cpu" else args.ref_batch
+    rate, cores, times = cpu_reference_rate(sample_B, args.steps, args.warmup, device=args.ref_device, tf32=args.ref_tf32)
+    sample = (f"{sample_B} clips per step (BASELINE configs[0]) of the {args.batch}-clip workload, torch CPU fp32"
+              if args.ref_device == "cpu" else
+              f"{sample_B} clips per step, stock PyTorch eager on {args.ref_device}, tf32={args.ref_tf32} (informational)")
     line = {"impl": "reference", "metric": "clip-seconds/sec embed+detect (1 s@16 kHz)", "value": rate,
             "unit": "clip-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
@@ -327,6 +339,9 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="clips per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
+    ap.add_argument("--ref-device", default="cpu", help="--impl reference: cpu (the judged arm) or cuda (informational)")
+    ap.add_argument("--ref-batch", type=int, default=256, help="clips per step of --impl reference --ref-device cuda")
+    ap.add_argument("--ref-tf32", action="store_true", help="--ref-device cuda: allow TF32 (the reference's setting)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

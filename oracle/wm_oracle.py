@@ -155,7 +155,8 @@ def fir_taps(cutoff: float = 4000, taps: int = 101) -> Tensor:
 
 
 def fir_lowpass(delta: Tensor, cutoff: float = 4000, taps: int = 101) -> Tensor:
-    return F.conv1d(delta, fir_taps(cutoff, taps).view(1, 1, -1), padding=(taps - 1) // 2)
+    # the reference builds the taps on delta.device (py/main16.py:58)
+    return F.conv1d(delta, fir_taps(cutoff, taps).to(delta.device).view(1, 1, -1), padding=(taps - 1) // 2)
 
 
 def clamp_peak(d: Tensor, thr: float = 0.02) -> Tensor:

@@ -685,3 +685,24 @@ def test_pcm16_roundtrip_and_file_metrics():
         assert abs(float(m[b, 0]) - rms) < 1e-6 * max(rms, 1e-3)
         if n > 1:
             assert abs(float(m[b, 1]) - si) < 2e-3 and abs(float(m[b, 2]) - pr) < 1e-3
+
+
+def test_parity_on_many_random_clips(gen_B, det):
+    """The headline parity numbers on a wider sample than the five fixtures: 192 random clips of three loudness
+    levels through the oracle (CPU fp32) and through the CUDA path; tolerances are the north star's."""
+    g = torch.Generator().manual_seed(2024)
+    amp = torch.tensor([0.02, 0.1, 0.4]).repeat_interleave(64).view(-1, 1, 1)
+    s = (amp * torch.randn(192, 1, 16000, generator=g)).clamp(-0.99, 0.99)
+    ids = torch.from_numpy(np.concatenate([IO["messages"], IO["rng_messages"]]).astype(np.int64))
+    msg = ids[torch.randint(0, len(ids), (192,), generator=g)]
+    gsd, rows = H.gen_sd(W, "B")
+    torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
+    with torch.no_grad():
+        ref = O.embed_detect(gsd, H.det_sd(W), s, msg, emb_rows=H.emb_for(IO, rows, msg))
+    r = wmb200.embed_detect(gen_B, det, s.to(DEV), msg.to(DEV), want_votes=False)
+    e_delta, e_prob = maxerr(r["delta"], ref["delta"]), maxerr(r["probs"], ref["probs"])
+    e_ml = maxerr(r["msg_logits"], ref["msg_logits"])
+    print(f"192 clips: delta err {e_delta:.2e}, prob err {e_prob:.2e}, mean-logit err {e_ml:.2e}")
+    assert e_delta < DELTA_TOL and e_prob < PROB_TOL and e_ml < 1e-3
+    safe = ref["msg_logits"].abs() > 4 * max(e_ml, 1e-6)                 # bit-exact where the sign is decidable
+    assert torch.equal((r["msg_logits"].cpu() > 0)[safe], (ref["msg_logits"] > 0)[safe]) and float(safe.float().mean()) > 0.9
