@@ -706,3 +706,47 @@ def test_parity_on_many_random_clips(gen_B, det):
     assert e_delta < DELTA_TOL and e_prob < PROB_TOL and e_ml < 1e-3
     safe = ref["msg_logits"].abs() > 4 * max(e_ml, 1e-6)                 # bit-exact where the sign is decidable
     assert torch.equal((r["msg_logits"].cpu() > 0)[safe], (ref["msg_logits"] > 0)[safe]) and float(safe.float().mean()) > 0.9
+
+
+def test_validate_and_evaluate_twins_vs_oracle(gen_B, det, monkeypatch):
+    """validate_one_epoch (py/main16.py:297-364) and evaluate_model (:378-421) over a two-batch loader against the
+    same loops written with the oracle; the per-batch message draw is replayed from a fixed list."""
+    g = torch.Generator().manual_seed(12)
+    loader = [(0.1 * torch.randn(3, 1, 16000, generator=g)).clamp(-0.99, 0.99),
+              (0.05 * torch.randn(2, 1, 16000, generator=g)).clamp(-0.99, 0.99)]
+    ids = torch.from_numpy(np.concatenate([IO["messages"], IO["rng_messages"]]).astype(np.int64))
+    draws = [ids[[0, 5, 9]], ids[[12, 3]], ids[[1, 2, 4]], ids[[7, 8]]]
+    calls = {"i": 0}
+    real = torch.randint
+
+    def fake(lo, hi, size, device=None, **kw):
+        if tuple(size) in ((3,), (2,)) and hi == 65536:
+            m = draws[calls["i"] % len(draws)]
+            calls["i"] += 1
+            return m.to(device) if device is not None else m
+        return real(lo, hi, size, device=device, **kw)
+    monkeypatch.setattr(torch, "randint", fake)
+    v = wmb200.validate_one_epoch(gen_B, det, loader, None, DEV)
+    e = wmb200.evaluate_model(gen_B, det, loader, DEV)
+    monkeypatch.setattr(torch, "randint", real)
+    gsd, rows = H.gen_sd(W, "B")
+    gsd_full = dict(gsd, **{"embedding.weight": H.full_embedding(IO, rows)})
+    dsd = H.det_sd(W)
+    ref_v = {k: 0.0 for k in ("l1", "mel", "loud", "loc", "bce", "total")}
+    for s, m in zip(loader, draws[:2]):
+        r = O.losses(gsd_full, dsd, s, m)
+        for k in ref_v:
+            ref_v[k] += float(r[k]) / 2
+    for k, tol in (("l1", 1e-4), ("mel", 2e-3), ("loud", 2e-3), ("loc", 1e-3), ("bce", 1e-3), ("total", 2e-3)):
+        assert abs(v[k] - ref_v[k]) <= tol * max(abs(ref_v[k]), 1e-6), (k, v[k], ref_v[k])
+    assert set(v) == {"total", "raw_total", "l1", "mel", "loud", "loc", "bce"}
+    pw, pc, ba, rm = [], [], [], []
+    for s, m in zip(loader, draws[2:]):
+        r = O.embed_detect(gsd_full, dsd, s, m, detect_clean=True)
+        B = s.shape[0]
+        pw += r["clip_prob"][:B].tolist(); pc += r["clip_prob"][B:].tolist()
+        ba += (r["bits_vote"][:B] == (O.bit_targets(m) > 0.5)).float().mean(1).tolist()
+        rm += r["delta"][:, 0].pow(2).mean(1).sqrt().tolist()
+    assert abs(e["watermarked_prob"] - np.mean(pw)) < PROB_TOL and abs(e["clean_prob"] - np.mean(pc)) < PROB_TOL
+    assert abs(e["bit_accuracy"] - np.mean(ba)) < 0.05 and abs(e["delta_rms"] - np.mean(rm)) < 1e-6
+    assert set(e) == {"watermarked_prob", "clean_prob", "bit_accuracy", "delta_rms"}
