@@ -10,6 +10,7 @@ from . import _lib, audio, main14b_2, ops, packing
 from .audio import Resample, file_metrics, from_pcm16, resample, to_pcm16
 from .api import detect_prob, detect_watermark, generate_watermarked_audio, load_audio, save_audio, segment
 from .evaluate import evaluate_model, validate_one_epoch
+from .train import DetectorTrainer
 from .functional import (AUDIO_LEN, HF_PENALTY_W, LAMBDA_DEC, LAMBDA_L1, LAMBDA_LOC, LAMBDA_LOUD,
                          LAMBDA_MSSPEC, MAX_RMS, MESSAGE_BITS, SAMPLE_RATE, bit_targets, clamp_peak,
                          embed_detect, fir_lowpass, limit_rms, postprocess_delta)
@@ -24,4 +25,5 @@ __all__ = ["Generator", "Detector", "ResBlock", "generate_watermarked_audio", "d
            "SAMPLE_RATE", "AUDIO_LEN", "MESSAGE_BITS", "MAX_RMS", "LAMBDA_L1", "LAMBDA_MSSPEC", "LAMBDA_LOUD",
            "LAMBDA_LOC", "LAMBDA_DEC", "HF_PENALTY_W", "MultiScaleMelLoss", "TFLoudnessLoss", "high_freq_penalty",
            "step_losses", "stft_magnitude", "embed_detect_stream", "process_folder_with_tqdm", "detect_watermark_folder",
-           "Resample", "resample", "to_pcm16", "from_pcm16", "file_metrics", "evaluate_model", "validate_one_epoch"]
+           "Resample", "resample", "to_pcm16", "from_pcm16", "file_metrics", "evaluate_model", "validate_one_epoch",
+           "DetectorTrainer"]

@@ -12,7 +12,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwmb200.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 # blob offsets (floats) — mirror of the enums in include/wmb200.h
 RB_W1 = 0
@@ -58,6 +58,23 @@ D_SIZE = D_FIN + FIN_SIZE
 D_TC = (D_SIZE + 63) // 64 * 64
 D_BLOB = D_TC + 4 * TC_IMG3
 PLANAR_PAD = 4
+# training-mode detector parameters (WM_DT_* in include/wmb200.h)
+DT_RB_W1 = 0
+DT_RB_B1 = DT_RB_W1 + 3 * 64 * 64
+DT_RB_G1 = DT_RB_B1 + 64
+DT_RB_BE1 = DT_RB_G1 + 64
+DT_RB_W2 = DT_RB_BE1 + 64
+DT_RB_B2 = DT_RB_W2 + 3 * 64 * 64
+DT_RB_G2 = DT_RB_B2 + 64
+DT_RB_BE2 = DT_RB_G2 + 64
+DT_RB_SIZE = DT_RB_BE2 + 64
+DT_IN_W = 0
+DT_IN_B = DT_IN_W + 7 * 64
+DT_RB0 = DT_IN_B + 64
+DT_HEAD_W = DT_RB0 + 2 * DT_RB_SIZE
+DT_HEAD_B = DT_HEAD_W + 32 * 64
+DT_SIZE = DT_HEAD_B + 32
+DT_STATS = 2 * 4 * 64
 MAX_HEAD = 32
 POST_FIR, POST_CLAMP, POST_RMS, POST_ALL = 1, 2, 4, 7
 MATH_FP32, MATH_BF16X2 = 0, 1
@@ -67,6 +84,7 @@ _i = C.c_int
 _f = C.c_float
 _sz = C.c_size_t
 _i64 = C.c_int64
+_ll = C.c_longlong
 
 # name -> (restype, argtypes); every entry here must be declared in include/wmb200.h
 SIGNATURES = {
@@ -122,6 +140,15 @@ SIGNATURES = {
     "wm_pcm16_quantize_fwd": (_i, [_p, _p, _sz, _p]),
     "wm_pcm16_dequantize_fwd": (_i, [_p, _p, _sz, _f, _p]),
     "wm_file_metrics_fwd": (_i, [_p, _p, _p, _p, _i, _i, _p]),
+    "wm_detector_train_workspace_bytes": (_sz, [_i, _i, _i]),
+    "wm_detector_train_step": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f, _i, _p, _p, _p,
+                                    _sz, _p]),
+    "wm_bn_train_workspace_bytes": (_sz, [_ll]),
+    "wm_bn_train_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _p, _sz, _p]),
+    "wm_bn_train_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _p, _sz, _p]),
+    "wm_conv64_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "wm_conv64_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _sz, _p]),
+    "wm_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p]),
     "wm_embed_detect_host_workspace_bytes": (_sz, [_i, _i, _i]),
     "wm_embed_detect_host": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
                                   _i, _i, _i, _i, _i, _p]),

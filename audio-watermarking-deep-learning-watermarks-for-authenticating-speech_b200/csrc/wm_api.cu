@@ -528,6 +528,87 @@ int wm_abs_mean_fwd(const float *x, float *out, void *workspace, size_t workspac
   return launch_abs_mean(x, (long long)B * T, out, (float *)workspace, as_stream(stream));
 }
 
+/* ---- training (wm_train.cu) ---- */
+size_t wm_detector_train_workspace_bytes(int B_total, int T, int nout) {
+  if (B_total <= 0 || T <= 0 || nout < 1 || nout > WM_MAX_HEAD) return 0;
+  return detector_train_workspace_bytes(B_total, T, nout);
+}
+
+int wm_detector_train_step(float *params, float *grads, float *adam_m, float *adam_v, float *run_stats, const float *x,
+                           const int64_t *message, int B_wm, int B_total, int T, int nout, float lam_loc, float lam_dec,
+                           float lr, float beta1, float beta2, float eps, int adam_step, float *losses_out,
+                           float *d_input, void *workspace, size_t workspace_bytes, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B_total > 0 && T > 0 && B_wm >= 0 && B_wm <= B_total, "detector_train_step: bad batch sizes");
+  WM_CHECK_ARG((long long)B_total * T > 1, "detector_train_step: BatchNorm needs more than one value per channel");
+  WM_CHECK_ARG(nout >= 1 && nout <= WM_MAX_HEAD, "detector_train_step: nout must be in [1,%d]", WM_MAX_HEAD);
+  WM_CHECK_ARG(params && grads && run_stats && x && workspace && (message || nout == 1 || B_wm == 0),
+               "detector_train_step: null pointer");
+  WM_CHECK_ARG(adam_step >= 0 && (adam_step == 0 || (adam_m && adam_v)), "detector_train_step: Adam state missing");
+  WM_CHECK_ARG(workspace_bytes >= detector_train_workspace_bytes(B_total, T, nout),
+               "detector_train_step: workspace too small");
+  return detector_train_step(params, grads, adam_m, adam_v, run_stats, x, message, B_wm, B_total, T, nout, lam_loc,
+                             lam_dec, lr, beta1, beta2, eps, adam_step, losses_out, d_input, workspace,
+                             as_stream(stream));
+}
+
+size_t wm_bn_train_workspace_bytes(long long rows) { return rows > 0 ? train_scratch_doubles(rows) * sizeof(double) : 0; }
+
+int wm_bn_train_fwd(const float *z, const float *gamma, const float *beta, const float *residual, float *out,
+                    float *mean, float *rstd, float *run_mean, float *run_var, long long rows, int relu,
+                    void *workspace, size_t workspace_bytes, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(rows > 1, "bn_train_fwd: needs more than one row");
+  WM_CHECK_ARG(z && gamma && beta && out && mean && rstd && workspace && (!run_mean == !run_var),
+               "bn_train_fwd: null pointer");
+  WM_CHECK_ARG(workspace_bytes >= wm_bn_train_workspace_bytes(rows), "bn_train_fwd: workspace too small");
+  return launch_bn_train_fwd(z, gamma, beta, residual, out, mean, rstd, run_mean, run_var, rows, relu,
+                             (double *)workspace, as_stream(stream));
+}
+
+int wm_bn_train_bwd(const float *dout, const float *act, const float *z, const float *mean, const float *rstd,
+                    const float *gamma, float *dz, float *dres, float *dgamma, float *dbeta, long long rows,
+                    void *workspace, size_t workspace_bytes, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(rows > 1, "bn_train_bwd: needs more than one row");
+  WM_CHECK_ARG(dout && z && mean && rstd && gamma && dz && dgamma && dbeta && workspace, "bn_train_bwd: null pointer");
+  WM_CHECK_ARG(workspace_bytes >= wm_bn_train_workspace_bytes(rows), "bn_train_bwd: workspace too small");
+  return launch_bn_train_bwd(dout, act, z, mean, rstd, gamma, dz, dres, dgamma, dbeta, rows, (double *)workspace,
+                             as_stream(stream));
+}
+
+size_t wm_conv64_bwd_workspace_bytes(int B, int T, int K) {
+  if (B <= 0 || T <= 0 || K <= 0) return 0;
+  return (conv_wgrad_scratch_floats(B, T, K) + (size_t)K * 4096 + 64) * sizeof(float);
+}
+
+int wm_conv64_bwd(const float *x, const float *dy, const float *w, float *dw, float *db, float *dx, int B, int T, int K,
+                  void *workspace, size_t workspace_bytes, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B > 0 && T > 0, "conv64_bwd: bad size");
+  WM_CHECK_ARG(K == 1 || K == 3 || K == 7, "conv64_bwd: K must be 1, 3 or 7 (got %d)", K);
+  WM_CHECK_ARG(x && dy && dw && db && workspace && (!dx || w), "conv64_bwd: null pointer");
+  WM_CHECK_ARG(workspace_bytes >= wm_conv64_bwd_workspace_bytes(B, T, K), "conv64_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  float *scratch = (float *)workspace;
+  WM_TRY(launch_conv_wgrad(x, dy, dw, db, B, T, K, scratch, st));
+  if (dx) {
+    float *wt = scratch + conv_wgrad_scratch_floats(B, T, K), *zero = wt + (size_t)K * 4096;
+    WM_CHECK_CUDA(cudaMemsetAsync(zero, 0, 64 * sizeof(float), st));
+    WM_TRY(launch_transpose_flip(w, wt, K, st));
+    WM_TRY(launch_conv64_fp32(dy, wt, zero, nullptr, nullptr, dx, B, T, K, 0, st));
+  }
+  return 0;
+}
+
+int wm_adam_step(float *p, const float *g, float *m, float *v, long long n, float lr, float beta1, float beta2,
+                 float eps, int step, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(p && g && m && v && n >= 0 && step >= 1, "adam_step: bad arguments");
+  if (n == 0) return 0;
+  return launch_adam(p, g, m, v, n, lr, beta1, beta2, eps, step, as_stream(stream));
+}
+
 /* ---- generic operators of the main14b_2 stack (py/main14b_2.py:83-224) ---- */
 int wm_conv1d_out_len(int Tin, int K, int stride, int pad) { return (Tin + 2 * pad - K) / stride + 1; }
 int wm_convtranspose1d_out_len(int Tin, int K, int stride, int pad) { return (Tin - 1) * stride - 2 * pad + K; }

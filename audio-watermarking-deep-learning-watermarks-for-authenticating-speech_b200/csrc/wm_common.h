@@ -115,6 +115,25 @@ int launch_mel_log_l1(const float *clean, const float *wmk, const float *fb, con
 int launch_bce_heads(const float *logits, const int64_t *message, float *loc_out, float *bce_out, float *partials,
                      int B_wm, int B2, int T, int nout, cudaStream_t st);
 int launch_abs_mean(const float *x, long long n, float *out, float *partials, cudaStream_t st);
+// training building blocks (wm_train.cu)
+size_t train_scratch_doubles(long long N);
+size_t conv_wgrad_scratch_floats(int B, int T, int K);
+size_t detector_train_workspace_bytes(int B2, int T, int nout);
+int launch_bn_train_fwd(const float *z, const float *gamma, const float *beta, const float *residual, float *out,
+                        float *mean, float *rstd, float *run_mean, float *run_var, long long N, int relu, double *scratch,
+                        cudaStream_t st);
+int launch_bn_train_bwd(const float *dout, const float *act, const float *z, const float *mean, const float *rstd,
+                        const float *gamma, float *dz, float *dres, float *dgamma, float *dbeta, long long N,
+                        double *scratch, cudaStream_t st);
+int launch_transpose_flip(const float *w, float *wt, int K, cudaStream_t st);
+int launch_conv_wgrad(const float *x, const float *dz, float *dw, float *db, int B, int T, int K, float *scratch,
+                      cudaStream_t st);
+int launch_adam(float *p, const float *g, float *m, float *v, long long n, float lr, float b1, float b2, float eps,
+                int step, cudaStream_t st);
+int detector_train_step(float *params, float *grads, float *adam_m, float *adam_v, float *run_stats, const float *x,
+                        const int64_t *message, int B_wm, int B2, int T, int nout, float lam_loc, float lam_dec, float lr,
+                        float beta1, float beta2, float eps, int adam_step, float *losses_out, float *d_input,
+                        void *workspace, cudaStream_t st);
 // generic fp32 operators of the main14b_2 stack (wm_generic.cu); channels-first x[b][c][t]
 int launch_conv1d_generic(const float *x, const float *w, const float *bias, const float *chan_add, const float *res,
                           float *y, int B, int Cin, int Tin, int Cout, int K, int stride, int pad, int act,

@@ -1,0 +1,566 @@
+// Training-mode building blocks of the main16 path (py/main16.py:238-278), fp32 on the CUDA cores, channels-last
+// activations x[n][64] (n = b * T + t): batch-statistics BatchNorm forward / backward, convolution weight and data
+// gradients, 1x1-head and BCE gradients, Adam — and the detector's complete training step assembled from them
+// (forward in train mode, detection + message BCE, backward, Adam on one flat parameter buffer).  Every reduction
+// goes through per-block partial sums added in a fixed order, so a step is deterministic.
+// The generator's backward (LSTM through 16 000 steps, STFT losses) is not built yet: this file is the groundwork of
+// BASELINE config 4 and is exercised against PyTorch autograd in tests/test_train.py.
+#include "wm_common.h"
+
+namespace wm {
+
+namespace {
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---- per-channel sums over rows: partial[blk][k][64] (double), k < NK ---------------------------------------
+// MODE 0: {z, z^2}            MODE 1: {d, d * zhat} with d = dout * [act > 0], zhat = (z - mean) * rstd
+template <int MODE>
+__global__ void __launch_bounds__(NT)
+    chan_sums_kernel(const float *__restrict__ a, const float *__restrict__ b, const float *__restrict__ act,
+                     const float *__restrict__ mean, const float *__restrict__ rstd, long long N, int rows_per_block,
+                     double *__restrict__ partial) {
+  __shared__ double red[2][16][64];
+  const int c4 = (threadIdx.x & 15) * 4, rl = threadIdx.x >> 4;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < N ? r0 + rows_per_block : N;
+  float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+  float mu[4] = {0, 0, 0, 0}, rs[4] = {1, 1, 1, 1};
+  if (MODE == 1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { mu[k] = mean[c4 + k]; rs[k] = rstd[c4 + k]; }
+  }
+  for (long long r = r0 + rl; r < r1; r += 16) {
+    const float4 av = *reinterpret_cast<const float4 *>(a + r * 64 + c4);
+    const float v[4] = {av.x, av.y, av.z, av.w};
+    if (MODE == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { s0[k] += v[k]; s1[k] = fmaf(v[k], v[k], s1[k]); }
+    } else {
+      const float4 zv = *reinterpret_cast<const float4 *>(b + r * 64 + c4);
+      const float z[4] = {zv.x, zv.y, zv.z, zv.w};
+      float m[4] = {1, 1, 1, 1};
+      if (act) {
+        const float4 ov = *reinterpret_cast<const float4 *>(act + r * 64 + c4);
+        m[0] = ov.x > 0.f; m[1] = ov.y > 0.f; m[2] = ov.z > 0.f; m[3] = ov.w > 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float d = v[k] * m[k];
+        s0[k] += d;
+        s1[k] = fmaf(d, (z[k] - mu[k]) * rs[k], s1[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { red[0][rl][c4 + k] = s0[k]; red[1][rl][c4 + k] = s1[k]; }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+    double t = 0.0;
+    for (int i = 0; i < 16; ++i) t += red[which][i][c];
+    partial[((size_t)blockIdx.x * 2 + which) * 64 + c] = t;
+  }
+}
+
+// out[k][c] = sum_blk partial[blk][k][c]   (k < 2), fixed order
+__global__ void sum2_kernel(const double *__restrict__ partial, int nblk, double *__restrict__ out) {
+  const int i = threadIdx.x;   // 128 threads
+  double t = 0.0;
+  for (int b = 0; b < nblk; ++b) t += partial[(size_t)b * 128 + i];
+  out[i] = t;
+}
+
+// batch statistics from {sum z, sum z^2}; running stats as nn.BatchNorm1d (momentum 0.1, unbiased variance)
+__global__ void bn_finish_stats_kernel(const double *__restrict__ sums, long long N, float eps, float momentum,
+                                       float *__restrict__ mean, float *__restrict__ rstd, float *__restrict__ run_mean,
+                                       float *__restrict__ run_var) {
+  const int c = threadIdx.x;
+  const double m = sums[c] / (double)N;
+  double var = sums[64 + c] / (double)N - m * m;
+  if (var < 0) var = 0;
+  mean[c] = (float)m;
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (run_mean) {
+    run_mean[c] = (1.0f - momentum) * run_mean[c] + momentum * (float)m;
+    const double unb = N > 1 ? var * (double)N / (double)(N - 1) : var;
+    run_var[c] = (1.0f - momentum) * run_var[c] + momentum * (float)unb;
+  }
+}
+
+// out = relu?( gamma * (z - mean) * rstd + beta + residual )
+__global__ void bn_apply_kernel(const float *__restrict__ z, const float *__restrict__ mean, const float *__restrict__ rstd,
+                                const float *__restrict__ gamma, const float *__restrict__ beta,
+                                const float *__restrict__ residual, float *__restrict__ out, long long n4, int relu) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 15) * 4;
+    const float4 v = reinterpret_cast<const float4 *>(z)[i];
+    float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = gamma[c + k] * (o[k] - mean[c + k]) * rstd[c + k] + beta[c + k];
+    if (residual) {
+      const float4 r = reinterpret_cast<const float4 *>(residual)[i];
+      o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = fmaxf(o[k], 0.0f);
+    }
+    reinterpret_cast<float4 *>(out)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// d = dout * [act > 0];  dz = gamma * rstd * (d - S1/N - zhat * S2/N);  dres (nullable) = d;  sums = {S1, S2}
+__global__ void bn_bwd_apply_kernel(const float *__restrict__ dout, const float *__restrict__ act, const float *__restrict__ z,
+                                    const float *__restrict__ mean, const float *__restrict__ rstd,
+                                    const float *__restrict__ gamma, const double *__restrict__ sums, long long N,
+                                    float *__restrict__ dz, float *__restrict__ dres, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 15) * 4;
+    const float4 dv = reinterpret_cast<const float4 *>(dout)[i], zv = reinterpret_cast<const float4 *>(z)[i];
+    float d[4] = {dv.x, dv.y, dv.z, dv.w};
+    const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+    if (act) {
+      const float4 ov = reinterpret_cast<const float4 *>(act)[i];
+      d[0] *= ov.x > 0.f; d[1] *= ov.y > 0.f; d[2] *= ov.z > 0.f; d[3] *= ov.w > 0.f;
+    }
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float zh = (zz[k] - mean[c + k]) * rstd[c + k];
+      const float m1 = (float)(sums[c + k] / (double)N), m2 = (float)(sums[64 + c + k] / (double)N);
+      o[k] = gamma[c + k] * rstd[c + k] * (d[k] - m1 - zh * m2);
+    }
+    reinterpret_cast<float4 *>(dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (dres) reinterpret_cast<float4 *>(dres)[i] = make_float4(d[0], d[1], d[2], d[3]);
+  }
+}
+
+// dgamma = S2, dbeta = S1
+__global__ void bn_param_grads_kernel(const double *__restrict__ sums, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+  const int c = threadIdx.x;
+  dbeta[c] = (float)sums[c];
+  dgamma[c] = (float)sums[64 + c];
+}
+
+// w[j][ci][co] -> wt[K-1-j][co][ci]  (data-gradient weights of a stride-1 'same' convolution)
+__global__ void transpose_flip_kernel(const float *__restrict__ w, float *__restrict__ wt, int K) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= K * 4096) return;
+  const int co = e & 63, ci = (e >> 6) & 63, j = e >> 12;
+  wt[((K - 1 - j) * 64 + co) * 64 + ci] = w[e];
+}
+
+// weight gradient of y[t][co] = sum_j sum_ci w[j][ci][co] x[t + j - P][ci], one tap per blockIdx.z:
+// partial[blk][j][ci][co] = sum over the block's rows of x[t + j - P][ci] * dz[t][co];  bias partial on j == P
+constexpr int WG_ROWS = 512, WG_SUB = 64;
+__global__ void __launch_bounds__(NT)
+    conv_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ dz, int T, int K, int nchunk,
+                      float *__restrict__ partial_w, float *__restrict__ partial_b) {
+  __shared__ __align__(16) float xs[WG_SUB][68], ds[WG_SUB][68];
+  const int P = K / 2, j = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
+  const int t_begin = chunk * WG_ROWS, t_end = min(T, t_begin + WG_ROWS);
+  const int ci0 = (threadIdx.x >> 4) * 4, co0 = (threadIdx.x & 15) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.0f;
+  float bacc = 0.0f;   // threads < 64: bias gradient of channel threadIdx.x
+  const float *xb = x + (size_t)b * T * 64, *db = dz + (size_t)b * T * 64;
+  for (int t0 = t_begin; t0 < t_end; t0 += WG_SUB) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < WG_SUB * 16; i += NT) {
+      const int r = i >> 4, c4 = (i & 15) * 4, t = t0 + r, tx = t + j - P;
+      float4 xv = make_float4(0, 0, 0, 0), dv = make_float4(0, 0, 0, 0);
+      if (t < t_end) {
+        dv = *reinterpret_cast<const float4 *>(db + (size_t)t * 64 + c4);
+        if (tx >= 0 && tx < T) xv = *reinterpret_cast<const float4 *>(xb + (size_t)tx * 64 + c4);
+      }
+      *reinterpret_cast<float4 *>(&xs[r][c4]) = xv;
+      *reinterpret_cast<float4 *>(&ds[r][c4]) = dv;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < WG_SUB; ++r) {
+      const float4 xv = *reinterpret_cast<const float4 *>(&xs[r][ci0]);
+      const float4 dv = *reinterpret_cast<const float4 *>(&ds[r][co0]);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(xa[a], da[c], acc[a][c]);
+    }
+    if (j == P && threadIdx.x < 64) {
+      for (int r = 0; r < WG_SUB; ++r) bacc += ds[r][threadIdx.x];
+    }
+  }
+  const size_t blk = (size_t)b * nchunk + chunk;
+  float *pw = partial_w + (blk * K + j) * 4096;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+    *reinterpret_cast<float4 *>(&pw[(ci0 + a) * 64 + co0]) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+  if (j == P && threadIdx.x < 64) partial_b[blk * 64 + threadIdx.x] = bacc;
+}
+
+// out[i] = sum_blk partial[blk * n + i], fixed order
+__global__ void sum_partials_f_kernel(const float *__restrict__ partial, int nblk, int n, float *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double t = 0.0;
+  for (int b = 0; b < nblk; ++b) t += (double)partial[(size_t)b * n + i];
+  out[i] = (float)t;
+}
+
+// Conv1d(1,64,7,p=3) gradients: partial dw[blk][7][64], db[blk][64] from s[b][t], dx[b][t][64]
+constexpr int IN_ROWS = 1024;
+__global__ void __launch_bounds__(NT)
+    conv_in_wgrad_kernel(const float *__restrict__ s, const float *__restrict__ dx, int T, int nchunk,
+                         float *__restrict__ partial) {
+  __shared__ float red[4][8][64];
+  const int b = blockIdx.y, chunk = blockIdx.x, c = threadIdx.x & 63, part = threadIdx.x >> 6;
+  const int t_begin = chunk * IN_ROWS, t_end = min(T, t_begin + IN_ROWS);
+  const float *sb = s + (size_t)b * T, *db = dx + (size_t)b * T * 64;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int t = t_begin + part; t < t_end; t += 4) {
+    const float d = db[(size_t)t * 64 + c];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int ts = t + j - 3;
+      acc[j] = fmaf((ts >= 0 && ts < T) ? sb[ts] : 0.0f, d, acc[j]);
+    }
+    acc[7] += d;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[part][j][c] = acc[j];
+  __syncthreads();
+  if (part == 0) {
+    float *p = partial + ((size_t)b * nchunk + chunk) * 512;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p[j * 64 + c] = red[0][j][c] + red[1][j][c] + red[2][j][c] + red[3][j][c];
+  }
+}
+
+// ds[b][t] = sum_j sum_c w[j][c] dx[b][t - j + 3][c]
+__global__ void conv_in_dgrad_kernel(const float *__restrict__ dx, const float *__restrict__ w, float *__restrict__ ds, int T) {
+  __shared__ float ws[7 * 64];
+  for (int i = threadIdx.x; i < 448; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float *db = dx + (size_t)b * T * 64;
+  float a = 0.0f;
+  for (int j = 0; j < 7; ++j) {
+    const int tt = t - j + 3;
+    if (tt < 0 || tt >= T) continue;
+    const float4 *row = reinterpret_cast<const float4 *>(db + (size_t)tt * 64);
+    for (int c4 = 0; c4 < 16; ++c4) {
+      const float4 v = row[c4];
+      a = fmaf(v.x, ws[j * 64 + c4 * 4], a); a = fmaf(v.y, ws[j * 64 + c4 * 4 + 1], a);
+      a = fmaf(v.z, ws[j * 64 + c4 * 4 + 2], a); a = fmaf(v.w, ws[j * 64 + c4 * 4 + 3], a);
+    }
+  }
+  ds[(size_t)b * T + t] = a;
+}
+
+// BCE-with-logits gradients of  lam_loc * mean(BCE(ch 0, [b < B_wm])) + lam_dec * mean over b < B_wm of BCE(ch 1+j, bit j)
+__global__ void bce_heads_bwd_kernel(const float *__restrict__ logits, const long long *__restrict__ message, int B_wm,
+                                     int B2, int T, int nout, float lam_loc, float lam_dec, float *__restrict__ dlog) {
+  const long long rows = (long long)B2 * T;
+  const float s_loc = lam_loc / (float)rows;
+  const float s_dec = (B_wm > 0 && nout > 1) ? lam_dec / ((float)B_wm * (float)T * (float)(nout - 1)) : 0.0f;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(r / T);
+    const float *p = logits + r * nout;
+    float *g = dlog + r * nout;
+    g[0] = s_loc * (sigmoidf_(p[0]) - (b < B_wm ? 1.0f : 0.0f));
+    const long long m = b < B_wm ? message[b] : 0;
+    for (int j = 1; j < nout; ++j)
+      g[j] = b < B_wm ? s_dec * (sigmoidf_(p[j]) - (float)((m >> (j - 1)) & 1)) : 0.0f;
+  }
+}
+
+// 1x1 head (64 -> nout): dy[n][c] = sum_o dlog[n][o] w[o][c]
+__global__ void __launch_bounds__(NT)
+    head_dgrad_kernel(const float *__restrict__ dlog, const float *__restrict__ w, float *__restrict__ dy, long long N, int nout) {
+  __shared__ float ws[WM_MAX_HEAD * 64];
+  for (int i = threadIdx.x; i < nout * 64; i += NT) ws[i] = w[i];
+  __syncthreads();
+  const int c = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  for (long long r = (long long)blockIdx.x * 4 + rl; r < N; r += (long long)gridDim.x * 4) {
+    float a = 0.0f;
+    for (int o = 0; o < nout; ++o) a = fmaf(dlog[r * nout + o], ws[o * 64 + c], a);
+    dy[r * 64 + c] = a;
+  }
+}
+
+// partial dW[blk][o][c] = sum_rows dlog[r][o] y[r][c];  partial db[blk][o] = sum_rows dlog[r][o]
+constexpr int HW_ROWS = 1024;
+__global__ void __launch_bounds__(NT)
+    head_wgrad_kernel(const float *__restrict__ dlog, const float *__restrict__ y, long long N, int nout,
+                      float *__restrict__ partial_w, float *__restrict__ partial_b) {
+  const int c = threadIdx.x & 63, og = threadIdx.x >> 6;   // outputs og, og + 4, ...
+  const long long r0 = (long long)blockIdx.x * HW_ROWS, r1 = r0 + HW_ROWS < N ? r0 + HW_ROWS : N;
+  float acc[WM_MAX_HEAD / 4], bacc[WM_MAX_HEAD / 4];
+#pragma unroll
+  for (int k = 0; k < WM_MAX_HEAD / 4; ++k) { acc[k] = 0.0f; bacc[k] = 0.0f; }
+  for (long long r = r0; r < r1; ++r) {
+    const float yv = y[r * 64 + c];
+#pragma unroll
+    for (int k = 0; k < WM_MAX_HEAD / 4; ++k) {
+      const int o = og + 4 * k;
+      if (o < nout) {
+        const float d = dlog[r * nout + o];
+        acc[k] = fmaf(d, yv, acc[k]);
+        bacc[k] += d;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < WM_MAX_HEAD / 4; ++k) {
+    const int o = og + 4 * k;
+    if (o < nout) {
+      partial_w[((size_t)blockIdx.x * nout + o) * 64 + c] = acc[k];
+      if (c == 0) partial_b[(size_t)blockIdx.x * nout + o] = bacc[k];
+    }
+  }
+}
+
+// torch.optim.Adam (no weight decay, no amsgrad), bias-corrected
+__global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+  }
+}
+
+int grid_for(long long n, int per_block) {
+  long long g = (n + per_block - 1) / per_block;
+  return (int)(g < 1 ? 1 : (g > 8LL * sm_count() ? 8LL * sm_count() : g));
+}
+
+}  // namespace
+
+// ---- launchers (all async on st) --------------------------------------------------------------------------
+// scratch: doubles [nblk * 128 + 128]; returns sums {S1, S2} at scratch + nblk * 128
+static int chan_sums(int mode, const float *a, const float *b, const float *act, const float *mean, const float *rstd,
+                     long long N, double *scratch, double **sums_out, cudaStream_t st) {
+  const int rows_per_block = 1024;
+  const int nblk = (int)((N + rows_per_block - 1) / rows_per_block);
+  if (mode == 0) chan_sums_kernel<0><<<nblk, NT, 0, st>>>(a, b, act, mean, rstd, N, rows_per_block, scratch);
+  else chan_sums_kernel<1><<<nblk, NT, 0, st>>>(a, b, act, mean, rstd, N, rows_per_block, scratch);
+  WM_CHECK_LAUNCH("chan_sums");
+  double *sums = scratch + (size_t)nblk * 128;
+  sum2_kernel<<<1, 128, 0, st>>>(scratch, nblk, sums);
+  WM_CHECK_LAUNCH("sum2");
+  *sums_out = sums;
+  return 0;
+}
+
+size_t train_scratch_doubles(long long N) { return (size_t)((N + 1023) / 1024) * 128 + 128; }
+
+// z -> batch statistics (mean, rstd [64] each, running stats updated) -> out = relu?(bn(z) + residual)
+int launch_bn_train_fwd(const float *z, const float *gamma, const float *beta, const float *residual, float *out,
+                        float *mean, float *rstd, float *run_mean, float *run_var, long long N, int relu, double *scratch,
+                        cudaStream_t st) {
+  double *sums = nullptr;
+  WM_TRY(chan_sums(0, z, nullptr, nullptr, nullptr, nullptr, N, scratch, &sums, st));
+  bn_finish_stats_kernel<<<1, 64, 0, st>>>(sums, N, 1e-5f, 0.1f, mean, rstd, run_mean, run_var);
+  WM_CHECK_LAUNCH("bn_finish_stats");
+  bn_apply_kernel<<<grid_for(N * 16, NT), NT, 0, st>>>(z, mean, rstd, gamma, beta, residual, out, N * 16, relu);
+  WM_CHECK_LAUNCH("bn_apply");
+  return 0;
+}
+
+// dout (grad of the block's post-activation output `act`, nullable = no ReLU) -> dz, dres (nullable), dgamma, dbeta
+int launch_bn_train_bwd(const float *dout, const float *act, const float *z, const float *mean, const float *rstd,
+                        const float *gamma, float *dz, float *dres, float *dgamma, float *dbeta, long long N,
+                        double *scratch, cudaStream_t st) {
+  double *sums = nullptr;
+  WM_TRY(chan_sums(1, dout, z, act, mean, rstd, N, scratch, &sums, st));
+  bn_bwd_apply_kernel<<<grid_for(N * 16, NT), NT, 0, st>>>(dout, act, z, mean, rstd, gamma, sums, N, dz, dres, N * 16);
+  WM_CHECK_LAUNCH("bn_bwd_apply");
+  bn_param_grads_kernel<<<1, 64, 0, st>>>(sums, dgamma, dbeta);
+  WM_CHECK_LAUNCH("bn_param_grads");
+  return 0;
+}
+
+int launch_transpose_flip(const float *w, float *wt, int K, cudaStream_t st) {
+  transpose_flip_kernel<<<(K * 4096 + 255) / 256, 256, 0, st>>>(w, wt, K);
+  WM_CHECK_LAUNCH("transpose_flip");
+  return 0;
+}
+
+size_t conv_wgrad_scratch_floats(int B, int T, int K) {
+  const size_t nblk = (size_t)B * ((T + WG_ROWS - 1) / WG_ROWS);
+  return nblk * ((size_t)K * 4096 + 64);
+}
+
+// dW[K][64][64], db[64] of a 64->64 'same' convolution from its input x and output gradient dz
+int launch_conv_wgrad(const float *x, const float *dz, float *dw, float *db, int B, int T, int K, float *scratch,
+                      cudaStream_t st) {
+  const int nchunk = (T + WG_ROWS - 1) / WG_ROWS, nblk = B * nchunk;
+  float *pw = scratch, *pb = scratch + (size_t)nblk * K * 4096;
+  conv_wgrad_kernel<<<dim3(nchunk, B, K), NT, 0, st>>>(x, dz, T, K, nchunk, pw, pb);
+  WM_CHECK_LAUNCH("conv_wgrad");
+  sum_partials_f_kernel<<<(K * 4096 + 255) / 256, 256, 0, st>>>(pw, nblk, K * 4096, dw);
+  WM_CHECK_LAUNCH("sum_partials(w)");
+  sum_partials_f_kernel<<<1, 64, 0, st>>>(pb, nblk, 64, db);
+  WM_CHECK_LAUNCH("sum_partials(b)");
+  return 0;
+}
+
+int launch_conv_in_grads(const float *s, const float *dx, const float *w, float *dw, float *db, float *ds, int B, int T,
+                         float *scratch, cudaStream_t st) {
+  const int nchunk = (T + IN_ROWS - 1) / IN_ROWS, nblk = B * nchunk;
+  conv_in_wgrad_kernel<<<dim3(nchunk, B), NT, 0, st>>>(s, dx, T, nchunk, scratch);
+  WM_CHECK_LAUNCH("conv_in_wgrad");
+  sum_partials_f_kernel<<<2, 256, 0, st>>>(scratch, nblk, 512, scratch + (size_t)nblk * 512);
+  WM_CHECK_LAUNCH("sum_partials(in)");
+  WM_CHECK_CUDA(cudaMemcpyAsync(dw, scratch + (size_t)nblk * 512, 448 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  WM_CHECK_CUDA(cudaMemcpyAsync(db, scratch + (size_t)nblk * 512 + 448, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (ds) {
+    conv_in_dgrad_kernel<<<dim3((T + 255) / 256, B), 256, 0, st>>>(dx, w, ds, T);
+    WM_CHECK_LAUNCH("conv_in_dgrad");
+  }
+  return 0;
+}
+
+int launch_bce_heads_bwd(const float *logits, const int64_t *message, int B_wm, int B2, int T, int nout, float lam_loc,
+                         float lam_dec, float *dlog, cudaStream_t st) {
+  bce_heads_bwd_kernel<<<grid_for((long long)B2 * T, NT), NT, 0, st>>>(logits, reinterpret_cast<const long long *>(message),
+                                                                      B_wm, B2, T, nout, lam_loc, lam_dec, dlog);
+  WM_CHECK_LAUNCH("bce_heads_bwd");
+  return 0;
+}
+
+int launch_head_bwd(const float *dlog, const float *y, const float *w, float *dy, float *dw, float *db, long long N,
+                    int nout, float *scratch, cudaStream_t st) {
+  head_dgrad_kernel<<<grid_for(N, 4), NT, 0, st>>>(dlog, w, dy, N, nout);
+  WM_CHECK_LAUNCH("head_dgrad");
+  const int nblk = (int)((N + HW_ROWS - 1) / HW_ROWS);
+  float *pw = scratch, *pb = scratch + (size_t)nblk * nout * 64;
+  head_wgrad_kernel<<<nblk, NT, 0, st>>>(dlog, y, N, nout, pw, pb);
+  WM_CHECK_LAUNCH("head_wgrad");
+  sum_partials_f_kernel<<<(nout * 64 + 255) / 256, 256, 0, st>>>(pw, nblk, nout * 64, dw);
+  WM_CHECK_LAUNCH("sum_partials(hw)");
+  sum_partials_f_kernel<<<1, 64, 0, st>>>(pb, nblk, nout, db);
+  WM_CHECK_LAUNCH("sum_partials(hb)");
+  return 0;
+}
+
+int launch_adam(float *p, const float *g, float *m, float *v, long long n, float lr, float b1, float b2, float eps,
+                int step, cudaStream_t st) {
+  const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
+  adam_kernel<<<grid_for(n, NT), NT, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2);
+  WM_CHECK_LAUNCH("adam");
+  return 0;
+}
+
+// ---- the detector's training step ---------------------------------------------------------------------------
+namespace {
+struct DetWs {
+  float *x0, *act[2][4] /* z1, u, z2, y */, *logits, *dlog, *g[3], *wt, *stats, *zero64, *fscratch, *losses;
+  double *dscratch;
+  size_t bytes;
+};
+size_t align64(size_t n) { return (n + 63) / 64 * 64; }
+DetWs det_ws(void *base, int B2, int T, int nout) {
+  const size_t N = (size_t)B2 * T, A = align64(N * 64), L = align64(N * nout);
+  const size_t nb_h = (N + HW_ROWS - 1) / HW_ROWS, nb_in = (size_t)B2 * ((T + IN_ROWS - 1) / IN_ROWS);
+  size_t fs = conv_wgrad_scratch_floats(B2, T, 3);
+  if (fs < nb_h * (nout * 64 + nout)) fs = nb_h * (nout * 64 + nout);
+  if (fs < nb_in * 512 + 512) fs = nb_in * 512 + 512;
+  const size_t loss_f = wm_loss_workspace_bytes(B2, T) / sizeof(float);
+  if (fs < loss_f) fs = loss_f;
+  DetWs w;
+  float *p = (float *)base;
+  size_t off = 0;
+  auto take = [&](size_t n) { float *q = p ? p + off : nullptr; off += align64(n); return q; };
+  w.x0 = take(A);
+  for (int k = 0; k < 2; ++k)
+    for (int i = 0; i < 4; ++i) w.act[k][i] = take(A);
+  w.logits = take(L);
+  w.dlog = take(L);
+  for (int i = 0; i < 3; ++i) w.g[i] = take(A);
+  w.wt = take(3 * 4096);
+  w.stats = take(4 * 128);
+  w.zero64 = take(64);
+  w.losses = take(64);
+  w.fscratch = take(fs);
+  w.dscratch = (double *)take(2 * train_scratch_doubles((long long)N));
+  w.bytes = off * sizeof(float);
+  return w;
+}
+}  // namespace
+
+size_t detector_train_workspace_bytes(int B2, int T, int nout) { return det_ws(nullptr, B2, T, nout).bytes; }
+
+// One training step of the Detector (py/main16.py:160-176 in train mode, losses of :249-264) on x[B2][T] whose first
+// B_wm clips carry message[b]:  loss = lam_loc * loc + lam_dec * bce.  params / grads / adam_m / adam_v: WM_DT_SIZE
+// floats; run_stats: WM_DT_STATS floats (running mean, var of the four BatchNorms); losses_out: {loc, bce} (device).
+// d_input (nullable): gradient of the loss w.r.t. x.  adam_step = 0 skips the optimizer (gradients only).
+int detector_train_step(float *params, float *grads, float *adam_m, float *adam_v, float *run_stats, const float *x,
+                        const int64_t *message, int B_wm, int B2, int T, int nout, float lam_loc, float lam_dec, float lr,
+                        float beta1, float beta2, float eps, int adam_step, float *losses_out, float *d_input,
+                        void *workspace, cudaStream_t st) {
+  DetWs w = det_ws(workspace, B2, T, nout);
+  const long long N = (long long)B2 * T;
+  WM_CHECK_CUDA(cudaMemsetAsync(w.zero64, 0, 64 * sizeof(float), st));
+  WM_CHECK_CUDA(cudaMemsetAsync(w.losses, 0, 2 * sizeof(float), st));
+  WM_CHECK_CUDA(cudaMemsetAsync(grads, 0, (size_t)WM_DT_SIZE * sizeof(float), st));
+  // forward
+  WM_TRY(launch_conv_in_k7(x, params + WM_DT_IN_W, params + WM_DT_IN_B, w.x0, B2, T, st));
+  const float *in = w.x0;
+  for (int k = 0; k < 2; ++k) {
+    const float *rb = params + WM_DT_RB0 + k * WM_DT_RB_SIZE;
+    float *rs = run_stats + k * 256, *stt = w.stats + k * 256;
+    float *z1 = w.act[k][0], *u = w.act[k][1], *z2 = w.act[k][2], *y = w.act[k][3];
+    WM_TRY(launch_conv64_fp32(in, rb + WM_DT_RB_W1, rb + WM_DT_RB_B1, nullptr, nullptr, z1, B2, T, 3, 0, st));
+    WM_TRY(launch_bn_train_fwd(z1, rb + WM_DT_RB_G1, rb + WM_DT_RB_BE1, nullptr, u, stt, stt + 64, rs, rs + 64, N, 1,
+                               w.dscratch, st));
+    WM_TRY(launch_conv64_fp32(u, rb + WM_DT_RB_W2, rb + WM_DT_RB_B2, nullptr, nullptr, z2, B2, T, 3, 0, st));
+    WM_TRY(launch_bn_train_fwd(z2, rb + WM_DT_RB_G2, rb + WM_DT_RB_BE2, in, y, stt + 128, stt + 192, rs + 128, rs + 192, N,
+                               1, w.dscratch, st));
+    in = y;
+  }
+  WM_TRY(launch_head(in, params + WM_DT_HEAD_W, params + WM_DT_HEAD_B, w.logits, B2, T, nout, st));
+  WM_TRY(launch_bce_heads(w.logits, message, w.losses, nout > 1 ? w.losses + 1 : nullptr, w.fscratch, B_wm, B2, T, nout, st));
+  if (losses_out) WM_CHECK_CUDA(cudaMemcpyAsync(losses_out, w.losses, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // backward
+  WM_TRY(launch_bce_heads_bwd(w.logits, message, B_wm, B2, T, nout, lam_loc, lam_dec, w.dlog, st));
+  float *gA = w.g[0], *gB = w.g[1], *gC = w.g[2];
+  WM_TRY(launch_head_bwd(w.dlog, in, params + WM_DT_HEAD_W, gA, grads + WM_DT_HEAD_W, grads + WM_DT_HEAD_B, N, nout,
+                         w.fscratch, st));
+  for (int k = 1; k >= 0; --k) {
+    const float *rb = params + WM_DT_RB0 + k * WM_DT_RB_SIZE;
+    float *gr = grads + WM_DT_RB0 + k * WM_DT_RB_SIZE;
+    const float *stt = w.stats + k * 256;
+    const float *xin = k == 0 ? w.x0 : w.act[0][3];
+    const float *z1 = w.act[k][0], *u = w.act[k][1], *z2 = w.act[k][2], *y = w.act[k][3];
+    WM_TRY(launch_bn_train_bwd(gA, y, z2, stt + 128, stt + 192, rb + WM_DT_RB_G2, gB, gC, gr + WM_DT_RB_G2,
+                               gr + WM_DT_RB_BE2, N, w.dscratch, st));
+    WM_TRY(launch_conv_wgrad(u, gB, gr + WM_DT_RB_W2, gr + WM_DT_RB_B2, B2, T, 3, w.fscratch, st));
+    WM_TRY(launch_transpose_flip(rb + WM_DT_RB_W2, w.wt, 3, st));
+    WM_TRY(launch_conv64_fp32(gB, w.wt, w.zero64, nullptr, nullptr, gA, B2, T, 3, 0, st));
+    WM_TRY(launch_bn_train_bwd(gA, u, z1, stt, stt + 64, rb + WM_DT_RB_G1, gB, nullptr, gr + WM_DT_RB_G1, gr + WM_DT_RB_BE1,
+                               N, w.dscratch, st));
+    WM_TRY(launch_conv_wgrad(xin, gB, gr + WM_DT_RB_W1, gr + WM_DT_RB_B1, B2, T, 3, w.fscratch, st));
+    WM_TRY(launch_transpose_flip(rb + WM_DT_RB_W1, w.wt, 3, st));
+    WM_TRY(launch_conv64_fp32(gB, w.wt, w.zero64, gC, nullptr, gA, B2, T, 3, 0, st));
+  }
+  WM_TRY(launch_conv_in_grads(x, gA, params + WM_DT_IN_W, grads + WM_DT_IN_W, grads + WM_DT_IN_B, d_input, B2, T,
+                              w.fscratch, st));
+  if (adam_step > 0)
+    WM_TRY(launch_adam(params, grads, adam_m, adam_v, WM_DT_SIZE, lr, beta1, beta2, eps, adam_step, st));
+  return 0;
+}
+
+}  // namespace wm

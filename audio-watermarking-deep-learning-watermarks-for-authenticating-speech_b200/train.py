@@ -1,0 +1,238 @@
+"""Training-mode pieces of the main16 path (py/main16.py:223-294, BASELINE config 4).
+
+Built so far: the Detector's half of `train_one_epoch` — forward with batch-statistics BatchNorm, the detection and
+message BCE losses, backward through the whole network and Adam, all inside one C-ABI call
+(`wm_detector_train_step`) on one flat parameter buffer — plus the operators it is made of (`bn_train_fwd/bwd`,
+`conv64_bwd`, `adam_step`).  The Generator's backward (the LSTM through 16 000 steps and the spectral losses) is not
+built: `DetectorTrainer.step` returns the gradient w.r.t. the detector input, which is where it would attach.
+Everything runs in fp32 on the CUDA cores and is deterministic (fixed-order partial sums).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from .ops import _req, _stream, _ws
+
+LR = 1e-3            # py/main16.py:33
+LAMBDA_LOC = 10.0    # py/main16.py:41
+LAMBDA_DEC = 1.0     # py/main16.py:42
+
+
+# ---- operators ------------------------------------------------------------------------------------------------
+def bn_train_fwd(z: torch.Tensor, gamma, beta, residual: Optional[torch.Tensor] = None, relu: bool = True,
+                 running_mean: Optional[torch.Tensor] = None, running_var: Optional[torch.Tensor] = None):
+    """relu?(BatchNorm1d(64)(z) + residual) with batch statistics on channels-last z (..., 64); running stats
+    (momentum 0.1, unbiased variance) are updated in place when given.  Returns (out, mean, rstd)."""
+    lib = L.load()
+    z = _req(z, "z")
+    rows = z.numel() // 64
+    out = torch.empty_like(z)
+    mean, rstd = torch.empty(64, device=z.device), torch.empty(64, device=z.device)
+    res = _req(residual, "residual") if residual is not None else None
+    n = lib.wm_bn_train_workspace_bytes(rows)
+    ws = _ws(n, z.device)
+    L.check(lib.wm_bn_train_fwd(L.ptr(z), L.ptr(_req(gamma, "gamma")), L.ptr(_req(beta, "beta")), L.ptr(res), L.ptr(out),
+                                L.ptr(mean), L.ptr(rstd), L.ptr(running_mean), L.ptr(running_var), rows, int(relu),
+                                L.ptr(ws), n, _stream()), "wm_bn_train_fwd")
+    return out, mean, rstd
+
+
+def bn_train_bwd(dout: torch.Tensor, act: Optional[torch.Tensor], z: torch.Tensor, mean, rstd, gamma,
+                 want_residual_grad: bool = False):
+    """Backward of bn_train_fwd: returns (dz, dres or None, dgamma, dbeta)."""
+    lib = L.load()
+    dout, z = _req(dout, "dout"), _req(z, "z")
+    rows = z.numel() // 64
+    dz = torch.empty_like(z)
+    dres = torch.empty_like(z) if want_residual_grad else None
+    dg, db = torch.empty(64, device=z.device), torch.empty(64, device=z.device)
+    n = lib.wm_bn_train_workspace_bytes(rows)
+    ws = _ws(n, z.device)
+    L.check(lib.wm_bn_train_bwd(L.ptr(dout), L.ptr(_req(act, "act")) if act is not None else None, L.ptr(z),
+                                L.ptr(_req(mean, "mean")), L.ptr(_req(rstd, "rstd")), L.ptr(_req(gamma, "gamma")),
+                                L.ptr(dz), L.ptr(dres), L.ptr(dg), L.ptr(db), rows, L.ptr(ws), n, _stream()),
+            "wm_bn_train_bwd")
+    return dz, dres, dg, db
+
+
+def conv64_bwd(x: torch.Tensor, dy: torch.Tensor, weight: torch.Tensor, want_dx: bool = True):
+    """Gradients of Conv1d(64,64,K,padding=K//2) on channels-last x, dy (B,T,64); `weight` in the reference's
+    (co,ci,K) layout.  Returns (dweight (co,ci,K), dbias (64), dx or None)."""
+    lib = L.load()
+    x, dy = _req(x, "x"), _req(dy, "dy")
+    B, T, _ = x.shape
+    K = weight.shape[-1]
+    w_t = _req(weight, "weight").permute(2, 1, 0).contiguous()          # [k][ci][co]
+    dw = torch.empty(K, 64, 64, device=x.device)
+    db = torch.empty(64, device=x.device)
+    dx = torch.empty_like(x) if want_dx else None
+    n = lib.wm_conv64_bwd_workspace_bytes(B, T, K)
+    ws = _ws(n, x.device)
+    L.check(lib.wm_conv64_bwd(L.ptr(x), L.ptr(dy), L.ptr(w_t), L.ptr(dw), L.ptr(db), L.ptr(dx), B, T, K, L.ptr(ws), n,
+                              _stream()), "wm_conv64_bwd")
+    return dw.permute(2, 1, 0).contiguous(), db, dx
+
+
+def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int, lr: float = LR,
+              betas=(0.9, 0.999), eps: float = 1e-8) -> None:
+    """torch.optim.Adam's update of the flat fp32 buffer p in place (py/main16.py:504)."""
+    lib = L.load()
+    for t, name in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError(f"adam_step: {name} must be a contiguous fp32 CUDA tensor")
+    L.check(lib.wm_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), lr, betas[0], betas[1], eps, step,
+                             _stream()), "wm_adam_step")
+
+
+# ---- flat parameter buffer <-> state dict -----------------------------------------------------------------------
+def _dt_slices(nout: int):
+    """name -> (offset, shape in the flat buffer, whether the state-dict layout is its (2,1,0) transpose)."""
+    out = {"model.0.weight": (L.DT_IN_W, (7, 1, 64), True), "model.0.bias": (L.DT_IN_B, (64,), False)}
+    for k in range(2):
+        base, pre = L.DT_RB0 + k * L.DT_RB_SIZE, f"model.{1 + k}.block."
+        out[pre + "0.weight"] = (base + L.DT_RB_W1, (3, 64, 64), True)
+        out[pre + "0.bias"] = (base + L.DT_RB_B1, (64,), False)
+        out[pre + "1.weight"] = (base + L.DT_RB_G1, (64,), False)
+        out[pre + "1.bias"] = (base + L.DT_RB_BE1, (64,), False)
+        out[pre + "3.weight"] = (base + L.DT_RB_W2, (3, 64, 64), True)
+        out[pre + "3.bias"] = (base + L.DT_RB_B2, (64,), False)
+        out[pre + "4.weight"] = (base + L.DT_RB_G2, (64,), False)
+        out[pre + "4.bias"] = (base + L.DT_RB_BE2, (64,), False)
+    out["model.3.weight"] = (L.DT_HEAD_W, (nout, 64, 1), False)
+    out["model.3.bias"] = (L.DT_HEAD_B, (nout,), False)
+    return out
+
+
+def _dt_stat_slices():
+    out = {}
+    for k in range(2):
+        for i, bn in enumerate(("1", "4")):
+            pre = f"model.{1 + k}.block.{bn}."
+            out[pre + "running_mean"] = k * 256 + i * 128
+            out[pre + "running_var"] = k * 256 + i * 128 + 64
+    return out
+
+
+def flatten_detector(sd: Dict[str, torch.Tensor], nout: int, device) -> torch.Tensor:
+    flat = torch.zeros(L.DT_SIZE, dtype=torch.float32, device=device)
+    for name, (off, shape, perm) in _dt_slices(nout).items():
+        t = sd[name].detach().to(device=device, dtype=torch.float32)
+        if perm:
+            t = t.permute(2, 1, 0)
+        flat[off:off + t.numel()] = t.reshape(-1)
+    return flat
+
+
+def unflatten_detector(flat: torch.Tensor, nout: int) -> Dict[str, torch.Tensor]:
+    out = {}
+    for name, (off, shape, perm) in _dt_slices(nout).items():
+        n = 1
+        for d in shape:
+            n *= d
+        t = flat[off:off + n].reshape(shape)
+        if perm:
+            t = t.permute(2, 1, 0)
+        out[name] = t.contiguous().clone()
+    return out
+
+
+class DetectorTrainer:
+    """Holds a Detector's training state on the device (parameters, gradients, Adam moments, BatchNorm running stats)
+    and advances it one `train_one_epoch` iteration at a time (py/main16.py:249-264,277-278, detector part).
+
+        tr = DetectorTrainer(detector)          # wmb200.Detector or the reference's Detector (same state dict)
+        for s_w, s, message in batches:
+            out = tr.step(torch.cat([s_w, s]), message)     # {"loc": ..., "bce": ...}
+        tr.write_back(detector)                 # parameters + running stats into the module
+    """
+
+    def __init__(self, detector: torch.nn.Module, lr: float = LR, betas=(0.9, 0.999), eps: float = 1e-8,
+                 lambda_loc: float = LAMBDA_LOC, lambda_dec: float = LAMBDA_DEC, device=None):
+        sd = detector.state_dict()
+        self.nout = int(sd["model.3.weight"].shape[0])
+        if self.nout > L.MAX_HEAD:
+            raise ValueError(f"detector head has {self.nout} outputs; at most {L.MAX_HEAD} are supported")
+        if device is None:
+            device = sd["model.3.weight"].device
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("DetectorTrainer runs on a B200 (sm_100a) only; there is no CPU fallback — move the "
+                               "detector to cuda first")
+        L.load()
+        self.device = device
+        self.params = flatten_detector(sd, self.nout, device)
+        self.grads = torch.zeros_like(self.params)
+        self.adam_m = torch.zeros_like(self.params)
+        self.adam_v = torch.zeros_like(self.params)
+        self.run_stats = torch.zeros(L.DT_STATS, dtype=torch.float32, device=device)
+        for name, off in _dt_stat_slices().items():
+            self.run_stats[off:off + 64] = sd[name].to(device=device, dtype=torch.float32)
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.lambda_loc, self.lambda_dec = float(lambda_loc), float(lambda_dec)
+        self.steps = 0
+        self._ws = None
+        self._ws_key = None
+
+    def _workspace(self, B2: int, T: int):
+        key = (B2, T)
+        if self._ws_key != key:
+            n = L.load().wm_detector_train_workspace_bytes(B2, T, self.nout)
+            self._ws, self._ws_key = (_ws(n, self.device), n), key
+        return self._ws
+
+    def step(self, x: torch.Tensor, message: Optional[torch.Tensor], n_watermarked: Optional[int] = None,
+             update: bool = True, want_input_grad: bool = False) -> Dict[str, torch.Tensor]:
+        """x (B_total, T) or (B_total, 1, T): the first n_watermarked clips (default: len(message)) carry message[b].
+        Returns {"loc", "bce"} (0-d device tensors, the unweighted losses) and "d_input" when asked.
+        update=False computes the gradients (self.grads) and BatchNorm statistics without touching the parameters."""
+        lib = L.load()
+        x = _req(x, "x")
+        if x.dim() == 3 and x.shape[1] == 1:
+            x = x[:, 0]
+        if x.dim() != 2:
+            raise ValueError(f"x must be (B,T) or (B,1,T), got {tuple(x.shape)}")
+        B2, T = x.shape
+        x = x.contiguous()
+        msg = _req(message, "message", torch.int64) if message is not None else None
+        if n_watermarked is None:
+            n_watermarked = 0 if msg is None else int(msg.numel())
+        if msg is not None and msg.numel() < n_watermarked:
+            raise ValueError("message must hold one value per watermarked clip")
+        losses = torch.zeros(2, device=self.device)
+        d_in = torch.empty_like(x) if want_input_grad else None
+        ws, n = self._workspace(B2, T)
+        step_no = self.steps + 1 if update else 0
+        L.check(lib.wm_detector_train_step(L.ptr(self.params), L.ptr(self.grads), L.ptr(self.adam_m), L.ptr(self.adam_v),
+                                           L.ptr(self.run_stats), L.ptr(x), L.ptr(msg), n_watermarked, B2, T, self.nout,
+                                           self.lambda_loc, self.lambda_dec, self.lr, self.betas[0], self.betas[1],
+                                           self.eps, step_no, L.ptr(losses), L.ptr(d_in), L.ptr(ws), n, _stream()),
+                "wm_detector_train_step")
+        if update:
+            self.steps += 1
+        out = {"loc": losses[0], "bce": losses[1]}
+        if want_input_grad:
+            out["d_input"] = d_in
+        return out
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """The detector's state dict (reference key names and layouts) at the current step."""
+        sd = unflatten_detector(self.params, self.nout)
+        for name, off in _dt_stat_slices().items():
+            sd[name] = self.run_stats[off:off + 64].clone()
+        return sd
+
+    def grad_dict(self) -> Dict[str, torch.Tensor]:
+        """Gradients of the last step, keyed and laid out like the parameters of the state dict."""
+        return unflatten_detector(self.grads, self.nout)
+
+    @torch.no_grad()
+    def write_back(self, detector: torch.nn.Module) -> None:
+        own = detector.state_dict()
+        for k, v in self.state_dict().items():
+            own[k].copy_(v.to(own[k].device))
+        for k in own:
+            if k.endswith("num_batches_tracked"):
+                own[k] += self.steps

@@ -32,7 +32,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 12
+#define WM_ABI_VERSION 13
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -99,6 +99,27 @@ enum {                                   /* Detector, py/main16.py:170-186 */
   WM_D_SIZE = WM_D_FIN + WM_FIN_SIZE,
   WM_D_TC = (WM_D_SIZE + 63) / 64 * 64,  /* model.1 conv1, conv2, model.2 conv1, conv2 */
   WM_D_BLOB = WM_D_TC + 4 * WM_TC_IMG3
+};
+
+/* Training-mode Detector parameters (BatchNorm NOT folded), one flat fp32 buffer that Adam updates in place;
+ * gradients and both Adam moments use the same layout.  Convolution weights are tap-major [k][ci][co]. */
+enum {
+  WM_DT_RB_W1 = 0,                         /* conv1.weight [3][64][64]                  */
+  WM_DT_RB_B1 = WM_DT_RB_W1 + 3 * 64 * 64, /* conv1.bias                                 */
+  WM_DT_RB_G1 = WM_DT_RB_B1 + 64,          /* bn1.weight                                 */
+  WM_DT_RB_BE1 = WM_DT_RB_G1 + 64,         /* bn1.bias                                   */
+  WM_DT_RB_W2 = WM_DT_RB_BE1 + 64,
+  WM_DT_RB_B2 = WM_DT_RB_W2 + 3 * 64 * 64,
+  WM_DT_RB_G2 = WM_DT_RB_B2 + 64,
+  WM_DT_RB_BE2 = WM_DT_RB_G2 + 64,
+  WM_DT_RB_SIZE = WM_DT_RB_BE2 + 64,
+  WM_DT_IN_W = 0,                          /* model.0 [7][64]                            */
+  WM_DT_IN_B = WM_DT_IN_W + 7 * 64,
+  WM_DT_RB0 = WM_DT_IN_B + 64,             /* model.1, model.2                           */
+  WM_DT_HEAD_W = WM_DT_RB0 + 2 * WM_DT_RB_SIZE, /* model.3 [32][64] (rows >= nout zero)  */
+  WM_DT_HEAD_B = WM_DT_HEAD_W + 32 * 64,
+  WM_DT_SIZE = WM_DT_HEAD_B + 32,
+  WM_DT_STATS = 2 * 4 * 64                 /* per ResBlock: bn1 running_mean, running_var, bn2 ... */
 };
 
 /* Arithmetic of the 64->64 convolutions (the tensor-pipe part of the path).
@@ -310,6 +331,39 @@ int wm_pcm16_dequantize_fwd(const int16_t *q, float *x, size_t n, float scale, v
 /* Per-row quality metrics of generate_watermarked_audio (py/main16.py:1030-1049; compute_si_snr :764-773):
  * out[b] = {watermark_rms, si_snr_db, power_ratio_db} over the first valid_len[b] samples (nullable = T). */
 int wm_file_metrics_fwd(const float *s, const float *s_w, const int *valid_len, float *out, int B, int T, void *stream);
+
+/* ---- training (BASELINE config 4): the Detector's half of train_one_epoch ----
+ * One optimisation step of the Detector (py/main16.py:160-176 in train mode: batch-statistics BatchNorm, running
+ * stats updated with momentum 0.1) on x[B_total][T] whose first B_wm clips are watermarked with message[b]
+ * (py/main16.py:249-264): loss = lam_loc * BCE(ch 0, [b < B_wm]) + lam_dec * BCE(ch 1.., bits), backward through
+ * the whole network, then torch.optim.Adam (bias-corrected, no weight decay) when adam_step >= 1 (adam_step = 0
+ * leaves params untouched: gradients only).  params / grads / adam_m / adam_v: WM_DT_SIZE floats, run_stats:
+ * WM_DT_STATS floats, losses_out (device, nullable): {loc, bce}; d_input (nullable) [B_total][T] receives the
+ * gradient w.r.t. x (what the generator's backward consumes).  fp32 on the CUDA cores, deterministic. */
+size_t wm_detector_train_workspace_bytes(int B_total, int T, int nout);
+int wm_detector_train_step(float *params, float *grads, float *adam_m, float *adam_v, float *run_stats, const float *x,
+                           const int64_t *message, int B_wm, int B_total, int T, int nout, float lam_loc, float lam_dec,
+                           float lr, float beta1, float beta2, float eps, int adam_step, float *losses_out,
+                           float *d_input, void *workspace, size_t workspace_bytes, void *stream);
+/* Building blocks of the step, exposed for the parity tests (channels-last x[n][64], n = B*T rows):
+ * nn.BatchNorm1d(64) in train mode fused with the residual add and ReLU of py/main16.py:118-127 ... */
+int wm_bn_train_fwd(const float *z, const float *gamma, const float *beta, const float *residual, float *out,
+                    float *mean, float *rstd, float *run_mean, float *run_var, long long rows, int relu,
+                    void *workspace, size_t workspace_bytes, void *stream);
+/* ... its backward: dout is the gradient of `act` (the block output after ReLU, nullable = no ReLU); dres (nullable)
+ * receives the gradient of the residual input. */
+int wm_bn_train_bwd(const float *dout, const float *act, const float *z, const float *mean, const float *rstd,
+                    const float *gamma, float *dz, float *dres, float *dgamma, float *dbeta, long long rows,
+                    void *workspace, size_t workspace_bytes, void *stream);
+/* Gradients of y = Conv1d(64,64,K,padding=K/2)(x) given dy: dw [K][64][64] tap-major, db [64], dx (nullable; needs
+ * w, the forward weight in the same layout).  K in {1,3,7}. */
+size_t wm_conv64_bwd_workspace_bytes(int B, int T, int K);
+int wm_conv64_bwd(const float *x, const float *dy, const float *w, float *dw, float *db, float *dx, int B, int T, int K,
+                  void *workspace, size_t workspace_bytes, void *stream);
+size_t wm_bn_train_workspace_bytes(long long rows);
+/* torch.optim.Adam step `step` (>= 1) on n floats. */
+int wm_adam_step(float *p, const float *g, float *m, float *v, long long n, float lr, float beta1, float beta2,
+                 float eps, int step, void *stream);
 
 /* Same unit with HOST (pinned) buffers: H2D of s and message, the device pipeline in
  * micro-batches of `chunk` clips, D2H of s_w, probs, clip_prob and msg_logits, all on
