@@ -148,6 +148,9 @@ SIGNATURES = {
     "wm_bn_train_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _p, _sz, _p]),
     "wm_conv64_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "wm_conv64_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _sz, _p]),
+    "wm_lstm_train_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
+    "wm_lstm_train_bwd_workspace_bytes": (_sz, [_i, _i]),
+    "wm_lstm_train_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _sz, _p]),
     "wm_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p]),
     "wm_embed_detect_host_workspace_bytes": (_sz, [_i, _i, _i]),
     "wm_embed_detect_host": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,

@@ -601,6 +601,30 @@ int wm_conv64_bwd(const float *x, const float *dy, const float *w, float *dw, fl
   return 0;
 }
 
+int wm_lstm_train_fwd(const float *x, const float *wT_ih, const float *wT_hh, const float *b_ih, const float *b_hh,
+                      float *h, float *gates, float *cell, int B, int T, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "lstm_train_fwd: bad size");
+  WM_CHECK_ARG(x && wT_ih && wT_hh && b_ih && b_hh && h && gates && cell, "lstm_train_fwd: null pointer");
+  return launch_lstm_train_fwd(x, wT_ih, wT_hh, b_ih, b_hh, h, gates, cell, B, T, as_stream(stream));
+}
+
+size_t wm_lstm_train_bwd_workspace_bytes(int B, int T) {
+  return B > 0 && T > 0 ? lstm_train_bwd_scratch_floats(B, T) * sizeof(float) : 0;
+}
+
+int wm_lstm_train_bwd(const float *dy, const float *x, const float *h, const float *wT_ih, const float *wT_hh,
+                      const float *gates, const float *cell, float *dx, float *dwT_ih, float *dwT_hh, float *db, int B,
+                      int T, void *workspace, size_t workspace_bytes, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B > 0 && T > 0, "lstm_train_bwd: bad size");
+  WM_CHECK_ARG(dy && x && h && wT_ih && wT_hh && gates && cell && dx && dwT_ih && dwT_hh && db && workspace,
+               "lstm_train_bwd: null pointer");
+  WM_CHECK_ARG(workspace_bytes >= wm_lstm_train_bwd_workspace_bytes(B, T), "lstm_train_bwd: workspace too small");
+  return launch_lstm_train_bwd(dy, x, h, wT_ih, wT_hh, gates, cell, dx, dwT_ih, dwT_hh, db, B, T, (float *)workspace,
+                               as_stream(stream));
+}
+
 int wm_adam_step(float *p, const float *g, float *m, float *v, long long n, float lr, float beta1, float beta2,
                  float eps, int step, void *stream) {
   WM_ENTRY();

@@ -128,6 +128,15 @@ int launch_bn_train_bwd(const float *dout, const float *act, const float *z, con
 int launch_transpose_flip(const float *w, float *wt, int K, cudaStream_t st);
 int launch_conv_wgrad(const float *x, const float *dz, float *dw, float *db, int B, int T, int K, float *scratch,
                       cudaStream_t st);
+int launch_conv_wgrad_ex(const float *x, const float *dz, float *dw, float *db, int B, int T, int K, int P, int bias_tap,
+                         float *scratch, cudaStream_t st);
+// training LSTM (wm_train_lstm.cu); weights per-gate transposed wT[q][k][r] = W[q*64 + r][k]
+int launch_lstm_train_fwd(const float *x, const float *wT_ih, const float *wT_hh, const float *b_ih, const float *b_hh,
+                          float *h, float *gates, float *cell, int B, int T, cudaStream_t st);
+size_t lstm_train_bwd_scratch_floats(int B, int T);
+int launch_lstm_train_bwd(const float *dy, const float *x, const float *h, const float *wT_ih, const float *wT_hh,
+                          const float *gates, const float *cell, float *dx, float *dwT_ih, float *dwT_hh, float *db,
+                          int B, int T, float *scratch, cudaStream_t st);
 int launch_adam(float *p, const float *g, float *m, float *v, long long n, float lr, float b1, float b2, float eps,
                 int step, cudaStream_t st);
 int detector_train_step(float *params, float *grads, float *adam_m, float *adam_v, float *run_stats, const float *x,

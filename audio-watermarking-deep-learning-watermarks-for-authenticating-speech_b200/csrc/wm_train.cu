@@ -154,13 +154,13 @@ __global__ void transpose_flip_kernel(const float *__restrict__ w, float *__rest
 }
 
 // weight gradient of y[t][co] = sum_j sum_ci w[j][ci][co] x[t + j - P][ci], one tap per blockIdx.z:
-// partial[blk][j][ci][co] = sum over the block's rows of x[t + j - P][ci] * dz[t][co];  bias partial on j == P
+// partial[blk][j][ci][co] = sum over the block's rows of x[t + j - P][ci] * dz[t][co];  bias partial on j == bias_tap
 constexpr int WG_ROWS = 512, WG_SUB = 64;
 __global__ void __launch_bounds__(NT)
-    conv_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ dz, int T, int K, int nchunk,
-                      float *__restrict__ partial_w, float *__restrict__ partial_b) {
+    conv_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ dz, int T, int K, int P, int bias_tap,
+                      int nchunk, float *__restrict__ partial_w, float *__restrict__ partial_b) {
   __shared__ __align__(16) float xs[WG_SUB][68], ds[WG_SUB][68];
-  const int P = K / 2, j = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
+  const int j = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
   const int t_begin = chunk * WG_ROWS, t_end = min(T, t_begin + WG_ROWS);
   const int ci0 = (threadIdx.x >> 4) * 4, co0 = (threadIdx.x & 15) * 4;
   float acc[4][4];
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(NT)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(xa[a], da[c], acc[a][c]);
     }
-    if (j == P && threadIdx.x < 64) {
+    if (j == bias_tap && threadIdx.x < 64) {
       for (int r = 0; r < WG_SUB; ++r) bacc += ds[r][threadIdx.x];
     }
   }
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(NT)
 #pragma unroll
   for (int a = 0; a < 4; ++a)
     *reinterpret_cast<float4 *>(&pw[(ci0 + a) * 64 + co0]) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-  if (j == P && threadIdx.x < 64) partial_b[blk * 64 + threadIdx.x] = bacc;
+  if (j == bias_tap && threadIdx.x < 64) partial_b[blk * 64 + threadIdx.x] = bacc;
 }
 
 // out[i] = sum_blk partial[blk * n + i], fixed order
@@ -404,17 +404,25 @@ size_t conv_wgrad_scratch_floats(int B, int T, int K) {
 }
 
 // dW[K][64][64], db[64] of a 64->64 'same' convolution from its input x and output gradient dz
-int launch_conv_wgrad(const float *x, const float *dz, float *dw, float *db, int B, int T, int K, float *scratch,
-                      cudaStream_t st) {
+// general form: tap j pairs x[t + j - P] with dz[t]; db (nullable) sums dz on tap `bias_tap`
+int launch_conv_wgrad_ex(const float *x, const float *dz, float *dw, float *db, int B, int T, int K, int P, int bias_tap,
+                         float *scratch, cudaStream_t st) {
   const int nchunk = (T + WG_ROWS - 1) / WG_ROWS, nblk = B * nchunk;
   float *pw = scratch, *pb = scratch + (size_t)nblk * K * 4096;
-  conv_wgrad_kernel<<<dim3(nchunk, B, K), NT, 0, st>>>(x, dz, T, K, nchunk, pw, pb);
+  conv_wgrad_kernel<<<dim3(nchunk, B, K), NT, 0, st>>>(x, dz, T, K, P, db ? bias_tap : -1, nchunk, pw, pb);
   WM_CHECK_LAUNCH("conv_wgrad");
   sum_partials_f_kernel<<<(K * 4096 + 255) / 256, 256, 0, st>>>(pw, nblk, K * 4096, dw);
   WM_CHECK_LAUNCH("sum_partials(w)");
-  sum_partials_f_kernel<<<1, 64, 0, st>>>(pb, nblk, 64, db);
-  WM_CHECK_LAUNCH("sum_partials(b)");
+  if (db) {
+    sum_partials_f_kernel<<<1, 64, 0, st>>>(pb, nblk, 64, db);
+    WM_CHECK_LAUNCH("sum_partials(b)");
+  }
   return 0;
+}
+
+int launch_conv_wgrad(const float *x, const float *dz, float *dw, float *db, int B, int T, int K, float *scratch,
+                      cudaStream_t st) {
+  return launch_conv_wgrad_ex(x, dz, dw, db, B, T, K, K / 2, K / 2, scratch, st);
 }
 
 int launch_conv_in_grads(const float *s, const float *dx, const float *w, float *dw, float *db, float *ds, int B, int T,

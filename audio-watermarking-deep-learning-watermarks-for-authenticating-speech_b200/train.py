@@ -76,6 +76,43 @@ def conv64_bwd(x: torch.Tensor, dy: torch.Tensor, weight: torch.Tensor, want_dx:
     return dw.permute(2, 1, 0).contiguous(), db, dx
 
 
+def _gate_t(w: torch.Tensor) -> torch.Tensor:
+    """(256,64) PyTorch LSTM weight -> per-gate transposed wT[q][k][r] = W[q*64 + r][k]; its own inverse."""
+    return w.reshape(4, 64, 64).permute(0, 2, 1).contiguous()
+
+
+def lstm_train_fwd(x: torch.Tensor, w_ih, w_hh, b_ih, b_hh):
+    """nn.LSTM(64,64,batch_first)(x)[0] on x (B,T,64) with PyTorch-layout weights; returns (h, saved) where `saved`
+    feeds lstm_train_bwd."""
+    lib = L.load()
+    x = _req(x, "x")
+    B, T, _ = x.shape
+    wti, wth = _gate_t(_req(w_ih, "w_ih")), _gate_t(_req(w_hh, "w_hh"))
+    h = torch.empty_like(x)
+    gates = torch.empty(B, T, 256, device=x.device)
+    cell = torch.empty(B, T, 64, device=x.device)
+    L.check(lib.wm_lstm_train_fwd(L.ptr(x), L.ptr(wti), L.ptr(wth), L.ptr(_req(b_ih, "b_ih")), L.ptr(_req(b_hh, "b_hh")),
+                                  L.ptr(h), L.ptr(gates), L.ptr(cell), B, T, _stream()), "wm_lstm_train_fwd")
+    return h, (x, h, wti, wth, gates, cell)
+
+
+def lstm_train_bwd(dy: torch.Tensor, saved):
+    """-> (dx, dw_ih (256,64), dw_hh (256,64), db (256,)); db is the gradient of b_ih and of b_hh."""
+    lib = L.load()
+    x, h, wti, wth, gates, cell = saved
+    dy = _req(dy, "dy")
+    B, T, _ = x.shape
+    dx = torch.empty_like(x)
+    dwi, dwh = torch.empty(4, 64, 64, device=x.device), torch.empty(4, 64, 64, device=x.device)
+    db = torch.empty(256, device=x.device)
+    n = lib.wm_lstm_train_bwd_workspace_bytes(B, T)
+    ws = _ws(n, x.device)
+    L.check(lib.wm_lstm_train_bwd(L.ptr(dy), L.ptr(x), L.ptr(h), L.ptr(wti), L.ptr(wth), L.ptr(gates), L.ptr(cell),
+                                  L.ptr(dx), L.ptr(dwi), L.ptr(dwh), L.ptr(db), B, T, L.ptr(ws), n, _stream()),
+            "wm_lstm_train_bwd")
+    return dx, _gate_t(dwi).reshape(256, 64), _gate_t(dwh).reshape(256, 64), db
+
+
 def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int, lr: float = LR,
               betas=(0.9, 0.999), eps: float = 1e-8) -> None:
     """torch.optim.Adam's update of the flat fp32 buffer p in place (py/main16.py:504)."""

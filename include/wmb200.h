@@ -361,6 +361,15 @@ size_t wm_conv64_bwd_workspace_bytes(int B, int T, int K);
 int wm_conv64_bwd(const float *x, const float *dy, const float *w, float *dw, float *db, float *dx, int B, int T, int K,
                   void *workspace, size_t workspace_bytes, void *stream);
 size_t wm_bn_train_workspace_bytes(long long rows);
+/* nn.LSTM(64,64,batch_first) in training (py/main16.py:138,153).  Weights "per-gate transposed":
+ * wT[q][k][r] = W[q*64 + r][k], q over (i,f,g,o).  Forward keeps the activated gates [B][T][256] and cell states
+ * [B][T][64]; backward turns dy into dx, dwT_ih, dwT_hh [4][64][64] and db [256] (gradient of b_ih and of b_hh). */
+int wm_lstm_train_fwd(const float *x, const float *wT_ih, const float *wT_hh, const float *b_ih, const float *b_hh,
+                      float *h, float *gates, float *cell, int B, int T, void *stream);
+size_t wm_lstm_train_bwd_workspace_bytes(int B, int T);
+int wm_lstm_train_bwd(const float *dy, const float *x, const float *h, const float *wT_ih, const float *wT_hh,
+                      const float *gates, const float *cell, float *dx, float *dwT_ih, float *dwT_hh, float *db, int B,
+                      int T, void *workspace, size_t workspace_bytes, void *stream);
 /* torch.optim.Adam step `step` (>= 1) on n floats. */
 int wm_adam_step(float *p, const float *g, float *m, float *v, long long n, float lr, float beta1, float beta2,
                  float eps, int step, void *stream);

@@ -279,3 +279,23 @@ def test_update_false_leaves_parameters_alone_and_is_deterministic():
     assert torch.equal(tr.params, p0) and tr.steps == 0
     tr.step(x, msg, update=False)
     assert torch.equal(tr.grads, g1)                  # fixed-order reductions: bit-identical gradients
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 300), (2, 4000)])
+def test_lstm_train_forward_backward_match_autograd(B, T):
+    from wmb200 import train as TR
+    torch.manual_seed(T)
+    lstm = torch.nn.LSTM(64, 64, batch_first=True).cuda().double()
+    x = torch.randn(B, T, 64, device="cuda", dtype=torch.float64, requires_grad=True)
+    dy = torch.randn(B, T, 64, device="cuda")
+    y, _ = lstm(x)
+    y.backward(dy.double())
+    p = {k: v.detach().float() for k, v in lstm.named_parameters()}
+    h, saved = TR.lstm_train_fwd(x.detach().float(), p["weight_ih_l0"], p["weight_hh_l0"], p["bias_ih_l0"], p["bias_hh_l0"])
+    assert float((h.double() - y.detach()).abs().max()) < 2e-5
+    dx, dwi, dwh, db = TR.lstm_train_bwd(dy, saved)
+    assert rel(dx, x.grad) < 1e-4
+    assert rel(dwi, lstm.weight_ih_l0.grad) < 1e-4
+    assert rel(dwh, lstm.weight_hh_l0.grad) < 1e-4
+    assert rel(db, lstm.bias_ih_l0.grad) < 1e-4 and rel(db, lstm.bias_hh_l0.grad) < 1e-4
