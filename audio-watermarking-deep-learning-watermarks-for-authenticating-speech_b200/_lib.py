@@ -75,6 +75,23 @@ DT_HEAD_W = DT_RB0 + 2 * DT_RB_SIZE
 DT_HEAD_B = DT_HEAD_W + 32 * 64
 DT_SIZE = DT_HEAD_B + 32
 DT_STATS = 2 * 4 * 64
+# training-mode generator parameters (WM_GT_*)
+GT_IN_W = 0
+GT_IN_B = GT_IN_W + 7 * 64
+GT_RB0 = GT_IN_B + 64
+GT_RB1 = GT_RB0 + DT_RB_SIZE
+GT_LSTM_WIH = GT_RB1 + DT_RB_SIZE
+GT_LSTM_WHH = GT_LSTM_WIH + 256 * 64
+GT_LSTM_BIH = GT_LSTM_WHH + 256 * 64
+GT_LSTM_BHH = GT_LSTM_BIH + 256
+GT_CT_W = GT_LSTM_BHH + 256
+GT_CT_B = GT_CT_W + 7 * 64 * 64
+GT_RB2 = GT_CT_B + 64
+GT_HEAD_W = GT_RB2 + DT_RB_SIZE
+GT_HEAD_B = GT_HEAD_W + 64
+GT_EMB = GT_HEAD_B + 64
+GT_SIZE = GT_EMB + 65536 * 64
+GT_STATS = 3 * 4 * 64
 MAX_HEAD = 32
 POST_FIR, POST_CLAMP, POST_RMS, POST_ALL = 1, 2, 4, 7
 MATH_FP32, MATH_BF16X2 = 0, 1
@@ -140,9 +157,18 @@ SIGNATURES = {
     "wm_pcm16_quantize_fwd": (_i, [_p, _p, _sz, _p]),
     "wm_pcm16_dequantize_fwd": (_i, [_p, _p, _sz, _f, _p]),
     "wm_file_metrics_fwd": (_i, [_p, _p, _p, _p, _i, _i, _p]),
+    "wm_stft_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "wm_hf_penalty_bwd": (_i, [_p, _p, _p, _sz, _i, _i, _i, _i, _f, _i, _p]),
+    "wm_loud_bwd": (_i, [_p, _p, _p, _p, _sz, _i, _i, _i, _i, _f, _f, _i, _p]),
+    "wm_mel_log_l1_bwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _sz, _i, _i, _i, _i, _f, _i, _p]),
+    "wm_abs_mean_bwd": (_i, [_p, _p, _i, _i, _f, _i, _p]),
+    "wm_postprocess_bwd": (_i, [_p, _p, _p, _p, _p, _sz, _i, _i, _i, _f, _f, _f, _p]),
     "wm_detector_train_workspace_bytes": (_sz, [_i, _i, _i]),
     "wm_detector_train_step": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f, _i, _p, _p, _p,
                                     _sz, _p]),
+    "wm_train_step_workspace_bytes": (_sz, [_i, _i, _i]),
+    "wm_train_forward_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p, _p, _p, _sz,
+                                       _p]),
     "wm_bn_train_workspace_bytes": (_sz, [_ll]),
     "wm_bn_train_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _p, _sz, _p]),
     "wm_bn_train_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _p, _sz, _p]),

@@ -528,6 +528,62 @@ int wm_abs_mean_fwd(const float *x, float *out, void *workspace, size_t workspac
   return launch_abs_mean(x, (long long)B * T, out, (float *)workspace, as_stream(stream));
 }
 
+/* ---- backward of the losses / post-processing ---- */
+size_t wm_stft_bwd_workspace_bytes(int B, int T, int n_fft, int hop) {
+  if (B <= 0 || T <= 0 || n_fft <= 0 || hop <= 0) return 0;
+  return align256(stft_bwd_scratch_floats(B, T, n_fft, hop) * sizeof(float));
+}
+
+#define WM_LOSS_BWD_ARGS(name, hop_)                                                                       \
+  WM_ENTRY();                                                                                              \
+  WM_CHECK_ARG(B > 0 && T > 0, name ": the mean over an empty batch is undefined");                        \
+  WM_CHECK_ARG(workspace && (hop_) >= 64, name ": null workspace or hop < 64");                            \
+  WM_CHECK_ARG(workspace_bytes >= wm_stft_bwd_workspace_bytes(B, T, n_fft, (hop_)), name ": workspace too small")
+
+int wm_hf_penalty_bwd(const float *delta, float *d_delta, void *workspace, size_t workspace_bytes, int B, int T,
+                      int n_fft, int first_bin, float weight, int accumulate, void *stream) {
+  WM_LOSS_BWD_ARGS("hf_penalty_bwd", n_fft / 4);
+  WM_CHECK_ARG(delta && d_delta, "hf_penalty_bwd: null pointer");
+  WM_CHECK_ARG(first_bin >= 0 && first_bin <= n_fft / 2 + 1, "hf_penalty_bwd: first_bin out of range");
+  return launch_hf_penalty_bwd(delta, d_delta, (float *)workspace, B, T, n_fft, first_bin, weight, accumulate,
+                               as_stream(stream));
+}
+
+int wm_loud_bwd(const float *clean, const float *wmk, float *d_wmk, void *workspace, size_t workspace_bytes, int B,
+                int T, int n_fft, int hop, float thresh, float weight, int accumulate, void *stream) {
+  WM_LOSS_BWD_ARGS("loud_bwd", hop);
+  WM_CHECK_ARG(clean && wmk && d_wmk, "loud_bwd: null pointer");
+  return launch_loudness_bwd(clean, wmk, d_wmk, (float *)workspace, B, T, n_fft, hop, thresh, weight, accumulate,
+                             as_stream(stream));
+}
+
+int wm_mel_log_l1_bwd(const float *clean, const float *wmk, const float *fb, const int *band, int n_mels, float *d_wmk,
+                      void *workspace, size_t workspace_bytes, int B, int T, int n_fft, int hop, float weight,
+                      int accumulate, void *stream) {
+  WM_LOSS_BWD_ARGS("mel_log_l1_bwd", hop);
+  WM_CHECK_ARG(clean && wmk && fb && band && d_wmk && n_mels > 0 && n_mels <= 128, "mel_log_l1_bwd: bad arguments");
+  return launch_mel_log_l1_bwd(clean, wmk, fb, band, n_mels, d_wmk, (float *)workspace, B, T, n_fft, hop, weight,
+                               accumulate, as_stream(stream));
+}
+
+int wm_abs_mean_bwd(const float *x, float *dx, int B, int T, float weight, int accumulate, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B > 0 && T > 0 && x && dx, "abs_mean_bwd: bad arguments");
+  return launch_abs_mean_bwd(x, dx, (long long)B * T, weight, accumulate, as_stream(stream));
+}
+
+int wm_postprocess_bwd(const float *g, const float *delta_fir, const float *fir, float *d_delta_raw, void *workspace,
+                       size_t workspace_bytes, int B, int T, int mode, float peak, float max_rms, float eps,
+                       void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "postprocess_bwd: negative size");
+  if (B == 0 || T == 0) return 0;
+  WM_CHECK_ARG(g && delta_fir && d_delta_raw && workspace && (fir || !(mode & 1)), "postprocess_bwd: null pointer");
+  WM_CHECK_ARG(workspace_bytes >= (size_t)B * T * sizeof(float), "postprocess_bwd: workspace too small");
+  return launch_postprocess_bwd(g, delta_fir, fir, d_delta_raw, (float *)workspace, B, T, mode, peak, max_rms, eps,
+                                as_stream(stream));
+}
+
 /* ---- training (wm_train.cu) ---- */
 size_t wm_detector_train_workspace_bytes(int B_total, int T, int nout) {
   if (B_total <= 0 || T <= 0 || nout < 1 || nout > WM_MAX_HEAD) return 0;
@@ -550,6 +606,29 @@ int wm_detector_train_step(float *params, float *grads, float *adam_m, float *ad
   return detector_train_step(params, grads, adam_m, adam_v, run_stats, x, message, B_wm, B_total, T, nout, lam_loc,
                              lam_dec, lr, beta1, beta2, eps, adam_step, losses_out, d_input, workspace,
                              as_stream(stream));
+}
+
+size_t wm_train_step_workspace_bytes(int B, int T, int nout) {
+  if (B <= 0 || T <= 0 || nout < 1 || nout > WM_MAX_HEAD) return 0;
+  return train_step_workspace_bytes(B, T, nout);
+}
+
+int wm_train_forward_backward(const float *g_params, float *g_grads, float *g_stats, const float *d_params,
+                              float *d_grads, float *d_stats, const float *s, const int64_t *message, const float *fir,
+                              const float *mel_fb, const int *mel_band, int n_mels, const float *lam, int B, int T,
+                              int nout, float *losses_out, float *s_w_out, void *workspace, size_t workspace_bytes,
+                              void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B > 0 && T > 0, "train_forward_backward: bad batch size");
+  WM_CHECK_ARG(T > 1024, "train_forward_backward: the 2048-point STFT's reflect padding needs T > 1024 (T=%d)", T);
+  WM_CHECK_ARG(nout >= 1 && nout <= WM_MAX_HEAD, "train_forward_backward: nout must be in [1,%d]", WM_MAX_HEAD);
+  WM_CHECK_ARG(g_params && g_grads && g_stats && d_params && d_grads && d_stats && s && message && fir && mel_fb &&
+                   mel_band && lam && workspace,
+               "train_forward_backward: null pointer");
+  WM_CHECK_ARG(n_mels > 0 && n_mels <= 128, "train_forward_backward: n_mels must be in [1,128]");
+  WM_CHECK_ARG(workspace_bytes >= train_step_workspace_bytes(B, T, nout), "train_forward_backward: workspace too small");
+  return train_forward_backward(g_params, g_grads, g_stats, d_params, d_grads, d_stats, s, message, fir, mel_fb, mel_band,
+                                n_mels, lam, B, T, nout, losses_out, s_w_out, workspace, as_stream(stream));
 }
 
 size_t wm_bn_train_workspace_bytes(long long rows) { return rows > 0 ? train_scratch_doubles(rows) * sizeof(double) : 0; }

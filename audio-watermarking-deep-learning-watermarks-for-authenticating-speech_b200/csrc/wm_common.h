@@ -115,6 +115,17 @@ int launch_mel_log_l1(const float *clean, const float *wmk, const float *fb, con
 int launch_bce_heads(const float *logits, const int64_t *message, float *loc_out, float *bce_out, float *partials,
                      int B_wm, int B2, int T, int nout, cudaStream_t st);
 int launch_abs_mean(const float *x, long long n, float *out, float *partials, cudaStream_t st);
+size_t stft_bwd_scratch_floats(int B, int T, int n_fft, int hop);
+int launch_hf_penalty_bwd(const float *delta, float *d_delta, float *gframes, int B, int T, int n_fft, int first_bin,
+                          float weight, int accumulate, cudaStream_t st);
+int launch_loudness_bwd(const float *clean, const float *wmk, float *d_wmk, float *gframes, int B, int T, int n_fft,
+                        int hop, float thresh, float weight, int accumulate, cudaStream_t st);
+int launch_mel_log_l1_bwd(const float *clean, const float *wmk, const float *fb, const int *band, int n_mels,
+                          float *d_wmk, float *gframes, int B, int T, int n_fft, int hop, float weight, int accumulate,
+                          cudaStream_t st);
+int launch_abs_mean_bwd(const float *x, float *dx, long long n, float weight, int accumulate, cudaStream_t st);
+int launch_postprocess_bwd(const float *g, const float *d1, const float *fir, float *d_delta_raw, float *scratch, int B,
+                           int T, int mode, float peak, float max_rms, float eps, cudaStream_t st);
 // training building blocks (wm_train.cu)
 size_t train_scratch_doubles(long long N);
 size_t conv_wgrad_scratch_floats(int B, int T, int K);
@@ -137,6 +148,11 @@ size_t lstm_train_bwd_scratch_floats(int B, int T);
 int launch_lstm_train_bwd(const float *dy, const float *x, const float *h, const float *wT_ih, const float *wT_hh,
                           const float *gates, const float *cell, float *dx, float *dwT_ih, float *dwT_hh, float *db,
                           int B, int T, float *scratch, cudaStream_t st);
+size_t train_step_workspace_bytes(int B, int T, int nout);
+int train_forward_backward(const float *g_params, float *g_grads, float *g_stats, const float *d_params, float *d_grads,
+                           float *d_stats, const float *s, const int64_t *message, const float *fir, const float *mel_fb,
+                           const int *mel_band, int n_mels, const float *lam, int B, int T, int nout, float *losses_out,
+                           float *s_w_out, void *workspace, cudaStream_t st);
 int launch_adam(float *p, const float *g, float *m, float *v, long long n, float lr, float b1, float b2, float eps,
                 int step, cudaStream_t st);
 int detector_train_step(float *params, float *grads, float *adam_m, float *adam_v, float *run_stats, const float *x,

@@ -256,6 +256,187 @@ int launch_stft(const float *x0, const float *x1, int B, int T, int n_fft, int h
   return 0;
 }
 
+// ---- backward of the STFT losses ---------------------------------------------------------------------------
+// For a real frame x[n] and its one-sided spectrum X[k] (k <= N/2), with G[k] = dL/dRe X[k] + i dL/dIm X[k]:
+//   dL/dx[n] = Re sum_{k <= N/2} G[k] e^{+2 pi i k n / N} = Re FFT(conj G)[n]
+// so the same forward stages turn the spectrum gradient into the frame gradient.  A CTA recomputes the forward
+// spectra of its item (as stft_kernel does), forms G of the signal the gradient is wanted for, transforms it and
+// writes win[n] * Re(.) to gframes[b][f][N]; overlap_add_kernel then GATHERS, per sample, the frames (and the
+// reflected padding positions) that touch it — no atomics, so the gradient is deterministic.
+//   MODE_HF:   x0 = delta, gradient w.r.t. delta     G = coef * [k >= first_bin] * S / |S|
+//   MODE_LOUD: gradient w.r.t. x1 (watermarked)      G = coef * 2 [ |C| > thresh ] (|W| - |C|) W / |W|
+//   MODE_MEL:  gradient w.r.t. x1                    G = 2 W sum_m fb[k][m] dmel[m],
+//                                                    dmel[m] = -coef * sign(log(mc+eps) - log(mw+eps)) / (mw+eps)
+// coef carries 1 / (number of terms of the mean).
+template <int N, int LOG2N, int MODE>
+__global__ void __launch_bounds__(FFT_THREADS)
+    stft_bwd_kernel(const float *__restrict__ x0, const float *__restrict__ x1, int B, int T, int hop, int F,
+                    float *__restrict__ gframes, int first_bin, float thresh, const float *__restrict__ fb,
+                    const int *__restrict__ band, int n_mels, float coef) {
+  __shared__ float2 z[N];
+  __shared__ float2 zg[N];
+  __shared__ float2 tw[N / 2];
+  constexpr bool TWO_SIGNALS = MODE == MODE_LOUD || MODE == MODE_MEL;
+  constexpr int NB = N / 2 + 1;
+  __shared__ float pw[MODE == MODE_MEL ? 2 * NB : 2];
+  __shared__ float dmel[MODE == MODE_MEL ? 128 : 2];
+  const int per_clip = TWO_SIGNALS ? F : (F + 1) / 2;
+  const long long items = (long long)B * per_clip;
+  auto winf = [](int n) { const float sn = sinpif((float)n / (float)N); return sn * sn; };
+
+  for (int k = threadIdx.x; k < N / 2; k += FFT_THREADS) {
+    float sn, cs;
+    sincospif(-2.0f * (float)k / (float)N, &sn, &cs);
+    tw[k] = make_float2(cs, sn);
+  }
+  __syncthreads();
+
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = (int)(item / per_clip), u = (int)(item % per_clip);
+    const int fa = TWO_SIGNALS ? u : 2 * u;
+    const int fbm = TWO_SIGNALS ? u : 2 * u + 1;
+    const bool has_b = TWO_SIGNALS || fbm < F;
+    const float *pa = x0 + (size_t)b * T;
+    const float *pb = (TWO_SIGNALS ? x1 : x0) + (size_t)b * T;
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += FFT_THREADS) {
+      const int ja = reflect_idx(fa * hop + n - N / 2, T);
+      const int jb = reflect_idx(fbm * hop + n - N / 2, T);
+      const float w = winf(n);
+      const float va = __ldg(pa + ja) * w;
+      const float vb = has_b ? __ldg(pb + jb) * w : 0.0f;
+      z[__brev((unsigned)n) >> (32 - LOG2N)] = make_float2(va, vb);
+    }
+    fft_stages<N, LOG2N>(z, tw);
+
+    if constexpr (MODE == MODE_MEL) {
+      for (int k = threadIdx.x; k < NB; k += FFT_THREADS) {
+        float2 C, Wv;
+        unpack_pair<N>(z, k, C, Wv);
+        pw[k] = C.x * C.x + C.y * C.y;
+        pw[NB + k] = Wv.x * Wv.x + Wv.y * Wv.y;
+      }
+      __syncthreads();
+      for (int m = threadIdx.x; m < n_mels; m += FFT_THREADS) {
+        float mc = 0.0f, mw = 0.0f;
+        for (int k = band[2 * m]; k < band[2 * m + 1]; ++k) {
+          const float f = __ldg(fb + (size_t)k * n_mels + m);
+          mc = fmaf(f, pw[k], mc);
+          mw = fmaf(f, pw[NB + k], mw);
+        }
+        const float d = logf(mc + 1e-5f) - logf(mw + 1e-5f);
+        dmel[m] = -coef * (float)((d > 0.0f) - (d < 0.0f)) / (mw + 1e-5f);
+      }
+      __syncthreads();
+    }
+
+    // one inverse transform per target frame: HF has two (a, b), the two-signal losses one (the watermarked frame)
+    const int ntargets = TWO_SIGNALS ? 1 : (has_b ? 2 : 1);
+    for (int tg = 0; tg < ntargets; ++tg) {
+      for (int k = threadIdx.x; k < N; k += FFT_THREADS) {
+        float2 g = make_float2(0.0f, 0.0f);
+        if (k < NB) {
+          float2 A, Bv;
+          unpack_pair<N>(z, k, A, Bv);
+          if constexpr (MODE == MODE_HF) {
+            const float2 S = tg == 0 ? A : Bv;
+            const float m = sqrtf(S.x * S.x + S.y * S.y);
+            if (k >= first_bin && m > 0.0f) g = make_float2(coef * S.x / m, coef * S.y / m);
+          } else if constexpr (MODE == MODE_LOUD) {
+            const float mc = sqrtf(A.x * A.x + A.y * A.y), mw = sqrtf(Bv.x * Bv.x + Bv.y * Bv.y);
+            if (mc > thresh && mw > 0.0f) {
+              const float c = coef * 2.0f * (mw - mc) / mw;
+              g = make_float2(c * Bv.x, c * Bv.y);
+            }
+          } else {
+            float gs = 0.0f;
+            for (int m = 0; m < n_mels; ++m)
+              if (k >= band[2 * m] && k < band[2 * m + 1]) gs = fmaf(__ldg(fb + (size_t)k * n_mels + m), dmel[m], gs);
+            g = make_float2(2.0f * gs * Bv.x, 2.0f * gs * Bv.y);
+          }
+        }
+        zg[__brev((unsigned)k) >> (32 - LOG2N)] = make_float2(g.x, -g.y);   // conj(G)
+      }
+      fft_stages<N, LOG2N>(zg, tw);
+      const int f = TWO_SIGNALS ? fa : (tg == 0 ? fa : fbm);
+      float *dst = gframes + ((size_t)b * F + f) * N;
+      for (int n = threadIdx.x; n < N; n += FFT_THREADS) dst[n] = winf(n) * zg[n].x;
+      __syncthreads();
+    }
+  }
+}
+
+// dx[b][t] (+)= sum of gframes over every (frame, offset) whose padded position maps to sample t
+__global__ void __launch_bounds__(256)
+    overlap_add_kernel(const float *__restrict__ gframes, float *__restrict__ dx, int T, int N, int hop, int F,
+                       int accumulate) {
+  const int b = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float *g = gframes + (size_t)b * F * N;
+  float acc = 0.0f;
+  auto add_pos = [&](int p) {   // p: index into the reflect-padded signal of length T + N
+    int fhi = p / hop;
+    if (fhi > F - 1) fhi = F - 1;
+    int flo = p - N + 1 <= 0 ? 0 : (p - N + hop) / hop;   // ceil((p - N + 1) / hop)
+    for (int f = flo; f <= fhi; ++f) acc += g[(size_t)f * N + (p - f * hop)];
+  };
+  add_pos(t + N / 2);
+  if (t >= 1 && t <= N / 2) add_pos(N / 2 - t);
+  const int p2 = 2 * (T - 1) - t + N / 2;
+  if (t <= T - 2 && p2 < T + N) add_pos(p2);
+  float *o = dx + (size_t)b * T + t;
+  *o = accumulate ? *o + acc : acc;
+}
+
+// dx (+)= coef * sign(x)
+__global__ void __launch_bounds__(256)
+    sign_kernel(const float *__restrict__ x, float *__restrict__ dx, long long n, float coef, int accumulate) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float g = coef * (float)((v > 0.0f) - (v < 0.0f));
+    dx[i] = accumulate ? dx[i] + g : g;
+  }
+}
+
+template <int MODE>
+int launch_stft_bwd(const float *x0, const float *x1, int B, int T, int n_fft, int hop, float *gframes, float *dx,
+                    int first_bin, float thresh, const float *fb, const int *band, int n_mels, float coef,
+                    int accumulate, cudaStream_t st) {
+  const int F = 1 + T / hop;
+  const bool two = MODE == MODE_LOUD || MODE == MODE_MEL;
+  const long long items = (long long)B * (two ? F : (F + 1) / 2);
+  if (items == 0) return 0;
+  if (T <= n_fft / 2) {
+    set_error("stft: reflect padding needs T > n_fft/2 (T=%d, n_fft=%d)", T, n_fft);
+    return -1;
+  }
+  if (MODE == MODE_MEL && n_mels > 128) { set_error("mel backward: n_mels must be <= 128"); return -1; }
+  const int grid = (int)(items < 8LL * sm_count() ? items : 8LL * sm_count());
+  switch (n_fft) {
+    case 512:
+      stft_bwd_kernel<512, 9, MODE><<<grid, FFT_THREADS, 0, st>>>(x0, x1, B, T, hop, F, gframes, first_bin, thresh, fb, band, n_mels, coef);
+      break;
+    case 1024:
+      stft_bwd_kernel<1024, 10, MODE><<<grid, FFT_THREADS, 0, st>>>(x0, x1, B, T, hop, F, gframes, first_bin, thresh, fb, band, n_mels, coef);
+      break;
+    case 2048:
+      if constexpr (MODE != MODE_MEL) {
+        stft_bwd_kernel<2048, 11, MODE><<<grid, FFT_THREADS, 0, st>>>(x0, x1, B, T, hop, F, gframes, first_bin, thresh, fb, band, n_mels, coef);
+      } else {   // two 2048-point buffers + the power spectra exceed the 48 KB of static shared memory
+        set_error("mel backward: n_fft must be 512 or 1024");
+        return -1;
+      }
+      break;
+    default:
+      set_error("stft: n_fft must be 512, 1024 or 2048 (got %d)", n_fft);
+      return -1;
+  }
+  WM_CHECK_LAUNCH("stft_bwd");
+  overlap_add_kernel<<<dim3((T + 255) / 256, B), 256, 0, st>>>(gframes, dx, T, n_fft, hop, F, accumulate);
+  WM_CHECK_LAUNCH("overlap_add");
+  return 0;
+}
+
 int finish(const float *partials, long long n, double scale, float *out, cudaStream_t st) {
   sum_partials_kernel<<<1, 1024, 0, st>>>(partials, n, scale, out);
   WM_CHECK_LAUNCH("sum_partials");
@@ -315,6 +496,42 @@ int launch_abs_mean(const float *x, long long n, float *out, float *partials, cu
   abs_sum_kernel<<<grid, FFT_THREADS, 0, st>>>(x, n, partials);
   WM_CHECK_LAUNCH("abs_sum");
   return finish(partials, grid, 1.0 / (double)n, out, st);
+}
+
+size_t stft_bwd_scratch_floats(int B, int T, int n_fft, int hop) { return (size_t)B * (1 + T / hop) * n_fft; }
+
+// d_delta (+)= weight * d high_freq_penalty / d delta
+int launch_hf_penalty_bwd(const float *delta, float *d_delta, float *gframes, int B, int T, int n_fft, int first_bin,
+                          float weight, int accumulate, cudaStream_t st) {
+  const int hop = n_fft / 4, F = 1 + T / hop;
+  const float coef = (float)((double)weight / ((double)B * (n_fft / 2 + 1) * F));
+  return launch_stft_bwd<MODE_HF>(delta, nullptr, B, T, n_fft, hop, gframes, d_delta, first_bin, 0.0f, nullptr, nullptr, 0,
+                                  coef, accumulate, st);
+}
+
+int launch_loudness_bwd(const float *clean, const float *wmk, float *d_wmk, float *gframes, int B, int T, int n_fft,
+                        int hop, float thresh, float weight, int accumulate, cudaStream_t st) {
+  const int F = 1 + T / hop;
+  const float coef = (float)((double)weight / ((double)B * (n_fft / 2 + 1) * F));
+  return launch_stft_bwd<MODE_LOUD>(clean, wmk, B, T, n_fft, hop, gframes, d_wmk, 0, thresh, nullptr, nullptr, 0, coef,
+                                    accumulate, st);
+}
+
+int launch_mel_log_l1_bwd(const float *clean, const float *wmk, const float *fb, const int *band, int n_mels,
+                          float *d_wmk, float *gframes, int B, int T, int n_fft, int hop, float weight, int accumulate,
+                          cudaStream_t st) {
+  const int F = 1 + T / hop;
+  const float coef = (float)((double)weight / ((double)B * n_mels * F));
+  return launch_stft_bwd<MODE_MEL>(clean, wmk, B, T, n_fft, hop, gframes, d_wmk, 0, 0.0f, fb, band, n_mels, coef,
+                                   accumulate, st);
+}
+
+int launch_abs_mean_bwd(const float *x, float *dx, long long n, float weight, int accumulate, cudaStream_t st) {
+  if (n == 0) return 0;
+  const int grid = (int)((n + 255) / 256 < 8LL * sm_count() ? (n + 255) / 256 : 8LL * sm_count());
+  sign_kernel<<<grid, 256, 0, st>>>(x, dx, n, (float)((double)weight / (double)n), accumulate);
+  WM_CHECK_LAUNCH("sign");
+  return 0;
 }
 
 }  // namespace wm

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kPostThreads)
     for (int t = tid; t < T; t += kPostThreads) {
       float d = flt[t] * gain;
       if (delta) delta[(size_t)b * T + t] = d;
-      if (s_w) s_w[(size_t)b * T + t] = sb[t] + d;
+      if (s_w) s_w[(size_t)b * T + t] = sb[t] + d;   // s is only read when s_w is wanted
     }
   } else {
     const float *sb = s + (size_t)b * T;
@@ -125,6 +125,52 @@ int launch_postprocess(const float *delta_raw, const float *s, const float *fir,
   postprocess_kernel<<<B, kPostThreads, smem, st>>>(delta_raw, s, fir, delta, s_w, rms_out, T, mode,
                                                     peak, max_rms, eps);
   WM_CHECK_LAUNCH("postprocess");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Backward of clamp_peak -> limit_rms (py/main16.py:66-72) on the filtered delta d1 (= fir_lowpass(delta_raw)):
+//   d2 = clamp(d1), rms = sqrt(mean(d2^2) + eps), gain = min(max_rms / rms, 1), delta = gain * d2
+//   dL/dd2 = gain * g - [gain < 1] * d2 * gain / rms^2 * mean(g * d2);   dL/dd1 = dL/dd2 * [|d1| <= peak]
+// One block per clip.  The FIR's own backward is the same FIR (its taps are symmetric) applied to dL/dd1.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPostThreads)
+    postprocess_bwd_kernel(const float *__restrict__ g, const float *__restrict__ d1, float *__restrict__ dd1, int T,
+                           int mode, float peak, float max_rms, float eps) {
+  __shared__ float red[kPostThreads / 32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const bool do_clamp = mode & 2, do_rms = mode & 4;
+  const float *gb = g + (size_t)b * T, *db = d1 + (size_t)b * T;
+  float sumsq = 0.0f, dot = 0.0f;
+  for (int t = tid; t < T; t += kPostThreads) {
+    const float v = db[t];
+    const float d2 = do_clamp ? fminf(fmaxf(v, -peak), peak) : v;
+    sumsq = fmaf(d2, d2, sumsq);
+    dot = fmaf(gb[t], d2, dot);
+  }
+  const float ms = block_sum<kPostThreads>(sumsq, red) / (float)T;
+  const float gd = block_sum<kPostThreads>(dot, red) / (float)T;
+  const float rms2 = ms + eps, ratio = max_rms / sqrtf(rms2);
+  const bool scaled = do_rms && ratio < 1.0f;
+  const float gain = scaled ? ratio : 1.0f;
+  const float back = scaled ? gain / rms2 * gd : 0.0f;
+  for (int t = tid; t < T; t += kPostThreads) {
+    const float v = db[t];
+    const bool inside = !do_clamp || (v >= -peak && v <= peak);
+    const float d2 = do_clamp ? fminf(fmaxf(v, -peak), peak) : v;
+    dd1[(size_t)b * T + t] = inside ? gain * gb[t] - back * d2 : 0.0f;
+  }
+}
+
+// g = dL/d delta, d1 = the filtered (pre-clamp) delta -> d_delta_raw; scratch: B*T floats
+int launch_postprocess_bwd(const float *g, const float *d1, const float *fir, float *d_delta_raw, float *scratch, int B,
+                           int T, int mode, float peak, float max_rms, float eps, cudaStream_t st) {
+  if (B == 0 || T == 0) return 0;
+  if (mode < 0 || mode > 7) { set_error("postprocess_bwd: mode must be a bit mask in [0,7]"); return -1; }
+  float *dd1 = (mode & 1) ? scratch : d_delta_raw;
+  postprocess_bwd_kernel<<<B, kPostThreads, 0, st>>>(g, d1, dd1, T, mode, peak, max_rms, eps);
+  WM_CHECK_LAUNCH("postprocess_bwd");
+  if (mode & 1) return launch_postprocess(dd1, nullptr, fir, d_delta_raw, nullptr, nullptr, B, T, WM_POST_FIR, peak, max_rms, eps, st);
   return 0;
 }
 

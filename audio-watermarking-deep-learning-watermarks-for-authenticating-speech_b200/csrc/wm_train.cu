@@ -341,6 +341,43 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
   }
 }
 
+// y[b][t][c] = x[b][t][c] + e[message[b]][c]                  (py/main16.py:155-157)
+__global__ void add_embedding_kernel(const float *__restrict__ x, const float *__restrict__ emb,
+                                     const long long *__restrict__ message, float *__restrict__ y, int T, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i & 15) * 4;
+    const int b = (int)(i / ((long long)T * 16));
+    const float4 v = reinterpret_cast<const float4 *>(x)[i];
+    const float4 e = *reinterpret_cast<const float4 *>(emb + message[b] * 64 + c4);
+    reinterpret_cast<float4 *>(y)[i] = make_float4(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w);
+  }
+}
+
+// colsum[b][c] = sum_t g[b][t][c]  (one block per clip, fixed order)
+__global__ void __launch_bounds__(NT) clip_colsum_kernel(const float *__restrict__ g, float *__restrict__ colsum, int T) {
+  __shared__ double red[4][64];
+  const int b = blockIdx.x, c = threadIdx.x & 63, part = threadIdx.x >> 6;
+  const float *gb = g + (size_t)b * T * 64;
+  double a = 0.0;
+  for (int t = part; t < T; t += 4) a += (double)gb[(size_t)t * 64 + c];
+  red[part][c] = a;
+  __syncthreads();
+  if (part == 0) colsum[b * 64 + c] = (float)((red[0][c] + red[1][c]) + (red[2][c] + red[3][c]));
+}
+
+// demb[message[b]][c] += colsum[b][c], clips in order (repeated messages accumulate deterministically)
+__global__ void embedding_scatter_kernel(const float *__restrict__ colsum, const long long *__restrict__ message,
+                                         float *__restrict__ demb, int B) {
+  const int c = threadIdx.x;
+  for (int b = 0; b < B; ++b) demb[message[b] * 64 + c] += colsum[b * 64 + c];
+}
+
+// losses: {l1, mel, loud, loc, bce, hf, total, raw_total}
+__global__ void train_totals_kernel(float *losses, float l1, float ms, float ld, float lc, float dc, float hf) {
+  losses[7] = losses[0] + losses[1] + losses[2] + losses[3] + losses[4];
+  losses[6] = l1 * losses[0] + ms * losses[1] + ld * losses[2] + lc * losses[3] + dc * losses[4] + hf * losses[5];
+}
+
 int grid_for(long long n, int per_block) {
   long long g = (n + per_block - 1) / per_block;
   return (int)(g < 1 ? 1 : (g > 8LL * sm_count() ? 8LL * sm_count() : g));
@@ -568,6 +605,167 @@ int detector_train_step(float *params, float *grads, float *adam_m, float *adam_
                               w.fscratch, st));
   if (adam_step > 0)
     WM_TRY(launch_adam(params, grads, adam_m, adam_v, WM_DT_SIZE, lr, beta1, beta2, eps, adam_step, st));
+  return 0;
+}
+
+// ---- the whole training step: forward and backward of py/main16.py:244-277 ------------------------------------
+namespace {
+
+struct RbActs { float *z1, *u, *z2, *y; };
+
+// relu(x + BN(conv3(relu(BN(conv3(x)))))) in train mode; rb: WM_DT_RB_* block, rs: 256 running stats, stt: 256 batch stats
+int rb_train_fwd(const float *in, const float *rb, float *rs, float *stt, RbActs a, int B, int T, double *dscratch,
+                 cudaStream_t st) {
+  const long long N = (long long)B * T;
+  WM_TRY(launch_conv64_fp32(in, rb + WM_DT_RB_W1, rb + WM_DT_RB_B1, nullptr, nullptr, a.z1, B, T, 3, 0, st));
+  WM_TRY(launch_bn_train_fwd(a.z1, rb + WM_DT_RB_G1, rb + WM_DT_RB_BE1, nullptr, a.u, stt, stt + 64, rs, rs + 64, N, 1,
+                             dscratch, st));
+  WM_TRY(launch_conv64_fp32(a.u, rb + WM_DT_RB_W2, rb + WM_DT_RB_B2, nullptr, nullptr, a.z2, B, T, 3, 0, st));
+  return launch_bn_train_fwd(a.z2, rb + WM_DT_RB_G2, rb + WM_DT_RB_BE2, in, a.y, stt + 128, stt + 192, rs + 128, rs + 192,
+                             N, 1, dscratch, st);
+}
+
+// gA holds dL/dy on entry and dL/dx on exit; gB, gC scratch activations; wt [3*4096], zero64 as in DetWs
+int rb_train_bwd(const float *xin, const float *rb, float *gr, const float *stt, RbActs a, float *gA, float *gB, float *gC,
+                 float *wt, const float *zero64, int B, int T, float *fscratch, double *dscratch, cudaStream_t st) {
+  const long long N = (long long)B * T;
+  WM_TRY(launch_bn_train_bwd(gA, a.y, a.z2, stt + 128, stt + 192, rb + WM_DT_RB_G2, gB, gC, gr + WM_DT_RB_G2,
+                             gr + WM_DT_RB_BE2, N, dscratch, st));
+  WM_TRY(launch_conv_wgrad(a.u, gB, gr + WM_DT_RB_W2, gr + WM_DT_RB_B2, B, T, 3, fscratch, st));
+  WM_TRY(launch_transpose_flip(rb + WM_DT_RB_W2, wt, 3, st));
+  WM_TRY(launch_conv64_fp32(gB, wt, zero64, nullptr, nullptr, gA, B, T, 3, 0, st));
+  WM_TRY(launch_bn_train_bwd(gA, a.u, a.z1, stt, stt + 64, rb + WM_DT_RB_G1, gB, nullptr, gr + WM_DT_RB_G1,
+                             gr + WM_DT_RB_BE1, N, dscratch, st));
+  WM_TRY(launch_conv_wgrad(xin, gB, gr + WM_DT_RB_W1, gr + WM_DT_RB_B1, B, T, 3, fscratch, st));
+  WM_TRY(launch_transpose_flip(rb + WM_DT_RB_W1, wt, 3, st));
+  return launch_conv64_fp32(gB, wt, zero64, gC, nullptr, gA, B, T, 3, 0, st);
+}
+
+struct GenWs {
+  float *x0, *h, *hE, *ct, *gates, *cell, *g[3], *wt, *stats, *zero64, *losses, *colsum;
+  RbActs rb[3];
+  float *draw, *d1, *delta, *xdet /* [2B][T]: s_w then s */, *gsw, *gdraw, *dxdet, *fscratch, *lstm_scratch;
+  double *dscratch;
+  void *det_ws;
+  size_t bytes;
+};
+
+GenWs gen_ws(void *base, int B, int T, int nout) {
+  const size_t N = (size_t)B * T, A = align64(N * 64), V = align64(N);
+  size_t fs = conv_wgrad_scratch_floats(B, T, 7);
+  const size_t nb_h = (N + HW_ROWS - 1) / HW_ROWS, nb_in = (size_t)B * ((T + IN_ROWS - 1) / IN_ROWS);
+  if (fs < nb_h * 65) fs = nb_h * 65;
+  if (fs < nb_in * 512 + 512) fs = nb_in * 512 + 512;
+  const size_t loss_f = wm_loss_workspace_bytes(B, T) / sizeof(float);
+  if (fs < loss_f) fs = loss_f;
+  size_t gf = stft_bwd_scratch_floats(B, T, 2048, 512);
+  if (gf < stft_bwd_scratch_floats(B, T, 1024, 256)) gf = stft_bwd_scratch_floats(B, T, 1024, 256);
+  if (gf < stft_bwd_scratch_floats(B, T, 512, 128)) gf = stft_bwd_scratch_floats(B, T, 512, 128);
+  if (fs < gf) fs = gf;
+  if (fs < N) fs = N;
+  GenWs w;
+  float *p = (float *)base;
+  size_t off = 0;
+  auto take = [&](size_t n) { float *q = p ? p + off : nullptr; off += align64(n); return q; };
+  w.x0 = take(A);
+  for (int k = 0; k < 3; ++k) { w.rb[k].z1 = take(A); w.rb[k].u = take(A); w.rb[k].z2 = take(A); w.rb[k].y = take(A); }
+  w.h = take(A); w.hE = take(A); w.ct = take(A);
+  w.gates = take(4 * A); w.cell = take(A);
+  for (int i = 0; i < 3; ++i) w.g[i] = take(A);
+  w.wt = take(7 * 4096);
+  w.stats = take(3 * 256);
+  w.zero64 = take(64);
+  w.losses = take(64);
+  w.colsum = take((size_t)B * 64);
+  w.draw = take(V); w.d1 = take(V); w.delta = take(V); w.xdet = take(2 * V); w.gsw = take(V); w.gdraw = take(V);
+  w.dxdet = take(2 * V);
+  w.fscratch = take(fs);
+  w.lstm_scratch = take(lstm_train_bwd_scratch_floats(B, T));
+  w.dscratch = (double *)take(2 * train_scratch_doubles((long long)N));
+  w.det_ws = p ? (void *)(p + off) : nullptr;
+  off += align64(detector_train_workspace_bytes(2 * B, T, nout) / sizeof(float) + 64);
+  w.bytes = off * sizeof(float);
+  return w;
+}
+
+}  // namespace
+
+size_t train_step_workspace_bytes(int B, int T, int nout) { return gen_ws(nullptr, B, T, nout).bytes; }
+
+// Forward + backward of one train_one_epoch iteration (py/main16.py:244-277) on s[B][T], message[B]; gradients of
+// every parameter land in g_grads (WM_GT_SIZE, embedding rows included, dense) and d_grads (WM_DT_SIZE); the caller
+// all-reduces them if it wants to and applies Adam (wm_adam_step) to both.  losses_out[8] (device):
+// {l1, mel, loud, loc, bce, hf, total, raw_total}.  lam[6] = {l1, msspec, loud, loc, dec, hf}.
+int train_forward_backward(const float *g_params, float *g_grads, float *g_stats, const float *d_params, float *d_grads,
+                           float *d_stats, const float *s, const int64_t *message, const float *fir, const float *mel_fb,
+                           const int *mel_band, int n_mels, const float *lam, int B, int T, int nout, float *losses_out,
+                           float *s_w_out, void *workspace, cudaStream_t st) {
+  GenWs w = gen_ws(workspace, B, T, nout);
+  const long long N = (long long)B * T;
+  const size_t V = (size_t)N;
+  const long long *msg = reinterpret_cast<const long long *>(message);
+  WM_CHECK_CUDA(cudaMemsetAsync(w.zero64, 0, 64 * sizeof(float), st));
+  WM_CHECK_CUDA(cudaMemsetAsync(w.losses, 0, 8 * sizeof(float), st));
+  WM_CHECK_CUDA(cudaMemsetAsync(g_grads, 0, (size_t)WM_GT_SIZE * sizeof(float), st));
+  // ---- generator forward (py/main16.py:148-162 in train mode) ----
+  WM_TRY(launch_conv_in_k7(s, g_params + WM_GT_IN_W, g_params + WM_GT_IN_B, w.x0, B, T, st));
+  WM_TRY(rb_train_fwd(w.x0, g_params + WM_GT_RB0, g_stats, w.stats, w.rb[0], B, T, w.dscratch, st));
+  WM_TRY(rb_train_fwd(w.rb[0].y, g_params + WM_GT_RB1, g_stats + 256, w.stats + 256, w.rb[1], B, T, w.dscratch, st));
+  WM_TRY(launch_lstm_train_fwd(w.rb[1].y, g_params + WM_GT_LSTM_WIH, g_params + WM_GT_LSTM_WHH, g_params + WM_GT_LSTM_BIH,
+                               g_params + WM_GT_LSTM_BHH, w.h, w.gates, w.cell, B, T, st));
+  add_embedding_kernel<<<grid_for(N * 16, NT), NT, 0, st>>>(w.h, g_params + WM_GT_EMB, msg, w.hE, T, N * 16);
+  WM_CHECK_LAUNCH("add_embedding");
+  WM_TRY(launch_conv64_fp32(w.hE, g_params + WM_GT_CT_W, g_params + WM_GT_CT_B, nullptr, nullptr, w.ct, B, T, 7, 0, st));
+  WM_TRY(rb_train_fwd(w.ct, g_params + WM_GT_RB2, g_stats + 512, w.stats + 512, w.rb[2], B, T, w.dscratch, st));
+  WM_TRY(launch_head(w.rb[2].y, g_params + WM_GT_HEAD_W, g_params + WM_GT_HEAD_B, w.draw, B, T, 1, st));
+  // ---- post-processing (py/main16.py:245-248): d1 = fir(delta_raw) kept for the backward ----
+  WM_TRY(launch_postprocess(w.draw, nullptr, fir, w.d1, nullptr, nullptr, B, T, WM_POST_FIR, 0.02f, 0.005f, 1e-8f, st));
+  WM_TRY(launch_postprocess(w.draw, s, fir, w.delta, w.xdet, nullptr, B, T, WM_POST_ALL, 0.02f, 0.005f, 1e-8f, st));
+  WM_CHECK_CUDA(cudaMemcpyAsync(w.xdet + V, s, V * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (s_w_out) WM_CHECK_CUDA(cudaMemcpyAsync(s_w_out, w.xdet, V * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // ---- detector on cat(s_w, s): losses, its gradients, and dL/d s_w (py/main16.py:249-264) ----
+  WM_TRY(detector_train_step(const_cast<float *>(d_params), d_grads, nullptr, nullptr, d_stats, w.xdet, message, B, 2 * B, T,
+                             nout, lam[3], lam[4], 0.f, 0.f, 0.f, 0.f, 0, w.losses + 3, w.dxdet, w.det_ws, st));
+  // ---- the perceptual losses and their gradients (py/main16.py:266-276) ----
+  const float *sw = w.xdet;
+  WM_TRY(launch_abs_mean(w.delta, N, w.losses + 0, w.fscratch, st));
+  WM_TRY(launch_mel_log_l1(s, sw, mel_fb, mel_band, n_mels, w.losses + 1, w.fscratch, B, T, 1024, 256, st));
+  WM_TRY(launch_loudness(s, sw, w.losses + 2, w.fscratch, B, T, 2048, 512, 0.01f, st));
+  WM_TRY(launch_hf_penalty(w.delta, w.losses + 5, w.fscratch, B, T, 512, 113, st));
+  WM_CHECK_CUDA(cudaMemcpyAsync(w.gsw, w.dxdet, V * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  WM_TRY(launch_mel_log_l1_bwd(s, sw, mel_fb, mel_band, n_mels, w.gsw, w.fscratch, B, T, 1024, 256, lam[1], 1, st));
+  WM_TRY(launch_loudness_bwd(s, sw, w.gsw, w.fscratch, B, T, 2048, 512, 0.01f, lam[2], 1, st));
+  WM_TRY(launch_abs_mean_bwd(w.delta, w.gsw, N, lam[0], 1, st));            // s_w = s + delta: same gradient buffer
+  WM_TRY(launch_hf_penalty_bwd(w.delta, w.gsw, w.fscratch, B, T, 512, 113, lam[5], 1, st));
+  WM_TRY(launch_postprocess_bwd(w.gsw, w.d1, fir, w.gdraw, w.fscratch, B, T, WM_POST_ALL, 0.02f, 0.005f, 1e-8f, st));
+  // ---- generator backward ----
+  float *gA = w.g[0], *gB = w.g[1], *gC = w.g[2];
+  WM_TRY(launch_head_bwd(w.gdraw, w.rb[2].y, g_params + WM_GT_HEAD_W, gA, g_grads + WM_GT_HEAD_W, g_grads + WM_GT_HEAD_B, N,
+                         1, w.fscratch, st));
+  WM_TRY(rb_train_bwd(w.ct, g_params + WM_GT_RB2, g_grads + WM_GT_RB2, w.stats + 512, w.rb[2], gA, gB, gC, w.wt, w.zero64,
+                      B, T, w.fscratch, w.dscratch, st));
+  WM_TRY(launch_conv_wgrad(w.hE, gA, g_grads + WM_GT_CT_W, g_grads + WM_GT_CT_B, B, T, 7, w.fscratch, st));
+  WM_TRY(launch_transpose_flip(g_params + WM_GT_CT_W, w.wt, 7, st));
+  WM_TRY(launch_conv64_fp32(gA, w.wt, w.zero64, nullptr, nullptr, gB, B, T, 7, 0, st));     // gB = dL/d(h + e)
+  clip_colsum_kernel<<<B, NT, 0, st>>>(gB, w.colsum, T);
+  WM_CHECK_LAUNCH("clip_colsum");
+  embedding_scatter_kernel<<<1, 64, 0, st>>>(w.colsum, msg, g_grads + WM_GT_EMB, B);
+  WM_CHECK_LAUNCH("embedding_scatter");
+  WM_TRY(launch_lstm_train_bwd(gB, w.rb[1].y, w.h, g_params + WM_GT_LSTM_WIH, g_params + WM_GT_LSTM_WHH, w.gates, w.cell, gA,
+                               g_grads + WM_GT_LSTM_WIH, g_grads + WM_GT_LSTM_WHH, g_grads + WM_GT_LSTM_BIH, B, T,
+                               w.lstm_scratch, st));
+  WM_CHECK_CUDA(cudaMemcpyAsync(g_grads + WM_GT_LSTM_BHH, g_grads + WM_GT_LSTM_BIH, 256 * sizeof(float),
+                                cudaMemcpyDeviceToDevice, st));
+  WM_TRY(rb_train_bwd(w.rb[0].y, g_params + WM_GT_RB1, g_grads + WM_GT_RB1, w.stats + 256, w.rb[1], gA, gB, gC, w.wt,
+                      w.zero64, B, T, w.fscratch, w.dscratch, st));
+  WM_TRY(rb_train_bwd(w.x0, g_params + WM_GT_RB0, g_grads + WM_GT_RB0, w.stats, w.rb[0], gA, gB, gC, w.wt, w.zero64, B, T,
+                      w.fscratch, w.dscratch, st));
+  WM_TRY(launch_conv_in_grads(s, gA, g_params + WM_GT_IN_W, g_grads + WM_GT_IN_W, g_grads + WM_GT_IN_B, nullptr, B, T,
+                              w.fscratch, st));
+  // totals (py/main16.py:273-276)
+  train_totals_kernel<<<1, 1, 0, st>>>(w.losses, lam[0], lam[1], lam[2], lam[3], lam[4], lam[5]);
+  WM_CHECK_LAUNCH("train_totals");
+  if (losses_out) WM_CHECK_CUDA(cudaMemcpyAsync(losses_out, w.losses, 8 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 

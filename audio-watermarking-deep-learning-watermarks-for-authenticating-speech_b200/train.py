@@ -11,14 +11,20 @@ from __future__ import annotations
 
 from typing import Dict, Optional
 
+import ctypes as C
+
 import torch
 
 from . import _lib as L
 from .ops import _req, _stream, _ws
 
 LR = 1e-3            # py/main16.py:33
+LAMBDA_L1 = 1.0      # py/main16.py:38
+LAMBDA_MSSPEC = 4.0  # py/main16.py:39
+LAMBDA_LOUD = 20.0   # py/main16.py:40
 LAMBDA_LOC = 10.0    # py/main16.py:41
 LAMBDA_DEC = 1.0     # py/main16.py:42
+HF_PENALTY_W = 5.0   # py/main16.py:43
 
 
 # ---- operators ------------------------------------------------------------------------------------------------
@@ -122,6 +128,86 @@ def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor
             raise ValueError(f"adam_step: {name} must be a contiguous fp32 CUDA tensor")
     L.check(lib.wm_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), lr, betas[0], betas[1], eps, step,
                              _stream()), "wm_adam_step")
+
+
+# ---- backward of the losses and of the post-processing ----------------------------------------------------------
+def _stft_bwd_ws(lib, B, T, n_fft, hop, dev):
+    n = lib.wm_stft_bwd_workspace_bytes(B, T, n_fft, hop)
+    return _ws(n, dev), n
+
+
+def _grad_target(like: torch.Tensor, into: Optional[torch.Tensor]):
+    if into is None:
+        return torch.empty_like(like), 0
+    if not (into.is_cuda and into.dtype == torch.float32 and into.is_contiguous() and into.shape == like.shape):
+        raise ValueError("the gradient to accumulate into must be a contiguous fp32 CUDA tensor of the input's shape")
+    return into, 1
+
+
+def hf_penalty_bwd(delta: torch.Tensor, n_fft: int = 512, first_bin: int = 113, weight: float = 1.0,
+                   into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """weight * d high_freq_penalty(delta) / d delta for delta (B,T); added to `into` when given."""
+    lib = L.load()
+    d = _req(delta, "delta")
+    B, T = d.shape
+    g, acc = _grad_target(d, into)
+    ws, n = _stft_bwd_ws(lib, B, T, n_fft, n_fft // 4, d.device)
+    L.check(lib.wm_hf_penalty_bwd(L.ptr(d), L.ptr(g), L.ptr(ws), n, B, T, n_fft, first_bin, weight, acc, _stream()),
+            "wm_hf_penalty_bwd")
+    return g
+
+
+def loudness_bwd(clean, wm, n_fft: int = 2048, hop: int = 512, thresh: float = 0.01, weight: float = 1.0,
+                 into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """weight * d TFLoudnessLoss(clean, wm) / d wm."""
+    lib = L.load()
+    c, w = _req(clean, "clean"), _req(wm, "watermarked")
+    B, T = c.shape
+    g, acc = _grad_target(w, into)
+    ws, n = _stft_bwd_ws(lib, B, T, n_fft, hop, c.device)
+    L.check(lib.wm_loud_bwd(L.ptr(c), L.ptr(w), L.ptr(g), L.ptr(ws), n, B, T, n_fft, hop, thresh, weight, acc,
+                            _stream()), "wm_loud_bwd")
+    return g
+
+
+def mel_log_l1_bwd(clean, wm, fb, band, n_fft: int = 1024, hop: int = 256, weight: float = 1.0,
+                   into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """weight * d MultiScaleMelLoss(clean, wm) / d wm."""
+    lib = L.load()
+    c, w = _req(clean, "clean"), _req(wm, "watermarked")
+    fb, band = _req(fb, "fb"), _req(band, "band", torch.int32)
+    B, T = c.shape
+    g, acc = _grad_target(w, into)
+    ws, n = _stft_bwd_ws(lib, B, T, n_fft, hop, c.device)
+    L.check(lib.wm_mel_log_l1_bwd(L.ptr(c), L.ptr(w), L.ptr(fb), L.ptr(band), fb.shape[1], L.ptr(g), L.ptr(ws), n, B, T,
+                                  n_fft, hop, weight, acc, _stream()), "wm_mel_log_l1_bwd")
+    return g
+
+
+def abs_mean_bwd(x: torch.Tensor, weight: float = 1.0, into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """weight * d mean|x| / dx (F.l1_loss(delta, 0), py/main16.py:266)."""
+    x = _req(x, "x")
+    B, T = x.shape
+    g, acc = _grad_target(x, into)
+    L.check(L.load().wm_abs_mean_bwd(L.ptr(x), L.ptr(g), B, T, weight, acc, _stream()), "wm_abs_mean_bwd")
+    return g
+
+
+def postprocess_bwd(g: torch.Tensor, delta_raw: torch.Tensor, fir: Optional[torch.Tensor], mode: int = L.POST_ALL,
+                    peak: float = 0.02, max_rms: float = 0.005, eps: float = 1e-8) -> torch.Tensor:
+    """Gradient w.r.t. delta_raw of limit_rms(clamp_peak(fir_lowpass(delta_raw))) given g = dL/d delta."""
+    from . import ops
+    lib = L.load()
+    g, dr = _req(g, "g"), _req(delta_raw, "delta_raw")
+    B, T = dr.shape
+    f = _req(fir, "fir") if fir is not None else None
+    d1 = ops.postprocess(dr, None, f, mode & L.POST_FIR, want_sw=False)[0] if mode & L.POST_FIR else dr
+    out = torch.empty_like(dr)
+    n = B * T * 4
+    ws = _ws(n, dr.device)
+    L.check(lib.wm_postprocess_bwd(L.ptr(g), L.ptr(d1), L.ptr(f), L.ptr(out), L.ptr(ws), n, B, T, mode, peak, max_rms,
+                                   eps, _stream()), "wm_postprocess_bwd")
+    return out
 
 
 # ---- flat parameter buffer <-> state dict -----------------------------------------------------------------------
@@ -273,3 +359,220 @@ class DetectorTrainer:
         for k in own:
             if k.endswith("num_batches_tracked"):
                 own[k] += self.steps
+
+
+# ---- the whole training step (py/main16.py:238-278) ---------------------------------------------------------------
+def _rb_slices(out, base, pre):
+    out[pre + "0.weight"] = (base + L.DT_RB_W1, (3, 64, 64), "t210")
+    out[pre + "0.bias"] = (base + L.DT_RB_B1, (64,), None)
+    out[pre + "1.weight"] = (base + L.DT_RB_G1, (64,), None)
+    out[pre + "1.bias"] = (base + L.DT_RB_BE1, (64,), None)
+    out[pre + "3.weight"] = (base + L.DT_RB_W2, (3, 64, 64), "t210")
+    out[pre + "3.bias"] = (base + L.DT_RB_B2, (64,), None)
+    out[pre + "4.weight"] = (base + L.DT_RB_G2, (64,), None)
+    out[pre + "4.bias"] = (base + L.DT_RB_BE2, (64,), None)
+
+
+def _gt_slices():
+    """name -> (offset, flat shape, layout transform); transforms are involutions or come with an inverse below."""
+    out = {"encoder.0.weight": (L.GT_IN_W, (7, 1, 64), "t210"), "encoder.0.bias": (L.GT_IN_B, (64,), None)}
+    _rb_slices(out, L.GT_RB0, "encoder.1.block.")
+    _rb_slices(out, L.GT_RB1, "encoder.2.block.")
+    out["lstm.weight_ih_l0"] = (L.GT_LSTM_WIH, (4, 64, 64), "gate")
+    out["lstm.weight_hh_l0"] = (L.GT_LSTM_WHH, (4, 64, 64), "gate")
+    out["lstm.bias_ih_l0"] = (L.GT_LSTM_BIH, (256,), None)
+    out["lstm.bias_hh_l0"] = (L.GT_LSTM_BHH, (256,), None)
+    out["decoder.0.weight"] = (L.GT_CT_W, (7, 64, 64), "convT")
+    out["decoder.0.bias"] = (L.GT_CT_B, (64,), None)
+    _rb_slices(out, L.GT_RB2, "decoder.1.block.")
+    out["decoder.2.weight"] = (L.GT_HEAD_W, (1, 64, 1), None)
+    out["decoder.2.bias"] = (L.GT_HEAD_B, (1,), None)
+    out["embedding.weight"] = (L.GT_EMB, (65536, 64), None)
+    return out
+
+
+def _gt_stat_slices():
+    out = {}
+    for k, mod in enumerate(("encoder.1", "encoder.2", "decoder.1")):
+        for i, bn in enumerate(("1", "4")):
+            out[f"{mod}.block.{bn}.running_mean"] = k * 256 + i * 128
+            out[f"{mod}.block.{bn}.running_var"] = k * 256 + i * 128 + 64
+    return out
+
+
+def _to_flat(t: torch.Tensor, how) -> torch.Tensor:
+    if how == "t210":
+        return t.permute(2, 1, 0)
+    if how == "gate":
+        return _gate_t(t)
+    if how == "convT":            # ConvTranspose1d (ci,co,k) -> convolution taps [j][ci][co] = w[ci][co][6-j]
+        return t.flip(-1).permute(2, 0, 1)
+    return t
+
+
+def _from_flat(t: torch.Tensor, how) -> torch.Tensor:
+    if how == "t210":
+        return t.permute(2, 1, 0)
+    if how == "gate":
+        return _gate_t(t).reshape(256, 64)
+    if how == "convT":
+        return t.permute(1, 2, 0).flip(-1)
+    return t
+
+
+def flatten_generator(sd: Dict[str, torch.Tensor], device) -> torch.Tensor:
+    flat = torch.zeros(L.GT_SIZE, dtype=torch.float32, device=device)
+    for name, (off, shape, how) in _gt_slices().items():
+        t = _to_flat(sd[name].detach().to(device=device, dtype=torch.float32), how)
+        flat[off:off + t.numel()] = t.reshape(-1)
+    return flat
+
+
+def unflatten_generator(flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+    out = {}
+    for name, (off, shape, how) in _gt_slices().items():
+        n = 1
+        for d in shape:
+            n *= d
+        out[name] = _from_flat(flat[off:off + n].reshape(shape), how).contiguous().clone()
+    return out
+
+
+class Trainer:
+    """`train_one_epoch`'s loop body (py/main16.py:238-278) for a Generator / Detector pair, on the device:
+
+        tr = Trainer(generator, detector)                  # modules with the reference's state-dict layout
+        for s in loader:                                    # s (B,1,T) or (B,T) on cuda
+            message = torch.randint(0, 2 ** 16, (s.shape[0],), device=s.device)
+            losses = tr.step(s, message)                    # {"total","raw_total","l1","mel","loud","loc","bce","hf"}
+        tr.write_back(generator, detector)
+
+    Both networks run in train mode (batch-statistics BatchNorm), every gradient comes from hand-written backward
+    kernels, and one Adam (lr 1e-3) updates both flat parameter buffers.  With torch.distributed initialised
+    (one process per GPU, NCCL), `step` averages the two gradient buffers across ranks between backward and Adam —
+    data-parallel training with per-replica BatchNorm statistics, as DistributedDataParallel would do."""
+
+    LOSS_KEYS = ("l1", "mel", "loud", "loc", "bce", "hf", "total", "raw_total")
+
+    def __init__(self, generator: torch.nn.Module, detector: torch.nn.Module, lr: float = LR, betas=(0.9, 0.999),
+                 eps: float = 1e-8, lambdas=None, device=None):
+        from . import functional as Fn
+        from . import packing
+        gsd, dsd = generator.state_dict(), detector.state_dict()
+        self.nout = int(dsd["model.3.weight"].shape[0])
+        if device is None:
+            device = dsd["model.3.weight"].device
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("Trainer runs on a B200 (sm_100a) only; there is no CPU fallback — move the modules to "
+                               "cuda first")
+        if tuple(gsd["embedding.weight"].shape) != (65536, 64):
+            raise ValueError("Trainer supports the reference's 16-bit message embedding (65536 x 64) only")
+        L.load()
+        self.device = device
+        self.g_params, self.d_params = flatten_generator(gsd, device), flatten_detector(dsd, self.nout, device)
+        self.g_grads, self.d_grads = torch.zeros_like(self.g_params), torch.zeros_like(self.d_params)
+        self.g_m, self.g_v = torch.zeros_like(self.g_params), torch.zeros_like(self.g_params)
+        self.d_m, self.d_v = torch.zeros_like(self.d_params), torch.zeros_like(self.d_params)
+        self.g_stats = torch.zeros(L.GT_STATS, dtype=torch.float32, device=device)
+        self.d_stats = torch.zeros(L.DT_STATS, dtype=torch.float32, device=device)
+        for name, off in _gt_stat_slices().items():
+            self.g_stats[off:off + 64] = gsd[name].to(device=device, dtype=torch.float32)
+        for name, off in _dt_stat_slices().items():
+            self.d_stats[off:off + 64] = dsd[name].to(device=device, dtype=torch.float32)
+        lam = dict(l1=LAMBDA_L1, msspec=LAMBDA_MSSPEC, loud=LAMBDA_LOUD, loc=LAMBDA_LOC, dec=LAMBDA_DEC, hf=HF_PENALTY_W)
+        lam.update(lambdas or {})
+        self.lambdas = lam
+        self._lam = (C.c_float * 6)(lam["l1"], lam["msspec"], lam["loud"], lam["loc"], lam["dec"], lam["hf"])
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.fir = Fn.fir_taps_on(device)
+        fb, band = packing.mel_filterbank(513, 64, 16000)
+        self.mel_fb, self.mel_band = fb.to(device).contiguous(), band.to(device=device, dtype=torch.int32).contiguous()
+        self.steps = 0
+        self._ws, self._ws_key = None, None
+
+    def _workspace(self, B: int, T: int):
+        if self._ws_key != (B, T):
+            n = L.load().wm_train_step_workspace_bytes(B, T, self.nout)
+            self._ws, self._ws_key = (_ws(n, self.device), n), (B, T)
+        return self._ws
+
+    def forward_backward(self, s: torch.Tensor, message: torch.Tensor, want_s_w: bool = False):
+        """Losses and gradients (self.g_grads / self.d_grads) of one batch; parameters untouched."""
+        lib = L.load()
+        s = _req(s, "s")
+        if s.dim() == 3 and s.shape[1] == 1:
+            s = s[:, 0]
+        if s.dim() != 2:
+            raise ValueError(f"s must be (B,T) or (B,1,T), got {tuple(s.shape)}")
+        s = s.contiguous()
+        B, T = s.shape
+        msg = _req(message, "message", torch.int64)
+        if msg.numel() != B:
+            raise ValueError("message must hold one value per clip")
+        if B and (int(msg.min()) < 0 or int(msg.max()) >= 65536):
+            raise IndexError("message out of range for the 16-bit embedding")
+        losses = torch.zeros(8, device=self.device)
+        s_w = torch.empty_like(s) if want_s_w else None
+        ws, n = self._workspace(B, T)
+        L.check(lib.wm_train_forward_backward(
+            L.ptr(self.g_params), L.ptr(self.g_grads), L.ptr(self.g_stats), L.ptr(self.d_params), L.ptr(self.d_grads),
+            L.ptr(self.d_stats), L.ptr(s), L.ptr(msg), L.ptr(self.fir), L.ptr(self.mel_fb), L.ptr(self.mel_band),
+            self.mel_fb.shape[1], C.cast(self._lam, C.c_void_p), B, T, self.nout, L.ptr(losses), L.ptr(s_w), L.ptr(ws),
+            n, _stream()), "wm_train_forward_backward")
+        out = {k: losses[i] for i, k in enumerate(self.LOSS_KEYS)}
+        if want_s_w:
+            out["s_w"] = s_w
+        return out
+
+    def all_reduce_gradients(self) -> None:
+        """Average both gradient buffers over the ranks of the default process group (NCCL over NVLink on a B200 box)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        average_gradients((self.g_grads, self.d_grads))
+
+    def apply(self) -> None:
+        """torch.optim.Adam step on both parameter buffers (py/main16.py:278,504)."""
+        self.steps += 1
+        adam_step(self.g_params, self.g_grads, self.g_m, self.g_v, self.steps, self.lr, self.betas, self.eps)
+        adam_step(self.d_params, self.d_grads, self.d_m, self.d_v, self.steps, self.lr, self.betas, self.eps)
+
+    def step(self, s: torch.Tensor, message: torch.Tensor) -> Dict[str, torch.Tensor]:
+        out = self.forward_backward(s, message)
+        self.all_reduce_gradients()
+        self.apply()
+        return out
+
+    def state_dicts(self):
+        g = unflatten_generator(self.g_params)
+        for name, off in _gt_stat_slices().items():
+            g[name] = self.g_stats[off:off + 64].clone()
+        d = unflatten_detector(self.d_params, self.nout)
+        for name, off in _dt_stat_slices().items():
+            d[name] = self.d_stats[off:off + 64].clone()
+        return g, d
+
+    def grad_dicts(self):
+        return unflatten_generator(self.g_grads), unflatten_detector(self.d_grads, self.nout)
+
+    @torch.no_grad()
+    def write_back(self, generator: torch.nn.Module, detector: torch.nn.Module) -> None:
+        for mod, sd in zip((generator, detector), self.state_dicts()):
+            own = mod.state_dict()
+            for k, v in sd.items():
+                own[k].copy_(v.to(own[k].device))
+            for k in own:
+                if k.endswith("num_batches_tracked"):
+                    own[k] += self.steps
+
+
+def average_gradients(buffers) -> None:
+    """all_reduce(SUM) / world_size of flat gradient buffers over the default process group — the one exchange of the
+    data-parallel training step.  Works on whatever backend the group was created with (NCCL on the
+    GPU box; gloo in the CPU tests of this host-side logic)."""
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    for b in buffers:
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        b.div_(world)

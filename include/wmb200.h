@@ -122,6 +122,27 @@ enum {
   WM_DT_STATS = 2 * 4 * 64                 /* per ResBlock: bn1 running_mean, running_var, bn2 ... */
 };
 
+/* Training-mode Generator parameters, same conventions (ResBlocks use the WM_DT_RB_* block; LSTM weights per-gate
+ * transposed wT[q][k][r] = W[q*64 + r][k]; decoder.0 as a convolution [7][ci][co] = weight[ci][co][6 - j]). */
+enum {
+  WM_GT_IN_W = 0,                           /* encoder.0 [7][64]                          */
+  WM_GT_IN_B = WM_GT_IN_W + 7 * 64,
+  WM_GT_RB0 = WM_GT_IN_B + 64,              /* encoder.1                                  */
+  WM_GT_RB1 = WM_GT_RB0 + WM_DT_RB_SIZE,    /* encoder.2                                  */
+  WM_GT_LSTM_WIH = WM_GT_RB1 + WM_DT_RB_SIZE,
+  WM_GT_LSTM_WHH = WM_GT_LSTM_WIH + 256 * 64,
+  WM_GT_LSTM_BIH = WM_GT_LSTM_WHH + 256 * 64,
+  WM_GT_LSTM_BHH = WM_GT_LSTM_BIH + 256,
+  WM_GT_CT_W = WM_GT_LSTM_BHH + 256,        /* decoder.0                                  */
+  WM_GT_CT_B = WM_GT_CT_W + 7 * 64 * 64,
+  WM_GT_RB2 = WM_GT_CT_B + 64,              /* decoder.1                                  */
+  WM_GT_HEAD_W = WM_GT_RB2 + WM_DT_RB_SIZE, /* decoder.2 [64]                             */
+  WM_GT_HEAD_B = WM_GT_HEAD_W + 64,         /* [1] (+63 pad)                              */
+  WM_GT_EMB = WM_GT_HEAD_B + 64,            /* embedding.weight [65536][64]               */
+  WM_GT_SIZE = WM_GT_EMB + 65536 * 64,
+  WM_GT_STATS = 3 * 4 * 64
+};
+
 /* Arithmetic of the 64->64 convolutions (the tensor-pipe part of the path).
  *   WM_MATH_FP32   CUDA-core fp32 FMA (bit-for-bit the reference's operation order
  *                  up to summation order; the on-GPU cross-check for the other mode)
@@ -294,6 +315,25 @@ int wm_bce_heads_fwd(const float *logits, const int64_t *message, float *loc_out
 /* F.l1_loss(delta, 0) — py/main16.py:266. */
 int wm_abs_mean_fwd(const float *x, float *out, void *workspace, size_t workspace_bytes, int B, int T, void *stream);
 
+/* ---- backward of the losses and of the post-processing (py/main16.py:266-277 through autograd) ----
+ * Each adds (accumulate != 0) or writes `weight` * dLoss/dSignal into a [B][T] gradient; `workspace` holds the
+ * per-frame gradients (wm_stft_bwd_workspace_bytes) that a gather kernel overlap-adds, so results are deterministic. */
+size_t wm_stft_bwd_workspace_bytes(int B, int T, int n_fft, int hop);
+int wm_hf_penalty_bwd(const float *delta, float *d_delta, void *workspace, size_t workspace_bytes, int B, int T,
+                      int n_fft, int first_bin, float weight, int accumulate, void *stream);
+int wm_loud_bwd(const float *clean, const float *watermarked, float *d_watermarked, void *workspace,
+                size_t workspace_bytes, int B, int T, int n_fft, int hop, float thresh, float weight, int accumulate,
+                void *stream);
+int wm_mel_log_l1_bwd(const float *clean, const float *watermarked, const float *fb, const int *band, int n_mels,
+                      float *d_watermarked, void *workspace, size_t workspace_bytes, int B, int T, int n_fft, int hop,
+                      float weight, int accumulate, void *stream);
+int wm_abs_mean_bwd(const float *x, float *dx, int B, int T, float weight, int accumulate, void *stream);
+/* Backward of wm_postprocess_fwd: g = dL/d delta, delta_fir = fir_lowpass(delta_raw) (wm_postprocess_fwd with
+ * mode WM_POST_FIR; delta_raw itself when the FIR bit of `mode` is clear) -> d_delta_raw.  workspace: B*T floats. */
+int wm_postprocess_bwd(const float *g, const float *delta_fir, const float *fir, float *d_delta_raw, void *workspace,
+                       size_t workspace_bytes, int B, int T, int mode, float peak, float max_rms, float eps,
+                       void *stream);
+
 /* ---- generic fp32 operators of the main14b_2 residual stack (py/main14b_2.py:83-224, BASELINE config 3) ----
  * channels-first tensors x[b][c][t] and the reference's own parameter layouts, no packing.           */
 int wm_conv1d_out_len(int Tin, int K, int stride, int pad);
@@ -345,6 +385,20 @@ int wm_detector_train_step(float *params, float *grads, float *adam_m, float *ad
                            const int64_t *message, int B_wm, int B_total, int T, int nout, float lam_loc, float lam_dec,
                            float lr, float beta1, float beta2, float eps, int adam_step, float *losses_out,
                            float *d_input, void *workspace, size_t workspace_bytes, void *stream);
+/* Forward + backward of one train_one_epoch iteration (py/main16.py:244-277), both networks in train mode:
+ * delta = limit_rms(clamp_peak(fir_lowpass(G(s, message)))), s_w = s + delta, logits = D(cat(s_w, s)),
+ * loss = lam[0] l1 + lam[1] mel + lam[2] loud + lam[3] loc + lam[4] bce + lam[5] hf  (lam on the HOST).
+ * Gradients land in g_grads (WM_GT_SIZE, dense embedding rows included) and d_grads (WM_DT_SIZE); the BatchNorm
+ * running stats (g_stats WM_GT_STATS, d_stats WM_DT_STATS) are updated; parameters are NOT touched — the caller
+ * all-reduces the gradient buffers across ranks if it wants to and then calls wm_adam_step on each
+ * (py/main16.py:278,504).  losses_out[8] (device): {l1, mel, loud, loc, bce, hf, total, raw_total};
+ * s_w_out (nullable) [B][T].  mel_fb / mel_band as for wm_mel_log_l1_fwd (n_fft 1024). */
+size_t wm_train_step_workspace_bytes(int B, int T, int nout);
+int wm_train_forward_backward(const float *g_params, float *g_grads, float *g_stats, const float *d_params,
+                              float *d_grads, float *d_stats, const float *s, const int64_t *message, const float *fir,
+                              const float *mel_fb, const int *mel_band, int n_mels, const float *lam, int B, int T,
+                              int nout, float *losses_out, float *s_w_out, void *workspace, size_t workspace_bytes,
+                              void *stream);
 /* Building blocks of the step, exposed for the parity tests (channels-last x[n][64], n = B*T rows):
  * nn.BatchNorm1d(64) in train mode fused with the residual add and ReLU of py/main16.py:118-127 ... */
 int wm_bn_train_fwd(const float *z, const float *gamma, const float *beta, const float *residual, float *out,

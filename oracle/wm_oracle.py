@@ -156,7 +156,7 @@ def fir_taps(cutoff: float = 4000, taps: int = 101) -> Tensor:
 
 def fir_lowpass(delta: Tensor, cutoff: float = 4000, taps: int = 101) -> Tensor:
     # the reference builds the taps on delta.device (py/main16.py:58)
-    return F.conv1d(delta, fir_taps(cutoff, taps).to(delta.device).view(1, 1, -1), padding=(taps - 1) // 2)
+    return F.conv1d(delta, fir_taps(cutoff, taps).to(delta).view(1, 1, -1), padding=(taps - 1) // 2)
 
 
 def clamp_peak(d: Tensor, thr: float = 0.02) -> Tensor:
@@ -178,14 +178,14 @@ def postprocess(delta: Tensor) -> Tensor:
 # --------------------------------------------------------------------------
 def stft_mag(x: Tensor, n_fft: int, hop: int) -> Tensor:
     """|torch.stft| with periodic Hann, centre + reflect pad: (B,T)->(B,n_fft/2+1,1+T//hop)."""
-    return torch.stft(x, n_fft, hop, window=torch.hann_window(n_fft),
+    return torch.stft(x, n_fft, hop, window=torch.hann_window(n_fft).to(x),
                       return_complex=True).abs()
 
 
 def high_freq_penalty(delta: Tensor, cutoff: float = 3500, n_fft: int = 512) -> Tensor:
     spec = stft_mag(delta.squeeze(1), n_fft, n_fft // 4)
     freqs = torch.fft.rfftfreq(n_fft, 1 / SAMPLE_RATE)
-    return (spec * (freqs > cutoff).float().view(1, -1, 1)).mean()
+    return (spec * (freqs > cutoff).to(spec).view(1, -1, 1)).mean()
 
 
 def mel_filterbank(n_freqs: int = 513, n_mels: int = 64, sr: int = 16000) -> Tensor:
@@ -204,7 +204,7 @@ def mel_filterbank(n_freqs: int = 513, n_mels: int = 64, sr: int = 16000) -> Ten
 def mel_spectrogram(x: Tensor) -> Tensor:
     """MelSpectrogram(16k, n_fft 1024, hop 256, 64 mels, power 2): (B,1,T)->(B,1,64,63)."""
     p = stft_mag(x.reshape(-1, x.shape[-1]), 1024, 256) ** 2           # (B,513,F)
-    m = torch.matmul(p.transpose(-1, -2), mel_filterbank()).transpose(-1, -2)
+    m = torch.matmul(p.transpose(-1, -2), mel_filterbank().to(p)).transpose(-1, -2)
     return m.reshape(x.shape[:-1] + m.shape[-2:])
 
 
@@ -216,7 +216,7 @@ def mel_loss(clean: Tensor, wm: Tensor) -> Tensor:
 def loudness_loss(clean: Tensor, wm: Tensor) -> Tensor:
     sc = stft_mag(clean.squeeze(1), 2048, 512)
     sw = stft_mag(wm.squeeze(1), 2048, 512)
-    return (((sw - sc) ** 2) * (sc > 0.01).float()).mean()
+    return (((sw - sc) ** 2) * (sc > 0.01).to(sw)).mean()
 
 
 def bit_targets(message: Tensor, bits: int = MESSAGE_BITS) -> Tensor:

@@ -299,3 +299,62 @@ def test_lstm_train_forward_backward_match_autograd(B, T):
     assert rel(dwi, lstm.weight_ih_l0.grad) < 1e-4
     assert rel(dwh, lstm.weight_hh_l0.grad) < 1e-4
     assert rel(db, lstm.bias_ih_l0.grad) < 1e-4 and rel(db, lstm.bias_hh_l0.grad) < 1e-4
+
+
+# ---- backward of the losses and of the post-processing against autograd of the oracle's definitions -------------
+def _signals(B, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(T) / 16000.0
+    s = 0.1 * torch.randn(B, T, generator=g) + 0.2 * torch.sin(2 * np.pi * 300.0 * t)[None]
+    delta = 0.004 * torch.randn(B, T, generator=g)
+    delta[0] *= 4.0             # one clip above the RMS cap with samples beyond the peak clamp
+    return s.cuda(), delta.cuda()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T", [(2, 16000), (3, 4097)])
+def test_loss_gradients_match_autograd(B, T):
+    from oracle import wm_oracle as O
+    from wmb200 import packing
+    from wmb200 import train as TR
+    s, delta = _signals(B, T, T)
+    sd, dd = s.double(), delta.double().requires_grad_(True)
+    swd = sd + dd
+    # hf penalty w.r.t. delta
+    (g_ref,) = torch.autograd.grad(O.high_freq_penalty(dd.unsqueeze(1)), dd)
+    got = TR.hf_penalty_bwd(delta, 512, 113, weight=5.0)
+    assert rel(got, 5.0 * g_ref) < 2e-4
+    # loudness and mel w.r.t. the watermarked signal
+    (g_ref,) = torch.autograd.grad(O.loudness_loss(sd, swd), dd)
+    got = TR.loudness_bwd(s, s + delta, weight=20.0)
+    assert rel(got, 20.0 * g_ref) < 2e-4
+    (g_ref,) = torch.autograd.grad(O.mel_loss(sd.unsqueeze(1), swd.unsqueeze(1)), dd)
+    fb, band = packing.mel_filterbank(513, 64, 16000)
+    got = TR.mel_log_l1_bwd(s, s + delta, fb.cuda(), band.cuda(), weight=4.0)
+    assert rel(got, 4.0 * g_ref) < 1e-3
+    # |delta| mean, accumulated on top of the previous gradient
+    assert rel(TR.abs_mean_bwd(delta, weight=2.0), 2.0 * torch.sign(delta) / delta.numel()) < 1e-6
+    acc = got.clone()
+    TR.abs_mean_bwd(delta, weight=1.0, into=acc)
+    assert rel(acc, got + torch.sign(delta) / delta.numel()) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [7, 6, 4, 1, 0])
+def test_postprocess_backward_matches_autograd(mode):
+    from oracle import wm_oracle as O
+    from wmb200 import train as TR
+    _, delta = _signals(3, 16000, 3)
+    raw = (delta * 1.5).double().requires_grad_(True)
+    d = raw.unsqueeze(1)
+    if mode & 1:
+        d = O.fir_lowpass(d)
+    if mode & 2:
+        d = O.clamp_peak(d)
+    if mode & 4:
+        d = O.limit_rms(d)
+    g = torch.randn(3, 16000, device="cuda")
+    (want,) = torch.autograd.grad((d[:, 0] * g.double()).sum(), raw)
+    fir = O.fir_taps().float().cuda()
+    got = TR.postprocess_bwd(g, raw.detach().float(), fir, mode)
+    assert rel(got, want) < 2e-4
