@@ -10,7 +10,7 @@ from . import _lib, audio, main14b_2, ops, packing
 from .audio import Resample, file_metrics, from_pcm16, resample, to_pcm16
 from .api import detect_prob, detect_watermark, generate_watermarked_audio, load_audio, save_audio, segment
 from .evaluate import evaluate_model, validate_one_epoch
-from .train import DetectorTrainer
+from .train import DetectorTrainer, Trainer
 from .functional import (AUDIO_LEN, HF_PENALTY_W, LAMBDA_DEC, LAMBDA_L1, LAMBDA_LOC, LAMBDA_LOUD,
                          LAMBDA_MSSPEC, MAX_RMS, MESSAGE_BITS, SAMPLE_RATE, bit_targets, clamp_peak,
                          embed_detect, fir_lowpass, limit_rms, postprocess_delta)
@@ -26,4 +26,4 @@ __all__ = ["Generator", "Detector", "ResBlock", "generate_watermarked_audio", "d
            "LAMBDA_LOC", "LAMBDA_DEC", "HF_PENALTY_W", "MultiScaleMelLoss", "TFLoudnessLoss", "high_freq_penalty",
            "step_losses", "stft_magnitude", "embed_detect_stream", "process_folder_with_tqdm", "detect_watermark_folder",
            "Resample", "resample", "to_pcm16", "from_pcm16", "file_metrics", "evaluate_model", "validate_one_epoch",
-           "DetectorTrainer"]
+           "DetectorTrainer", "Trainer"]

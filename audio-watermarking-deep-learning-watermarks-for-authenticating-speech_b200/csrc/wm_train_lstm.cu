@@ -6,7 +6,7 @@
 // (i, f, g, o), which is at once the [ci][co] layout the weight-gradient kernel produces.
 //
 //   forward  t = 0..T-1   a = b + W_ih x_t + W_hh h_{t-1};  i,f,o = sigmoid, g = tanh;  c_t = f c_{t-1} + i g;
-//                         h_t = o tanh(c_t)                              -> gates[b][t][4][64], cell[b][t][64], h
+//                         h_t = o tanh(c_t)                              -> gates[q][b][t][64], cell[b][t][64], h
 //   backward t = T-1..0   dh = dy_t + W_hh^T da_{t+1};  dc = dc_carry + dh o (1 - tanh^2 c_t);
 //                         da = (dc g i(1-i), dc c_{t-1} f(1-f), dc i (1-g^2), dh tanh(c_t) o(1-o));  dc_carry = dc f
 //                         -> da[q][b][t][64] (gate-planar: each plane is a dense [rows][64] matrix for the GEMMs)
@@ -17,65 +17,92 @@ namespace wm {
 
 namespace {
 
-__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanhx(float x) { return 2.0f / (1.0f + __expf(-2.0f * x)) - 1.0f; }
+__device__ __forceinline__ float sigm(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhx(float x) { return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
 
-// thread r = q * 64 + j owns gate row r (W_ih[r,:], W_hh[r,:] in registers)
+constexpr int TC = 16;   // time steps staged per cp.async chunk
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// b_ih + b_hh
+__global__ void bias_sum_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ o) {
+  o[threadIdx.x] = a[threadIdx.x] + b[threadIdx.x];
+}
+
+// The input half of the gates, W_ih x_t + b, does not depend on the recurrence: it is computed for all steps by four
+// 1-tap convolutions into the gate planes, and this kernel walks the chain with only the 64-term W_hh h_{t-1} dot
+// per thread, overwriting each pre-activation with the activated gate.  thread (q, j) owns gate row q*64 + j.
 __global__ void __launch_bounds__(256, 1)
-    lstm_train_fwd_kernel(const float *__restrict__ x, const float *__restrict__ wT_ih, const float *__restrict__ wT_hh,
-                          const float *__restrict__ b_ih, const float *__restrict__ b_hh, float *__restrict__ h_out,
-                          float *__restrict__ gates, float *__restrict__ cell, int T) {
-  __shared__ __align__(16) float xs[2][64], hs[64], gs[256];
+    lstm_train_fwd_kernel(float *__restrict__ gates, const float *__restrict__ wT_hh, float *__restrict__ h_out,
+                          float *__restrict__ cell, long long plane, int T) {
+  __shared__ __align__(16) float xs[2][TC][256];
+  __shared__ __align__(16) float hs[64];
+  __shared__ float gs[256];
   const int tid = threadIdx.x, q = tid >> 6, j = tid & 63, b = blockIdx.x;
-  float wi[64], wh[64];
+  float wh[64];
 #pragma unroll
-  for (int k = 0; k < 64; ++k) {
-    wi[k] = wT_ih[(q * 64 + k) * 64 + j];
-    wh[k] = wT_hh[(q * 64 + k) * 64 + j];
-  }
-  const float br = b_ih[tid] + b_hh[tid];
-  const float *xb = x + (size_t)b * T * 64;
-  float *hb = h_out + (size_t)b * T * 64, *gb = gates + (size_t)b * T * 256, *cb = cell + (size_t)b * T * 64;
-  if (tid < 64) { hs[tid] = 0.0f; xs[0][tid] = xb[tid]; }
+  for (int k = 0; k < 64; ++k) wh[k] = wT_hh[(q * 64 + k) * 64 + j];
+  float *gq = gates + (size_t)q * plane + (size_t)b * T * 64;
+  const float *gb = gates + (size_t)b * T * 64;
+  float *hb = h_out + (size_t)b * T * 64, *cb = cell + (size_t)b * T * 64;
+  auto stage = [&](int chunk, int buf) {
+    const int t0 = chunk * TC;
+    for (int i = tid; i < TC * 64; i += 256) {
+      const int tt = i >> 6, qq = (i >> 4) & 3, c4 = (i & 15) * 4;
+      if (t0 + tt < T) cp_async16(&xs[buf][tt][qq * 64 + c4], gb + (size_t)qq * plane + (size_t)(t0 + tt) * 64 + c4);
+    }
+    cp_async_commit();
+  };
+  if (tid < 64) hs[tid] = 0.0f;
   float c_prev = 0.0f;
-  __syncthreads();
-  for (int t = 0; t < T; ++t) {
-    const int buf = t & 1;
-    float xn = 0.0f;
-    if (tid < 64 && t + 1 < T) xn = xb[(size_t)(t + 1) * 64 + tid];   // next step's input, in flight during the dot
-    float a0 = br, a1 = 0.0f;
+  const int nchunks = (T + TC - 1) / TC;
+  stage(0, 0);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunks) { stage(ch + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const int tend = min(TC, T - ch * TC);
+    for (int tt = 0; tt < tend; ++tt) {
+      const int t = ch * TC + tt;
+      float a0 = xs[buf][tt][tid], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 64; k += 4) {
-      const float4 xv = *reinterpret_cast<const float4 *>(&xs[buf][k]);
-      const float4 hv = *reinterpret_cast<const float4 *>(&hs[k]);
-      a0 = fmaf(wi[k], xv.x, a0); a1 = fmaf(wh[k], hv.x, a1);
-      a0 = fmaf(wi[k + 1], xv.y, a0); a1 = fmaf(wh[k + 1], hv.y, a1);
-      a0 = fmaf(wi[k + 2], xv.z, a0); a1 = fmaf(wh[k + 2], hv.z, a1);
-      a0 = fmaf(wi[k + 3], xv.w, a0); a1 = fmaf(wh[k + 3], hv.w, a1);
+      for (int k = 0; k < 64; k += 4) {
+        const float4 hv = *reinterpret_cast<const float4 *>(&hs[k]);
+        a0 = fmaf(wh[k], hv.x, a0); a1 = fmaf(wh[k + 1], hv.y, a1);
+        a2 = fmaf(wh[k + 2], hv.z, a2); a3 = fmaf(wh[k + 3], hv.w, a3);
+      }
+      const float a = (a0 + a1) + (a2 + a3);
+      const float g = q == 2 ? tanhx(a) : sigm(a);
+      gs[tid] = g;
+      gq[(size_t)t * 64 + j] = g;
+      __syncthreads();
+      if (tid < 64) {
+        const float c = fmaf(gs[64 + tid], c_prev, gs[tid] * gs[128 + tid]);
+        c_prev = c;
+        const float h = gs[192 + tid] * tanhx(c);
+        hs[tid] = h;
+        hb[(size_t)t * 64 + tid] = h;
+        cb[(size_t)t * 64 + tid] = c;
+      }
+      __syncthreads();
     }
-    const float a = a0 + a1;
-    const float g = q == 2 ? tanhx(a) : sigm(a);
-    gs[tid] = g;
-    gb[(size_t)t * 256 + tid] = g;
-    __syncthreads();
-    if (tid < 64) {
-      const float c = fmaf(gs[64 + tid], c_prev, gs[tid] * gs[128 + tid]);
-      c_prev = c;
-      const float h = gs[192 + tid] * tanhx(c);
-      hs[tid] = h;
-      hb[(size_t)t * 64 + tid] = h;
-      cb[(size_t)t * 64 + tid] = c;
-      xs[buf ^ 1][tid] = xn;
-    }
-    __syncthreads();
   }
 }
 
 // thread (q, j): phase A makes da[q*64 + j] of step t; phase B makes the partial of W_hh^T da over gate q's 64 rows
-// for hidden unit j (W_hh[q*64 + rr][j], rr = 0..63, in registers).
+// for hidden unit j (W_hh[q*64 + rr][j], rr = 0..63, in registers).  Operands of TC steps are staged by cp.async,
+// chunks walked from the last to the first.
+constexpr int BWD_BUF = TC * 256 + (TC + 1) * 64 + TC * 64;   // floats per staging buffer
 __global__ void __launch_bounds__(256, 1)
     lstm_train_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ wT_hh, const float *__restrict__ gates,
                           const float *__restrict__ cell, float *__restrict__ da, long long plane, int T) {
+  extern __shared__ __align__(16) float bsm[];
   __shared__ __align__(16) float das[256], part[4][64];
   const int tid = threadIdx.x, q = tid >> 6, j = tid & 63, b = blockIdx.x;
   float w[64];   // w[rr] = W_hh[q*64 + rr][j] = wT_hh[q][j][rr]
@@ -84,56 +111,80 @@ __global__ void __launch_bounds__(256, 1)
     const float4 v = *reinterpret_cast<const float4 *>(&wT_hh[(q * 64 + j) * 64 + rr]);
     w[rr] = v.x; w[rr + 1] = v.y; w[rr + 2] = v.z; w[rr + 3] = v.w;
   }
-  const float *dyb = dy + (size_t)b * T * 64, *gb = gates + (size_t)b * T * 256, *cb = cell + (size_t)b * T * 64;
+  const float *dyb = dy + (size_t)b * T * 64, *gb = gates + (size_t)b * T * 64, *cb = cell + (size_t)b * T * 64;
   float *dab = da + (size_t)q * plane + (size_t)b * T * 64;
+  auto stage = [&](int chunk, int buf) {
+    float *gsm = bsm + buf * BWD_BUF, *csm = gsm + TC * 256, *dsm = csm + (TC + 1) * 64;
+    const int t0 = chunk * TC;
+    for (int i = tid; i < TC * 64; i += 256) {
+      const int tt = i >> 6, qq = (i >> 4) & 3, c4 = (i & 15) * 4;
+      if (t0 + tt < T) cp_async16(&gsm[tt * 256 + qq * 64 + c4], gb + (size_t)qq * plane + (size_t)(t0 + tt) * 64 + c4);
+    }
+    for (int i = tid; i < (TC + 1) * 16; i += 256) {
+      const int r = i >> 4, c4 = (i & 15) * 4, t = t0 - 1 + r;
+      if (t >= 0 && t < T) cp_async16(&csm[r * 64 + c4], cb + (size_t)t * 64 + c4);
+      else *reinterpret_cast<float4 *>(&csm[r * 64 + c4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = tid; i < TC * 16; i += 256) {
+      const int tt = i >> 4, c4 = (i & 15) * 4;
+      if (t0 + tt < T) cp_async16(&dsm[tt * 64 + c4], dyb + (size_t)(t0 + tt) * 64 + c4);
+    }
+    cp_async_commit();
+  };
   part[q][j] = 0.0f;
   float dc_carry = 0.0f;
-  // operands of step t, loaded one step ahead
-  float gi, gf, gg, go, ct, cp, dyt;
-  auto load = [&](int t, float &i_, float &f_, float &g_, float &o_, float &c_, float &cprev_, float &dy_) {
-    const float *gr = gb + (size_t)t * 256;
-    i_ = gr[j]; f_ = gr[64 + j]; g_ = gr[128 + j]; o_ = gr[192 + j];
-    c_ = cb[(size_t)t * 64 + j];
-    cprev_ = t > 0 ? cb[(size_t)(t - 1) * 64 + j] : 0.0f;
-    dy_ = dyb[(size_t)t * 64 + j];
-  };
-  load(T - 1, gi, gf, gg, go, ct, cp, dyt);
-  __syncthreads();
-  for (int t = T - 1; t >= 0; --t) {
-    float ni = 0, nf = 0, ng = 0, no = 0, nc = 0, ncp = 0, ndy = 0;
-    if (t > 0) load(t - 1, ni, nf, ng, no, nc, ncp, ndy);
-    const float dh = dyt + (part[0][j] + part[1][j]) + (part[2][j] + part[3][j]);
-    const float th = tanhx(ct);
-    const float dc = fmaf(dh * go, 1.0f - th * th, dc_carry);
-    dc_carry = dc * gf;
-    float d;
-    if (q == 0) d = dc * gg * gi * (1.0f - gi);
-    else if (q == 1) d = dc * cp * gf * (1.0f - gf);
-    else if (q == 2) d = dc * gi * (1.0f - gg * gg);
-    else d = dh * th * go * (1.0f - go);
-    das[tid] = d;
-    dab[(size_t)t * 64 + j] = d;
+  const int nchunks = (T + TC - 1) / TC;
+  stage(nchunks - 1, 0);
+  for (int ci = 0; ci < nchunks; ++ci) {
+    const int ch = nchunks - 1 - ci, buf = ci & 1;
+    if (ch > 0) { stage(ch - 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
-    float p0 = 0.0f, p1 = 0.0f;
+    const float *gsm = bsm + buf * BWD_BUF, *csm = gsm + TC * 256, *dsm = csm + (TC + 1) * 64;
+    const int tend = min(TC, T - ch * TC);
+    for (int tt = tend - 1; tt >= 0; --tt) {
+      const int t = ch * TC + tt;
+      const float gi = gsm[tt * 256 + j], gf = gsm[tt * 256 + 64 + j], gg = gsm[tt * 256 + 128 + j],
+                  go = gsm[tt * 256 + 192 + j];
+      const float ct = csm[(tt + 1) * 64 + j], cp = csm[tt * 64 + j];
+      const float dh = dsm[tt * 64 + j] + (part[0][j] + part[1][j]) + (part[2][j] + part[3][j]);
+      const float th = tanhx(ct);
+      const float dc = fmaf(dh * go, 1.0f - th * th, dc_carry);
+      dc_carry = dc * gf;
+      float d;
+      if (q == 0) d = dc * gg * gi * (1.0f - gi);
+      else if (q == 1) d = dc * cp * gf * (1.0f - gf);
+      else if (q == 2) d = dc * gi * (1.0f - gg * gg);
+      else d = dh * th * go * (1.0f - go);
+      das[tid] = d;
+      dab[(size_t)t * 64 + j] = d;
+      __syncthreads();
+      float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
 #pragma unroll
-    for (int rr = 0; rr < 64; rr += 4) {
-      const float4 v = *reinterpret_cast<const float4 *>(&das[q * 64 + rr]);
-      p0 = fmaf(w[rr], v.x, p0); p1 = fmaf(w[rr + 1], v.y, p1);
-      p0 = fmaf(w[rr + 2], v.z, p0); p1 = fmaf(w[rr + 3], v.w, p1);
+      for (int rr = 0; rr < 64; rr += 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(&das[q * 64 + rr]);
+        p0 = fmaf(w[rr], v.x, p0); p1 = fmaf(w[rr + 1], v.y, p1);
+        p2 = fmaf(w[rr + 2], v.z, p2); p3 = fmaf(w[rr + 3], v.w, p3);
+      }
+      part[q][j] = (p0 + p1) + (p2 + p3);
+      __syncthreads();
     }
-    part[q][j] = p0 + p1;
-    gi = ni; gf = nf; gg = ng; go = no; ct = nc; cp = ncp; dyt = ndy;
-    __syncthreads();
   }
 }
 
 }  // namespace
 
-// x [B][T][64] -> h [B][T][64]; gates [B][T][256], cell [B][T][64] kept for the backward
+// x [B][T][64] -> h [B][T][64]; gates [4][B][T][64] (gate-planar, activated) and cell [B][T][64] kept for the backward
 int launch_lstm_train_fwd(const float *x, const float *wT_ih, const float *wT_hh, const float *b_ih, const float *b_hh,
                           float *h, float *gates, float *cell, int B, int T, cudaStream_t st) {
   if (B == 0 || T == 0) return 0;
-  lstm_train_fwd_kernel<<<B, 256, 0, st>>>(x, wT_ih, wT_hh, b_ih, b_hh, h, gates, cell, T);
+  const size_t plane = (size_t)B * T * 64;
+  // gate q's bias sum sits in the first 64 floats of `h` while its convolution runs (h is written later)
+  for (int q = 0; q < 4; ++q) {
+    bias_sum_kernel<<<1, 64, 0, st>>>(b_ih + q * 64, b_hh + q * 64, h);
+    WM_CHECK_LAUNCH("bias_sum");
+    WM_TRY(launch_conv64_fp32(x, wT_ih + q * 4096, h, nullptr, nullptr, gates + q * plane, B, T, 1, 0, st));
+  }
+  lstm_train_fwd_kernel<<<B, 256, 0, st>>>(gates, wT_hh, h, cell, (long long)plane, T);
   WM_CHECK_LAUNCH("lstm_train_fwd");
   return 0;
 }
@@ -152,7 +203,13 @@ int launch_lstm_train_bwd(const float *dy, const float *x, const float *h, const
   const size_t n = (size_t)B * T * 64;
   float *da = scratch, *ping = da + 4 * n, *wg = ping + n, *wt = wg + conv_wgrad_scratch_floats(B, T, 1),
         *zero = wt + 4096;
-  lstm_train_bwd_kernel<<<B, 256, 0, st>>>(dy, wT_hh, gates, cell, da, (long long)n, T);
+  constexpr int SMEM = 2 * BWD_BUF * (int)sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    WM_CHECK_CUDA(cudaFuncSetAttribute(lstm_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_set = true;
+  }
+  lstm_train_bwd_kernel<<<B, 256, SMEM, st>>>(dy, wT_hh, gates, cell, da, (long long)n, T);
   WM_CHECK_LAUNCH("lstm_train_bwd");
   WM_CHECK_CUDA(cudaMemsetAsync(zero, 0, 64 * sizeof(float), st));
   for (int q = 0; q < 4; ++q) {

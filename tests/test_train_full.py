@@ -226,3 +226,17 @@ def test_forward_backward_is_deterministic():
     tr.forward_backward(s, msg)
     assert torch.equal(tr.g_grads, g1) and torch.equal(tr.d_grads, d1)
     assert not torch.equal(tr.g_stats, stats)               # running stats moved a second time
+
+
+@pytest.mark.gpu
+def test_data_parallel_step_two_gpus():
+    """Two ranks over NCCL: averaged gradients equal the mean of the per-rank ones and the replicas stay
+    bit-identical (tools/train_ddp.py does the checking and exits non-zero otherwise)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    port = str(29800 + os.getpid() % 100)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", port, os.path.join(ROOT, "tools", "train_ddp.py"), "--batch", "2", "--steps", "2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert '"params_identical_across_ranks": true' in r.stdout and '"allreduce_equals_mean": true' in r.stdout
