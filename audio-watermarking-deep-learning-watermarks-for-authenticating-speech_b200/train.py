@@ -296,6 +296,8 @@ class DetectorTrainer:
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.lambda_loc, self.lambda_dec = float(lambda_loc), float(lambda_dec)
         self.steps = 0
+        self._steps0 = 0
+        self._nbt0 = {k: int(v) for k, v in sd.items() if k.endswith("num_batches_tracked")}
         self._ws = None
         self._ws_key = None
 
@@ -356,9 +358,8 @@ class DetectorTrainer:
         own = detector.state_dict()
         for k, v in self.state_dict().items():
             own[k].copy_(v.to(own[k].device))
-        for k in own:
-            if k.endswith("num_batches_tracked"):
-                own[k] += self.steps
+        for k, n0 in self._nbt0.items():
+            own[k].fill_(n0 + self.steps - self._steps0)
 
 
 # ---- the whole training step (py/main16.py:238-278) ---------------------------------------------------------------
@@ -489,6 +490,8 @@ class Trainer:
         fb, band = packing.mel_filterbank(513, 64, 16000)
         self.mel_fb, self.mel_band = fb.to(device).contiguous(), band.to(device=device, dtype=torch.int32).contiguous()
         self.steps = 0
+        self._steps0 = 0          # optimiser steps already behind the state this trainer was built from (resume)
+        self._nbt0 = [{k: int(v) for k, v in sd.items() if k.endswith("num_batches_tracked")} for sd in (gsd, dsd)]
         self._ws, self._ws_key = None, None
 
     def _workspace(self, B: int, T: int):
@@ -558,13 +561,12 @@ class Trainer:
 
     @torch.no_grad()
     def write_back(self, generator: torch.nn.Module, detector: torch.nn.Module) -> None:
-        for mod, sd in zip((generator, detector), self.state_dicts()):
+        for mod, sd, nbt0 in zip((generator, detector), self.state_dicts(), self._nbt0):
             own = mod.state_dict()
             for k, v in sd.items():
                 own[k].copy_(v.to(own[k].device))
-            for k in own:
-                if k.endswith("num_batches_tracked"):
-                    own[k] += self.steps
+            for k, n0 in nbt0.items():
+                own[k].fill_(n0 + self.steps - self._steps0)
 
 
 def average_gradients(buffers) -> None:
