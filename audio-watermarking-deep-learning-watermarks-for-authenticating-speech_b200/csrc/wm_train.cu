@@ -65,12 +65,16 @@ __global__ void __launch_bounds__(NT)
   }
 }
 
-// out[k][c] = sum_blk partial[blk][k][c]   (k < 2), fixed order
-__global__ void sum2_kernel(const double *__restrict__ partial, int nblk, double *__restrict__ out) {
-  const int i = threadIdx.x;   // 128 threads
+// out[k][c] = sum_blk partial[blk][k][c]   (k < 2), fixed order: 8 interleaved segments per output, then a fixed tree
+__global__ void __launch_bounds__(1024) sum2_kernel(const double *__restrict__ partial, int nblk, double *__restrict__ out) {
+  __shared__ double red[8][128];
+  const int i = threadIdx.x & 127, seg = threadIdx.x >> 7;
   double t = 0.0;
-  for (int b = 0; b < nblk; ++b) t += partial[(size_t)b * 128 + i];
-  out[i] = t;
+  for (int b = seg; b < nblk; b += 8) t += partial[(size_t)b * 128 + i];
+  red[seg][i] = t;
+  __syncthreads();
+  if (seg == 0)
+    out[i] = ((red[0][i] + red[1][i]) + (red[2][i] + red[3][i])) + ((red[4][i] + red[5][i]) + (red[6][i] + red[7][i]));
 }
 
 // batch statistics from {sum z, sum z^2}; running stats as nn.BatchNorm1d (momentum 0.1, unbiased variance)
@@ -154,54 +158,95 @@ __global__ void transpose_flip_kernel(const float *__restrict__ w, float *__rest
 }
 
 // weight gradient of y[t][co] = sum_j sum_ci w[j][ci][co] x[t + j - P][ci], one tap per blockIdx.z:
-// partial[blk][j][ci][co] = sum over the block's rows of x[t + j - P][ci] * dz[t][co];  bias partial on j == bias_tap
-constexpr int WG_ROWS = 512, WG_SUB = 64;
+// partial[blk][j][ci][co] = sum over the block's rows of x[t + j - P][ci] * dz[t][co];  bias partial on j == bias_tap.
+// 64 rows at a time are staged in shared memory; the four 64-thread groups take 16 rows each and every thread owns
+// an 8 x 8 block of the 64 x 64 result (4 LDS.128 per 64 FMA), the groups' blocks are added through shared memory
+// at the end.  The rows per block are chosen on the host (wg_rows) so that a launch fills the GPU a few times over
+// while keeping the number of partials — the fixed-order reduction that follows — small.
+constexpr int WG_SUB = 64, WG_LD = 68, WG_BUF = 2 * WG_SUB * WG_LD;   // floats per stage: x rows then dz rows
+constexpr int WG_SMEM = 2 * WG_BUF * (int)sizeof(float);
+
+// 16-byte async copy; src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, int src_bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+
 __global__ void __launch_bounds__(NT)
     conv_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ dz, int T, int K, int P, int bias_tap,
-                      int nchunk, float *__restrict__ partial_w, float *__restrict__ partial_b) {
-  __shared__ __align__(16) float xs[WG_SUB][68], ds[WG_SUB][68];
+                      int rows, int nchunk, float *__restrict__ partial_w, float *__restrict__ partial_b) {
+  extern __shared__ __align__(16) float wsm[];
   const int j = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
-  const int t_begin = chunk * WG_ROWS, t_end = min(T, t_begin + WG_ROWS);
-  const int ci0 = (threadIdx.x >> 4) * 4, co0 = (threadIdx.x & 15) * 4;
-  float acc[4][4];
+  const int t_begin = chunk * rows, t_end = min(T, t_begin + rows);
+  const int g = threadIdx.x >> 6, l = threadIdx.x & 63, ci0 = (l >> 3) * 8, co0 = (l & 7) * 8;
+  float acc[8][8];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[a][c] = 0.0f;
+    for (int c = 0; c < 8; ++c) acc[a][c] = 0.0f;
   float bacc = 0.0f;   // threads < 64: bias gradient of channel threadIdx.x
   const float *xb = x + (size_t)b * T * 64, *db = dz + (size_t)b * T * 64;
-  for (int t0 = t_begin; t0 < t_end; t0 += WG_SUB) {
-    __syncthreads();
+  auto stage = [&](int t0, int buf) {
+    float *xs = wsm + buf * WG_BUF, *ds = xs + WG_SUB * WG_LD;
     for (int i = threadIdx.x; i < WG_SUB * 16; i += NT) {
       const int r = i >> 4, c4 = (i & 15) * 4, t = t0 + r, tx = t + j - P;
-      float4 xv = make_float4(0, 0, 0, 0), dv = make_float4(0, 0, 0, 0);
-      if (t < t_end) {
-        dv = *reinterpret_cast<const float4 *>(db + (size_t)t * 64 + c4);
-        if (tx >= 0 && tx < T) xv = *reinterpret_cast<const float4 *>(xb + (size_t)tx * 64 + c4);
-      }
-      *reinterpret_cast<float4 *>(&xs[r][c4]) = xv;
-      *reinterpret_cast<float4 *>(&ds[r][c4]) = dv;
+      const bool okd = t < t_end, okx = okd && tx >= 0 && tx < T;
+      cp_async16_zfill(&ds[r * WG_LD + c4], okd ? db + (size_t)t * 64 + c4 : db, okd ? 16 : 0);
+      cp_async16_zfill(&xs[r * WG_LD + c4], okx ? xb + (size_t)tx * 64 + c4 : xb, okx ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;\n");
+  };
+  const int nsub = (t_end - t_begin + WG_SUB - 1) / WG_SUB;
+  stage(t_begin, 0);
+  for (int sub = 0; sub < nsub; ++sub) {
+    const int buf = sub & 1;
+    if (sub + 1 < nsub) {
+      stage(t_begin + (sub + 1) * WG_SUB, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;\n");
+    } else {
+      asm volatile("cp.async.wait_group 0;\n");
     }
     __syncthreads();
-#pragma unroll 4
-    for (int r = 0; r < WG_SUB; ++r) {
-      const float4 xv = *reinterpret_cast<const float4 *>(&xs[r][ci0]);
-      const float4 dv = *reinterpret_cast<const float4 *>(&ds[r][co0]);
-      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
+    const float *xs = wsm + buf * WG_BUF, *ds = xs + WG_SUB * WG_LD;
+#pragma unroll 2
+    for (int rr = 0; rr < WG_SUB / 4; ++rr) {
+      const int r = g * (WG_SUB / 4) + rr;
+      const float4 x0 = *reinterpret_cast<const float4 *>(&xs[r * WG_LD + ci0]);
+      const float4 x1 = *reinterpret_cast<const float4 *>(&xs[r * WG_LD + ci0 + 4]);
+      const float4 d0 = *reinterpret_cast<const float4 *>(&ds[r * WG_LD + co0]);
+      const float4 d1 = *reinterpret_cast<const float4 *>(&ds[r * WG_LD + co0 + 4]);
+      const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      const float da[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(xa[a], da[c], acc[a][c]);
+        for (int c = 0; c < 8; ++c) acc[a][c] = fmaf(xa[a], da[c], acc[a][c]);
     }
     if (j == bias_tap && threadIdx.x < 64) {
-      for (int r = 0; r < WG_SUB; ++r) bacc += ds[r][threadIdx.x];
+      for (int r = 0; r < WG_SUB; ++r) bacc += ds[r * WG_LD + threadIdx.x];
     }
+    __syncthreads();   // this buffer is refilled two iterations from now, by the stage() issued next iteration
+  }
+  // add the four row groups' blocks in a fixed order through shared memory (a 64 x 64 tile, pitch 68)
+  float *tile = wsm;
+  for (int gg = 0; gg < 4; ++gg) {
+    if (g == gg) {
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float *p = &tile[(ci0 + a) * WG_LD + co0 + c];
+          *p = gg == 0 ? acc[a][c] : *p + acc[a][c];
+        }
+    }
+    __syncthreads();
   }
   const size_t blk = (size_t)b * nchunk + chunk;
   float *pw = partial_w + (blk * K + j) * 4096;
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-    *reinterpret_cast<float4 *>(&pw[(ci0 + a) * 64 + co0]) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+  for (int i = threadIdx.x; i < 1024; i += NT) {
+    const int r = i >> 4, c4 = (i & 15) * 4;
+    *reinterpret_cast<float4 *>(&pw[r * 64 + c4]) = *reinterpret_cast<const float4 *>(&tile[r * WG_LD + c4]);
+  }
   if (j == bias_tap && threadIdx.x < 64) partial_b[blk * 64 + threadIdx.x] = bacc;
 }
 
@@ -395,7 +440,7 @@ static int chan_sums(int mode, const float *a, const float *b, const float *act,
   else chan_sums_kernel<1><<<nblk, NT, 0, st>>>(a, b, act, mean, rstd, N, rows_per_block, scratch);
   WM_CHECK_LAUNCH("chan_sums");
   double *sums = scratch + (size_t)nblk * 128;
-  sum2_kernel<<<1, 128, 0, st>>>(scratch, nblk, sums);
+  sum2_kernel<<<1, 1024, 0, st>>>(scratch, nblk, sums);
   WM_CHECK_LAUNCH("sum2");
   *sums_out = sums;
   return 0;
@@ -435,8 +480,19 @@ int launch_transpose_flip(const float *w, float *wt, int K, cudaStream_t st) {
   return 0;
 }
 
+// rows of one clip per weight-gradient block: about eight blocks per SM over the launch, never below 512 rows
+static int wg_rows(int B, int T, int K) {
+  int per_clip = (8 * sm_count()) / (B * K > 0 ? B * K : 1);
+  const int most = (T + 511) / 512;
+  if (per_clip > most) per_clip = most;
+  if (per_clip < 1) per_clip = 1;
+  const int rows = (T + per_clip - 1) / per_clip;
+  return (rows + WG_SUB - 1) / WG_SUB * WG_SUB;
+}
+
 size_t conv_wgrad_scratch_floats(int B, int T, int K) {
-  const size_t nblk = (size_t)B * ((T + WG_ROWS - 1) / WG_ROWS);
+  const int rows = wg_rows(B, T, K);
+  const size_t nblk = (size_t)B * ((T + rows - 1) / rows);
   return nblk * ((size_t)K * 4096 + 64);
 }
 
@@ -444,9 +500,14 @@ size_t conv_wgrad_scratch_floats(int B, int T, int K) {
 // general form: tap j pairs x[t + j - P] with dz[t]; db (nullable) sums dz on tap `bias_tap`
 int launch_conv_wgrad_ex(const float *x, const float *dz, float *dw, float *db, int B, int T, int K, int P, int bias_tap,
                          float *scratch, cudaStream_t st) {
-  const int nchunk = (T + WG_ROWS - 1) / WG_ROWS, nblk = B * nchunk;
+  const int rows = wg_rows(B, T, K), nchunk = (T + rows - 1) / rows, nblk = B * nchunk;
   float *pw = scratch, *pb = scratch + (size_t)nblk * K * 4096;
-  conv_wgrad_kernel<<<dim3(nchunk, B, K), NT, 0, st>>>(x, dz, T, K, P, db ? bias_tap : -1, nchunk, pw, pb);
+  static bool attr_set = false;
+  if (!attr_set) {
+    WM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+    attr_set = true;
+  }
+  conv_wgrad_kernel<<<dim3(nchunk, B, K), NT, WG_SMEM, st>>>(x, dz, T, K, P, db ? bias_tap : -1, rows, nchunk, pw, pb);
   WM_CHECK_LAUNCH("conv_wgrad");
   sum_partials_f_kernel<<<(K * 4096 + 255) / 256, 256, 0, st>>>(pw, nblk, K * 4096, dw);
   WM_CHECK_LAUNCH("sum_partials(w)");
