@@ -5,6 +5,8 @@
 // parameter tensors (Conv1d (co,ci,k), ConvTranspose1d (ci,co,k)), no packing.
 // First correct CUDA path for this model family: CUDA-core FMA with shared-memory tiling (the tcgen05
 // kernels of the main16 path are specialised to 64 channels, stride 1).
+#include <stdlib.h>
+
 #include "wm_common.h"
 
 namespace wm {
@@ -85,6 +87,162 @@ __global__ void __launch_bounds__(GTHREADS)
       y[o] = act ? elu1(v) : v;
     }
   }
+}
+
+// ---- the same convolution as a register-tiled implicit GEMM ---------------------------------------------------------
+// M = output channels, N = (clip, output time) flattened, Kdim = Cin * K.  A block of 128 threads owns COG*8 output
+// channels x (128/COG)*8 positions; a thread owns 8 channels x 8 positions.  Per stage of FCI input
+// channels the block builds in shared memory  xs[ci][k][n] = x[b(n)][c0+ci][t(n)*stride + k - pad]  (an im2col slice:
+// every tap gets its own aligned row, so strided convolutions read only the phases they use and all inner-loop loads
+// are LDS.128) and  ws[ci][k][co]  (co contiguous);  per (ci, k): 2 + 2 LDS.128 feed 64 FMAs.
+__device__ __forceinline__ void cp_async4_zfill(void *smem, const void *gmem, int src_bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+
+template <int COG, int FCI>
+__global__ void __launch_bounds__(128, 4)
+    conv1d_tiled_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+                        const float *__restrict__ chan_add, const float *__restrict__ res, float *__restrict__ y,
+                        int Cin, int Tin, int Cout, int Tout, int K, int stride, int pad, int act, int shuffle, int Tstore,
+                        long long Ntot) {
+  constexpr int CO_T = COG * 8, TG = 128 / COG, N_T = TG * 8;
+  extern __shared__ __align__(16) float sm[];          // two stages of { xs [FCI][K][N_T], ws [FCI][K][CO_T] }
+  const int co0 = blockIdx.y * CO_T;
+  const long long n0 = (long long)blockIdx.x * N_T;
+  const int cg = threadIdx.x % COG, tg = threadIdx.x / COG;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+  // staging ownership: thread -> positions n0 + threadIdx.x + 128 q; which of the K taps fall inside [0, Tin) is a
+  // per-position bit mask computed once
+  constexpr int NQ = N_T / 128;
+  const float *xpos[NQ];      // &x[b][0][t*stride - pad]
+  unsigned kmask[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const long long n = n0 + threadIdx.x + 128 * q;
+    xpos[q] = x;
+    kmask[q] = 0u;
+    if (n < Ntot) {
+      const int b = (int)(n / Tout), t = (int)(n - (long long)b * Tout), ti0 = t * stride - pad;
+      xpos[q] = x + (size_t)b * Cin * Tin + ti0;
+      for (int k = 0; k < K; ++k)
+        if (ti0 + k >= 0 && ti0 + k < Tin) kmask[q] |= 1u << k;
+    }
+  }
+  const int wrun = FCI * K;                         // contiguous weights per output channel and stage
+  const int stage_floats = FCI * K * (N_T + CO_T);
+  const int w_dq = 128 / wrun, w_dr = 128 % wrun;   // e += 128  <=>  (co, r) += (w_dq, w_dr) with carry
+  const int w_co_first = threadIdx.x / wrun, w_r_first = threadIdx.x % wrun;
+  // 4-byte cp.async (zero-filled when out of range): the ~36 loads a thread issues per stage are all in flight at
+  // once, and the next stage is fetched while this one is multiplied
+  auto stage = [&](int c0, int buf) {
+    float *xs = sm + buf * stage_floats, *ws = xs + FCI * K * N_T;
+    const int nci = min(FCI, Cin - c0);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      float *dst = xs + threadIdx.x + 128 * q;
+      const float *src = xpos[q] + (size_t)c0 * Tin;
+      for (int ci = 0; ci < nci; ++ci, src += Tin) {
+        for (int k = 0; k < K; ++k, dst += N_T) {
+          const bool ok = (kmask[q] >> k) & 1u;
+          cp_async4_zfill(dst, ok ? src + k : x, ok ? 4 : 0);
+        }
+      }
+    }
+    const int nrk = nci * K;
+    int co = w_co_first, r = w_r_first;
+    for (int e = threadIdx.x; e < CO_T * wrun; e += 128) {
+      const bool ok = co0 + co < Cout && r < nrk;
+      cp_async4_zfill(&ws[r * CO_T + co], ok ? w + ((size_t)(co0 + co) * Cin + c0) * K + r : w, ok ? 4 : 0);
+      co += w_dq;
+      r += w_dr;
+      if (r >= wrun) { r -= wrun; ++co; }
+    }
+    asm volatile("cp.async.commit_group;\n");
+  };
+  stage(0, 0);
+  int it = 0;
+  for (int c0 = 0; c0 < Cin; c0 += FCI, ++it) {
+    const int buf = it & 1;
+    const int nci = min(FCI, Cin - c0);
+    if (c0 + FCI < Cin) {
+      stage(c0 + FCI, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;\n");
+    } else {
+      asm volatile("cp.async.wait_group 0;\n");
+    }
+    __syncthreads();
+    const float *xs = sm + buf * stage_floats, *ws = xs + FCI * K * N_T;
+    const int nr = nci * K;
+#pragma unroll 2
+    for (int r = 0; r < nr; ++r) {
+      // a thread's 8 channels / positions are two runs of 4, half a tile apart: consecutive lanes read consecutive
+      // 16-byte words (no bank conflicts)
+      const float4 w0 = *reinterpret_cast<const float4 *>(&ws[r * CO_T + cg * 4]);
+      const float4 w1 = *reinterpret_cast<const float4 *>(&ws[r * CO_T + CO_T / 2 + cg * 4]);
+      const float4 x0 = *reinterpret_cast<const float4 *>(&xs[r * N_T + tg * 4]);
+      const float4 x1 = *reinterpret_cast<const float4 *>(&xs[r * N_T + N_T / 2 + tg * 4]);
+      const float wq[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float xq[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wq[i], xq[j], acc[i][j]);
+    }
+    __syncthreads();   // the buffer is refilled by the stage() issued at the top of the next iteration
+  }
+  // epilogue
+  int bj[8], tj[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const long long n = n0 + (j < 4 ? tg * 4 + j : N_T / 2 + tg * 4 + j - 4);
+    bj[j] = n < Ntot ? (int)(n / Tout) : -1;
+    tj[j] = n < Ntot ? (int)(n - (long long)bj[j] * Tout) : 0;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int co = co0 + (i < 4 ? cg * 4 + i : CO_T / 2 + cg * 4 + i - 4);
+    if (co >= Cout) continue;
+    const float bv = bias[co];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (bj[j] < 0) continue;
+      const int b = bj[j], t = tj[j];
+      float v = acc[i][j] + bv + (chan_add ? chan_add[(size_t)b * Cout + co] : 0.0f);
+      if (shuffle > 1) {   // channel co = (c, r) is phase r of output channel c: y[b][c][t * shuffle + r]
+        const int ts = t * shuffle + co % shuffle;
+        if (ts < Tstore) y[((size_t)b * (Cout / shuffle) + co / shuffle) * Tstore + ts] = v;
+        continue;
+      }
+      const size_t o = ((size_t)b * Cout + co) * Tout + t;
+      if (res) v += res[o];
+      y[o] = act ? elu1(v) : v;
+    }
+  }
+}
+
+template <int COG, int FCI>
+int launch_conv1d_tiled(const float *x, const float *w, const float *bias, const float *chan_add, const float *res,
+                        float *y, int B, int Cin, int Tin, int Cout, int Tout, int K, int stride, int pad, int act,
+                        int shuffle, int Tstore, cudaStream_t st) {
+  constexpr int CO_T = COG * 8, N_T = (128 / COG) * 8;
+  const size_t smem = 2 * (size_t)FCI * K * (N_T + CO_T) * sizeof(float);
+  static size_t attr = 0;
+  if (smem > attr) {
+    WM_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tiled_kernel<COG, FCI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    attr = smem;
+  }
+  const long long Ntot = (long long)B * Tout;
+  dim3 grid((unsigned)((Ntot + N_T - 1) / N_T), (Cout + CO_T - 1) / CO_T);
+  conv1d_tiled_kernel<COG, FCI><<<grid, 128, smem, st>>>(x, w, bias, chan_add, res, y, Cin, Tin, Cout, Tout, K, stride, pad,
+                                                         act, shuffle, Tstore, Ntot);
+  WM_CHECK_LAUNCH("conv1d_tiled");
+  return 0;
 }
 
 // nn.ConvTranspose1d(Cin, Cout, K, stride, padding):  y[b][co][t] = bias[co] + sum_ci sum_k [ (t + pad - k) % stride == 0 ]
@@ -224,6 +382,15 @@ int launch_conv1d_generic(const float *x, const float *w, const float *bias, con
   if (K > GMAXK || stride > GMAXS || K < 1 || stride < 1) {
     set_error("conv1d: kernel size %d / stride %d outside the supported range (<= %d / <= %d)", K, stride, GMAXK, GMAXS);
     return -1;
+  }
+  // register-tiled implicit GEMM: 64 channels x 128 positions per block, or 16 x 512 for the narrow heads
+  if (getenv("WMB200_CONV1D_SIMPLE") == nullptr) {
+    if (Cout > 16) {
+      if (K <= 8) return launch_conv1d_tiled<8, 8>(x, w, bias, chan_add, res, y, B, Cin, Tin, Cout, Tout, K, stride, pad, act, shuffle, Tstore, st);
+      return launch_conv1d_tiled<8, 4>(x, w, bias, chan_add, res, y, B, Cin, Tin, Cout, Tout, K, stride, pad, act, shuffle, Tstore, st);
+    }
+    if (K <= 8) return launch_conv1d_tiled<2, 4>(x, w, bias, chan_add, res, y, B, Cin, Tin, Cout, Tout, K, stride, pad, act, shuffle, Tstore, st);
+    return launch_conv1d_tiled<2, 2>(x, w, bias, chan_add, res, y, B, Cin, Tin, Cout, Tout, K, stride, pad, act, shuffle, Tstore, st);
   }
   const size_t smem = (size_t)(GCI * ((GT - 1) * stride + K) + GCI * K * GCO) * sizeof(float);
   static bool attr_set = false;
