@@ -492,6 +492,7 @@ class Trainer:
         self.steps = 0
         self._steps0 = 0          # optimiser steps already behind the state this trainer was built from (resume)
         self._nbt0 = [{k: int(v) for k, v in sd.items() if k.endswith("num_batches_tracked")} for sd in (gsd, dsd)]
+        self._bad_message = torch.zeros((), dtype=torch.bool, device=device)
         self._ws, self._ws_key = None, None
 
     def _workspace(self, B: int, T: int):
@@ -513,8 +514,11 @@ class Trainer:
         msg = _req(message, "message", torch.int64)
         if msg.numel() != B:
             raise ValueError("message must hold one value per clip")
-        if B and (int(msg.min()) < 0 or int(msg.max()) >= 65536):
-            raise IndexError("message out of range for the 16-bit embedding")
+        # range check without a host sync (the loop must be free to run ahead of the GPU): out-of-range ids are
+        # clamped for the kernels and remembered on the device; the error surfaces at the next host read
+        # (state_dicts / write_back / check_messages)
+        self._bad_message |= ((msg < 0) | (msg > 65535)).any()
+        msg = msg.clamp(0, 65535)
         losses = torch.zeros(8, device=self.device)
         s_w = torch.empty_like(s) if want_s_w else None
         ws, n = self._workspace(B, T)
@@ -547,7 +551,14 @@ class Trainer:
         self.apply()
         return out
 
+    def check_messages(self) -> None:
+        """Raises if any step so far was given a message outside [0, 65536) (what nn.Embedding would have raised at
+        once; here the check is deferred so that training steps never wait for the GPU)."""
+        if bool(self._bad_message):
+            raise IndexError("message out of range for the 16-bit embedding in an earlier training step")
+
     def state_dicts(self):
+        self.check_messages()
         g = unflatten_generator(self.g_params)
         for name, off in _gt_stat_slices().items():
             g[name] = self.g_stats[off:off + 64].clone()

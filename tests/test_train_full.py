@@ -240,3 +240,17 @@ def test_data_parallel_step_two_gpus():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert '"params_identical_across_ranks": true' in r.stdout and '"allreduce_equals_mean": true' in r.stdout
+
+
+@pytest.mark.gpu
+def test_out_of_range_message_is_reported():
+    import wmb200
+    from wmb200 import train as TR
+    torch.manual_seed(8)
+    tr = TR.Trainer(wmb200.Generator(message_bits=16).cuda(), wmb200.Detector(message_bits=16).cuda())
+    s = 0.1 * torch.randn(2, 2400, device="cuda")
+    tr.forward_backward(s, torch.tensor([3, 65535], device="cuda"))
+    tr.check_messages()
+    tr.forward_backward(s, torch.tensor([3, 65536], device="cuda"))
+    with pytest.raises(IndexError, match="out of range"):
+        tr.state_dicts()
