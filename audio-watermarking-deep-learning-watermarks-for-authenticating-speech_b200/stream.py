@@ -32,15 +32,44 @@ def _pin(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_pinned() else t.pin_memory()
 
 
+_STAGING: dict = {}
+
+
+def _staging(name: str, shape, dtype) -> torch.Tensor:
+    """Pinned input staging buffer, cached per (name, dtype) and grown on demand (free_stream_buffers() drops it)."""
+    n = 1
+    for d in shape:
+        n *= d
+    buf = _STAGING.get((name, dtype))
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(n, dtype=dtype, pin_memory=True)
+        _STAGING[(name, dtype)] = buf
+    return buf[:n].view(shape)
+
+
+def _result(buffers: dict, name: str, shape) -> torch.Tensor:
+    t = buffers.get(name)
+    if t is None or tuple(t.shape) != tuple(shape) or not t.is_pinned():
+        t = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        buffers[name] = t
+    return t
+
+
+def free_stream_buffers() -> None:
+    _STAGING.clear()
+
+
 @torch.no_grad()
 def embed_detect_stream(generator, detector, waveform: torch.Tensor, messages: Optional[torch.Tensor] = None,
                         postprocess: bool = True, chunk: Optional[int] = None, rank: int = 0, world: int = 1,
-                        group=None, reduce: bool = True) -> dict:
+                        group=None, reduce: bool = True, buffers: Optional[dict] = None) -> dict:
     """waveform: host fp32 (N,) or (1,N) at 16 kHz.  Rank `rank` of `world` embeds and detects segments
     [lo, hi) = shard_range(n_segments, rank, world) and returns, for ITS range, host tensors
     `watermarked` (samples,), `probs` (samples,), `clip_prob` (segments,), `msg_logits` (segments, bits),
     `messages` (segments,), `segment_range`; plus file-level `mean_probability` / `mean_msg_logits`
-    (all-reduced over the job when torch.distributed is initialised and `reduce`)."""
+    (all-reduced over the job when torch.distributed is initialised and `reduce`).  The big results are pinned host
+    tensors; pass the same `buffers` dict to successive calls to have them reused (and overwritten) instead of
+    pinned afresh."""
     if generator.training or detector.training:
         raise NotImplementedError("embed_detect_stream is the eval-mode path; call .eval() on both modules")
     x = waveform.reshape(-1).to("cpu", torch.float32)
@@ -63,11 +92,19 @@ def embed_detect_stream(generator, detector, waveform: torch.Tensor, messages: O
                    msg_logits=torch.empty(0, bits))
         sum_prob, n_samp, sum_ml = 0.0, 0, torch.zeros(bits, device=dev)
     else:
-        hs = torch.zeros(nb, SEG).pin_memory()
+        # host staging: the input buffer is cached between calls (pinning gigabytes costs more than the GPU pass);
+        # result buffers are the caller's — fresh pinned tensors unless `buffers` hands reusable ones in
+        hs = _staging("hs", (nb, SEG), torch.float32)
         hs.view(-1)[:s1 - s0] = x[s0:s1]
-        hm = _pin(messages[lo:hi].contiguous())
-        h_sw, h_pr = torch.empty(nb, SEG).pin_memory(), torch.empty(nb, SEG).pin_memory()
-        h_cp, h_ml = torch.empty(nb).pin_memory(), torch.empty(nb, max(bits, 1)).pin_memory()
+        if s1 - s0 < nb * SEG:
+            hs.view(-1)[s1 - s0:] = 0.0
+        hm = _staging("hm", (nb,), torch.int64)
+        hm.copy_(messages[lo:hi])
+        buffers = buffers if buffers is not None else {}
+        h_sw = _result(buffers, "watermarked", (nb, SEG))
+        h_pr = _result(buffers, "probs", (nb, SEG))
+        h_cp = _result(buffers, "clip_prob", (nb,))
+        h_ml = _result(buffers, "msg_logits", (nb, max(bits, 1)))
         use_msg = generator.message_bits > 0
         pipe = ops.HostPipeline(generator.packed(), generator.embedding_table() if use_msg else None,
                                 detector.packed(), fir_taps_on(dev), detector.nout, SEG,
@@ -91,9 +128,12 @@ def embed_detect_stream(generator, detector, waveform: torch.Tensor, messages: O
             if bits:
                 ml[nb - 1] = r["msg_logits"][0].cpu()
             h_cp[nb - 1] = r["clip_prob"][0].cpu()
-        out.update(watermarked=h_sw.view(-1)[:s1 - s0].clone(), probs=probs.clone(), clip_prob=h_cp.clone(),
-                   msg_logits=ml)
-        sum_prob, n_samp, sum_ml = float(probs.double().sum()), int(probs.numel()), ml.sum(0).to(dev)
+        out.update(watermarked=h_sw.view(-1)[:s1 - s0], probs=probs, clip_prob=h_cp, msg_logits=ml)
+        # file-level probability sum from the per-segment means the detector epilogue already produced (every
+        # segment has SEG valid samples except the cropped tail): no second pass over gigabytes of host memory
+        w = torch.full((nb,), float(SEG), dtype=torch.float64)
+        w[nb - 1] = float(tail)
+        sum_prob, n_samp, sum_ml = float((h_cp.double() * w).sum()), int(probs.numel()), ml.sum(0).to(dev)
     if reduce:
         mp, mlg = reduce_file_stats(sum_prob, n_samp, sum_ml, nb, group)
     else:
