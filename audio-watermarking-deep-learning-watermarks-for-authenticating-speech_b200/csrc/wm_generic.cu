@@ -107,7 +107,9 @@ __global__ void __launch_bounds__(128, 4)
                         int Cin, int Tin, int Cout, int Tout, int K, int stride, int pad, int act, int shuffle, int Tstore,
                         long long Ntot) {
   constexpr int CO_T = COG * 8, TG = 128 / COG, N_T = TG * 8;
-  extern __shared__ __align__(16) float sm[];          // two stages of { xs [FCI][K][N_T], ws [FCI][K][CO_T] }
+  constexpr int WLD = CO_T + 4;   // pitch of a weight row: consecutive (ci,k) rows start 4 banks apart (the staging writes
+                                  // walk down a column)
+  extern __shared__ __align__(16) float sm[];          // two stages of { xs [FCI][K][N_T], ws [FCI][K][WLD] }
   const int co0 = blockIdx.y * CO_T;
   const long long n0 = (long long)blockIdx.x * N_T;
   const int cg = threadIdx.x % COG, tg = threadIdx.x / COG;
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(128, 4)
     }
   }
   const int wrun = FCI * K;                         // contiguous weights per output channel and stage
-  const int stage_floats = FCI * K * (N_T + CO_T);
+  const int stage_floats = FCI * K * (N_T + WLD);
   const int w_dq = 128 / wrun, w_dr = 128 % wrun;   // e += 128  <=>  (co, r) += (w_dq, w_dr) with carry
   const int w_co_first = threadIdx.x / wrun, w_r_first = threadIdx.x % wrun;
   // 4-byte cp.async (zero-filled when out of range): the ~36 loads a thread issues per stage are all in flight at
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(128, 4)
     int co = w_co_first, r = w_r_first;
     for (int e = threadIdx.x; e < CO_T * wrun; e += 128) {
       const bool ok = co0 + co < Cout && r < nrk;
-      cp_async4_zfill(&ws[r * CO_T + co], ok ? w + ((size_t)(co0 + co) * Cin + c0) * K + r : w, ok ? 4 : 0);
+      cp_async4_zfill(&ws[r * WLD + co], ok ? w + ((size_t)(co0 + co) * Cin + c0) * K + r : w, ok ? 4 : 0);
       co += w_dq;
       r += w_dr;
       if (r >= wrun) { r -= wrun; ++co; }
@@ -182,8 +184,8 @@ __global__ void __launch_bounds__(128, 4)
     for (int r = 0; r < nr; ++r) {
       // a thread's 8 channels / positions are two runs of 4, half a tile apart: consecutive lanes read consecutive
       // 16-byte words (no bank conflicts)
-      const float4 w0 = *reinterpret_cast<const float4 *>(&ws[r * CO_T + cg * 4]);
-      const float4 w1 = *reinterpret_cast<const float4 *>(&ws[r * CO_T + CO_T / 2 + cg * 4]);
+      const float4 w0 = *reinterpret_cast<const float4 *>(&ws[r * WLD + cg * 4]);
+      const float4 w1 = *reinterpret_cast<const float4 *>(&ws[r * WLD + CO_T / 2 + cg * 4]);
       const float4 x0 = *reinterpret_cast<const float4 *>(&xs[r * N_T + tg * 4]);
       const float4 x1 = *reinterpret_cast<const float4 *>(&xs[r * N_T + N_T / 2 + tg * 4]);
       const float wq[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -230,7 +232,7 @@ int launch_conv1d_tiled(const float *x, const float *w, const float *bias, const
                         float *y, int B, int Cin, int Tin, int Cout, int Tout, int K, int stride, int pad, int act,
                         int shuffle, int Tstore, cudaStream_t st) {
   constexpr int CO_T = COG * 8, N_T = (128 / COG) * 8;
-  const size_t smem = 2 * (size_t)FCI * K * (N_T + CO_T) * sizeof(float);
+  const size_t smem = 2 * (size_t)FCI * K * (N_T + CO_T + 4) * sizeof(float);
   static size_t attr = 0;
   if (smem > attr) {
     WM_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tiled_kernel<COG, FCI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
