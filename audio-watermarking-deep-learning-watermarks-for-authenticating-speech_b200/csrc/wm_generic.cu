@@ -125,11 +125,11 @@ __global__ void __launch_bounds__(128, 4)
   unsigned kmask[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
-    const long long n = n0 + threadIdx.x + 128 * q;
+    const unsigned n = (unsigned)n0 + threadIdx.x + 128 * q;
     xpos[q] = x;
     kmask[q] = 0u;
-    if (n < Ntot) {
-      const int b = (int)(n / Tout), t = (int)(n - (long long)b * Tout), ti0 = t * stride - pad;
+    if (n < (unsigned)Ntot) {
+      const int b = (int)(n / (unsigned)Tout), t = (int)(n - (unsigned)b * (unsigned)Tout), ti0 = t * stride - pad;
       xpos[q] = x + (size_t)b * Cin * Tin + ti0;
       for (int k = 0; k < K; ++k)
         if (ti0 + k >= 0 && ti0 + k < Tin) kmask[q] |= 1u << k;
@@ -197,32 +197,50 @@ __global__ void __launch_bounds__(128, 4)
     }
     __syncthreads();   // the buffer is refilled by the stage() issued at the top of the next iteration
   }
-  // epilogue
-  int bj[8], tj[8];
+  // epilogue: the thread's positions are two runs of 4 consecutive n; with Tout % 4 == 0 a run never straddles a clip
+  // and is 16-byte aligned in y, so it is stored (and the residual read) as one float4.  32-bit index math: the
+  // launcher guarantees B * Tout < 2^31.
+  const unsigned Nt = (unsigned)Ntot, uT = (unsigned)Tout;
+  const bool vec = shuffle <= 1 && (Tout & 3) == 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const long long n = n0 + (j < 4 ? tg * 4 + j : N_T / 2 + tg * 4 + j - 4);
-    bj[j] = n < Ntot ? (int)(n / Tout) : -1;
-    tj[j] = n < Ntot ? (int)(n - (long long)bj[j] * Tout) : 0;
-  }
+  for (int jr = 0; jr < 2; ++jr) {
+    const unsigned nb = (unsigned)n0 + (jr ? N_T / 2 : 0) + tg * 4;
+    if (nb >= Nt) continue;
+    const unsigned b0 = nb / uT, t0 = nb - b0 * uT;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int co = co0 + (i < 4 ? cg * 4 + i : CO_T / 2 + cg * 4 + i - 4);
-    if (co >= Cout) continue;
-    const float bv = bias[co];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (bj[j] < 0) continue;
-      const int b = bj[j], t = tj[j];
-      float v = acc[i][j] + bv + (chan_add ? chan_add[(size_t)b * Cout + co] : 0.0f);
-      if (shuffle > 1) {   // channel co = (c, r) is phase r of output channel c: y[b][c][t * shuffle + r]
-        const int ts = t * shuffle + co % shuffle;
-        if (ts < Tstore) y[((size_t)b * (Cout / shuffle) + co / shuffle) * Tstore + ts] = v;
+    for (int i = 0; i < 8; ++i) {
+      const int co = co0 + (i < 4 ? cg * 4 + i : CO_T / 2 + cg * 4 + i - 4);
+      if (co >= Cout) continue;
+      const float bv = bias[co];
+      if (vec) {
+        const float add = bv + (chan_add ? chan_add[(size_t)b0 * Cout + co] : 0.0f);
+        const size_t o = ((size_t)b0 * Cout + co) * Tout + t0;
+        float4 v = make_float4(acc[i][jr * 4] + add, acc[i][jr * 4 + 1] + add, acc[i][jr * 4 + 2] + add,
+                               acc[i][jr * 4 + 3] + add);
+        if (res) {
+          const float4 r = *reinterpret_cast<const float4 *>(res + o);
+          v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        if (act) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+        *reinterpret_cast<float4 *>(y + o) = v;
         continue;
       }
-      const size_t o = ((size_t)b * Cout + co) * Tout + t;
-      if (res) v += res[o];
-      y[o] = act ? elu1(v) : v;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const unsigned n = nb + jj;
+        if (n >= Nt) break;
+        unsigned b = b0, t = t0 + jj;
+        if (t >= uT) { b = n / uT; t = n - b * uT; }
+        float v = acc[i][jr * 4 + jj] + bv + (chan_add ? chan_add[(size_t)b * Cout + co] : 0.0f);
+        if (shuffle > 1) {   // channel co = (c, r) is phase r of output channel c: y[b][c][t * shuffle + r]
+          const int ts = (int)t * shuffle + co % shuffle;
+          if (ts < Tstore) y[((size_t)b * (Cout / shuffle) + co / shuffle) * Tstore + ts] = v;
+          continue;
+        }
+        const size_t o = ((size_t)b * Cout + co) * Tout + t;
+        if (res) v += res[o];
+        y[o] = act ? elu1(v) : v;
+      }
     }
   }
 }
@@ -386,7 +404,7 @@ int launch_conv1d_generic(const float *x, const float *w, const float *bias, con
     return -1;
   }
   // register-tiled implicit GEMM: 64 channels x 128 positions per block, or 16 x 512 for the narrow heads
-  if (getenv("WMB200_CONV1D_SIMPLE") == nullptr) {
+  if (getenv("WMB200_CONV1D_SIMPLE") == nullptr && (long long)B * Tout < (1LL << 31) - 1024) {
     if (Cout > 16) {
       if (K <= 8) return launch_conv1d_tiled<8, 8>(x, w, bias, chan_add, res, y, B, Cin, Tin, Cout, Tout, K, stride, pad, act, shuffle, Tstore, st);
       return launch_conv1d_tiled<8, 4>(x, w, bias, chan_add, res, y, B, Cin, Tin, Cout, Tout, K, stride, pad, act, shuffle, Tstore, st);
