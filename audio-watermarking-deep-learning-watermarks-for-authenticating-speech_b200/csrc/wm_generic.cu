@@ -207,6 +207,54 @@ __global__ void __launch_bounds__(128, 4)
     const unsigned nb = (unsigned)n0 + (jr ? N_T / 2 : 0) + tg * 4;
     if (nb >= Nt) continue;
     const unsigned b0 = nb / uT, t0 = nb - b0 * uT;
+    // phase-interleaved (transposed-convolution) output with stride 2, 4 or 8: a run of 4 channels x 4 positions is
+    // whole float4 pieces of the interleaved rows  y[b][co / s][t * s + co % s]
+    if ((shuffle == 2 || shuffle == 4 || shuffle == 8) && (Tstore & 3) == 0 && t0 + 3 < uT &&
+        (int)(t0 + 4) * shuffle <= Tstore) {
+#pragma unroll
+      for (int ir = 0; ir < 2; ++ir) {
+        const int cob = co0 + (ir ? CO_T / 2 : 0) + cg * 4;          // first of 4 consecutive output rows
+        if (cob + 3 >= Cout) {
+          if (cob >= Cout) continue;
+        }
+        float v[4][4];                                                 // [row][position] with bias (and clip add)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int co = cob + a;
+          const float add = co < Cout ? bias[co] + (chan_add ? chan_add[(size_t)b0 * Cout + co] : 0.0f) : 0.0f;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) v[a][jj] = acc[ir * 4 + a][jr * 4 + jj] + add;
+        }
+        const int C = Cout / shuffle;
+        if (cob + 3 < Cout) {
+          if (shuffle == 4) {
+            float *dst = y + ((size_t)b0 * C + cob / 4) * Tstore + (size_t)t0 * 4;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              *reinterpret_cast<float4 *>(dst + 4 * jj) = make_float4(v[0][jj], v[1][jj], v[2][jj], v[3][jj]);
+          } else if (shuffle == 8) {
+            float *dst = y + ((size_t)b0 * C + cob / 8) * Tstore + (size_t)t0 * 8 + (cob & 7);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              *reinterpret_cast<float4 *>(dst + 8 * jj) = make_float4(v[0][jj], v[1][jj], v[2][jj], v[3][jj]);
+          } else {
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              float *dst = y + ((size_t)b0 * C + cob / 2 + cc) * Tstore + (size_t)t0 * 2;
+              *reinterpret_cast<float4 *>(dst) = make_float4(v[2 * cc][0], v[2 * cc + 1][0], v[2 * cc][1], v[2 * cc + 1][1]);
+              *reinterpret_cast<float4 *>(dst + 4) = make_float4(v[2 * cc][2], v[2 * cc + 1][2], v[2 * cc][3], v[2 * cc + 1][3]);
+            }
+          }
+          continue;
+        }
+        for (int a = 0; a < 4 && cob + a < Cout; ++a)                  // ragged last rows: scalar
+          for (int jj = 0; jj < 4; ++jj) {
+            const int co = cob + a, ts = (int)(t0 + jj) * shuffle + co % shuffle;
+            if (ts < Tstore) y[((size_t)b0 * C + co / shuffle) * Tstore + ts] = v[a][jj];
+          }
+      }
+      continue;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int co = co0 + (i < 4 ? cg * 4 + i : CO_T / 2 + cg * 4 + i - 4);
