@@ -453,6 +453,10 @@ int launch_conv1d_generic(const float *x, const float *w, const float *bias, con
   }
   // register-tiled implicit GEMM: 64 channels x 128 positions per block, or 16 x 512 for the narrow heads
   if (getenv("WMB200_CONV1D_SIMPLE") == nullptr && (long long)B * Tout < (1LL << 31) - 1024) {
+    if (Cout > 16 && Cout <= 32) {   // one 32-channel tile x 256 positions: the input slice is staged once, not twice
+      if (K <= 8) return launch_conv1d_tiled<4, 4>(x, w, bias, chan_add, res, y, B, Cin, Tin, Cout, Tout, K, stride, pad, act, shuffle, Tstore, st);
+      return launch_conv1d_tiled<4, 2>(x, w, bias, chan_add, res, y, B, Cin, Tin, Cout, Tout, K, stride, pad, act, shuffle, Tstore, st);
+    }
     if (Cout > 16) {
       if (K <= 8) return launch_conv1d_tiled<8, 8>(x, w, bias, chan_add, res, y, B, Cin, Tin, Cout, Tout, K, stride, pad, act, shuffle, Tstore, st);
       return launch_conv1d_tiled<8, 4>(x, w, bias, chan_add, res, y, B, Cin, Tin, Cout, Tout, K, stride, pad, act, shuffle, Tstore, st);
