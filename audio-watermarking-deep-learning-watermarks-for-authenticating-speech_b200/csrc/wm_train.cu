@@ -250,13 +250,19 @@ __global__ void __launch_bounds__(NT)
   if (j == bias_tap && threadIdx.x < 64) partial_b[blk * 64 + threadIdx.x] = bacc;
 }
 
-// out[i] = sum_blk partial[blk * n + i], fixed order
-__global__ void sum_partials_f_kernel(const float *__restrict__ partial, int nblk, int n, float *__restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// out[i] = sum_blk partial[blk * n + i], fixed order: a block owns 32 outputs, 8 interleaved segments of the partials
+// are summed in parallel and then added in a fixed tree.  Launch with 256 threads, ceil(n / 32) blocks.
+__global__ void __launch_bounds__(256)
+    sum_partials_f_kernel(const float *__restrict__ partial, int nblk, int n, float *__restrict__ out) {
+  __shared__ double red[8][32];
+  const int o = threadIdx.x & 31, seg = threadIdx.x >> 5, i = blockIdx.x * 32 + o;
   double t = 0.0;
-  for (int b = 0; b < nblk; ++b) t += (double)partial[(size_t)b * n + i];
-  out[i] = (float)t;
+  if (i < n)
+    for (int b = seg; b < nblk; b += 8) t += (double)partial[(size_t)b * n + i];
+  red[seg][o] = t;
+  __syncthreads();
+  if (seg == 0 && i < n)
+    out[i] = (float)(((red[0][o] + red[1][o]) + (red[2][o] + red[3][o])) + ((red[4][o] + red[5][o]) + (red[6][o] + red[7][o])));
 }
 
 // Conv1d(1,64,7,p=3) gradients: partial dw[blk][7][64], db[blk][64] from s[b][t], dx[b][t][64]
@@ -509,10 +515,10 @@ int launch_conv_wgrad_ex(const float *x, const float *dz, float *dw, float *db, 
   }
   conv_wgrad_kernel<<<dim3(nchunk, B, K), NT, WG_SMEM, st>>>(x, dz, T, K, P, db ? bias_tap : -1, rows, nchunk, pw, pb);
   WM_CHECK_LAUNCH("conv_wgrad");
-  sum_partials_f_kernel<<<(K * 4096 + 255) / 256, 256, 0, st>>>(pw, nblk, K * 4096, dw);
+  sum_partials_f_kernel<<<(K * 4096 + 31) / 32, 256, 0, st>>>(pw, nblk, K * 4096, dw);
   WM_CHECK_LAUNCH("sum_partials(w)");
   if (db) {
-    sum_partials_f_kernel<<<1, 64, 0, st>>>(pb, nblk, 64, db);
+    sum_partials_f_kernel<<<2, 256, 0, st>>>(pb, nblk, 64, db);
     WM_CHECK_LAUNCH("sum_partials(b)");
   }
   return 0;
@@ -528,7 +534,7 @@ int launch_conv_in_grads(const float *s, const float *dx, const float *w, float 
   const int nchunk = (T + IN_ROWS - 1) / IN_ROWS, nblk = B * nchunk;
   conv_in_wgrad_kernel<<<dim3(nchunk, B), NT, 0, st>>>(s, dx, T, nchunk, scratch);
   WM_CHECK_LAUNCH("conv_in_wgrad");
-  sum_partials_f_kernel<<<2, 256, 0, st>>>(scratch, nblk, 512, scratch + (size_t)nblk * 512);
+  sum_partials_f_kernel<<<16, 256, 0, st>>>(scratch, nblk, 512, scratch + (size_t)nblk * 512);
   WM_CHECK_LAUNCH("sum_partials(in)");
   WM_CHECK_CUDA(cudaMemcpyAsync(dw, scratch + (size_t)nblk * 512, 448 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   WM_CHECK_CUDA(cudaMemcpyAsync(db, scratch + (size_t)nblk * 512 + 448, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -555,9 +561,9 @@ int launch_head_bwd(const float *dlog, const float *y, const float *w, float *dy
   float *pw = scratch, *pb = scratch + (size_t)nblk * nout * 64;
   head_wgrad_kernel<<<nblk, NT, 0, st>>>(dlog, y, N, nout, pw, pb);
   WM_CHECK_LAUNCH("head_wgrad");
-  sum_partials_f_kernel<<<(nout * 64 + 255) / 256, 256, 0, st>>>(pw, nblk, nout * 64, dw);
+  sum_partials_f_kernel<<<(nout * 64 + 31) / 32, 256, 0, st>>>(pw, nblk, nout * 64, dw);
   WM_CHECK_LAUNCH("sum_partials(hw)");
-  sum_partials_f_kernel<<<1, 64, 0, st>>>(pb, nblk, nout, db);
+  sum_partials_f_kernel<<<(nout + 31) / 32, 256, 0, st>>>(pb, nblk, nout, db);
   WM_CHECK_LAUNCH("sum_partials(hb)");
   return 0;
 }
