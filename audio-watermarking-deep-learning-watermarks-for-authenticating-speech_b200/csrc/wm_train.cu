@@ -166,6 +166,21 @@ __global__ void transpose_flip_kernel(const float *__restrict__ w, float *__rest
 constexpr int WG_SUB = 64, WG_LD = 68, WG_BUF = 2 * WG_SUB * WG_LD;   // floats per stage: x rows then dz rows
 constexpr int WG_SMEM = 2 * WG_BUF * (int)sizeof(float);
 
+// packed fp32 pairs in a 64-bit register (Blackwell fma.rn.f32x2: two FMAs per issued instruction)
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &a, float &b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2x(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 // 16-byte async copy; src_bytes = 0 zero-fills the destination
 __device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, int src_bytes) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -179,11 +194,11 @@ __global__ void __launch_bounds__(NT)
   const int j = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
   const int t_begin = chunk * rows, t_end = min(T, t_begin + rows);
   const int g = threadIdx.x >> 6, l = threadIdx.x & 63, ci0 = (l >> 3) * 8, co0 = (l & 7) * 8;
-  float acc[8][8];
+  unsigned long long acc2[8][4];          // [input channel][output channel pair], two fp32 each
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[a][c] = 0.0f;
+    for (int c = 0; c < 4; ++c) acc2[a][c] = 0ull;
   float bacc = 0.0f;   // threads < 64: bias gradient of channel threadIdx.x
   const float *xb = x + (size_t)b * T * 64, *db = dz + (size_t)b * T * 64;
   auto stage = [&](int t0, int buf) {
@@ -213,14 +228,17 @@ __global__ void __launch_bounds__(NT)
       const int r = g * (WG_SUB / 4) + rr;
       const float4 x0 = *reinterpret_cast<const float4 *>(&xs[r * WG_LD + ci0]);
       const float4 x1 = *reinterpret_cast<const float4 *>(&xs[r * WG_LD + ci0 + 4]);
-      const float4 d0 = *reinterpret_cast<const float4 *>(&ds[r * WG_LD + co0]);
-      const float4 d1 = *reinterpret_cast<const float4 *>(&ds[r * WG_LD + co0 + 4]);
+      // packed fp32 FMAs (fma.rn.f32x2): the dz row is read as four 64-bit pairs, x values are duplicated
+      const ulonglong2 d0 = *reinterpret_cast<const ulonglong2 *>(&ds[r * WG_LD + co0]);
+      const ulonglong2 d1 = *reinterpret_cast<const ulonglong2 *>(&ds[r * WG_LD + co0 + 4]);
       const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-      const float da[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      const unsigned long long dp[4] = {d0.x, d0.y, d1.x, d1.y};
 #pragma unroll
-      for (int a = 0; a < 8; ++a)
+      for (int a = 0; a < 8; ++a) {
+        const unsigned long long xx = pack2(xa[a], xa[a]);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[a][c] = fmaf(xa[a], da[c], acc[a][c]);
+        for (int c = 0; c < 4; ++c) acc2[a][c] = fma2x(xx, dp[c], acc2[a][c]);
+      }
     }
     if (j == bias_tap && threadIdx.x < 64) {
       for (int r = 0; r < WG_SUB; ++r) bacc += ds[r * WG_LD + threadIdx.x];
@@ -229,6 +247,11 @@ __global__ void __launch_bounds__(NT)
   }
   // add the four row groups' blocks in a fixed order through shared memory (a 64 x 64 tile, pitch 68)
   float *tile = wsm;
+  float acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) unpack2(acc2[a][c], acc[a][2 * c], acc[a][2 * c + 1]);
   for (int gg = 0; gg < 4; ++gg) {
     if (g == gg) {
 #pragma unroll
