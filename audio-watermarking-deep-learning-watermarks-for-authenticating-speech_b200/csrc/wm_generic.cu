@@ -95,6 +95,20 @@ __global__ void __launch_bounds__(GTHREADS)
 // channels the block builds in shared memory  xs[ci][k][n] = x[b(n)][c0+ci][t(n)*stride + k - pad]  (an im2col slice:
 // every tap gets its own aligned row, so strided convolutions read only the phases they use and all inner-loop loads
 // are LDS.128) and  ws[ci][k][co]  (co contiguous);  per (ci, k): 2 + 2 LDS.128 feed 64 FMAs.
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &a, float &b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2x(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 __device__ __forceinline__ void cp_async4_zfill(void *smem, const void *gmem, int src_bytes) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
@@ -113,11 +127,11 @@ __global__ void __launch_bounds__(128, 4)
   const int co0 = blockIdx.y * CO_T;
   const long long n0 = (long long)blockIdx.x * N_T;
   const int cg = threadIdx.x % COG, tg = threadIdx.x / COG;
-  float acc[8][8];
+  unsigned long long acc2[8][4];     // [channel][position pair], two fp32 each
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    for (int j = 0; j < 4; ++j) acc2[i][j] = 0ull;
   // staging ownership: thread -> positions n0 + threadIdx.x + 128 q; which of the K taps fall inside [0, Tin) is a
   // per-position bit mask computed once
   constexpr int NQ = N_T / 128;
@@ -186,20 +200,28 @@ __global__ void __launch_bounds__(128, 4)
       // 16-byte words (no bank conflicts)
       const float4 w0 = *reinterpret_cast<const float4 *>(&ws[r * WLD + cg * 4]);
       const float4 w1 = *reinterpret_cast<const float4 *>(&ws[r * WLD + CO_T / 2 + cg * 4]);
-      const float4 x0 = *reinterpret_cast<const float4 *>(&xs[r * N_T + tg * 4]);
-      const float4 x1 = *reinterpret_cast<const float4 *>(&xs[r * N_T + N_T / 2 + tg * 4]);
+      // packed fp32 FMAs (fma.rn.f32x2): positions are read as 64-bit pairs, the weight is duplicated
+      const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(&xs[r * N_T + tg * 4]);
+      const ulonglong2 x1 = *reinterpret_cast<const ulonglong2 *>(&xs[r * N_T + N_T / 2 + tg * 4]);
       const float wq[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-      const float xq[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      const unsigned long long xp[4] = {x0.x, x0.y, x1.x, x1.y};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i) {
+        const unsigned long long ww = pack2(wq[i], wq[i]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wq[i], xq[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc2[i][j] = fma2x(ww, xp[j], acc2[i][j]);
+      }
     }
     __syncthreads();   // the buffer is refilled by the stage() issued at the top of the next iteration
   }
   // epilogue: the thread's positions are two runs of 4 consecutive n; with Tout % 4 == 0 a run never straddles a clip
   // and is 16-byte aligned in y, so it is stored (and the residual read) as one float4.  32-bit index math: the
   // launcher guarantees B * Tout < 2^31.
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) unpack2(acc2[i][j], acc[i][2 * j], acc[i][2 * j + 1]);
   const unsigned Nt = (unsigned)Ntot, uT = (unsigned)Tout;
   const bool vec = shuffle <= 1 && (Tout & 3) == 0;
 #pragma unroll
