@@ -148,7 +148,7 @@ def test_trainer_matches_the_reference_golden():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,T,seed", [(2, 2400, 0), (3, 16000, 1)])
+@pytest.mark.parametrize("B,T,seed", [(2, 2400, 0), (3, 16000, 1), (1, 2401, 2)])
 def test_trainer_matches_oracle(B, T, seed):
     import wmb200
     from wmb200 import train as TR
