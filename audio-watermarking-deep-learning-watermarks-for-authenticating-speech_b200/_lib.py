@@ -12,7 +12,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwmb200.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 # blob offsets (floats) — mirror of the enums in include/wmb200.h
 RB_W1 = 0
@@ -169,6 +169,11 @@ SIGNATURES = {
     "wm_train_step_workspace_bytes": (_sz, [_i, _i, _i]),
     "wm_train_forward_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p, _p, _p, _sz,
                                        _p]),
+    "wm_bce_heads_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _f, _p]),
+    "wm_head_bwd_workspace_bytes": (_sz, [_ll, _i]),
+    "wm_head_bwd": (_i, [_p, _p, _p, _p, _p, _p, _ll, _i, _p, _sz, _p]),
+    "wm_conv_in_k7_bwd_workspace_bytes": (_sz, [_i, _i]),
+    "wm_conv_in_k7_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p, _sz, _p]),
     "wm_bn_train_workspace_bytes": (_sz, [_ll]),
     "wm_bn_train_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _p, _sz, _p]),
     "wm_bn_train_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _p, _sz, _p]),

@@ -631,6 +631,41 @@ int wm_train_forward_backward(const float *g_params, float *g_grads, float *g_st
                                 n_mels, lam, B, T, nout, losses_out, s_w_out, workspace, as_stream(stream));
 }
 
+int wm_bce_heads_bwd(const float *logits, const int64_t *message, float *dlogits, int B_wm, int B_total, int T, int nout,
+                     float lam_loc, float lam_dec, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B_total > 0 && T > 0 && B_wm >= 0 && B_wm <= B_total, "bce_heads_bwd: bad batch sizes");
+  WM_CHECK_ARG(nout >= 1 && nout <= WM_MAX_HEAD, "bce_heads_bwd: nout must be in [1,%d]", WM_MAX_HEAD);
+  WM_CHECK_ARG(logits && dlogits && (message || nout == 1 || B_wm == 0), "bce_heads_bwd: null pointer");
+  return launch_bce_heads_bwd(logits, message, B_wm, B_total, T, nout, lam_loc, lam_dec, dlogits, as_stream(stream));
+}
+
+size_t wm_head_bwd_workspace_bytes(long long rows, int nout) {
+  return rows > 0 && nout > 0 ? head_bwd_scratch_floats(rows, nout) * sizeof(float) : 0;
+}
+
+int wm_head_bwd(const float *dlogits, const float *y, const float *w, float *dy, float *dw, float *db, long long rows,
+                int nout, void *workspace, size_t workspace_bytes, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(rows > 0 && nout >= 1 && nout <= WM_MAX_HEAD, "head_bwd: bad size");
+  WM_CHECK_ARG(dlogits && y && w && dy && dw && db && workspace, "head_bwd: null pointer");
+  WM_CHECK_ARG(workspace_bytes >= wm_head_bwd_workspace_bytes(rows, nout), "head_bwd: workspace too small");
+  return launch_head_bwd(dlogits, y, w, dy, dw, db, rows, nout, (float *)workspace, as_stream(stream));
+}
+
+size_t wm_conv_in_k7_bwd_workspace_bytes(int B, int T) {
+  return B > 0 && T > 0 ? conv_in_grads_scratch_floats(B, T) * sizeof(float) : 0;
+}
+
+int wm_conv_in_k7_bwd(const float *s, const float *dx, const float *w, float *dw, float *db, float *ds, int B, int T,
+                      void *workspace, size_t workspace_bytes, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B > 0 && T > 0, "conv_in_k7_bwd: bad size");
+  WM_CHECK_ARG(s && dx && dw && db && workspace && (!ds || w), "conv_in_k7_bwd: null pointer");
+  WM_CHECK_ARG(workspace_bytes >= wm_conv_in_k7_bwd_workspace_bytes(B, T), "conv_in_k7_bwd: workspace too small");
+  return launch_conv_in_grads(s, dx, w, dw, db, ds, B, T, (float *)workspace, as_stream(stream));
+}
+
 size_t wm_bn_train_workspace_bytes(long long rows) { return rows > 0 ? train_scratch_doubles(rows) * sizeof(double) : 0; }
 
 int wm_bn_train_fwd(const float *z, const float *gamma, const float *beta, const float *residual, float *out,

@@ -137,6 +137,14 @@ int launch_bn_train_bwd(const float *dout, const float *act, const float *z, con
                         const float *gamma, float *dz, float *dres, float *dgamma, float *dbeta, long long N,
                         double *scratch, cudaStream_t st);
 int launch_transpose_flip(const float *w, float *wt, int K, cudaStream_t st);
+int launch_bce_heads_bwd(const float *logits, const int64_t *message, int B_wm, int B2, int T, int nout, float lam_loc,
+                         float lam_dec, float *dlog, cudaStream_t st);
+size_t head_bwd_scratch_floats(long long N, int nout);
+int launch_head_bwd(const float *dlog, const float *y, const float *w, float *dy, float *dw, float *db, long long N,
+                    int nout, float *scratch, cudaStream_t st);
+size_t conv_in_grads_scratch_floats(int B, int T);
+int launch_conv_in_grads(const float *s, const float *dx, const float *w, float *dw, float *db, float *ds, int B, int T,
+                         float *scratch, cudaStream_t st);
 int launch_conv_wgrad(const float *x, const float *dz, float *dw, float *db, int B, int T, int K, float *scratch,
                       cudaStream_t st);
 int launch_conv_wgrad_ex(const float *x, const float *dz, float *dw, float *db, int B, int T, int K, int P, int bias_tap,

@@ -552,6 +552,9 @@ int launch_conv_wgrad(const float *x, const float *dz, float *dw, float *db, int
   return launch_conv_wgrad_ex(x, dz, dw, db, B, T, K, K / 2, K / 2, scratch, st);
 }
 
+size_t conv_in_grads_scratch_floats(int B, int T) { return (size_t)B * ((T + IN_ROWS - 1) / IN_ROWS) * 512 + 512; }
+size_t head_bwd_scratch_floats(long long N, int nout) { return (size_t)((N + HW_ROWS - 1) / HW_ROWS) * (nout * 64 + nout); }
+
 int launch_conv_in_grads(const float *s, const float *dx, const float *w, float *dw, float *db, float *ds, int B, int T,
                          float *scratch, cudaStream_t st) {
   const int nchunk = (T + IN_ROWS - 1) / IN_ROWS, nblk = B * nchunk;

@@ -210,6 +210,49 @@ def postprocess_bwd(g: torch.Tensor, delta_raw: torch.Tensor, fir: Optional[torc
     return out
 
 
+def bce_heads_bwd(logits: torch.Tensor, message: Optional[torch.Tensor], n_watermarked: int, lam_loc: float = LAMBDA_LOC,
+                  lam_dec: float = LAMBDA_DEC) -> torch.Tensor:
+    """d(lam_loc * loc + lam_dec * bce) / d logits for logits (B_total, T, nout) (py/main16.py:255-264)."""
+    lg = _req(logits, "logits")
+    B2, T, nout = lg.shape
+    msg = _req(message, "message", torch.int64) if message is not None else None
+    out = torch.empty_like(lg)
+    L.check(L.load().wm_bce_heads_bwd(L.ptr(lg), L.ptr(msg), L.ptr(out), n_watermarked, B2, T, nout, lam_loc, lam_dec,
+                                      _stream()), "wm_bce_heads_bwd")
+    return out
+
+
+def head_bwd(dlogits: torch.Tensor, y: torch.Tensor, weight: torch.Tensor):
+    """Backward of Conv1d(64,nout,1) on channels-last y (..., 64): -> (dy, dweight (nout,64,1), dbias (nout,))."""
+    lib = L.load()
+    dl, y = _req(dlogits, "dlogits"), _req(y, "y")
+    nout = dl.shape[-1]
+    rows = y.numel() // 64
+    w = _req(weight, "weight").reshape(nout, 64).contiguous()
+    dy, dw, db = torch.empty_like(y), torch.empty(nout, 64, device=y.device), torch.empty(nout, device=y.device)
+    n = lib.wm_head_bwd_workspace_bytes(rows, nout)
+    ws = _ws(n, y.device)
+    L.check(lib.wm_head_bwd(L.ptr(dl), L.ptr(y), L.ptr(w), L.ptr(dy), L.ptr(dw), L.ptr(db), rows, nout, L.ptr(ws), n,
+                            _stream()), "wm_head_bwd")
+    return dy, dw.reshape(nout, 64, 1), db
+
+
+def conv_in_k7_bwd(s: torch.Tensor, dx: torch.Tensor, weight: torch.Tensor, want_ds: bool = True):
+    """Backward of Conv1d(1,64,7,padding=3): s (B,T), dx (B,T,64) channels-last, weight (64,1,7) ->
+    (dweight (64,1,7), dbias (64,), ds (B,T) or None)."""
+    lib = L.load()
+    s, dx = _req(s, "s"), _req(dx, "dx")
+    B, T = s.shape
+    w = _req(weight, "weight").permute(2, 1, 0).reshape(7, 64).contiguous()
+    dw, db = torch.empty(7, 64, device=s.device), torch.empty(64, device=s.device)
+    ds = torch.empty_like(s) if want_ds else None
+    n = lib.wm_conv_in_k7_bwd_workspace_bytes(B, T)
+    ws = _ws(n, s.device)
+    L.check(lib.wm_conv_in_k7_bwd(L.ptr(s), L.ptr(dx), L.ptr(w), L.ptr(dw), L.ptr(db), L.ptr(ds), B, T, L.ptr(ws), n,
+                                  _stream()), "wm_conv_in_k7_bwd")
+    return dw.reshape(7, 1, 64).permute(2, 1, 0).contiguous(), db, ds
+
+
 # ---- flat parameter buffer <-> state dict -----------------------------------------------------------------------
 def _dt_slices(nout: int):
     """name -> (offset, shape in the flat buffer, whether the state-dict layout is its (2,1,0) transpose)."""

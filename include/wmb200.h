@@ -32,7 +32,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 13
+#define WM_ABI_VERSION 14
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -414,6 +414,18 @@ int wm_bn_train_bwd(const float *dout, const float *act, const float *z, const f
 size_t wm_conv64_bwd_workspace_bytes(int B, int T, int K);
 int wm_conv64_bwd(const float *x, const float *dy, const float *w, float *dw, float *db, float *dx, int B, int T, int K,
                   void *workspace, size_t workspace_bytes, void *stream);
+/* Backward of the remaining single operators (each checked against autograd in tests/test_train.py):
+ * wm_bce_heads_bwd   d(lam_loc * loc + lam_dec * bce)/d logits for logits[B_total][T][nout] (py/main16.py:255-264);
+ * wm_head_bwd        Conv1d(64,nout,1) on channels-last y[rows][64]: dy, dw [nout][64], db [nout] from dlogits;
+ * wm_conv_in_k7_bwd  Conv1d(1,64,7,padding=3): dw [7][64], db [64] and (nullable) ds [B][T] from dx [B][T][64]. */
+int wm_bce_heads_bwd(const float *logits, const int64_t *message, float *dlogits, int B_wm, int B_total, int T, int nout,
+                     float lam_loc, float lam_dec, void *stream);
+size_t wm_head_bwd_workspace_bytes(long long rows, int nout);
+int wm_head_bwd(const float *dlogits, const float *y, const float *w, float *dy, float *dw, float *db, long long rows,
+                int nout, void *workspace, size_t workspace_bytes, void *stream);
+size_t wm_conv_in_k7_bwd_workspace_bytes(int B, int T);
+int wm_conv_in_k7_bwd(const float *s, const float *dx, const float *w, float *dw, float *db, float *ds, int B, int T,
+                      void *workspace, size_t workspace_bytes, void *stream);
 size_t wm_bn_train_workspace_bytes(long long rows);
 /* nn.LSTM(64,64,batch_first) in training (py/main16.py:138,153).  Weights "per-gate transposed":
  * wT[q][k][r] = W[q*64 + r][k], q over (i,f,g,o).  Forward keeps the activated gates [B][T][256] and cell states

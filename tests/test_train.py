@@ -358,3 +358,31 @@ def test_postprocess_backward_matches_autograd(mode):
     fir = O.fir_taps().float().cuda()
     got = TR.postprocess_bwd(g, raw.detach().float(), fir, mode)
     assert rel(got, want) < 2e-4
+
+
+@pytest.mark.gpu
+def test_head_bce_and_input_conv_backward_match_autograd():
+    import torch.nn.functional as Fn
+    from wmb200 import train as TR
+    torch.manual_seed(12)
+    B2, n_wm, T, nout = 4, 2, 1501, 17
+    y = torch.randn(B2, T, 64, device="cuda", dtype=torch.float64, requires_grad=True)
+    w = (torch.randn(nout, 64, 1, device="cuda", dtype=torch.float64) / 8).requires_grad_(True)
+    b = torch.zeros(nout, device="cuda", dtype=torch.float64, requires_grad=True)
+    msg = torch.randint(0, 65536, (n_wm,), device="cuda")
+    logits = Fn.conv1d(y.permute(0, 2, 1), w, b).permute(0, 2, 1)
+    loc, bce = OT.detector_losses(logits, msg, n_wm)
+    logits.retain_grad()
+    (10.0 * loc + 1.0 * bce).backward()
+    dl = TR.bce_heads_bwd(logits.detach().float(), msg, n_wm, 10.0, 1.0)
+    assert rel(dl, logits.grad) < 2e-5
+    dy, dw, db = TR.head_bwd(dl, y.detach().float(), w.detach().float())
+    assert rel(dy, y.grad) < 2e-5 and rel(dw, w.grad) < 2e-5
+    assert rel(db, b.grad) < 1e-4        # 6004 signed terms per output, fp32 within a 1024-row block
+    s = torch.randn(3, 2000, device="cuda", dtype=torch.float64, requires_grad=True)
+    wi = torch.randn(64, 1, 7, device="cuda", dtype=torch.float64, requires_grad=True)
+    bi = torch.zeros(64, device="cuda", dtype=torch.float64, requires_grad=True)
+    dx = torch.randn(3, 2000, 64, device="cuda")
+    Fn.conv1d(s.unsqueeze(1), wi, bi, padding=3).backward(dx.double().permute(0, 2, 1))
+    dwi, dbi, ds = TR.conv_in_k7_bwd(s.detach().float(), dx, wi.detach().float())
+    assert rel(dwi, wi.grad) < 2e-5 and rel(dbi, bi.grad) < 2e-5 and rel(ds, s.grad) < 2e-5
