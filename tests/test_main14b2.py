@@ -81,7 +81,11 @@ def test_detector_matches_reference_goldens():
 @pytest.mark.gpu
 @pytest.mark.parametrize("Cin,Cout,K,stride,pad,T", [(1, 32, 7, 1, 3, 300), (32, 64, 3, 2, 1, 301), (64, 128, 3, 4, 1, 1000),
                                                      (128, 256, 3, 5, 1, 77), (256, 512, 3, 8, 1, 400), (32, 64, 1, 2, 0, 129),
-                                                     (8, 1, 7, 1, 3, 500), (5, 70, 4, 3, 2, 200)])
+                                                     (8, 1, 7, 1, 3, 500), (5, 70, 4, 3, 2, 200),
+                                                     # the three tile shapes (64/32/16 channels), K > 8, output lengths
+                                                     # that are / are not multiples of 4 (vector and scalar epilogues)
+                                                     (32, 17, 7, 1, 3, 1000), (16, 24, 3, 1, 1, 403), (4, 33, 16, 2, 7, 500),
+                                                     (3, 9, 16, 1, 8, 260), (20, 20, 9, 1, 4, 257), (64, 64, 3, 1, 1, 128)])
 def test_generic_conv1d_vs_torch(Cin, Cout, K, stride, pad, T):
     g = torch.Generator().manual_seed(Cin * 131 + Cout)
     conv = torch.nn.Conv1d(Cin, Cout, K, stride=stride, padding=pad)
