@@ -12,7 +12,7 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
 
 // N: MMA N; NACC: accumulators cycled; A_TMEM: A operand from tensor memory; SWZ: 128B-swizzle descriptors
 // ELECT: issue from a converged warp under elect.sync instead of a lane-0 branch
-template <int N, int NACC, int A_TMEM, int SWZ, int ELECT>
+template <int N, int NACC, int A_TMEM, int SWZ, int ELECT, int M = 128>
 __global__ void __launch_bounds__(128, 1) bench(int reps, long long *out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128, 1) bench(int reps, long long *out) {
   tc_fence_after();
   const uint32_t tmem = slot;
   if (threadIdx.x < 32) {
-    constexpr uint32_t idesc = make_idesc(128, N);
+    constexpr uint32_t idesc = make_idesc(M, N);
     uint64_t ad[4], bd[4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
@@ -71,15 +71,16 @@ __global__ void __launch_bounds__(128, 1) bench(int reps, long long *out) {
   }
 }
 
-template <int N, int NACC, int A_TMEM, int SWZ, int ELECT>
+template <int N, int NACC, int A_TMEM, int SWZ, int ELECT, int M = 128>
 void run(long long *out, int grid) {
   const int reps = 4096;
-  cudaFuncSetAttribute(bench<N, NACC, A_TMEM, SWZ, ELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  bench<N, NACC, A_TMEM, SWZ, ELECT><<<grid, 128, 160 * 1024>>>(reps, out);
+  cudaFuncSetAttribute(bench<N, NACC, A_TMEM, SWZ, ELECT, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  bench<N, NACC, A_TMEM, SWZ, ELECT, M><<<grid, 128, 160 * 1024>>>(reps, out);
   long long h[2];
   cudaError_t e = cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
-  printf("%d,%d,%d,%d,%d,%d,%.1f,%.1f\n", N, NACC, A_TMEM, SWZ, ELECT, grid, (double)h[0] / reps, (double)h[1] / reps);
+  printf("%d,%d,%d,%d,%d,%d,%.1f,%.1f%s\n", N, NACC, A_TMEM, SWZ, ELECT, grid, (double)h[0] / reps, (double)h[1] / reps,
+         M == 64 ? ",M=64" : "");
 }
 
 int main() {
@@ -98,6 +99,9 @@ int main() {
     // small-N shapes of the LSTM (A = weights in TMEM)
     run<32, 1, 1, 0, 1>(out, grid);  run<16, 1, 1, 0, 1>(out, grid);  run<32, 2, 1, 0, 1>(out, grid);  run<16, 4, 1, 0, 1>(out, grid);
     run<32, 1, 0, 0, 1>(out, grid);  run<16, 1, 0, 0, 1>(out, grid);  run<256, 1, 0, 0, 1>(out, grid);  run<256, 1, 1, 0, 1>(out, grid);
+    // M = 64 (operand-role swap study: weights as the A operand, activations as B with N = 256)
+    run<256, 1, 1, 0, 1, 64>(out, grid);  run<256, 1, 0, 0, 1, 64>(out, grid);  run<128, 1, 1, 0, 1, 64>(out, grid);
+    run<128, 2, 1, 0, 1>(out, grid);
   }
   return 0;
 }
