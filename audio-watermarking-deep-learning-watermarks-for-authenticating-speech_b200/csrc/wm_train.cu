@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(NT)
     conv_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ dz, int T, int K, int P, int bias_tap,
                       int rows, int nchunk, float *__restrict__ partial_w, float *__restrict__ partial_b) {
   extern __shared__ __align__(16) float wsm[];
-  const int j = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
+  // the taps of one chunk are adjacent in launch order, so they run together and share its rows through L2
+  const int j = blockIdx.x % K, b = blockIdx.y, chunk = blockIdx.x / K;
   const int t_begin = chunk * rows, t_end = min(T, t_begin + rows);
   const int g = threadIdx.x >> 6, l = threadIdx.x & 63, ci0 = (l >> 3) * 8, co0 = (l & 7) * 8;
   unsigned long long acc2[8][4];          // [input channel][output channel pair], two fp32 each
@@ -536,7 +537,7 @@ int launch_conv_wgrad_ex(const float *x, const float *dz, float *dw, float *db, 
     WM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
     attr_set = true;
   }
-  conv_wgrad_kernel<<<dim3(nchunk, B, K), NT, WG_SMEM, st>>>(x, dz, T, K, P, db ? bias_tap : -1, rows, nchunk, pw, pb);
+  conv_wgrad_kernel<<<dim3(nchunk * K, B), NT, WG_SMEM, st>>>(x, dz, T, K, P, db ? bias_tap : -1, rows, nchunk, pw, pb);
   WM_CHECK_LAUNCH("conv_wgrad");
   sum_partials_f_kernel<<<(K * 4096 + 31) / 32, 256, 0, st>>>(pw, nblk, K * 4096, dw);
   WM_CHECK_LAUNCH("sum_partials(w)");
