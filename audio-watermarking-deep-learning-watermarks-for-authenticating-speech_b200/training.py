@@ -81,10 +81,38 @@ def _draw_messages(B: int, device, bits: int = 16) -> torch.Tensor:
     return torch.randint(0, 2 ** bits, (B,), device=device)                 # py/main16.py:241
 
 
-def train_one_epoch(trainer: TR.Trainer, train_loader: Iterable, schedule: Optional[OneCycle] = None,
+def train_one_epoch(trainer, train_loader: Iterable, *args, schedule: Optional[OneCycle] = None,
                     global_step: int = 0, message_fn: Callable = _draw_messages, progress: Callable = iter) -> Dict[str, float]:
     """One pass over `train_loader` (batches s of shape (B,1,T) or (B,T), any device): the mean of every loss term,
-    as py/main16.py:238-294 returns it.  With `schedule`, optimiser step k uses schedule.at(global_step + k)."""
+    as py/main16.py:238-294 returns it.  With `schedule`, optimiser step k uses schedule.at(global_step + k).
+
+    Two call forms:
+      train_one_epoch(trainer, train_loader, ...)                                        # a wmb200 Trainer
+      train_one_epoch(generator, detector, train_loader, optimizer, losses, device)       # the reference's signature
+    The second keeps the reference's training loop (py/main16.py:534-560) unchanged: a Trainer is created on the first
+    call and kept on the generator module, the learning rate is read from `optimizer.param_groups[0]` (the torch
+    optimizer itself is not stepped — Adam's moments live in the Trainer), `losses` is accepted and ignored (the
+    mel / loudness kernels are built in), and the modules receive the updated parameters and BatchNorm statistics
+    before the function returns, so `validate_one_epoch(generator, detector, ...)` sees the trained weights."""
+    if not isinstance(trainer, TR.Trainer):
+        generator, detector, loader = trainer, train_loader, args[0]
+        optimizer = args[1] if len(args) > 1 else None
+        device = args[3] if len(args) > 3 else "cuda"
+        tr = getattr(generator, "_wmb200_trainer", None)
+        if tr is None or tr._detector_ref() is not detector:
+            import weakref
+            generator.to(device)
+            detector.to(device)
+            lr = float(optimizer.param_groups[0]["lr"]) if optimizer is not None else TR.LR
+            tr = TR.Trainer(generator, detector, lr=lr)
+            tr._detector_ref = weakref.ref(detector)
+            object.__setattr__(generator, "_wmb200_trainer", tr)
+        elif optimizer is not None:
+            tr.lr = float(optimizer.param_groups[0]["lr"])
+        out = train_one_epoch(tr, loader, schedule=schedule, global_step=global_step, message_fn=message_fn,
+                              progress=progress)
+        tr.write_back(generator, detector)
+        return out
     sums = torch.zeros(len(LOG_KEYS), device=trainer.device, dtype=torch.float64)
     n = 0
     for s in progress(train_loader):
@@ -186,7 +214,8 @@ def fit(generator, detector, train_loader, val_loader, epochs: int, lr: float = 
     train_logs: List[dict] = []
     val_logs: List[dict] = []
     for epoch in range(start_epoch, epochs):
-        train_metrics = train_one_epoch(trainer, train_loader, schedule, global_step, message_fn)
+        train_metrics = train_one_epoch(trainer, train_loader, schedule=schedule, global_step=global_step,
+                                        message_fn=message_fn)
         global_step = trainer.steps
         trainer.write_back(generator, detector)
         generator.eval()

@@ -3,6 +3,7 @@ stopping semantics (py/main16.py:511-528), and on the GPU: checkpoints in the re
 torch.optim.Adam can load, and a resumed run that lands bit-for-bit where the uninterrupted one does."""
 import os
 
+import numpy as np
 import pytest
 import torch
 
@@ -94,3 +95,24 @@ def test_checkpoint_resume_is_bit_exact_and_torch_loadable(tmp_path):
     assert logs3[0] == logs0[1]
     assert int(g3.state_dict()["encoder.1.block.1.num_batches_tracked"]) == 6
     assert os.path.exists(tmp_path / "generator_best.pth") and os.path.exists(tmp_path / "ckpt_best.pth")
+
+
+@pytest.mark.gpu
+def test_reference_signature_of_train_one_epoch():
+    """The reference's loop body `train_one_epoch(generator, detector, train_loader, optimizer, losses, device)`
+    (py/main16.py:538) runs unchanged and leaves trained weights in the modules."""
+    import wmb200
+    torch.manual_seed(3)
+    g, d = wmb200.Generator(message_bits=16).cuda(), wmb200.Detector(message_bits=16).cuda()
+    opt = torch.optim.Adam(list(g.parameters()) + list(d.parameters()), lr=1e-3)
+    losses = {"mel": wmb200.MultiScaleMelLoss(), "loud": wmb200.TFLoudnessLoss()}
+    loader = _loader(2, 2, 2400, 5)
+    w0 = d.state_dict()["model.3.weight"].clone()
+    m1 = TG.train_one_epoch(g, d, loader, opt, losses, "cuda")
+    m2 = TG.train_one_epoch(g, d, loader, opt, losses, "cuda")
+    assert set(m1) == set(TG.LOG_KEYS) and all(np.isfinite(v) for v in m2.values())
+    assert g._wmb200_trainer.steps == 4                       # one Trainer across both epochs
+    assert float((d.state_dict()["model.3.weight"] - w0).abs().max()) > 1e-4
+    assert int(d.state_dict()["model.1.block.1.num_batches_tracked"]) == 4
+    v = wmb200.validate_one_epoch(g, d, loader, losses, "cuda")
+    assert np.isfinite(v["total"])
