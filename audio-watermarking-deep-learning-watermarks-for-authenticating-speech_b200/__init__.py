@@ -7,10 +7,11 @@ runs in libwmb200.so (hand-written CUDA, C ABI in include/wmb200.h); there is no
 PyTorch fallback — calls fail loudly when the library or the GPU is missing.
 """
 from . import _lib, audio, main14b_2, ops, packing
-from .audio import Resample, file_metrics, from_pcm16, resample, to_pcm16
+from .audio import Resample, compute_si_snr, file_metrics, from_pcm16, resample, to_pcm16
 from .api import detect_prob, detect_watermark, generate_watermarked_audio, load_audio, save_audio, segment
 from .evaluate import evaluate_model, validate_one_epoch
-from .train import DetectorTrainer, Trainer
+from .train import LR, DetectorTrainer, Trainer
+from .training import EarlyStopping, OneCycle, fit, load_ckpt, save_ckpt, train_one_epoch
 from .functional import (AUDIO_LEN, HF_PENALTY_W, LAMBDA_DEC, LAMBDA_L1, LAMBDA_LOC, LAMBDA_LOUD,
                          LAMBDA_MSSPEC, MAX_RMS, MESSAGE_BITS, SAMPLE_RATE, bit_targets, clamp_peak,
                          embed_detect, fir_lowpass, limit_rms, postprocess_delta)
@@ -26,4 +27,5 @@ __all__ = ["Generator", "Detector", "ResBlock", "generate_watermarked_audio", "d
            "LAMBDA_LOC", "LAMBDA_DEC", "HF_PENALTY_W", "MultiScaleMelLoss", "TFLoudnessLoss", "high_freq_penalty",
            "step_losses", "stft_magnitude", "embed_detect_stream", "process_folder_with_tqdm", "detect_watermark_folder",
            "Resample", "resample", "to_pcm16", "from_pcm16", "file_metrics", "evaluate_model", "validate_one_epoch",
-           "DetectorTrainer", "Trainer"]
+           "DetectorTrainer", "Trainer", "LR", "EarlyStopping", "OneCycle", "fit", "load_ckpt", "save_ckpt",
+           "train_one_epoch", "compute_si_snr"]

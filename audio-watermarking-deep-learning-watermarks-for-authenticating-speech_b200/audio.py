@@ -75,3 +75,14 @@ def file_metrics(original: torch.Tensor, watermarked: torch.Tensor, valid_len: O
     L.check(lib.wm_file_metrics_fwd(L.ptr(s), L.ptr(w), L.ptr(v), L.ptr(out), s.shape[0], s.shape[1], _stream()),
             "wm_file_metrics_fwd")
     return out
+
+
+def compute_si_snr(s: torch.Tensor, s_hat: torch.Tensor, eps: float = 1e-8) -> float:
+    """Scale-invariant SNR in dB, mean over the rows — py/main16.py:764-773.  s, s_hat: (B,T) (or (B,1,T) / (1,1,T) as
+    the later cells of the reference pass them), on the GPU; one block per row, sums in double precision.  `eps` is
+    the reference's default (the kernel's constant)."""
+    if eps != 1e-8:
+        raise ValueError("compute_si_snr: only the reference's eps = 1e-8 is built into the kernel")
+    a = s.reshape(-1, s.shape[-1])
+    b = s_hat.reshape(-1, s_hat.shape[-1])
+    return float(file_metrics(a, b)[:, 1].mean())

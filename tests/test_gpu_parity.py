@@ -750,3 +750,20 @@ def test_validate_and_evaluate_twins_vs_oracle(gen_B, det, monkeypatch):
     assert abs(e["watermarked_prob"] - np.mean(pw)) < PROB_TOL and abs(e["clean_prob"] - np.mean(pc)) < PROB_TOL
     assert abs(e["bit_accuracy"] - np.mean(ba)) < 0.05 and abs(e["delta_rms"] - np.mean(rm)) < 1e-6
     assert set(e) == {"watermarked_prob", "clean_prob", "bit_accuracy", "delta_rms"}
+
+
+def test_compute_si_snr_matches_reference_formula():
+    """py/main16.py:764-773 restated in fp64 against the kernel-backed wmb200.compute_si_snr."""
+    g = torch.Generator().manual_seed(77)
+    s = 0.1 * torch.randn(5, 16000, generator=g)
+    s_hat = s + 0.005 * torch.randn(5, 16000, generator=g)
+    a, b = s.double(), s_hat.double()
+    a = a - a.mean(dim=1, keepdim=True)
+    b = b - b.mean(dim=1, keepdim=True)
+    alpha = (a * b).sum(dim=1, keepdim=True) / ((a ** 2).sum(dim=1, keepdim=True) + 1e-8)
+    tgt = alpha * a
+    want = float((10 * torch.log10((tgt ** 2).sum(dim=1) / (((b - tgt) ** 2).sum(dim=1) + 1e-8))).mean())
+    got = wmb200.compute_si_snr(s.to(DEV), s_hat.to(DEV))
+    assert abs(got - want) < 1e-3
+    assert abs(wmb200.compute_si_snr(s[:1].view(1, 1, -1).to(DEV), s_hat[:1].view(1, 1, -1).to(DEV))
+               - float((10 * torch.log10((tgt[:1] ** 2).sum() / (((b[:1] - tgt[:1]) ** 2).sum() + 1e-8))))) < 1e-3
