@@ -8,7 +8,8 @@ PyTorch fallback — calls fail loudly when the library or the GPU is missing.
 """
 from . import _lib, audio, main14b_2, ops, packing
 from .audio import Resample, compute_si_snr, file_metrics, from_pcm16, resample, to_pcm16
-from .api import detect_prob, detect_watermark, generate_watermarked_audio, load_audio, save_audio, segment
+from .api import (detect_prob, detect_watermark, evaluate_unseen_file, generate_watermarked_audio, load_audio,
+                  process_audio_file_with_delta, run_inference_on_file, save_audio, segment, set_seed)
 from .evaluate import evaluate_model, validate_one_epoch
 from .train import LR, DetectorTrainer, Trainer
 from .training import EarlyStopping, OneCycle, fit, load_ckpt, save_ckpt, train_one_epoch
@@ -28,4 +29,5 @@ __all__ = ["Generator", "Detector", "ResBlock", "generate_watermarked_audio", "d
            "step_losses", "stft_magnitude", "embed_detect_stream", "process_folder_with_tqdm", "detect_watermark_folder",
            "Resample", "resample", "to_pcm16", "from_pcm16", "file_metrics", "evaluate_model", "validate_one_epoch",
            "DetectorTrainer", "Trainer", "LR", "EarlyStopping", "OneCycle", "fit", "load_ckpt", "save_ckpt",
-           "train_one_epoch", "compute_si_snr"]
+           "train_one_epoch", "compute_si_snr", "evaluate_unseen_file", "process_audio_file_with_delta",
+           "run_inference_on_file", "set_seed"]

@@ -180,3 +180,73 @@ def detect_watermark(input_file, detector, detection_threshold=0.5, visualize=Tr
 def detect_prob(path, detector, device="cuda") -> float:
     """Clip-level probability of a file (py/main16.py:1575-1596)."""
     return detect_watermark(path, detector, visualize=False, device=device)["mean_probability"]
+
+
+# ---- the remaining file-level callers of py/main16.py, on the batched path ------------------------------------------
+def set_seed(seed: int = 42) -> None:
+    """py/main16.py:21-25."""
+    import random
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
+@torch.no_grad()
+def process_audio_file_with_delta(file_path, generator, sample_rate: int = SAMPLE_RATE, message_bits: int = 16,
+                                  device="cuda", messages: Optional[Sequence[int]] = None):
+    """py/main16.py:723-762: (watermarked (1,N), delta (1,N), original (1,N)) CPU tensors; every 1 s segment (the last
+    one zero-padded and cropped) gets its own message, drawn as the reference draws it unless `messages` is given.
+    All segments run as one generator batch."""
+    if sample_rate != SAMPLE_RATE:
+        raise ValueError(f"the model works at {SAMPLE_RATE} Hz (got sample_rate={sample_rate})")
+    r = generate_watermarked_audio(file_path, generator, None, message_bits, device, messages)
+    return r["watermarked_waveform"], r["delta_waveform"], r["original_waveform"]
+
+
+@torch.no_grad()
+def run_inference_on_file(file_path, generator, detector, device="cuda", messages: Optional[Sequence[int]] = None):
+    """py/main16.py:775-800: embed per segment, then ONE detector pass over the whole watermarked recording (not per
+    segment — the reference feeds (1,1,N)), mean detection probability, watermark RMS and SI-SNR.
+    Returns (watermarked (1,N), detection_prob, watermark_rms, si_snr)."""
+    from .audio import compute_si_snr
+    detector.eval()
+    wm, delta, orig = process_audio_file_with_delta(file_path, generator, SAMPLE_RATE, generator.message_bits or 16,
+                                                    device, messages)
+    x = wm.to(device).reshape(1, 1, -1)
+    r = detector.detect(x, want_probs=False, want_votes=False)
+    detection_prob = float(r["clip_prob"][0])
+    watermark_rms = torch.sqrt((delta ** 2).mean()).item()
+    si_snr_val = compute_si_snr(orig.to(device), wm.to(device))
+    return wm, detection_prob, watermark_rms, si_snr_val
+
+
+@torch.no_grad()
+def evaluate_unseen_file(filepath, generator, detector, device="cuda", messages: Optional[Sequence[int]] = None):
+    """py/main16.py:1263-1299: per zero-padded 1 s segment, detection probability of the clean and of the watermarked
+    segment, SI-SNR and watermark RMS; returns the four means over the segments (clean, watermarked, si_snr, rms), or
+    four Nones when the file cannot be read.  Segments run as one batch through generator and detector."""
+    from .audio import file_metrics
+    try:
+        waveform = _prepare(filepath)
+    except Exception:
+        return None, None, None, None
+    generator.eval()
+    detector.eval()
+    batch, _ = segment(waveform)
+    n = batch.shape[0]
+    if n == 0:
+        return None, None, None, None
+    bits = generator.message_bits or 16
+    if messages is None:
+        msg = torch.cat([torch.randint(0, 2 ** bits, (1,), device=device) for _ in range(n)])     # :1285, one per segment
+    else:
+        msg = torch.as_tensor(list(messages), dtype=torch.int64, device=device)
+    seg = batch.to(device)
+    delta = generator(seg, msg)
+    seg_w = seg + delta
+    p_clean = detector.detect(seg, want_probs=False, want_votes=False)["clip_prob"]
+    p_wm = detector.detect(seg_w, want_probs=False, want_votes=False)["clip_prob"]
+    m = file_metrics(seg[:, 0], seg_w[:, 0])                    # per segment: rms, si_snr, power ratio
+    return (float(p_clean.mean()), float(p_wm.mean()), float(m[:, 1].mean()), float(m[:, 0].mean()))

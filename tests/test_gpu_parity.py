@@ -767,3 +767,38 @@ def test_compute_si_snr_matches_reference_formula():
     assert abs(got - want) < 1e-3
     assert abs(wmb200.compute_si_snr(s[:1].view(1, 1, -1).to(DEV), s_hat[:1].view(1, 1, -1).to(DEV))
                - float((10 * torch.log10((tgt[:1] ** 2).sum() / (((b[:1] - tgt[:1]) ** 2).sum() + 1e-8))))) < 1e-3
+
+
+def test_file_level_callers_match_per_segment_restatement(gen_B, det):
+    """process_audio_file_with_delta / run_inference_on_file / evaluate_unseen_file (py/main16.py:723-800,1263-1299)
+    against the oracle run segment by segment the way the reference loops, with the messages fixed."""
+    g = torch.Generator().manual_seed(55)
+    N = 3 * 16000 + 5300
+    wav = (0.1 * torch.randn(1, N, generator=g)).clamp(-0.99, 0.99)
+    ids = [int(v) for v in IO["messages"][:4]]
+    gsd, rows = H.gen_sd(W, "B")
+    dsd = H.det_sd(W)
+    segs, _ = wmb200.segment(wav)
+    msg = torch.tensor(ids)
+    delta = O.generator_forward(gsd, segs, msg, emb_rows=H.emb_for(IO, rows, msg))
+    seg_w = segs + delta
+    wm_ref = seg_w.reshape(1, -1)[:, :N]
+    # process_audio_file_with_delta
+    wm, dl, orig = wmb200.process_audio_file_with_delta(wav, gen_B, messages=ids)
+    assert wm.shape == (1, N) and dl.shape == (1, N) and torch.equal(orig, wav)
+    assert maxerr(wm, wm_ref) < DELTA_TOL
+    # run_inference_on_file: ONE detector pass over the whole (1,1,N) recording
+    wm2, prob, rms, si = wmb200.run_inference_on_file(wav, gen_B, det, messages=ids)
+    lg = O.detector_forward(dsd, wm_ref.unsqueeze(0))
+    assert abs(prob - float(torch.sigmoid(lg[:, :, 0]).mean())) < PROB_TOL
+    assert abs(rms - float(delta.reshape(-1)[:N].pow(2).mean().sqrt())) < 1e-6
+    a, b = wav.double() - wav.double().mean(), wm_ref.double() - wm_ref.double().mean()
+    tgt = (a * b).sum() / ((a ** 2).sum() + 1e-8) * a
+    assert abs(si - float(10 * torch.log10((tgt ** 2).sum() / (((b - tgt) ** 2).sum() + 1e-8)))) < 1e-2
+    # evaluate_unseen_file: per padded segment, means over the segments
+    pc, pw, si_m, rms_m = wmb200.evaluate_unseen_file(wav, gen_B, det, messages=ids)
+    want_pc = float(torch.sigmoid(O.detector_forward(dsd, segs)[:, :, 0]).mean(dim=1).mean())
+    want_pw = float(torch.sigmoid(O.detector_forward(dsd, seg_w)[:, :, 0]).mean(dim=1).mean())
+    assert abs(pc - want_pc) < PROB_TOL and abs(pw - want_pw) < PROB_TOL
+    assert abs(rms_m - float(delta.pow(2).mean(dim=(1, 2)).sqrt().mean())) < 1e-6
+    assert wmb200.evaluate_unseen_file("/nonexistent/file.wav", gen_B, det) == (None, None, None, None)
