@@ -171,7 +171,10 @@ def load_ckpt(path: str, generator, detector, device="cuda", **trainer_kwargs):
     """-> (trainer, next_epoch, global_step, best_val).  Accepts checkpoints written by save_ckpt or by the reference's
     own driver (same keys; `_orig_mod.` prefixes from torch.compile are stripped)."""
     from .models import load_state_dict_strip_prefix
-    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    try:                       # plain tensors / containers: the safe loader is enough for files written by save_ckpt
+        ckpt = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception:          # checkpoints of older torch versions pickle scheduler internals; the file is the user's own
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
     load_state_dict_strip_prefix(generator, ckpt["gen"])
     load_state_dict_strip_prefix(detector, ckpt["det"])
     generator.to(device)
