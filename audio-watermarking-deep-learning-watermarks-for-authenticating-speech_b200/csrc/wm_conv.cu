@@ -67,6 +67,20 @@ int launch_conv_in_k7(const float *s, const float *w, const float *b, float *y, 
 // smem: x tile (128 + TAPS - 1) rows padded to 68 floats, one tap of weights
 // (64 x 64) at a time.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pack2f(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2f(unsigned long long v, float &a, float &b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2f(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 template <int TAPS>
 __global__ void __launch_bounds__(256)
     conv64_fp32_kernel(const float *__restrict__ x, const float *__restrict__ w,
@@ -94,11 +108,13 @@ __global__ void __launch_bounds__(256)
   }
 
   const int tx = tid & 15, ty = tid >> 4, co0 = tx * 4;
-  float acc[8][4];
+  // accumulators as packed fp32 pairs (fma.rn.f32x2: two FMAs per issued instruction): [time step][channel pair]
+  unsigned long long acc2[8][2];
   {
     float4 bv = *reinterpret_cast<const float4 *>(&bias[co0]);
+    const unsigned long long b01 = pack2f(bv.x, bv.y), b23 = pack2f(bv.z, bv.w);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[i][0] = bv.x; acc[i][1] = bv.y; acc[i][2] = bv.z; acc[i][3] = bv.w; }
+    for (int i = 0; i < 8; ++i) { acc2[i][0] = b01; acc2[i][1] = b23; }
   }
 
   for (int j = 0; j < TAPS; ++j) {
@@ -108,22 +124,27 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
 #pragma unroll 4
     for (int c4 = 0; c4 < 16; ++c4) {
-      float4 wv[4];
+      ulonglong2 wv[4];      // weights of input channels c4*4 + q for this thread's 4 output channels, as two pairs
 #pragma unroll
-      for (int q = 0; q < 4; ++q) wv[q] = *reinterpret_cast<const float4 *>(&ws[(c4 * 4 + q) * 64 + co0]);
+      for (int q = 0; q < 4; ++q) wv[q] = *reinterpret_cast<const ulonglong2 *>(&ws[(c4 * 4 + q) * 64 + co0]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float4 xv = *reinterpret_cast<const float4 *>(&xs[(ty + 16 * i + j) * LD + c4 * 4]);
-        acc[i][0] = fmaf(xv.x, wv[0].x, acc[i][0]); acc[i][1] = fmaf(xv.x, wv[0].y, acc[i][1]);
-        acc[i][2] = fmaf(xv.x, wv[0].z, acc[i][2]); acc[i][3] = fmaf(xv.x, wv[0].w, acc[i][3]);
-        acc[i][0] = fmaf(xv.y, wv[1].x, acc[i][0]); acc[i][1] = fmaf(xv.y, wv[1].y, acc[i][1]);
-        acc[i][2] = fmaf(xv.y, wv[1].z, acc[i][2]); acc[i][3] = fmaf(xv.y, wv[1].w, acc[i][3]);
-        acc[i][0] = fmaf(xv.z, wv[2].x, acc[i][0]); acc[i][1] = fmaf(xv.z, wv[2].y, acc[i][1]);
-        acc[i][2] = fmaf(xv.z, wv[2].z, acc[i][2]); acc[i][3] = fmaf(xv.z, wv[2].w, acc[i][3]);
-        acc[i][0] = fmaf(xv.w, wv[3].x, acc[i][0]); acc[i][1] = fmaf(xv.w, wv[3].y, acc[i][1]);
-        acc[i][2] = fmaf(xv.w, wv[3].z, acc[i][2]); acc[i][3] = fmaf(xv.w, wv[3].w, acc[i][3]);
+        const unsigned long long x0 = pack2f(xv.x, xv.x), x1 = pack2f(xv.y, xv.y), x2 = pack2f(xv.z, xv.z),
+                                 x3 = pack2f(xv.w, xv.w);
+        acc2[i][0] = fma2f(x0, wv[0].x, acc2[i][0]); acc2[i][1] = fma2f(x0, wv[0].y, acc2[i][1]);
+        acc2[i][0] = fma2f(x1, wv[1].x, acc2[i][0]); acc2[i][1] = fma2f(x1, wv[1].y, acc2[i][1]);
+        acc2[i][0] = fma2f(x2, wv[2].x, acc2[i][0]); acc2[i][1] = fma2f(x2, wv[2].y, acc2[i][1]);
+        acc2[i][0] = fma2f(x3, wv[3].x, acc2[i][0]); acc2[i][1] = fma2f(x3, wv[3].y, acc2[i][1]);
       }
     }
+  }
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    unpack2f(acc2[i][0], acc[i][0], acc[i][1]);
+    unpack2f(acc2[i][1], acc[i][2], acc[i][3]);
   }
 
 #pragma unroll
