@@ -122,6 +122,7 @@ SIGNATURES = {
     "wm_resblock_tc_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "wm_pack_lstm_tc": (_i, [_p, _p, _p, _p, _p, _p]),
     "wm_debug_lstm_profile": (_i, [_p]),
+    "wm_debug_lstm_opts": (_i, [_i]),
     "wm_lstm_tc_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
     "wm_conv_in_k7_fwd": (_i, [_p, _p, _p, _p, _i, _i, _p]),
     "wm_conv64_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),

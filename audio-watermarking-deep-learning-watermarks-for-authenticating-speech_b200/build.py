@@ -39,7 +39,21 @@ def _digest() -> str:  # noqa
     return h.hexdigest()
 
 
+def _src_digest(src: str) -> str:
+    """Digest of one translation unit: its source, every header of csrc/ and include/, and the flags."""
+    h = hashlib.sha256()
+    hdrs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".h", ".cuh"))]
+    hdrs.append(os.path.join(os.path.dirname(HERE), "include", "wmb200.h"))
+    for f in [src] + hdrs:
+        h.update(f.encode())
+        h.update(open(f, "rb").read())
+    h.update(" ".join(ARCH + FLAGS).encode())
+    return h.hexdigest()
+
+
 def build_lib(force: bool = False, verbose: bool = False) -> str:
+    """Compile every csrc/*.cu for sm_100a (one nvcc per file, in parallel, only the files whose digest changed)
+    and link libwmb200.so.  build/stamp.txt holds the digest of the whole source set the library was linked from."""
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
@@ -49,17 +63,26 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        tag, sd = obj + ".digest", _src_digest(src)
+        if not force and os.path.exists(obj) and os.path.exists(tag) and open(tag).read().strip() == sd:
+            continue
         cmd = [nvcc, *ARCH, *[f for f in FLAGS if not f.startswith("--use_fast_math")], "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
-    for src, p in procs:
+        procs.append((src, tag, sd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = None
+    for src, tag, sd, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode != 0:
             sys.stderr.write(out)
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}")
+            failed = failed or src
+            continue
+        with open(tag, "w") as f:
+            f.write(sd)
+    if failed:
+        raise RuntimeError(f"nvcc failed on {failed}")
     cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda"]
     subprocess.run(cmd, check=True)
     with open(STAMP, "w") as f:

@@ -302,6 +302,10 @@ int wm_debug_lstm_profile(long long *buf16) {
   set_lstm_profile_buffer(buf16);
   return 0;
 }
+int wm_debug_lstm_opts(int opts) {
+  set_lstm_opts(opts);
+  return 0;
+}
 
 int wm_resblock_tc_fwd(const void *x, const void *w_img, const float *b1, const float *b2, void *y, float *y32,
                        int B, int T, void *stream) {

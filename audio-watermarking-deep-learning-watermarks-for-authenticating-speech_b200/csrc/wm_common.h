@@ -183,6 +183,7 @@ int launch_resample(const float *x, const float *kern, float *y, int B, int Tin,
 int launch_pcm16(const float *x, short *q, float *xo, long long n, int quantize, float scale, cudaStream_t st);
 int launch_file_metrics(const float *s, const float *sw, const int *valid_len, float *out, int B, int T, cudaStream_t st);
 void set_lstm_profile_buffer(long long *p);
+void set_lstm_opts(int opts);
 long long *get_profile_buffer();
 int launch_pack_lstm_tc(const float *w_ih, const float *w_hh, const float *bias, void *wpk, float *bias_p,
                         cudaStream_t st);

@@ -10,10 +10,20 @@
 // W_lo only the hi rows (the lo x lo product is below the parity budget), and the epilogue adds
 // accumulator column n and 16 + n.
 //
-// The step is a dependent chain (MMA -> TMEM load -> exp -> cell update -> h tile -> proxy fence -> MMA)
-// that leaves the tensor pipe and the ALUs idle most of the time, so the CTA runs two such chains,
-// half a step apart: each group has its own 8 epilogue warps, 2 loader warps, MMA-issuing warp,
-// barriers, accumulators and tiles; only the weights in TMEM are shared.
+// The step is a dependent chain (MMA -> TMEM load -> exp -> cell update -> h tile -> MMA) that leaves the
+// tensor pipe and the ALUs idle most of the time, so the CTA runs two such chains: each group has its
+// own 8 epilogue warps, MMA-issuing warp, barriers, accumulators and tiles; only the weights in TMEM are shared.
+//
+// Waiting is done on HARDWARE named barriers wherever a whole warp waits: a warp spinning on an mbarrier
+// keeps taking issue slots from the other group's warps on its scheduler (measured: the exponentials of one
+// group ran at half speed while the other group's 8 warps polled).  Only the elected MMA thread polls
+// mbarriers (accumulator complete, x stage landed / consumed) and relays "accumulator ready" to its epilogue
+// warps with bar.arrive.  The generic->async proxy fence for the h tile is issued by that thread too (after
+// the barrier that orders the epilogue warps' stores), not by the 256 epilogue threads on the critical path.
+//
+// x_t arrives by TMA: one 5-d tensor map over the planar input (16 B row, clip, hi/lo, 8-channel chunk, time)
+// whose box {16 B, 16 clips, 2, 8, 8 steps} lands in shared memory already transposed into 8 per-step
+// [chunk][hi/lo][clip] B tiles (UTMALDG); clips beyond B are zero-filled by the out-of-bounds rule.
 //
 // Gate rows are permuted so that M-tile m, lane 32*g + u is gate type g (i,f,g,o) of unit 32m + u:
 // TMEM lane quadrant q == gate type q.  The packed weights and biases are pre-multiplied by -log2(e)
@@ -25,9 +35,9 @@
 //     h  = (1-e_c) / ((1+e_o)(1+e_c)),  e_c = exp(-2c')                       [= s(o) tanh(c')]
 // The two half-lanes of a clip swap their bf16 hi / lo halves so that each writes one 16-byte row of
 // the h tile (the next step's B operand) and of the planar output.
-// x_t arrives through the loader warps (cp.async, transposing planar [clip][plane][t] into per-step
-// [plane][clip] tiles, 8 steps per stage, double buffered).
+#include <cuda.h>
 #include <cuda_bf16.h>
+#include <cudaTypedefs.h>
 
 #include "wm_common.h"
 #include "wm_tc.cuh"
@@ -43,8 +53,7 @@ constexpr int NCL = 16;                       // clips per group
 constexpr int NGRP = 2;                       // groups per CTA
 constexpr int TC_STEPS = 8;                   // steps per x stage
 constexpr int XTILE = 16 * NCL * 16;          // bytes of one step's x tile: [chunk 8][hi/lo 2][clip 16][16 B]
-constexpr int XSTEP = XTILE + 16;             // padded pitch between steps (bank spread for the transposing stores)
-constexpr int XSTAGE = TC_STEPS * XSTEP;
+constexpr int XSTAGE = TC_STEPS * XTILE;      // one TMA box
 constexpr int HTILE = XTILE;                  // h tile, same layout
 constexpr int ELD = NCL + 4;                  // row pitch of the exchange buffer: 16-byte rows; 20 words spreads both the
                                               // phase-1 STS.128 (rows = lanes) and the phase-2 reads (half-lanes 4 units apart) over all banks
@@ -55,28 +64,41 @@ constexpr int G_E = G_H + HTILE;
 constexpr int G_BYTES = ((G_E + EBYTES + 127) / 128) * 128;
 constexpr int OFF_BAR = NGRP * G_BYTES;
 constexpr int LSTM_SMEM = OFF_BAR + 256;
-constexpr int N_EPI = 256, N_LOAD = 64;       // per group
-constexpr int W_LOAD0 = NGRP * N_EPI / 32, W_MMA0 = W_LOAD0 + NGRP * N_LOAD / 32;
-constexpr int THREADS = NGRP * (N_EPI + N_LOAD + 32);
+constexpr int N_EPI = 256;                    // epilogue threads per group
+constexpr int W_MMA0 = NGRP * N_EPI / 32;
+constexpr int THREADS = NGRP * (N_EPI + 32);
 constexpr uint32_t kIdescHi = make_idesc(128, 2 * NCL);   // W_hi x [clips hi | clips lo]
 constexpr uint32_t kIdescLo = make_idesc(128, NCL);       // W_lo x  clips hi
 // TMEM columns: weights [mat 4][tile 2] x 32 columns, then accumulators [group 2][buf 2][tile 2] x 32 columns
 constexpr uint32_t TM_W = 0, TM_ACC = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kArgMax = 28.85f;             // ex2 argument cap: e <= 4.8e8, (1+e)^3 stays finite
+// hardware named barriers (0 = __syncthreads): per group g
+constexpr int BAR_PHASE = 1, BAR_HREADY = 3, BAR_ACC = 5, BAR_TURN = 7;
+
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 
 }  // namespace
 
 // wpk: bf16 [mat: Whh_hi, Whh_lo, Wih_hi, Wih_lo][tile 2][lane 128][64]; bias_p: fp32 [tile 2][lane 128]
-// (both pre-scaled by -log2 e / -2 log2 e, see launch_pack_lstm_tc)
+// (both pre-scaled by -log2 e / -2 log2 e, see launch_pack_lstm_tc); xmap: the planar input as a 5-d tensor
 template <bool PROF>
 __global__ void __launch_bounds__(THREADS, 1)
-    lstm_tc_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ wpk, const float *__restrict__ bias_p,
-                   const float *__restrict__ chan_add, uint4 *__restrict__ y, int B, int T,
-                   long long *__restrict__ prof) {
+    lstm_tc_kernel(const __grid_constant__ CUtensorMap xmap, const uint4 *__restrict__ wpk,
+                   const float *__restrict__ bias_p, const float *__restrict__ chan_add, uint4 *__restrict__ y, int B,
+                   int T, int opts, long long *__restrict__ prof) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 2 * 96);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 2 * 64);
+  const bool o_turns = opts & 1;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t RP = (size_t)T + 2 * PAD;
@@ -84,18 +106,16 @@ __global__ void __launch_bounds__(THREADS, 1)
 
   if (tid == 0) {
     for (int g = 0; g < NGRP; ++g) {
-      const uint32_t bars = s_base + OFF_BAR + 96 * g;
-      mbar_init(bars, N_EPI / 32);                       // h_ready
+      const uint32_t bars = s_base + OFF_BAR + 64 * g;
       for (int i = 0; i < 2; ++i) {
-        mbar_init(bars + 8 + 8 * i, 1);                  // acc_full
-        mbar_init(bars + 24 + 8 * i, N_EPI / 32);        // acc_empty
-        mbar_init(bars + 40 + 8 * i, N_LOAD / 32);       // x_full
-        mbar_init(bars + 56 + 8 * i, 1);                 // x_empty
+        mbar_init(bars + 8 * i, 1);                      // acc_full
+        mbar_init(bars + 16 + 8 * i, 1);                 // x_full
+        mbar_init(bars + 32 + 8 * i, 1);                 // x_empty
       }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // h_0 = 0 and clean x stages (columns of absent clips must at least be finite)
+  // h_0 = 0
   for (int i = tid; i < OFF_BAR / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (warp == W_MMA0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
@@ -129,18 +149,17 @@ __global__ void __launch_bounds__(THREADS, 1)
   tc_fence_after();
 
   // ---- role and group of this warp ----
-  int role, g;                                  // role 0 epilogue, 1 loader, 2 MMA issuer
-  if (warp < W_LOAD0) { role = 0; g = warp / (N_EPI / 32); }
-  else if (warp < W_MMA0) { role = 1; g = (warp - W_LOAD0) / (N_LOAD / 32); }
-  else { role = 2; g = warp - W_MMA0; }
+  const int role = warp < W_MMA0 ? 0 : 1;          // 0 epilogue, 1 MMA issuer (+ TMA producer)
+  const int g = role == 0 ? warp / (N_EPI / 32) : warp - W_MMA0;
   const int b0 = blockIdx.x * (NGRP * NCL) + g * NCL;      // first clip of the group
   const int nb = max(0, min(NCL, B - b0));
   const uint32_t gs = s_base + g * G_BYTES;
   uint8_t *gsm = smem + g * G_BYTES;
-  const uint32_t bars = s_base + OFF_BAR + 96 * g;
-  const uint32_t h_ready = bars, acc_full0 = bars + 8, acc_empty0 = bars + 24, x_full0 = bars + 40,
-                 x_empty0 = bars + 56;
+  const uint32_t bars = s_base + OFF_BAR + 64 * g;
+  const uint32_t acc_full0 = bars, x_full0 = bars + 16, x_empty0 = bars + 32;
   const uint32_t tm_acc = tmem + TM_ACC + g * 128;
+  // the two groups of a CTA take turns on the MUFU-heavy part of a step (only when both hold clips)
+  const bool turns = o_turns && (blockIdx.x * (NGRP * NCL) + NCL < B);
 
   if (nb > 0 && role == 0) {
     // ===================== epilogue / cell update =====================
@@ -173,14 +192,19 @@ __global__ void __launch_bounds__(THREADS, 1)
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       long long c0 = pf ? clock64() : 0;
-      mbar_wait_warp(acc_full0 + 8 * buf, (t >> 1) & 1);
+      bar_sync(BAR_ACC + g, N_EPI + 32);                    // the MMA thread saw this step's accumulator complete
       tc_fence_after();
       long long c1 = pf ? clock64() : 0;
       uint32_t r[32];
       tmem_ld32(tm_acc + buf * 64 + m * 32 + ((uint32_t)(q * 32) << 16), r);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive_warp(acc_empty0 + 8 * buf);
+      if (turns) {
+        if (g == 1) bar_sync(BAR_TURN + 1, 2 * N_EPI);
+        else if (t > 0) bar_sync(BAR_TURN, 2 * N_EPI);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) asm volatile("" : "+r"(r[j]));   // keep the exponentials behind the barrier
+      }
       long long c2 = pf ? clock64() : 0;
       // phase 1: e = 2^min(acc_hi + acc_lo + bias, cap) for this gate row and the 16 clips
 #pragma unroll
@@ -199,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         *reinterpret_cast<float4 *>(e_row + j4 * 4) = make_float4(e[0], e[1], e[2], e[3]);
       }
       long long c3 = pf ? clock64() : 0;
-      named_bar_sync(1 + g, N_EPI);
+      bar_sync(BAR_PHASE + g, N_EPI);
       long long c4 = pf ? clock64() : 0;
       // phase 2: cell update of units u0..u0+3 of clip n, two units per packed instruction
       float hv[4];
@@ -222,6 +246,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         upk2(mul2(add2(eo, one2), add2(ec, one2)), ha, hb);
         upk2(mul2(fma2(ec, mone2, one2), pk2(rcp_approx(ha), rcp_approx(hb))), hv[2 * p2], hv[2 * p2 + 1]);
       }
+      if (turns) bar_arrive(BAR_TURN + (g ^ 1), 2 * N_EPI);     // the other group may start its exponentials
       uint2 hi, lo;
       split4(hv, hi, lo);
       {  // half-lane 0 collects the 8 hi values of the chunk, half-lane 1 the 8 lo values
@@ -230,10 +255,9 @@ __global__ void __launch_bounds__(THREADS, 1)
         *h_row = hh ? make_uint4(rx, ry, lo.x, lo.y) : make_uint4(hi.x, hi.y, rx, ry);
       }
       long long c5 = pf ? clock64() : 0;
-      fence_async_smem();
-      // hand h_t to the MMA warp through a hardware named barrier (arrive here, sync there): cheaper than an
-      // mbarrier round trip on the step's critical path
-      asm volatile("bar.arrive %0, %1;" ::"r"(3 + g), "r"(N_EPI + 32) : "memory");
+      // hand h_t to the MMA warp through a hardware named barrier (arrive here, sync there): the barrier orders
+      // these stores before the MMA thread's proxy fence
+      bar_arrive(BAR_HREADY + g, N_EPI + 32);
       long long c6 = pf ? clock64() : 0;
       uint4 out;
       if (chan_add != nullptr) {   // warp-uniform
@@ -257,35 +281,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       for (int i = 0; i < 7; ++i) prof[i] = pa[i];
     }
   } else if (nb > 0 && role == 1) {
-    // ===================== x loader =====================
-    const int lt = tid - (W_LOAD0 * 32 + g * N_LOAD);   // 0..63: two (plane, step-in-stage) pairs each
-#pragma unroll 1
-    for (int ch = 0; ch < nchunk; ++ch) {
-      const int st = ch & 1;
-      if (ch >= 2) mbar_wait_warp(x_empty0 + 8 * st, ((ch >> 1) - 1) & 1);
-#pragma unroll
-      for (int rep = 0; rep < 2; ++rep) {
-        const int pr = lt + rep * N_LOAD;
-        const int pl = pr >> 3, tt = pr & 7;
-        const int t = ch * TC_STEPS + tt;
-        if (t < T) {
-          const uint4 *src = x + ((size_t)b0 * 16 + pl) * RP + PAD + t;
-          const uint32_t dst = gs + G_X + st * XSTAGE + tt * XSTEP + (pl & 7) * (2 * NCL * 16) + (pl >> 3) * (NCL * 16);
-          for (int nn = 0; nn < nb; ++nn) cp_async16(dst + nn * 16, src + (size_t)nn * 16 * RP);
-        }
-      }
-      cp_async_commit();
-      if (ch >= 1) {  // the previous stage has landed: publish it
-        cp_async_wait<1>();
-        fence_async_smem();
-        mbar_arrive_warp(x_full0 + 8 * ((ch - 1) & 1));
-      }
-    }
-    cp_async_wait<0>();
-    fence_async_smem();
-    mbar_arrive_warp(x_full0 + 8 * ((nchunk - 1) & 1));
-  } else if (nb > 0 && role == 2) {
-    // ===================== MMA issuer (whole warp walks the pipeline; one elected lane issues) =====
+    // ===================== MMA issuer + TMA producer (one elected lane works; the warp only relays barriers) =====
     const bool issuer = elect_one();
     const uint64_t h_desc = smem_desc(gs + G_H, 2 * NCL * 16, 128);
     // 2 M-tiles x 4 K steps x {W_hi (N = 32), W_lo (N = 16)}; B tile: 32 rows (16 hi + 16 lo clips), chunk pitch 512 B
@@ -303,44 +299,71 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
       }
     };
+    auto load_x = [&](int ch) {   // steps 8 ch .. 8 ch + 7 of the group's 16 clips -> stage ch & 1
+      const int st = ch & 1;
+      mbar_arrive_expect_tx(x_full0 + 8 * st, XSTAGE);
+      tma_load_5d(gs + G_X + st * XSTAGE, &xmap, x_full0 + 8 * st, 0, b0, 0, 0, PAD + ch * TC_STEPS);
+    };
     const bool pf = PROF && prof != nullptr && blockIdx.x == 0 && g == 0 && issuer;
-    long long pm[3] = {0, 0, 0};
-    // x part of step 0
-    mbar_wait_warp(x_full0, 0);
+    long long pm[4] = {0, 0, 0, 0};
+    // (waits and MMA issue live in separate single-lane regions: a region that mixes a polling loop with the MMAs
+    // makes ptxas wrap every tcgen05.mma in its own operand-uniformising loop)
+    if (issuer) {
+      load_x(0);
+      if (nchunk > 1) load_x(1);
+      mbar_wait(x_full0, 0);
+    }
+    __syncwarp();
     tc_fence_after();
-    if (issuer) issue(smem_desc(gs + G_X, 2 * NCL * 16, 128), 2, 0, 0);
+    if (issuer) issue(smem_desc(gs + G_X, 2 * NCL * 16, 128), 2, 0, 0);     // x part of step 0
     __syncwarp();
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       long long m0 = pf ? clock64() : 0;
       if (t > 0) {
-        asm volatile("bar.sync %0, %1;" ::"r"(3 + g), "r"(N_EPI + 32) : "memory");
+        bar_sync(BAR_HREADY + g, N_EPI + 32);               // h_{t-1} is in shared memory
+        if (issuer) fence_async_smem();                     // the epilogue warps' stores -> the MMA's operand fetch
         tc_fence_after();
       }
       long long m1 = pf ? clock64() : 0;
       if (issuer) {
-        issue(h_desc, 0, buf, 1);                 // + W_hh . h_{t-1}
+        issue(h_desc, 0, buf, 1);                           // + W_hh . h_{t-1}
         tc_commit(acc_full0 + 8 * buf);
       }
       __syncwarp();
       long long m2 = pf ? clock64() : 0;
+      if (issuer) mbar_wait(acc_full0 + 8 * buf, (uint32_t)((t >> 1) & 1));
+      __syncwarp();
+      tc_fence_before();
+      bar_arrive(BAR_ACC + g, N_EPI + 32);                  // release the epilogue warps
+      long long m3 = pf ? clock64() : 0;
       const int t1 = t + 1;
       if (t1 < T) {
+        // W_ih . x_{t+1} into the other accumulator (drained by the epilogue before it handed over h_{t-1})
         const int ch = t1 / TC_STEPS, tt = t1 % TC_STEPS, st = ch & 1;
-        if (tt == 0) mbar_wait_warp(x_full0 + 8 * st, (ch >> 1) & 1);
-        if (t1 >= 2) mbar_wait_warp(acc_empty0 + 8 * (buf ^ 1), ((t1 >> 1) - 1) & 1);
+        if (tt == 0) {
+          if (issuer) mbar_wait(x_full0 + 8 * st, (uint32_t)((ch >> 1) & 1));
+          __syncwarp();
+        }
         tc_fence_after();
         if (issuer) {
-          issue(smem_desc(gs + G_X + st * XSTAGE + tt * XSTEP, 2 * NCL * 16, 128), 2, buf ^ 1, 0);  // W_ih . x_{t+1}
+          issue(smem_desc(gs + G_X + st * XSTAGE + tt * XTILE, 2 * NCL * 16, 128), 2, buf ^ 1, 0);
           if (tt == TC_STEPS - 1) tc_commit(x_empty0 + 8 * st);
         }
         __syncwarp();
+        if (tt == 1 && ch >= 1 && ch + 1 < nchunk) {        // chunk ch - 1's stage has been read: refill it with chunk ch + 1
+          if (issuer) {
+            mbar_wait(x_empty0 + 8 * (st ^ 1), (uint32_t)(((ch - 1) >> 1) & 1));
+            load_x(ch + 1);
+          }
+          __syncwarp();
+        }
       }
-      if (pf) { long long m3 = clock64(); pm[0] += m1 - m0; pm[1] += m2 - m1; pm[2] += m3 - m2; }
+      if (pf) { long long m4 = clock64(); pm[0] += m1 - m0; pm[1] += m2 - m1; pm[2] += m3 - m2; pm[3] += m4 - m3; }
     }
     if (pf) {
-      for (int i = 0; i < 3; ++i) prof[8 + i] = pm[i];
+      for (int i = 0; i < 4; ++i) prof[8 + i] = pm[i];
     }
   }
   __syncwarp();
@@ -354,8 +377,40 @@ __global__ void __launch_bounds__(THREADS, 1)
 
 // optional device buffer of 32 int64 receiving per-phase cycle sums of block 0 (tools/*_profile.py)
 static long long *g_lstm_prof = nullptr;
+constexpr int kLstmDefaultOpts = 0;
+static int g_lstm_opts = kLstmDefaultOpts;
+void set_lstm_opts(int o) { g_lstm_opts = o < 0 ? kLstmDefaultOpts : o; }
 void set_lstm_profile_buffer(long long *p) { g_lstm_prof = p; }
 long long *get_profile_buffer() { return g_lstm_prof; }
+
+// The planar input [clip][plane = hi/lo x chunk][row T + 2 PAD][16 B] as a 5-d tensor of 32-bit words with the
+// dimensions ordered the way a step's B tile wants them in shared memory: {4 words, clip, hi/lo, chunk, row}.
+static int make_x_map(CUtensorMap *map, const void *x, int B, int T) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  if (encode == nullptr) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    WM_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available in this driver");
+      return -3;
+    }
+    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  const cuuint64_t RP = (cuuint64_t)T + 2 * PAD;
+  const cuuint64_t dims[5] = {4, (cuuint64_t)B, 2, 8, RP};
+  const cuuint64_t strides[4] = {16 * RP * 16, 8 * RP * 16, RP * 16, 16};   // bytes, dimensions 1..4
+  const cuuint32_t box[5] = {4, NCL, 2, 8, TC_STEPS};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, const_cast<void *>(x), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for the LSTM input (B=%d, T=%d)", (int)r, B, T);
+    return -3;
+  }
+  return 0;
+}
 
 int launch_lstm_tc(const void *x, const void *wpk, const float *bias_p, const float *chan_add, void *y, int B, int T,
                    cudaStream_t st) {
@@ -366,15 +421,15 @@ int launch_lstm_tc(const void *x, const void *wpk, const float *bias_p, const fl
     WM_CHECK_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LSTM_SMEM));
     attr_set = true;
   }
+  CUtensorMap xmap;
+  WM_TRY(make_x_map(&xmap, x, B, T));
   const int grid = (B + NGRP * NCL - 1) / (NGRP * NCL);
   if (g_lstm_prof != nullptr)   // developer build of the same kernel with per-phase cycle counters (tools/lstm_profile.py)
-    lstm_tc_kernel<true><<<grid, THREADS, LSTM_SMEM, st>>>(
-        reinterpret_cast<const uint4 *>(x), reinterpret_cast<const uint4 *>(wpk), bias_p, chan_add,
-        reinterpret_cast<uint4 *>(y), B, T, g_lstm_prof);
+    lstm_tc_kernel<true><<<grid, THREADS, LSTM_SMEM, st>>>(xmap, reinterpret_cast<const uint4 *>(wpk), bias_p, chan_add,
+                                                           reinterpret_cast<uint4 *>(y), B, T, g_lstm_opts, g_lstm_prof);
   else
-    lstm_tc_kernel<false><<<grid, THREADS, LSTM_SMEM, st>>>(
-        reinterpret_cast<const uint4 *>(x), reinterpret_cast<const uint4 *>(wpk), bias_p, chan_add,
-        reinterpret_cast<uint4 *>(y), B, T, nullptr);
+    lstm_tc_kernel<false><<<grid, THREADS, LSTM_SMEM, st>>>(xmap, reinterpret_cast<const uint4 *>(wpk), bias_p, chan_add,
+                                                            reinterpret_cast<uint4 *>(y), B, T, g_lstm_opts, nullptr);
   WM_CHECK_LAUNCH("lstm_tc");
   return 0;
 }

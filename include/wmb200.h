@@ -217,6 +217,11 @@ int wm_pack_lstm_tc(const float *w_ih, const float *w_hh, const float *bias, voi
 /* developer hook: when buf16 (device, 16 x int64) is non-null the LSTM kernel's block 0 stores
  * per-phase cycle sums there (tools/lstm_profile.py); pass NULL to switch it off. */
 int wm_debug_lstm_profile(long long *buf16);
+/* developer hook: scheduling variants of the LSTM kernel for A/B measurements (tools/lstm_profile.py);
+ * bit 0: the two clip groups of a CTA take turns on the MUFU-heavy part of a step, bit 1: generic->async proxy
+ * fence issued by the MMA thread instead of by every epilogue thread, bit 2: accumulator released after the
+ * exponentials.  -1 restores the library default.  Results are identical in every mode. */
+int wm_debug_lstm_opts(int opts);
 int wm_lstm_tc_fwd(const void *x, const void *wpk, const float *bias_p, const float *chan_add, void *y,
                    int B, int T, void *stream);
 
