@@ -12,7 +12,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwmb200.so")
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 # blob offsets (floats) — mirror of the enums in include/wmb200.h
 RB_W1 = 0
@@ -120,6 +120,7 @@ SIGNATURES = {
     "wm_pack_conv64_tc": (_i, [_p, _p, _i, _p]),
     "wm_conv64_tc_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "wm_resblock_tc_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p]),
+    "wm_resblock_tc_hostbias_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "wm_pack_lstm_tc": (_i, [_p, _p, _p, _p, _p, _p]),
     "wm_debug_lstm_profile": (_i, [_p]),
     "wm_debug_lstm_opts": (_i, [_i]),

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "wm_common.h"
 
@@ -52,29 +53,39 @@ int require_device() {
   return 0;
 }
 
-// Host copies of the 1x1 heads of every finalized blob, keyed by the blob's device address.  The fused
-// epilogues take the head weights as a kernel parameter (constant bank), which needs them on the host;
-// wm_finalize_*_blob reads them back once.  A blob must not be modified after it has been finalized.
-struct HeadCopy {
-  float v[64 + 1];   // output 0 of the 1x1 head: w[64] then b
+// Host copy of the fp32 parameter block of every finalized blob, keyed by the blob's device address.  The fused
+// kernels take biases and 1x1-head weights as a kernel parameter (constant bank), which needs them on the host;
+// wm_finalize_*_blob reads the block back once (that one-time set-up call synchronises its stream; nothing on the
+// per-batch path does).  A blob must not be modified after it has been finalized.
+struct HostBlob {
+  std::vector<float> v;                       // the fp32 block (WM_G_SIZE or WM_D_SIZE floats)
+  float head0[65];                            // output 0 of the 1x1 head: w[64] then b
+  float head_all[WM_MAX_HEAD * 65];           // detector: w[nout_max][64] then b[nout_max] is rebuilt per nout on use
+  const float *at(int off) const { return v.data() + off; }
 };
 static std::mutex g_head_mu;
-static std::unordered_map<const float *, HeadCopy> g_heads;
-static int remember_head(const float *blob, int w_off, int b_off, cudaStream_t st) {
-  HeadCopy h;
-  WM_CHECK_CUDA(cudaMemcpyAsync(h.v, blob + w_off, sizeof(float) * 64, cudaMemcpyDeviceToHost, st));
-  WM_CHECK_CUDA(cudaMemcpyAsync(h.v + 64, blob + b_off, sizeof(float), cudaMemcpyDeviceToHost, st));
+static std::unordered_map<const float *, HostBlob> g_heads;
+static int remember_blob(const float *blob, int nfloats, int w_off, int b_off, cudaStream_t st) {
+  HostBlob h;
+  h.v.resize(nfloats);
+  WM_CHECK_CUDA(cudaMemcpyAsync(h.v.data(), blob, sizeof(float) * nfloats, cudaMemcpyDeviceToHost, st));
   WM_CHECK_CUDA(cudaStreamSynchronize(st));
+  memcpy(h.head0, h.at(w_off), sizeof(float) * 64);
+  h.head0[64] = *h.at(b_off);
   std::lock_guard<std::mutex> lk(g_head_mu);
-  g_heads[blob] = h;
+  g_heads[blob] = std::move(h);
   return 0;
 }
-static bool lookup_head(const float *blob, HeadCopy *out) {
+// the map never erases: the returned pointer stays valid for the life of the process
+static const HostBlob *lookup_blob(const float *blob) {
   std::lock_guard<std::mutex> lk(g_head_mu);
   auto it = g_heads.find(blob);
-  if (it == g_heads.end()) return false;
-  *out = it->second;
-  return true;
+  return it == g_heads.end() ? nullptr : &it->second;
+}
+// b1[64] then b2[64] of the ResBlock at float offset `rb` (host), for the by-value kernel parameter
+static void host_bias_pair(const HostBlob *h, int rb, float *out128) {
+  memcpy(out128, h->at(rb + WM_RB_B1), sizeof(float) * 64);
+  memcpy(out128 + 64, h->at(rb + WM_RB_B2), sizeof(float) * 64);
 }
 
 static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
@@ -105,10 +116,14 @@ static int resblock_fp32(const float *rb, const float *x, float *tmp, float *y, 
   return 0;
 }
 // the same on planar tensors with the tcgen05 kernel; the second conv writes planar `y` and/or fp32 `y32`
-static int resblock_tc(const float *rb, const float *img /* two 3-tap images */, const void *x, void *tmp, void *y,
-                       float *y32, int B, int T, cudaStream_t st) {
+static int resblock_tc(const float *blob, int rb_off, const float *img /* two 3-tap images */, const void *x, void *tmp,
+                       void *y, float *y32, int B, int T, cudaStream_t st) {
   (void)tmp;
-  return launch_resblock_tc(x, img, rb + WM_RB_B1, rb + WM_RB_B2, y, y32, B, T, st);
+  const float *rb = blob + rb_off;
+  float hb[128];
+  const HostBlob *h = lookup_blob(blob);
+  if (h) host_bias_pair(h, rb_off, hb);
+  return launch_resblock_tc(x, img, rb + WM_RB_B1, rb + WM_RB_B2, y, y32, B, T, st, h ? hb : nullptr);
 }
 
 // The tcgen05 generator in three phases, so that a host-fed pipeline can run the two convolutional phases
@@ -120,7 +135,7 @@ static int generator_encoder_tc(const float *blob, const float *s, void *r0, voi
   (void)r0;   // input convolution folded into the first ResBlock: s -> r2 planar
   WM_TRY(launch_resblock_in_tc(s, blob + WM_G_FIN + WM_FIN_W9, blob + WM_G_IN_W, blob + WM_G_FIN, tc + WM_TC_IMG3,
                                blob + WM_G_RB0 + WM_RB_B2, r2, B, T, st));
-  return resblock_tc(blob + WM_G_RB1, tc + 2 * WM_TC_IMG3, r2, r0, r1, nullptr, B, T, st);      // -> r1 planar
+  return resblock_tc(blob, WM_G_RB1, tc + 2 * WM_TC_IMG3, r2, r0, r1, nullptr, B, T, st);      // -> r1 planar
 }
 // LSTM (+ message embedding added to its output)            (py/main16.py:152-159); x planar -> y planar
 static int generator_lstm_tc(const float *blob, const float *chan_add, const void *x, void *y, int B, int T,
@@ -131,10 +146,12 @@ static int generator_lstm_tc(const float *blob, const float *chan_add, const voi
 static int generator_decoder_tc(const float *blob, const void *x, void *tmp, float *delta_raw, int B, int T,
                                 cudaStream_t st) {
   WM_TRY(launch_conv64_tc(x, blob + WM_G_TC_CT, blob + WM_G_CT_B, nullptr, tmp, nullptr, B, T, 7, 0, st));
-  HeadCopy h;
-  if (lookup_head(blob, &h))
-    return launch_resblock_head1_tc(tmp, blob + WM_G_TC_RB2, blob + WM_G_RB2 + WM_RB_B1, blob + WM_G_RB2 + WM_RB_B2, h.v,
-                                    delta_raw, B, T, st);
+  if (const HostBlob *h = lookup_blob(blob)) {
+    float hb[128];
+    host_bias_pair(h, WM_G_RB2, hb);
+    return launch_resblock_head1_tc(tmp, blob + WM_G_TC_RB2, blob + WM_G_RB2 + WM_RB_B1, blob + WM_G_RB2 + WM_RB_B2,
+                                    h->head0, delta_raw, B, T, st, hb);
+  }
   // blob never went through wm_finalize_generator_blob on this process: un-fused head (x is dead by now)
   float *f = (float *)const_cast<void *>(x);
   WM_TRY(launch_resblock_tc(tmp, blob + WM_G_TC_RB2, blob + WM_G_RB2 + WM_RB_B1, blob + WM_G_RB2 + WM_RB_B2, nullptr, f, B,
@@ -183,7 +200,7 @@ static int detector_trunk(const float *blob, const float *x, void *r0, void *r1,
   (void)r0;   // input convolution folded into the first ResBlock: x -> r2 planar
   WM_TRY(launch_resblock_in_tc(x, blob + WM_D_FIN + WM_FIN_W9, blob + WM_D_IN_W, blob + WM_D_FIN, tc + WM_TC_IMG3,
                                blob + WM_D_RB0 + WM_RB_B2, r2, B, T, st));
-  return resblock_tc(blob + WM_D_RB1, tc + 2 * WM_TC_IMG3, r2, r0, nullptr, f1, B, T, st);
+  return resblock_tc(blob, WM_D_RB1, tc + 2 * WM_TC_IMG3, r2, r0, nullptr, f1, B, T, st);
 }
 
 // Detector + heads (py/main16.py:176-180,1142-1146): per-sample probability, clip mean, mean message logits.
@@ -193,19 +210,27 @@ static int detector_trunk(const float *blob, const float *x, void *r0, void *r1,
 static int detect_run(const float *blob, const float *x, const int *valid_len, float *probs, float *clip_prob,
                       float *msg_logits, float *vote_frac, void *r0, void *r1, void *r2, int B, int T, int nout,
                       cudaStream_t st) {
-  HeadCopy h;
-  if (g_math_mode.load() == WM_MATH_BF16X2 && vote_frac == nullptr &&
-      (size_t)B * resblock_tiles_per_clip(T) * 4 * WM_DET_PART * sizeof(float) <= act_bytes(B, T) &&
-      lookup_head(blob, &h)) {
+  const HostBlob *h = lookup_blob(blob);
+  if (g_math_mode.load() == WM_MATH_BF16X2 && (vote_frac == nullptr || nout <= WM_FUSED_VOTE_MAX) &&
+      (size_t)B * resblock_tiles_per_clip(T) * 4 * WM_DET_PART * sizeof(float) <= act_bytes(B, T) && h != nullptr) {
     const float *tc = blob + WM_D_TC;
     float *partials = (float *)r1;
     (void)r0;   // input convolution folded into the first ResBlock: x -> r2 planar
     WM_TRY(launch_resblock_in_tc(x, blob + WM_D_FIN + WM_FIN_W9, blob + WM_D_IN_W, blob + WM_D_FIN, tc + WM_TC_IMG3,
                                  blob + WM_D_RB0 + WM_RB_B2, r2, B, T, st));
-    WM_TRY(launch_resblock_detect_tc(r2, tc + 2 * WM_TC_IMG3, blob + WM_D_RB1 + WM_RB_B1, blob + WM_D_RB1 + WM_RB_B2, h.v,
-                                     valid_len, probs, partials, B, T, st));
-    return launch_detect_finalize(partials, valid_len, blob + WM_D_HEAD_W, blob + WM_D_HEAD_B, clip_prob, msg_logits, B,
-                                  T, nout, st);
+    float hb[128];
+    host_bias_pair(h, WM_D_RB1, hb);
+    const bool votes = vote_frac != nullptr && nout > 1;
+    float head_all[WM_MAX_HEAD * 65];
+    if (votes) {   // rows 0..nout-1 of the head, then their biases (majority vote in the epilogue)
+      memcpy(head_all, h->at(WM_D_HEAD_W), sizeof(float) * 64 * nout);
+      memcpy(head_all + 64 * nout, h->at(WM_D_HEAD_B), sizeof(float) * nout);
+    }
+    WM_TRY(launch_resblock_detect_tc(r2, tc + 2 * WM_TC_IMG3, blob + WM_D_RB1 + WM_RB_B1, blob + WM_D_RB1 + WM_RB_B2,
+                                     h->head0, valid_len, probs, partials, B, T, st, hb, votes ? head_all : nullptr,
+                                     votes ? nout : 0));
+    return launch_detect_finalize(partials, valid_len, blob + WM_D_HEAD_W, blob + WM_D_HEAD_B, clip_prob, msg_logits,
+                                  votes ? vote_frac : nullptr, B, T, nout, st);
   }
   float *out = nullptr;
   WM_TRY(detector_trunk(blob, x, r0, r1, r2, &out, B, T, st));
@@ -249,7 +274,7 @@ int wm_finalize_generator_blob(float *blob, void *stream) {
   WM_TRY(launch_pack_conv64_tc(blob + WM_G_CT_W, blob + WM_G_TC_CT, 7, st));
   WM_TRY(launch_pack_lstm_tc(blob + WM_G_LSTM_WIH, blob + WM_G_LSTM_WHH, blob + WM_G_LSTM_B, blob + WM_G_TC_LSTM_W,
                              blob + WM_G_TC_LSTM_B, st));
-  return remember_head(blob, WM_G_HEAD_W, WM_G_HEAD_B, st);   // synchronises `stream` (one-time set-up call)
+  return remember_blob(blob, WM_G_SIZE, WM_G_HEAD_W, WM_G_HEAD_B, st);   // synchronises `stream` (one-time set-up call)
 }
 
 int wm_finalize_detector_blob(float *blob, void *stream) {
@@ -261,7 +286,7 @@ int wm_finalize_detector_blob(float *blob, void *stream) {
     WM_TRY(launch_pack_conv64_tc(blob + rb[i] + WM_RB_W1, blob + WM_D_TC + (2 * i) * WM_TC_IMG3, 3, st));
     WM_TRY(launch_pack_conv64_tc(blob + rb[i] + WM_RB_W2, blob + WM_D_TC + (2 * i + 1) * WM_TC_IMG3, 3, st));
   }
-  return remember_head(blob, WM_D_HEAD_W, WM_D_HEAD_B, st);  // synchronises `stream` (one-time set-up call)
+  return remember_blob(blob, WM_D_SIZE, WM_D_HEAD_W, WM_D_HEAD_B, st);   // synchronises `stream` (one-time set-up call)
 }
 
 size_t wm_planar_bytes(int B, int T) { return (B <= 0 || T <= 0) ? 0 : planar_bytes(B, T); }
@@ -314,6 +339,18 @@ int wm_resblock_tc_fwd(const void *x, const void *w_img, const float *b1, const 
   WM_CHECK_ARG(B == 0 || T == 0 || (x && w_img && b1 && b2 && (y || y32)), "resblock_tc: null pointer");
   WM_CHECK_ARG(x != y, "resblock_tc: in-place operation is not supported");
   return launch_resblock_tc(x, w_img, b1, b2, y, y32, B, T, as_stream(stream));
+}
+
+int wm_resblock_tc_hostbias_fwd(const void *x, const void *w_img, const float *host_b1, const float *host_b2, void *y,
+                                float *y32, int B, int T, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "resblock_tc_hostbias: negative size");
+  WM_CHECK_ARG(B == 0 || T == 0 || (x && w_img && host_b1 && host_b2 && (y || y32)), "resblock_tc_hostbias: null pointer");
+  WM_CHECK_ARG(x != y, "resblock_tc_hostbias: in-place operation is not supported");
+  float hb[128];
+  memcpy(hb, host_b1, sizeof(float) * 64);
+  memcpy(hb + 64, host_b2, sizeof(float) * 64);
+  return launch_resblock_tc(x, w_img, nullptr, nullptr, y, y32, B, T, as_stream(stream), hb);
 }
 
 int wm_pack_lstm_tc(const float *w_ih, const float *w_hh, const float *bias, void *wpk, float *bias_p,

@@ -88,8 +88,9 @@ int launch_from_planar(const void *x, float *y, int B, int T, cudaStream_t st);
 int launch_conv_in_k7_planar(const float *s, const float *w, const float *b, void *y, int B, int T, cudaStream_t st);
 int launch_lstm_tc(const void *x, const void *wpk, const float *bias_p, const float *chan_add, void *y, int B, int T,
                    cudaStream_t st);
+// host_b12: HOST copy of b1[64] then b2[64] (biases become constant-bank operands), or null (read from b1 / b2)
 int launch_resblock_tc(const void *x, const void *w_img, const float *b1, const float *b2, void *y, float *y32, int B,
-                       int T, cudaStream_t st);
+                       int T, cudaStream_t st, const float *host_b12 = nullptr);
 int resblock_tiles_per_clip(int T);
 // first ResBlock fused with the input convolution (wm_resblock_in_tc.cu); w9b: device w9[9][64], b9[64];
 // winb: device w_in[7][64], b_in[64]; fin: device WM_FIN_* block; s[B][T] -> y planar
@@ -97,13 +98,17 @@ int launch_resblock_in_tc(const float *s, const float *w9b, const float *winb, c
                           const float *b2, void *y, int B, int T, cudaStream_t st);
 // host_head: HOST copy of output 0 of the 1x1 head (w[64] then b); it is passed to the kernel by value
 int launch_resblock_head1_tc(const void *x, const void *w_img, const float *b1, const float *b2,
-                             const float *host_head, float *delta_raw, int B, int T, cudaStream_t st);
-#define WM_DET_PART 68   // floats per (tile, warp) partial of the detector epilogue: 64 activation sums, prob sum, pad
+                             const float *host_head, float *delta_raw, int B, int T, cudaStream_t st,
+                             const float *host_b12 = nullptr);
+#define WM_DET_PART 84   // floats per (tile, warp) partial of the detector epilogue: 64 activation sums, prob sum, pad, 16 vote counts
+#define WM_DET_VOTE0 68  // first vote count inside a partial
+#define WM_FUSED_VOTE_MAX 17   // the fused majority-vote epilogue handles heads of up to 1 + 16 outputs (py/main16.py:34)
 int launch_resblock_detect_tc(const void *x, const void *w_img, const float *b1, const float *b2,
                               const float *host_head, const int *valid_len, float *probs, float *partials, int B, int T,
-                              cudaStream_t st);
+                              cudaStream_t st, const float *host_b12 = nullptr, const float *host_head_all = nullptr,
+                              int nout = 0);
 int launch_detect_finalize(const float *partials, const int *valid_len, const float *head_w, const float *head_b,
-                           float *clip_prob, float *msg_logits, int B, int T, int nout, cudaStream_t st);
+                           float *clip_prob, float *msg_logits, float *vote_frac, int B, int T, int nout, cudaStream_t st);
 // training-loss forward kernels (wm_loss.cu); `partials` is caller workspace (wm_loss_workspace_bytes)
 int launch_stft_mag(const float *x, float *mag, int B, int T, int n_fft, int hop, cudaStream_t st);
 int launch_hf_penalty(const float *delta, float *out, float *partials, int B, int T, int n_fft, int first_bin,

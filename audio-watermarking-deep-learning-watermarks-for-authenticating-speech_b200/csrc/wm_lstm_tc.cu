@@ -74,7 +74,7 @@ constexpr uint32_t TM_W = 0, TM_ACC = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kArgMax = 28.85f;             // ex2 argument cap: e <= 4.8e8, (1+e)^3 stays finite
 // hardware named barriers (0 = __syncthreads): per group g
-constexpr int BAR_PHASE = 1, BAR_HREADY = 3, BAR_ACC = 5, BAR_TURN = 7;
+constexpr int BAR_PHASE = 1, BAR_HREADY = 3, BAR_ACC = 5;
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 2 * 64);
-  const bool o_turns = opts & 1;
+  (void)opts;   // reserved for A/B switches (wm_debug_lstm_opts); none at present
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t RP = (size_t)T + 2 * PAD;
@@ -158,8 +158,6 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t bars = s_base + OFF_BAR + 64 * g;
   const uint32_t acc_full0 = bars, x_full0 = bars + 16, x_empty0 = bars + 32;
   const uint32_t tm_acc = tmem + TM_ACC + g * 128;
-  // the two groups of a CTA take turns on the MUFU-heavy part of a step (only when both hold clips)
-  const bool turns = o_turns && (blockIdx.x * (NGRP * NCL) + NCL < B);
 
   if (nb > 0 && role == 0) {
     // ===================== epilogue / cell update =====================
@@ -199,12 +197,6 @@ __global__ void __launch_bounds__(THREADS, 1)
       tmem_ld32(tm_acc + buf * 64 + m * 32 + ((uint32_t)(q * 32) << 16), r);
       tmem_ld_wait();
       tc_fence_before();
-      if (turns) {
-        if (g == 1) bar_sync(BAR_TURN + 1, 2 * N_EPI);
-        else if (t > 0) bar_sync(BAR_TURN, 2 * N_EPI);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) asm volatile("" : "+r"(r[j]));   // keep the exponentials behind the barrier
-      }
       long long c2 = pf ? clock64() : 0;
       // phase 1: e = 2^min(acc_hi + acc_lo + bias, cap) for this gate row and the 16 clips
 #pragma unroll
@@ -246,7 +238,6 @@ __global__ void __launch_bounds__(THREADS, 1)
         upk2(mul2(add2(eo, one2), add2(ec, one2)), ha, hb);
         upk2(mul2(fma2(ec, mone2, one2), pk2(rcp_approx(ha), rcp_approx(hb))), hv[2 * p2], hv[2 * p2 + 1]);
       }
-      if (turns) bar_arrive(BAR_TURN + (g ^ 1), 2 * N_EPI);     // the other group may start its exponentials
       uint2 hi, lo;
       split4(hv, hi, lo);
       {  // half-lane 0 collects the 8 hi values of the chunk, half-lane 1 the 8 lo values

@@ -67,17 +67,25 @@ static_assert(RB_SMEM <= 232448, "shared memory budget");
 
 }  // namespace
 
-// 1x1 head weights travel BY VALUE as a kernel parameter: parameters live in the constant bank, so every head
-// FFMA takes its weight as a constant operand (no load instruction, no latency to hide, no state shared
-// between launches).  Measured: with the weights fetched through L1 the 17-output epilogue stalled on every
-// FFMA and the kernel ran 2.4x slower than the plain ResBlock.
-template <int N>
-struct HeadParams {
-  float w[N * 64];   // [out][64]
-  float b[N];
+// Biases and 1x1 head weights travel BY VALUE as a kernel parameter: parameters live in the constant bank, so every
+// bias add / head FFMA takes its operand as a constant (no load instruction, no latency to hide, no state shared
+// between launches).  Measured: with the head weights fetched through L1 the 17-output epilogue stalled on every
+// FFMA and the kernel ran 2.4x slower than the plain ResBlock; with the biases in shared memory their (scalar,
+// predicated) loads were 60 % of the kernel's LSU shared-memory wavefronts (profiles/r2_resblock_smem_wavefronts.md).
+template <int NW>
+struct RbParams {
+  float b1[64], b2[64];   // folded BatchNorm biases of conv1 / conv2 (used when BIASP)
+  float w[NW * 64];       // 1x1 head rows [out][64]
+  float b[NW];
 };
+template <int NHEAD>
+struct RbParamsFor { using type = RbParams<NHEAD == 3 ? WM_FUSED_VOTE_MAX : 1>; };
 
 // NHEAD = 0: plain ResBlock.  NHEAD = 1: + Conv1d(64,1,1) -> head_out[b][t] (py/main16.py:146).
+// NHEAD = 3: NHEAD = 2 plus the per-sample message logits (all rows of the head, constant-bank FFMAs) reduced to
+// per-(tile, warp) counts of positive logits: the majority vote of evaluate_model (py/main16.py:398) without a
+// (B,T,1+bits) logits tensor.
+// BIASP: biases come from the kernel parameter (callers that hold a host copy), else from shared memory.
 // NHEAD = 2 (detector): + channel 0 of Conv1d(64,1+bits,1) -> head_out[b][t] = sigmoid(logit 0), and per
 // (tile, warp) partial sums over the valid samples of that probability and of the 64 ACTIVATIONS: the message
 // logits are only ever used as means over time (py/main16.py:1142-1146), and a mean of a linear map is the
@@ -88,12 +96,12 @@ struct HeadParams {
 // weight operand split between the two shared memories: 21 % fewer operand bytes per CTA, which is what this
 // kernel is bound by.  The odd CTA's MMA warp relays its "tile landed" barriers to the even CTA; its epilogue
 // warps arrive on the even CTA's barriers directly; MMA completions are multicast to both.
-template <int NHEAD, bool CTA2>
+template <int NHEAD, bool CTA2, bool BIASP>
 // 18 warps = 5 on one SM sub-partition (16 K registers each): 96 registers per thread is the ceiling
 __global__ void __launch_bounds__(RB_THREADS, 1)
     resblock_tc_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ w_img, const float *__restrict__ b1,
                        const float *__restrict__ b2, uint4 *__restrict__ y, float *__restrict__ y32, int B, int T,
-                       const __grid_constant__ HeadParams<1> hp,
+                       const __grid_constant__ typename RbParamsFor<NHEAD>::type hp, int nvote,
                        float *__restrict__ head_out, float *__restrict__ partials, const int *__restrict__ valid_len,
                        long long *__restrict__ prof) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -132,7 +140,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
     mbar_init(bar(PWBAR), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < 128) bias_s[threadIdx.x] = threadIdx.x < 64 ? b1[threadIdx.x] : b2[threadIdx.x - 64];
+  if (!BIASP && threadIdx.x < 128) bias_s[threadIdx.x] = threadIdx.x < 64 ? b1[threadIdx.x] : b2[threadIdx.x - 64];
   if (warp == W_MMA) {
     if constexpr (CTA2) {   // the same warp of both CTAs, same destination offset
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
@@ -287,11 +295,16 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
     __syncwarp();
   } else if (warp < N_GRP / 32) {
     // ===== group 1: conv1 accumulator -> intermediate tile (conv2's A operand) =====
-    const int q = warp & 3, half = warp >> 2;          // TMEM lane quadrant, 32-channel half
+    const int q = warp & 3;                            // TMEM lane quadrant; 32-channel half = warp >> 2
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const bool pfe = prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long pe[3] = {0, 0, 0};
+    // ONE copy of this loop for both 32-channel halves (runtime `half`): duplicating it per half (to make the bias
+    // indices immediates) pushed the kernel's hot code out of the instruction cache -- 48 % of all warp stalls became
+    // "no instruction" and the kernel ran 37 % longer (profiles/r2_resblock_icache.md).  With BIASP the biases are
+    // indexed constant-bank loads (LDC), which do not touch the shared-memory pipeline the MMAs are bound by.
+    const int half = warp >> 2;
     for (long long i = 0; i < my_tiles; ++i) {
       const long long tile = tile_of(i);
       const int t0 = (int)(tile % ntile_t) * TO;
@@ -306,7 +319,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
       long long e2 = pfe ? clock64() : 0;
       tc_fence_after();
       const uint32_t taddr = tmem + a * 128 + lane_off;
-#pragma unroll
+#pragma unroll 1
       for (int pp = 0; pp < 2; ++pp) {
         const int p = half * 2 + pp;
         float v1[16], v2[16];
@@ -315,7 +328,11 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
         tmem_ld_wait();
         float o[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) o[c] = inside ? fmaxf(v1[c] + v2[c] + bias_s[p * 16 + c], 0.0f) : 0.0f;
+        for (int c = 0; c < 16; ++c) {
+          const float bv = BIASP ? hp.b1[p * 16 + c] : bias_s[p * 16 + c];
+          const float v = fmaxf(v1[c] + v2[c] + bv, 0.0f);
+          o[c] = inside ? v : 0.0f;
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int ch = p * 2 + h;
@@ -379,12 +396,19 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
       float hacc = 0.0f;
       [[maybe_unused]] bool counted = false;
       [[maybe_unused]] float *pdst = nullptr;
-      if constexpr (NHEAD == 2) {
+      [[maybe_unused]] float lacc[NHEAD == 3 ? WM_FUSED_VOTE_MAX - 1 : 1];
+      if constexpr (NHEAD == 3) {
+#pragma unroll
+        for (int j = 0; j < WM_FUSED_VOTE_MAX - 1; ++j) lacc[j] = hp.b[1 + j];
+      }
+      if constexpr (NHEAD >= 2) {
         const int vl = valid_len != nullptr ? min(max(valid_len[b], 0), T) : T;
         counted = live && t < vl;
         pdst = partials + (((size_t)b * ntile_t + tt) * 4 + q) * WM_DET_PART;
       }
-#pragma unroll
+      // NOT unrolled: four copies of this body (~5 KB each) pushed the kernel's hot code (MMA issue + both epilogue
+      // groups + producer) past the 32 KB instruction cache; bias / head operands become indexed constant loads
+#pragma unroll 1
       for (int p = 0; p < 4; ++p) {
         float v1[16], v2[16], o[16];
         tmem_ld16(taddr + p * 16, v1);
@@ -400,7 +424,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
           join8(rres[2 * h], rres[2 * h + 1], r);
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            o[h * 8 + c] = fmaxf(v1[h * 8 + c] + v2[h * 8 + c] + bias_s[64 + p * 16 + h * 8 + c] + r[c], 0.0f);
+            o[h * 8 + c] = fmaxf(v1[h * 8 + c] + v2[h * 8 + c] +
+                                     (BIASP ? hp.b2[p * 16 + h * 8 + c] : bias_s[64 + p * 16 + h * 8 + c]) + r[c], 0.0f);
         }
         if (p < 3) fetch(p + 1);
         if (live) {
@@ -425,7 +450,15 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
 #pragma unroll
           for (int c = 0; c < 16; ++c) hacc = fmaf(o[c], hp.w[p * 16 + c], hacc);
         }
-        if constexpr (NHEAD == 2) {
+        if constexpr (NHEAD == 3) {
+          // per-sample message logits: rows 1.. of the head, weights as constant-bank operands
+#pragma unroll
+          for (int j = 0; j < WM_FUSED_VOTE_MAX - 1; ++j) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) lacc[j] = fmaf(o[c], hp.w[(1 + j) * 64 + p * 16 + c], lacc[j]);
+          }
+        }
+        if constexpr (NHEAD >= 2) {
           // sum of these 16 channels over the warp's 32 rows by recursive halving: after the steps 16, 8, 4, 2
           // lane l holds channel l / 2 summed over 16 lanes, the last exchange folds the lane pair
           float a8[8], a4[4], a2[2];
@@ -446,7 +479,14 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
       }
       if constexpr (NHEAD == 1) {
         if (live) head_out[(size_t)b * T + t] = hacc + hp.b[0];
-      } else if constexpr (NHEAD == 2) {
+      } else if constexpr (NHEAD >= 2) {
+        if constexpr (NHEAD == 3) {   // positive message logits among this warp's counted samples, per bit
+#pragma unroll
+          for (int j = 0; j < WM_FUSED_VOTE_MAX - 1; ++j) {
+            const unsigned m = __ballot_sync(0xffffffffu, counted && j < nvote && lacc[j] > 0.0f);
+            if (real_tile && lane == 0) pdst[WM_DET_VOTE0 + j] = (float)__popc(m);
+          }
+        }
         const float pr = sigmoid_acc(hacc + hp.b[0]);
         if (live && head_out != nullptr) head_out[(size_t)b * T + t] = pr;
         float red = counted ? pr : 0.0f;
@@ -495,27 +535,36 @@ static int cta2_clusters(const void *kernel) {
   return cached = n;
 }
 
+// host_head: HOST rows of the 1x1 head, w[nw][64] then b[nw] (nw = 1: output 0 only; NHEAD == 3: all outputs);
+// host_b12: HOST b1[64], b2[64] or null (then the kernel reads the device pointers b1 / b2 into shared memory)
 template <int NHEAD>
 static int launch_rb(const void *x, const void *w_img, const float *b1, const float *b2, void *y, float *y32, int B,
-                     int T, const float *host_head, float *head_out, float *partials, const int *valid_len,
-                     cudaStream_t st) {
-  HeadParams<1> hp;
-  if (NHEAD > 0) {   // host_head: w[64] then b[1] (output 0 of the head)
-    memcpy(hp.w, host_head, sizeof(float) * 64);
-    memcpy(hp.b, host_head + 64, sizeof(float));
-  } else {
-    hp.w[0] = 0.0f;
-    hp.b[0] = 0.0f;
+                     int T, const float *host_head, int nw, const float *host_b12, float *head_out, float *partials,
+                     const int *valid_len, cudaStream_t st) {
+  using P = typename RbParamsFor<NHEAD>::type;
+  static_assert(sizeof(P) <= 8192, "kernel parameter budget");
+  P hp;
+  memset(&hp, 0, sizeof(hp));
+  if (NHEAD > 0) {
+    memcpy(hp.w, host_head, sizeof(float) * 64 * nw);
+    memcpy(hp.b, host_head + 64 * nw, sizeof(float) * nw);
+  }
+  const bool biasp = host_b12 != nullptr;
+  if (biasp) {
+    memcpy(hp.b1, host_b12, sizeof(float) * 64);
+    memcpy(hp.b2, host_b12 + 64, sizeof(float) * 64);
   }
   static bool attr_set = false;
   if (!attr_set) {
-    WM_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel<NHEAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM));
-    WM_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel<NHEAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM));
+    WM_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel<NHEAD, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM));
+    WM_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel<NHEAD, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM));
+    WM_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel<NHEAD, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM));
     attr_set = true;
   }
+  const int nvote = NHEAD == 3 ? nw - 1 : 0;
   long long ntiles = (long long)B * ((T + TO - 1) / TO);
-  const int ncl = cta2_clusters(reinterpret_cast<const void *>(resblock_tc_kernel<NHEAD, true>));
-  if (ncl >= sm_count() / 2 - 2 && ntiles >= 2) {   // CTA pairs (one per TPC)
+  const int ncl = cta2_clusters(reinterpret_cast<const void *>(resblock_tc_kernel<NHEAD, true, false>));
+  if (ncl >= sm_count() / 2 - 2 && ntiles >= 2 && b1 != nullptr && b2 != nullptr) {   // CTA pairs (one per TPC); biases from device memory
     const long long npairs = (ntiles + 1) / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * (unsigned)(npairs < ncl ? npairs : ncl), 1, 1);
@@ -527,43 +576,55 @@ static int launch_rb(const void *x, const void *w_img, const float *b1, const fl
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    WM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, resblock_tc_kernel<NHEAD, true>, reinterpret_cast<const uint4 *>(x),
+    WM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, resblock_tc_kernel<NHEAD, true, false>, reinterpret_cast<const uint4 *>(x),
                                      reinterpret_cast<const uint4 *>(w_img), b1, b2, reinterpret_cast<uint4 *>(y), y32, B, T,
-                                     hp, head_out, partials, valid_len, get_profile_buffer()));
+                                     hp, nvote, head_out, partials, valid_len, get_profile_buffer()));
     WM_CHECK_LAUNCH("resblock_tc (CTA pairs)");
     return 0;
   }
   int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-  resblock_tc_kernel<NHEAD, false><<<grid, RB_THREADS, RB_SMEM, st>>>(
-      reinterpret_cast<const uint4 *>(x), reinterpret_cast<const uint4 *>(w_img), b1, b2, reinterpret_cast<uint4 *>(y),
-      y32, B, T, hp, head_out, partials, valid_len, get_profile_buffer());
+  auto kern = biasp ? resblock_tc_kernel<NHEAD, false, true> : resblock_tc_kernel<NHEAD, false, false>;
+  kern<<<grid, RB_THREADS, RB_SMEM, st>>>(reinterpret_cast<const uint4 *>(x), reinterpret_cast<const uint4 *>(w_img), b1, b2,
+                                          reinterpret_cast<uint4 *>(y), y32, B, T, hp, nvote, head_out, partials, valid_len,
+                                          get_profile_buffer());
   WM_CHECK_LAUNCH("resblock_tc");
   return 0;
 }
 
 int launch_resblock_tc(const void *x, const void *w_img, const float *b1, const float *b2, void *y, float *y32, int B,
-                       int T, cudaStream_t st) {
+                       int T, cudaStream_t st, const float *host_b12) {
   if (B == 0 || T == 0) return 0;
-  return launch_rb<0>(x, w_img, b1, b2, y, y32, B, T, nullptr, nullptr, nullptr, nullptr, st);
+  return launch_rb<0>(x, w_img, b1, b2, y, y32, B, T, nullptr, 0, host_b12, nullptr, nullptr, nullptr, st);
 }
 
 int resblock_tiles_per_clip(int T) { return (T + TO - 1) / TO; }
 
 // ResBlock + Conv1d(64,1,1): delta_raw[B][T]   (host_head: HOST copy of w[64], b[1])
 int launch_resblock_head1_tc(const void *x, const void *w_img, const float *b1, const float *b2,
-                             const float *host_head, float *delta_raw, int B, int T, cudaStream_t st) {
+                             const float *host_head, float *delta_raw, int B, int T, cudaStream_t st,
+                             const float *host_b12) {
   if (B == 0 || T == 0) return 0;
-  return launch_rb<1>(x, w_img, b1, b2, nullptr, nullptr, B, T, host_head, delta_raw, nullptr, nullptr, st);
+  return launch_rb<1>(x, w_img, b1, b2, nullptr, nullptr, B, T, host_head, 1, host_b12, delta_raw, nullptr, nullptr, st);
 }
 
 // Detector's last ResBlock + channel 0 of its 1x1 head + sigmoid + per-(tile, warp) partial sums of the
 // probability and of the 64 activations; finish with launch_detect_finalize.  host_head: HOST w0[64], b0.
+// With host_head_all (HOST w[nout][64] then b[nout], nout <= WM_FUSED_VOTE_MAX) the epilogue also evaluates the
+// message logits per sample and counts the positive ones (majority vote of py/main16.py:398).
 // partials: B * tiles_per_clip * 4 * WM_DET_PART floats.
 int launch_resblock_detect_tc(const void *x, const void *w_img, const float *b1, const float *b2,
                               const float *host_head, const int *valid_len, float *probs, float *partials, int B, int T,
-                              cudaStream_t st) {
+                              cudaStream_t st, const float *host_b12, const float *host_head_all, int nout) {
   if (B == 0 || T == 0) return 0;
-  return launch_rb<2>(x, w_img, b1, b2, nullptr, nullptr, B, T, host_head, probs, partials, valid_len, st);
+  if (host_head_all != nullptr && nout > 1 && nout <= WM_FUSED_VOTE_MAX) {
+    float packed[WM_FUSED_VOTE_MAX * 65];   // rows padded to WM_FUSED_VOTE_MAX (missing outputs: zero weights)
+    memset(packed, 0, sizeof(packed));
+    memcpy(packed, host_head_all, sizeof(float) * 64 * nout);
+    memcpy(packed + 64 * WM_FUSED_VOTE_MAX, host_head_all + 64 * nout, sizeof(float) * nout);
+    return launch_rb<3>(x, w_img, b1, b2, nullptr, nullptr, B, T, packed, WM_FUSED_VOTE_MAX, host_b12, probs, partials,
+                        valid_len, st);
+  }
+  return launch_rb<2>(x, w_img, b1, b2, nullptr, nullptr, B, T, host_head, 1, host_b12, probs, partials, valid_len, st);
 }
 
 // One block per clip: the partial sums are added in a fixed order, then
@@ -572,15 +633,17 @@ int launch_resblock_detect_tc(const void *x, const void *w_img, const float *b1,
 __global__ void __launch_bounds__(128)
     detect_finalize_kernel(const float *__restrict__ partials, const int *__restrict__ valid_len,
                            const float *__restrict__ head_w, const float *__restrict__ head_b,
-                           float *__restrict__ clip_prob, float *__restrict__ msg_logits, int nparts, int T, int nout) {
+                           float *__restrict__ clip_prob, float *__restrict__ msg_logits,
+                           float *__restrict__ vote_frac, int nparts, int T, int nout) {
   __shared__ float mean_s[WM_DET_PART];
   const int b = blockIdx.x, c = threadIdx.x;
   const int vl = valid_len != nullptr ? min(max(valid_len[b], 0), T) : T;
-  if (c <= 64) {
+  if (c <= 64 || (vote_frac != nullptr && c >= WM_DET_VOTE0 && c < WM_DET_VOTE0 + nout - 1)) {
     const float *src = partials + (size_t)b * nparts * WM_DET_PART + c;
     float s = 0.0f;
-    for (int i = 0; i < nparts; ++i) s += src[(size_t)i * WM_DET_PART];
+    for (int i = 0; i < nparts; ++i) s += src[(size_t)i * WM_DET_PART];   // (vote counts: integers, exact in fp32)
     mean_s[c] = vl > 0 ? s / (float)vl : 0.0f;
+    if (c >= WM_DET_VOTE0) vote_frac[(size_t)b * (nout - 1) + c - WM_DET_VOTE0] = mean_s[c];
   }
   __syncthreads();
   if (c == 0 && clip_prob) clip_prob[b] = mean_s[64];
@@ -592,9 +655,9 @@ __global__ void __launch_bounds__(128)
 }
 
 int launch_detect_finalize(const float *partials, const int *valid_len, const float *head_w, const float *head_b,
-                           float *clip_prob, float *msg_logits, int B, int T, int nout, cudaStream_t st) {
+                           float *clip_prob, float *msg_logits, float *vote_frac, int B, int T, int nout, cudaStream_t st) {
   if (B == 0) return 0;
-  detect_finalize_kernel<<<B, 128, 0, st>>>(partials, valid_len, head_w, head_b, clip_prob, msg_logits,
+  detect_finalize_kernel<<<B, 128, 0, st>>>(partials, valid_len, head_w, head_b, clip_prob, msg_logits, vote_frac,
                                             4 * ((T + TO - 1) / TO), T, nout);
   WM_CHECK_LAUNCH("detect_finalize");
   return 0;

@@ -115,15 +115,21 @@ def conv64_tc(xp, w_img, bias, B: int, T: int, taps: int, residual=None, relu=Fa
     return y, y32
 
 
-def resblock_tc(xp, w1, b1, w2, b2, B: int, T: int, want_planar=True, want_fp32=False):
-    """Fused ResBlock on planar x; w1/w2 fp32 [3][64][64] tap-major (BN folded)."""
+def resblock_tc(xp, w1, b1, w2, b2, B: int, T: int, want_planar=True, want_fp32=False, host_bias=False):
+    """Fused ResBlock on planar x; w1/w2 fp32 [3][64][64] tap-major (BN folded).  host_bias: biases read on the
+    host and passed to the kernel by value (the variant the module-level drivers run)."""
     lib = L.load()
     dev = xp.device
     img = torch.cat([pack_conv64_tc(w1), pack_conv64_tc(w2)])
     y = torch.empty(max(lib.wm_planar_bytes(B, T), 16), dtype=torch.uint8, device=dev) if want_planar else None
     y32 = torch.empty(B, T, 64, device=dev, dtype=torch.float32) if want_fp32 else None
-    L.check(lib.wm_resblock_tc_fwd(L.ptr(xp), L.ptr(img), L.ptr(_req(b1, "b1")), L.ptr(_req(b2, "b2")), L.ptr(y),
-                                   L.ptr(y32), B, T, _stream()), "wm_resblock_tc_fwd")
+    if host_bias:
+        hb1, hb2 = b1.detach().float().cpu().contiguous(), b2.detach().float().cpu().contiguous()
+        L.check(lib.wm_resblock_tc_hostbias_fwd(L.ptr(xp), L.ptr(img), L.ptr(hb1), L.ptr(hb2), L.ptr(y), L.ptr(y32), B, T,
+                                                _stream()), "wm_resblock_tc_hostbias_fwd")
+    else:
+        L.check(lib.wm_resblock_tc_fwd(L.ptr(xp), L.ptr(img), L.ptr(_req(b1, "b1")), L.ptr(_req(b2, "b2")), L.ptr(y),
+                                       L.ptr(y32), B, T, _stream()), "wm_resblock_tc_fwd")
     return y, y32
 
 

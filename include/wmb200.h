@@ -32,7 +32,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 14
+#define WM_ABI_VERSION 15
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -207,6 +207,10 @@ int wm_conv64_tc_fwd(const void *x, const void *w_img, const float *bias, const 
  * in shared memory, the residual is taken from the x tile already on chip. */
 int wm_resblock_tc_fwd(const void *x, const void *w_img, const float *b1, const float *b2, void *y,
                        float *y32, int B, int T, void *stream);
+/* The same with the two bias vectors read from HOST memory at call time and passed to the kernel by value
+ * (constant-bank operands: the variant the module-level drivers use once a blob has been finalized). */
+int wm_resblock_tc_hostbias_fwd(const void *x, const void *w_img, const float *host_b1, const float *host_b2,
+                                void *y, float *y32, int B, int T, void *stream);
 
 /* The LSTM on tensor cores: planar x -> planar h (+ chan_add[B][64] added to the OUTPUT only, i.e.
  * the message embedding of py/main16.py:156-159 fused into the store).  Weights resident in TMEM,

@@ -123,9 +123,11 @@ def test_conv64_tensor_core(B, T, taps, variant):
     assert int(planes[:, :L.PLANAR_PAD].max()) == 0 and int(planes[:, T + L.PLANAR_PAD:].max()) == 0
 
 
+@pytest.mark.parametrize("host_bias", [False, True])
 @pytest.mark.parametrize("B,T", [(1, 1), (2, 125), (1, 126), (3, 127), (2, 253), (4, 16000), (150, 1300)])
-def test_resblock_tensor_core_fused(B, T):
-    """One-kernel ResBlock (intermediate in shared memory) vs the fp64 reference."""
+def test_resblock_tensor_core_fused(B, T, host_bias):
+    """One-kernel ResBlock (intermediate in shared memory) vs the fp64 reference; biases from device memory
+    (shared-memory copy) and by value (constant-bank operands, the variant the module drivers launch)."""
     g = torch.Generator().manual_seed(B * 7 + T)
     x = torch.randn(B, 64, T, generator=g) * 2
     w1 = torch.randn(64, 64, 3, generator=g) / 14
@@ -136,7 +138,7 @@ def test_resblock_tensor_core_fused(B, T):
     ref = F.relu(xd + F.conv1d(u, w2.double(), b2.double(), padding=1)).float()
     xp = ops.to_planar(x.permute(0, 2, 1).contiguous().to(DEV))
     tm = lambda w: w.permute(2, 1, 0).contiguous().to(DEV)
-    yp, y32 = ops.resblock_tc(xp, tm(w1), b1.to(DEV), tm(w2), b2.to(DEV), B, T, want_fp32=True)
+    yp, y32 = ops.resblock_tc(xp, tm(w1), b1.to(DEV), tm(w2), b2.to(DEV), B, T, want_fp32=True, host_bias=host_bias)
     scale = max(1.0, float(ref.abs().max()))
     assert maxerr(y32.permute(0, 2, 1), ref) < 3e-5 * scale
     assert maxerr(ops.from_planar(yp, B, T).permute(0, 2, 1), ref) < 5e-5 * scale
@@ -290,8 +292,27 @@ def test_detector_matches_reference_goldens(tag, det):
     safe = np.abs(ml_ref) > 4 * max(err, 1e-6)                           # bit-exact where the sign is decidable
     assert np.array_equal((r["msg_logits"].cpu().numpy() > 0)[safe], (ml_ref > 0)[safe])
     assert safe.mean() > 0.9
-    vote = (r["vote_frac"] > 0.5).cpu().numpy()
-    assert (vote != IO[f"{tag}/bits_vote"]).mean() < 0.02
+    # majority vote (py/main16.py:398), fused into the last ResBlock's epilogue: the fraction of positive per-sample
+    # logits may differ from the reference's only by the samples whose reference logit is within the per-sample
+    # logit error of zero; the voted bit must be the reference's wherever that slack cannot move the fraction over 0.5
+    with torch.no_grad():
+        lg_ref = O.detector_forward(H.det_sd(W), x.cpu())[:, :, 1:]
+    e_logit = 2.0 * max(maxerr(lg[:, :, 1:], lg_ref.numpy()), 1e-6)
+    frac_ref = (lg_ref > 0).float().mean(dim=1).numpy()
+    slack = (lg_ref.abs() < e_logit).float().mean(dim=1).numpy() + 1.0 / lg_ref.shape[1]
+    frac = r["vote_frac"].cpu().numpy()
+    assert np.all(np.abs(frac - frac_ref) <= slack), (np.abs(frac - frac_ref) - slack).max()
+    vote, vote_ref = frac > 0.5, IO[f"{tag}/bits_vote"]
+    assert np.array_equal(frac_ref > 0.5, vote_ref)                      # the oracle restates the golden
+    decidable = np.abs(frac_ref - 0.5) > slack
+    n_mis = int((vote != vote_ref).sum())
+    print(f"[{tag}] vote bits: {n_mis} of {vote.size} differ from the reference; {int(decidable.sum())} decidable "
+          f"(|frac - 0.5| > slack, max slack {slack.max():.2e}); per-sample logit error bound {e_logit:.2e}")
+    assert np.array_equal(vote[decidable], vote_ref[decidable])
+    assert decidable.mean() > 0.9
+    # the same request through the un-fused route (logits tensor + detect_heads) agrees on every decidable bit
+    r2 = ops.detect_heads(lg.contiguous(), want_probs=False, want_votes=True)
+    assert np.array_equal((r2["vote_frac"] > 0.5).cpu().numpy()[decidable], vote_ref[decidable])
 
 
 @pytest.mark.parametrize("T", [16000, 1000, 127, 5])
