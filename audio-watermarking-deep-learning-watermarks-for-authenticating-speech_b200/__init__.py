@@ -6,8 +6,10 @@ functions fir_lowpass / clamp_peak / limit_rms and the module constants.  All ar
 runs in libwmb200.so (hand-written CUDA, C ABI in include/wmb200.h); there is no CPU or
 PyTorch fallback — calls fail loudly when the library or the GPU is missing.
 """
-from . import _lib, audio, main14b_2, ops, packing
-from .audio import Resample, compute_si_snr, file_metrics, from_pcm16, resample, to_pcm16
+from . import _lib, audio, main14b_2, metrics, ops, packing
+from .audio import (Resample, biquad, compute_si_snr, file_metrics, from_pcm16, lowpass_biquad, perceptual_postprocess,
+                    resample, save_audio_pcm16, to_pcm16)
+from .metrics import auc, classification_report, confusion_counts, roc_curve
 from .api import (detect_prob, detect_watermark, evaluate_unseen_file, generate_watermarked_audio, load_audio,
                   process_audio_file_with_delta, run_inference_on_file, save_audio, segment, set_seed)
 from .evaluate import evaluate_model, validate_one_epoch
@@ -30,4 +32,5 @@ __all__ = ["Generator", "Detector", "ResBlock", "generate_watermarked_audio", "d
            "Resample", "resample", "to_pcm16", "from_pcm16", "file_metrics", "evaluate_model", "validate_one_epoch",
            "DetectorTrainer", "Trainer", "LR", "EarlyStopping", "OneCycle", "fit", "load_ckpt", "save_ckpt",
            "train_one_epoch", "compute_si_snr", "evaluate_unseen_file", "process_audio_file_with_delta",
-           "run_inference_on_file", "set_seed"]
+           "run_inference_on_file", "set_seed", "biquad", "lowpass_biquad", "perceptual_postprocess", "save_audio_pcm16",
+           "confusion_counts", "classification_report", "roc_curve", "auc"]

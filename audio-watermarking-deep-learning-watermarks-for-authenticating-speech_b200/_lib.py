@@ -12,7 +12,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwmb200.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 # blob offsets (floats) — mirror of the enums in include/wmb200.h
 RB_W1 = 0
@@ -159,6 +159,11 @@ SIGNATURES = {
     "wm_pcm16_quantize_fwd": (_i, [_p, _p, _sz, _p]),
     "wm_pcm16_dequantize_fwd": (_i, [_p, _p, _sz, _f, _p]),
     "wm_file_metrics_fwd": (_i, [_p, _p, _p, _p, _i, _i, _p]),
+    "wm_biquad_workspace_bytes": (_sz, [_i, _ll]),
+    "wm_biquad_fwd": (_i, [_p, _p, _p, _i, _ll, _p, _p, _i, _p, _sz, _p]),
+    "wm_confusion_counts_fwd": (_i, [_p, _ll, _p, _ll, _f, _p, _p]),
+    "wm_roc_points_fwd": (_i, [_p, _ll, _p, _ll, _p, _i, _p, _p, _p]),
+    "wm_auc_pairs_fwd": (_i, [_p, _ll, _p, _ll, _p, _p]),
     "wm_stft_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "wm_hf_penalty_bwd": (_i, [_p, _p, _p, _sz, _i, _i, _i, _i, _f, _i, _p]),
     "wm_loud_bwd": (_i, [_p, _p, _p, _p, _sz, _i, _i, _i, _i, _f, _f, _i, _p]),

@@ -64,8 +64,10 @@ def save_audio(path: str, waveform: torch.Tensor, sample_rate: int = SAMPLE_RATE
     wavfile.write(path, sample_rate, np.ascontiguousarray(x.T))
 
 
-def _prepare(input_file):
-    """load -> mono -> 16 kHz  (py/main16.py:981-985)."""
+def _prepare(input_file, device="cuda"):
+    """load -> mono -> 16 kHz  (py/main16.py:981-985).  Returns the (1, N) waveform on the HOST (what the result
+    dictionaries carry); a file at another sample rate is resampled on `device` by the library's polyphase kernel
+    (audio.resample, torchaudio.transforms.Resample's arithmetic) -- there is no CPU resampler on this path."""
     if isinstance(input_file, torch.Tensor):
         waveform, sr = input_file.to("cpu", torch.float32), SAMPLE_RATE
         if waveform.dim() == 1:
@@ -75,8 +77,8 @@ def _prepare(input_file):
     if waveform.shape[0] > 1:
         waveform = waveform.mean(dim=0, keepdim=True)
     if sr != SAMPLE_RATE:
-        import torchaudio
-        waveform = torchaudio.transforms.Resample(sr, SAMPLE_RATE)(waveform)
+        from .audio import resample
+        waveform = resample(waveform.to(device, torch.float32), sr, SAMPLE_RATE).cpu()
     return waveform
 
 
@@ -98,7 +100,7 @@ def generate_watermarked_audio(input_file, generator, output_file=None, message_
     """py/main16.py:977-1066.  `messages` (optional, one id per 1 s segment) replaces the
     reference's per-segment torch.randint draws (:1001) for reproducible embedding."""
     generator.eval()
-    waveform = _prepare(input_file)
+    waveform = _prepare(input_file, device)
     total = waveform.shape[1]
     batch, _ = segment(waveform)
     n = batch.shape[0]
@@ -143,7 +145,7 @@ def generate_watermarked_audio(input_file, generator, output_file=None, message_
 def detect_watermark(input_file, detector, detection_threshold=0.5, visualize=True, device="cuda"):
     """py/main16.py:1114-1207."""
     detector.eval()
-    waveform = _prepare(input_file)
+    waveform = _prepare(input_file, device)
     total = waveform.shape[1]
     batch, valid = segment(waveform)
     if batch.shape[0] == 0:
@@ -229,7 +231,7 @@ def evaluate_unseen_file(filepath, generator, detector, device="cuda", messages:
     four Nones when the file cannot be read.  Segments run as one batch through generator and detector."""
     from .audio import file_metrics
     try:
-        waveform = _prepare(filepath)
+        waveform = _prepare(filepath, device)
     except Exception:
         return None, None, None, None
     generator.eval()

@@ -1,6 +1,7 @@
 """The data formats either side of the embed+detect path, on the GPU:
 `Resample` / `resample` (torchaudio.transforms.Resample as the reference uses it, py/main16.py:985,1121),
-`to_pcm16` / `from_pcm16` (py/main15.py:859-860) and `file_metrics` (py/main16.py:1030-1049)."""
+`to_pcm16` / `from_pcm16` (py/main15.py:859-860), `lowpass_biquad` / `save_audio_pcm16` (py/main15.py:850-867,
+main15c.ipynb cell 4) and `file_metrics` (py/main16.py:1030-1049)."""
 from __future__ import annotations
 
 import math
@@ -86,3 +87,64 @@ def compute_si_snr(s: torch.Tensor, s_hat: torch.Tensor, eps: float = 1e-8) -> f
     a = s.reshape(-1, s.shape[-1])
     b = s_hat.reshape(-1, s_hat.shape[-1])
     return float(file_metrics(a, b)[:, 1].mean())
+
+
+def biquad(waveform: torch.Tensor, b0: float, b1: float, b2: float, a0: float, a1: float, a2: float,
+           clamp: bool = True, want_pcm16: bool = False):
+    """torchaudio.functional.biquad / lfilter for CUDA tensors: (..., T) fp32 -> same shape (and, with want_pcm16, the
+    int16 codes `(y.clamp(-1, 1) * 32767).to(int16)` from the same pass).  Zero initial state, clamp as lfilter's
+    default.  A chunked scan in double precision (wm_eval.cu)."""
+    import ctypes as C
+    lib = L.load()
+    lead, T = waveform.shape[:-1], waveform.shape[-1]
+    x2 = _req(waveform.reshape(-1, T), "waveform")
+    rows = x2.shape[0]
+    y = torch.empty_like(x2)
+    q = torch.empty(x2.shape, dtype=torch.int16, device=x2.device) if want_pcm16 else None
+    n = lib.wm_biquad_workspace_bytes(rows, T)
+    ws = torch.empty(max(n, 256), dtype=torch.uint8, device=x2.device)
+    b3, a3 = (C.c_double * 3)(b0, b1, b2), (C.c_double * 3)(a0, a1, a2)
+    L.check(lib.wm_biquad_fwd(L.ptr(x2), L.ptr(y), L.ptr(q), rows, T, C.addressof(b3), C.addressof(a3), int(clamp),
+                              L.ptr(ws), n, _stream()), "wm_biquad_fwd")
+    y = y.reshape(*lead, T)
+    return (y, q.reshape(*lead, T)) if want_pcm16 else y
+
+
+def lowpass_biquad_coeffs(sample_rate: int, cutoff_freq: float, Q: float = 0.707):
+    """The six coefficients torchaudio.functional.lowpass_biquad builds, evaluated in fp32 like torchaudio does for an
+    fp32 waveform (so the filter is the same filter, not a double-precision cousin of it)."""
+    w0 = 2 * math.pi * torch.tensor(float(cutoff_freq), dtype=torch.float32) / sample_rate
+    alpha = torch.sin(w0) / 2 / torch.tensor(float(Q), dtype=torch.float32)
+    b0 = (1 - torch.cos(w0)) / 2
+    b1 = 1 - torch.cos(w0)
+    b2 = b0
+    a0 = 1 + alpha
+    a1 = -2 * torch.cos(w0)
+    a2 = 1 - alpha
+    return tuple(float(v) for v in (b0, b1, b2, a0, a1, a2))
+
+
+def lowpass_biquad(waveform: torch.Tensor, sample_rate: int, cutoff_freq: float, Q: float = 0.707) -> torch.Tensor:
+    """torchaudio.functional.lowpass_biquad(waveform, sample_rate, cutoff_freq, Q) on the GPU (py/main15.py:855)."""
+    return biquad(waveform, *lowpass_biquad_coeffs(sample_rate, cutoff_freq, Q))
+
+
+def perceptual_postprocess(waveform: torch.Tensor, sample_rate: int = 16000, cutoff_freq: float = 7000.0):
+    """7 kHz low-pass + 16-bit quantisation of py/main15.py:850-860: returns (filtered fp32, int16 codes)."""
+    return biquad(waveform, *lowpass_biquad_coeffs(sample_rate, cutoff_freq), want_pcm16=True)
+
+
+def save_audio_pcm16(waveform: torch.Tensor, output_path: str, sample_rate: int = 16000) -> None:
+    """py/main15.py:850-867 `save_audio`: low-pass at 7 kHz, quantise to signed 16-bit PCM, write a PCM_S WAV.  Filter
+    and quantiser run on the GPU for CUDA input; only the int16 codes cross to the host."""
+    import wave
+    w = waveform if waveform.dim() == 2 else waveform.reshape(1, -1)
+    if not w.is_cuda:
+        w = w.cuda()
+    _, q = perceptual_postprocess(w.float(), sample_rate)
+    codes = q.t().contiguous().cpu().numpy()          # (N, C) interleaved
+    with wave.open(output_path, "wb") as f:
+        f.setnchannels(codes.shape[1])
+        f.setsampwidth(2)
+        f.setframerate(sample_rate)
+        f.writeframes(codes.astype("<i2").tobytes())

@@ -880,6 +880,44 @@ int wm_file_metrics_fwd(const float *s, const float *s_w, const int *valid_len, 
   return launch_file_metrics(s, s_w, valid_len, out, B, T, as_stream(stream));
 }
 
+size_t wm_biquad_workspace_bytes(int rows, long long N) { return rows > 0 && N > 0 ? biquad_scratch_bytes(rows, N) : 0; }
+
+int wm_biquad_fwd(const float *x, float *y, int16_t *pcm16, int rows, long long N, const double *b3, const double *a3,
+                  int clamp, void *workspace, size_t workspace_bytes, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(rows >= 0 && N >= 0, "biquad: negative size");
+  if (rows == 0 || N == 0) return 0;
+  WM_CHECK_ARG(x && y && b3 && a3 && workspace, "biquad: null pointer");
+  WM_CHECK_ARG(x != y, "biquad: in-place operation is not supported");
+  WM_CHECK_ARG(a3[0] != 0.0, "biquad: a[0] must not be zero");
+  WM_CHECK_ARG(workspace_bytes >= biquad_scratch_bytes(rows, N), "biquad: workspace too small");
+  return launch_biquad(x, y, reinterpret_cast<short *>(pcm16), rows, N, b3, a3, clamp, workspace, as_stream(stream));
+}
+
+int wm_confusion_counts_fwd(const float *clean, long long n_clean, const float *wm, long long n_wm, float thresh,
+                            unsigned long long *out4, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(n_clean >= 0 && n_wm >= 0 && out4 && (clean || n_clean == 0) && (wm || n_wm == 0), "confusion_counts: bad arguments");
+  return launch_confusion(clean, n_clean, wm, n_wm, thresh, out4, as_stream(stream));
+}
+
+int wm_roc_points_fwd(const float *clean, long long n_clean, const float *wm, long long n_wm, const float *thresholds,
+                      int n_thresholds, int *fp, int *tp, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(n_clean >= 0 && n_wm >= 0 && n_thresholds >= 0, "roc_points: negative size");
+  WM_CHECK_ARG(n_clean < (1LL << 31) && n_wm < (1LL << 31), "roc_points: counts are 32-bit");
+  if (n_thresholds == 0) return 0;
+  WM_CHECK_ARG(thresholds && fp && tp && (clean || n_clean == 0) && (wm || n_wm == 0), "roc_points: null pointer");
+  return launch_roc_points(clean, n_clean, wm, n_wm, thresholds, n_thresholds, fp, tp, as_stream(stream));
+}
+
+int wm_auc_pairs_fwd(const float *clean, long long n_clean, const float *wm, long long n_wm, unsigned long long *out,
+                     void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(n_clean >= 0 && n_wm >= 0 && out && (clean || n_clean == 0) && (wm || n_wm == 0), "auc_pairs: bad arguments");
+  return launch_auc_pairs(clean, n_clean, wm, n_wm, out, as_stream(stream));
+}
+
 size_t wm_embed_detect_host_workspace_bytes(int chunk, int T, int nout) {
   if (chunk <= 0 || T <= 0 || nout < 1) return 0;
   size_t wave = align256((size_t)chunk * T * sizeof(float));

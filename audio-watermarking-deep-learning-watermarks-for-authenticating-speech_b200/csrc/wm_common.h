@@ -187,6 +187,15 @@ int launch_resample(const float *x, const float *kern, float *y, int B, int Tin,
                     int width, cudaStream_t st);
 int launch_pcm16(const float *x, short *q, float *xo, long long n, int quantize, float scale, cudaStream_t st);
 int launch_file_metrics(const float *s, const float *sw, const int *valid_len, float *out, int B, int T, cudaStream_t st);
+// wm_eval.cu: second-order IIR (lfilter semantics) + PCM16, detection statistics
+size_t biquad_scratch_bytes(int rows, long long N);
+int launch_biquad(const float *x, float *y, short *q, int rows, long long N, const double *b, const double *a, int clamp,
+                  void *scratch, cudaStream_t st);
+int launch_confusion(const float *clean, long long n0, const float *wm, long long n1, float thresh, unsigned long long *out4,
+                     cudaStream_t st);
+int launch_roc_points(const float *clean, long long n0, const float *wm, long long n1, const float *thr, int nt, int *fp,
+                      int *tp, cudaStream_t st);
+int launch_auc_pairs(const float *clean, long long n0, const float *wm, long long n1, unsigned long long *out, cudaStream_t st);
 void set_lstm_profile_buffer(long long *p);
 void set_lstm_opts(int opts);
 long long *get_profile_buffer();

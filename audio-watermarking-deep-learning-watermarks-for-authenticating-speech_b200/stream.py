@@ -189,7 +189,7 @@ def process_folder_with_tqdm(input_folder, generator, message_bits=16, device="c
     base = os.path.basename(os.path.abspath(input_folder))
     output_root = os.path.join(os.path.dirname(input_folder), f"watermarked_{base}")
     pairs = list_audio_files(input_folder, output_root)[rank::world]
-    load = loader or api._prepare
+    load = loader or (lambda path: api._prepare(path, device))
     save = saver or api.save_audio
     waves = [load(p) for p, _ in pairs]
     counts = [(w.shape[1] + SEG - 1) // SEG for w in waves]
@@ -237,7 +237,7 @@ def detect_watermark_folder(input_folder, detector, detection_threshold=0.5, dev
     detect_watermark minus the plot), segments of consecutive files batched together."""
     detector.eval()
     pairs = list_audio_files(input_folder, input_folder, prefix="")[rank::world]
-    load = loader or api._prepare
+    load = loader or (lambda path: api._prepare(path, device))
     waves = [load(p) for p, _ in pairs]
     counts = [(w.shape[1] + SEG - 1) // SEG for w in waves]
     results = []

@@ -32,7 +32,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 15
+#define WM_ABI_VERSION 16
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -380,6 +380,27 @@ int wm_pcm16_dequantize_fwd(const int16_t *q, float *x, size_t n, float scale, v
 /* Per-row quality metrics of generate_watermarked_audio (py/main16.py:1030-1049; compute_si_snr :764-773):
  * out[b] = {watermark_rms, si_snr_db, power_ratio_db} over the first valid_len[b] samples (nullable = T). */
 int wm_file_metrics_fwd(const float *s, const float *s_w, const int *valid_len, float *out, int B, int T, void *stream);
+
+/* Second-order IIR with torchaudio.functional.lfilter semantics (py/main15.py:855 lowpass_biquad; main15c.ipynb
+ * cell 4): y[n] = (b0 x[n] + b1 x[n-1] + b2 x[n-2] - a1 y[n-1] - a2 y[n-2]) / a0 per row of x[rows][N], zero initial
+ * state, clamp != 0 clamps y to [-1, 1] (lfilter's default); pcm16 (optional) additionally receives
+ * (int16)(clamp(y, -1, 1) * 32767) (py/main15.py:859-860).  b3 / a3: HOST pointers to 3 doubles each.  The
+ * recurrence is evaluated as a chunked scan in double precision.  Not in place. */
+size_t wm_biquad_workspace_bytes(int rows, long long N);
+int wm_biquad_fwd(const float *x, float *y, int16_t *pcm16, int rows, long long N, const double *b3, const double *a3,
+                  int clamp, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Detection statistics of the evaluation cells, on device scores.
+ * confusion_counts: out4 = {tn, fp, fn, tp} with prediction = score >= thresh (py/main16.py:1335-1341).
+ * roc_points: for every threshold t: fp[t] = #{clean >= t}, tp[t] = #{wm >= t} (the points sklearn's roc_curve
+ *             returns for these thresholds, py/main16.py:2372-2386).
+ * auc_pairs:  out = 2 * #{wm > clean} + #{wm == clean} over all pairs; AUC = out / (2 n_clean n_wm). */
+int wm_confusion_counts_fwd(const float *clean, long long n_clean, const float *wm, long long n_wm, float thresh,
+                            unsigned long long *out4, void *stream);
+int wm_roc_points_fwd(const float *clean, long long n_clean, const float *wm, long long n_wm, const float *thresholds,
+                      int n_thresholds, int *fp, int *tp, void *stream);
+int wm_auc_pairs_fwd(const float *clean, long long n_clean, const float *wm, long long n_wm, unsigned long long *out,
+                     void *stream);
 
 /* ---- training (BASELINE config 4): the Detector's half of train_one_epoch ----
  * One optimisation step of the Detector (py/main16.py:160-176 in train mode: batch-statistics BatchNorm, running
