@@ -7,6 +7,7 @@ from typing import Optional
 import torch
 
 from . import _lib as L
+from . import autograd as AG
 from . import ops, packing
 
 SAMPLE_RATE = 16000      # py/main16.py:30
@@ -40,18 +41,25 @@ def fir_lowpass(delta: torch.Tensor, cutoff: float = 4000, taps: int = 101) -> t
     """py/main16.py:53-64."""
     if taps != 101:
         raise ValueError("wmb200 implements the reference's 101-tap filter")
+    if AG.needs_graph(delta):
+        return AG.Postprocess.apply(ops._req(_b1t(delta), "delta"), fir_taps_on(delta.device, cutoff, taps), L.POST_FIR,
+                                    ops.PEAK, ops.MAX_RMS, ops.RMS_EPS).unsqueeze(1)
     d, _, _ = ops.postprocess(_b1t(delta), None, fir_taps_on(delta.device, cutoff, taps), L.POST_FIR, True, False)
     return d.unsqueeze(1)
 
 
 def clamp_peak(d: torch.Tensor, thr: float = 0.02) -> torch.Tensor:
     """py/main16.py:66-67."""
+    if AG.needs_graph(d):
+        return AG.Postprocess.apply(ops._req(_b1t(d), "d"), None, L.POST_CLAMP, thr, ops.MAX_RMS, ops.RMS_EPS).unsqueeze(1)
     out, _, _ = ops.postprocess(_b1t(d), None, None, L.POST_CLAMP, True, False, peak=thr)
     return out.unsqueeze(1)
 
 
 def limit_rms(delta: torch.Tensor, max_rms: float = MAX_RMS, eps: float = 1e-8) -> torch.Tensor:
     """py/main16.py:69-72."""
+    if AG.needs_graph(delta):
+        return AG.Postprocess.apply(ops._req(_b1t(delta), "delta"), None, L.POST_RMS, ops.PEAK, max_rms, eps).unsqueeze(1)
     out, _, _ = ops.postprocess(_b1t(delta), None, None, L.POST_RMS, True, False, max_rms=max_rms, eps=eps)
     return out.unsqueeze(1)
 

@@ -2,9 +2,10 @@
 train / validation step (py/main16.py:252-276), forward only, on libwmb200's staged-FFT kernels.
 
 Every function returns 0-dim fp32 tensors on the input's device; the scalars are produced by
-fixed-order reductions, so repeated calls are bit-identical.  The backward pass (config 4, the
-training step) is not built yet: these run under torch.no_grad() and raise if autograd is recording
-on their inputs.
+fixed-order reductions, so repeated calls are bit-identical.  When autograd is recording on the
+watermark-side input (delta / watermarked) the call goes through the matching autograd.Function
+(backward = the staged-FFT adjoint kernels); the clean signal is data and receives no gradient,
+as in the reference's loop.
 """
 from __future__ import annotations
 
@@ -13,15 +14,17 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
+from . import autograd as AG
 from . import functional as Fn
 from . import ops, packing
 
 _mel_cache = {}
 
 
-def _no_grad_inputs(*ts):
-    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts):
-        raise NotImplementedError("wmb200 losses are forward-only this round; wrap the call in torch.no_grad()")
+def _no_clean_grad(clean):
+    if torch.is_grad_enabled() and clean is not None and clean.requires_grad:
+        raise NotImplementedError("the clean signal is data in the reference's loop (py/main16.py:268-269): no gradient "
+                                  "w.r.t. it is implemented; detach it")
 
 
 def _bt(x: torch.Tensor, name: str) -> torch.Tensor:
@@ -34,10 +37,11 @@ def _bt(x: torch.Tensor, name: str) -> torch.Tensor:
 
 def high_freq_penalty(delta: torch.Tensor, cutoff: float = 3_500, n_fft: int = 512) -> torch.Tensor:
     """py/main16.py:74-81: mean over (B, n_fft/2+1, frames) of |STFT(delta)| * [rfftfreq > cutoff]."""
-    _no_grad_inputs(delta)
     freqs = torch.fft.rfftfreq(n_fft, 1 / Fn.SAMPLE_RATE)
     above = torch.nonzero(freqs > cutoff).flatten()
     first_bin = int(above[0]) if above.numel() else n_fft // 2 + 1
+    if AG.needs_graph(delta):
+        return AG.HighFreqPenalty.apply(ops._req(_bt(delta, "delta"), "delta"), n_fft, first_bin)
     return ops.hf_penalty(_bt(delta, "delta"), n_fft, first_bin)
 
 
@@ -56,8 +60,11 @@ class MultiScaleMelLoss(nn.Module):
         return _mel_cache[key]
 
     def forward(self, clean: torch.Tensor, watermarked: torch.Tensor) -> torch.Tensor:
-        _no_grad_inputs(clean, watermarked)
+        _no_clean_grad(clean)
         fb, band = self._tables(clean.device)
+        if AG.needs_graph(watermarked):
+            return AG.MelLogL1.apply(ops._req(_bt(clean, "clean"), "clean"), ops._req(_bt(watermarked, "watermarked"), "watermarked"),
+                                     fb, band, self.n_fft, self.hop_length)
         return ops.mel_log_l1(_bt(clean, "clean"), _bt(watermarked, "watermarked"), fb, band, self.n_fft,
                               self.hop_length)
 
@@ -71,7 +78,10 @@ class TFLoudnessLoss(nn.Module):
         self.hop = 512
 
     def forward(self, clean: torch.Tensor, watermarked: torch.Tensor) -> torch.Tensor:
-        _no_grad_inputs(clean, watermarked)
+        _no_clean_grad(clean)
+        if AG.needs_graph(watermarked):
+            return AG.Loudness.apply(ops._req(_bt(clean, "clean"), "clean"), ops._req(_bt(watermarked, "watermarked"), "watermarked"),
+                                     self.win_size, self.hop, 0.01)
         return ops.loudness(_bt(clean, "clean"), _bt(watermarked, "watermarked"), self.win_size, self.hop, 0.01)
 
 

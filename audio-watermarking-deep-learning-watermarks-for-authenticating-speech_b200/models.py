@@ -3,9 +3,11 @@ keys and call signatures (py/main16.py:112-186), running on libwmb200.
 
 The torch sub-modules below exist to own the parameters under the reference's names
 (`encoder.1.block.0.weight`, `lstm.weight_ih_l0`, `model.3.bias`, ...), so that the
-reference's `.pth` files load unchanged; they are never called.  `forward` packs the
-parameters once per parameter version (eval BatchNorm folded, see packing.py) and
-hands raw pointers to the C ABI.
+reference's `.pth` files load unchanged; they are never called.  In eval mode `forward`
+packs the parameters once per parameter version (eval BatchNorm folded, see packing.py)
+and hands raw pointers to the fused inference kernels; in train mode it runs the
+batch-statistics path operator by operator under autograd (autograd.py), so the
+reference's loop body (py/main16.py:238-278) works on these modules as written.
 """
 from __future__ import annotations
 
@@ -15,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
+from . import autograd as AG
 from . import ops, packing
 
 HIDDEN = 64
@@ -35,8 +38,9 @@ class ResBlock(nn.Module):
         self.relu = nn.ReLU()
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x (B,64,T) -> (B,64,T) through two wm_conv64_fwd launches."""
-        _no_training(self)
+        """x (B,64,T) -> (B,64,T) through two wm_conv64_fwd launches (train mode: batch statistics, under autograd)."""
+        if self.training:
+            return AG.resblock_train(self, x.permute(0, 2, 1).contiguous()).permute(0, 2, 1)
         sd = {"rb." + k: v for k, v in self.state_dict().items()}
         w1, b1 = packing.fold_conv_bn(sd, "rb.block.0", "rb.block.1")
         w2, b2 = packing.fold_conv_bn(sd, "rb.block.3", "rb.block.4")
@@ -50,9 +54,9 @@ class ResBlock(nn.Module):
 
 def _no_training(m: nn.Module) -> None:
     if m.training:
-        raise NotImplementedError(
-            "wmb200 implements the inference path (eval-mode BatchNorm, py/main16.py:979,1115); "
-            "call .eval() first — training-mode batch statistics are not built yet")
+        raise RuntimeError(
+            "this entry point is the fused inference path (eval-mode BatchNorm, py/main16.py:979,1115); call .eval() "
+            "first.  Train-mode modules run through forward() (autograd) or wmb200.Trainer.step")
 
 
 class _Packed(nn.Module):
@@ -118,15 +122,16 @@ class Generator(_Packed):
     def embedding_table(self) -> Optional[torch.Tensor]:
         return self.embedding.weight.detach() if self.message_bits > 0 else None
 
-    @torch.no_grad()
     def forward(self, s: torch.Tensor, message: Optional[torch.Tensor] = None) -> torch.Tensor:
-        _no_training(self)
         x = _as_bt(s, "s")
         use_msg = self.message_bits > 0 and message is not None
         if use_msg and message.shape != (x.shape[0],):
             raise ValueError(f"message: expected shape ({x.shape[0]},), got {tuple(message.shape)}")
-        delta = ops.generator_fwd(self.packed(), self.embedding_table() if use_msg else None,
-                                  message if use_msg else None, x)
+        if self.training:       # batch-statistics BatchNorm, operator by operator under autograd (py/main16.py:244)
+            return AG.generator_train(self, ops._req(x, "s"), message if use_msg else None).unsqueeze(1)
+        with torch.no_grad():
+            delta = ops.generator_fwd(self.packed(), self.embedding_table() if use_msg else None,
+                                      message if use_msg else None, x)
         return delta.unsqueeze(1)
 
 
@@ -152,10 +157,11 @@ class Detector(_Packed):
     def nout(self) -> int:
         return 1 + self.message_bits
 
-    @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        _no_training(self)
-        return ops.detector_fwd(self.packed(), _as_bt(x, "x"), self.nout)
+        if self.training:       # py/main16.py:250 in the training loop
+            return AG.detector_train(self, ops._req(_as_bt(x, "x"), "x"))
+        with torch.no_grad():
+            return ops.detector_fwd(self.packed(), _as_bt(x, "x"), self.nout)
 
     @torch.no_grad()
     def detect(self, x: torch.Tensor, valid_len: Optional[torch.Tensor] = None, want_probs: bool = True,

@@ -90,25 +90,30 @@ def train_one_epoch(trainer, train_loader: Iterable, *args, schedule: Optional[O
       train_one_epoch(trainer, train_loader, ...)                                        # a wmb200 Trainer
       train_one_epoch(generator, detector, train_loader, optimizer, losses, device)       # the reference's signature
     The second keeps the reference's training loop (py/main16.py:534-560) unchanged: a Trainer is created on the first
-    call and kept on the generator module, the learning rate is read from `optimizer.param_groups[0]` (the torch
-    optimizer itself is not stepped — Adam's moments live in the Trainer), `losses` is accepted and ignored (the
+    call and kept on the generator module; lr, betas and eps are read from `optimizer.param_groups[0]` on every call
+    (the torch optimizer itself is not stepped — Adam's moments live in the Trainer) and an optimizer the fused step
+    does not implement (another class, several groups, weight decay, amsgrad) raises; `losses` is accepted and ignored (the
     mel / loudness kernels are built in), and the modules receive the updated parameters and BatchNorm statistics
     before the function returns, so `validate_one_epoch(generator, detector, ...)` sees the trained weights."""
     if not isinstance(trainer, TR.Trainer):
         generator, detector, loader = trainer, train_loader, args[0]
         optimizer = args[1] if len(args) > 1 else None
         device = args[3] if len(args) > 3 else "cuda"
+        _check_optimizer(optimizer)
         tr = getattr(generator, "_wmb200_trainer", None)
         if tr is None or tr._detector_ref() is not detector:
             import weakref
             generator.to(device)
             detector.to(device)
-            lr = float(optimizer.param_groups[0]["lr"]) if optimizer is not None else TR.LR
-            tr = TR.Trainer(generator, detector, lr=lr)
+            g0 = optimizer.param_groups[0] if optimizer is not None else {}
+            tr = TR.Trainer(generator, detector, lr=float(g0.get("lr", TR.LR)),
+                            betas=tuple(float(b) for b in g0.get("betas", (0.9, 0.999))), eps=float(g0.get("eps", 1e-8)))
             tr._detector_ref = weakref.ref(detector)
             object.__setattr__(generator, "_wmb200_trainer", tr)
         elif optimizer is not None:
-            tr.lr = float(optimizer.param_groups[0]["lr"])
+            g0 = optimizer.param_groups[0]
+            tr.lr = float(g0["lr"])
+            tr.betas, tr.eps = tuple(float(b) for b in g0.get("betas", tr.betas)), float(g0.get("eps", tr.eps))
         out = train_one_epoch(tr, loader, schedule=schedule, global_step=global_step, message_fn=message_fn,
                               progress=progress)
         tr.write_back(generator, detector)
@@ -127,6 +132,25 @@ def train_one_epoch(trainer, train_loader: Iterable, *args, schedule: Optional[O
     if n == 0:
         raise ValueError("train_one_epoch: the loader produced no batches")
     return {k: float(v) / n for k, v in zip(LOG_KEYS, sums.tolist())}
+
+
+def _check_optimizer(optimizer) -> None:
+    """The Trainer implements torch.optim.Adam as the reference configures it (py/main16.py:504): one parameter group,
+    no weight decay, no amsgrad / maximize.  lr, betas and eps are taken from the optimizer; anything else that would
+    silently change the update is refused."""
+    if optimizer is None:
+        return
+    if not isinstance(optimizer, torch.optim.Adam) or isinstance(optimizer, torch.optim.AdamW):
+        raise TypeError(f"train_one_epoch: only torch.optim.Adam is implemented (got {type(optimizer).__name__}); "
+                        "run the loop under autograd (generator.train(), loss.backward()) to use another optimizer")
+    if len(optimizer.param_groups) != 1:
+        raise ValueError("train_one_epoch: the fused optimizer updates one parameter group (py/main16.py:504); got "
+                         f"{len(optimizer.param_groups)} — use the autograd path for per-group settings")
+    g = optimizer.param_groups[0]
+    bad = {k: g.get(k) for k, ok in (("weight_decay", 0), ("amsgrad", False), ("maximize", False)) if g.get(k, ok) != ok}
+    if bad:
+        raise ValueError(f"train_one_epoch: optimizer settings {bad} are not implemented by the fused Adam step; "
+                         "use the autograd path (loss.backward(); optimizer.step()) for them")
 
 
 # ---- checkpoints in the reference's format (py/main14d.py:540-560) --------------------------------------------------

@@ -12,7 +12,15 @@
  *   - waveforms are fp32 [b][t]; hidden activations of the single-operator
  *     entry points are fp32 channels-last x[b][t][c], c = 0..63 contiguous;
  *   - every function is asynchronous on `stream` (a cudaStream_t passed as
- *     void*), never allocates, never synchronises;
+ *     void*), never allocates device memory and never synchronises, with two
+ *     documented exceptions: wm_finalize_generator_blob / wm_finalize_detector_blob
+ *     (one-time set-up per weight blob) read the blob's fp32 block back to the host
+ *     and wait for that copy -- the fused kernels take biases and 1x1-head weights by
+ *     value (constant bank), which needs them on the host; and wm_embed_detect_host
+ *     keeps two copy streams and a handful of events per calling host thread
+ *     (created on first use, never destroyed) to overlap H2D / D2H with the kernels:
+ *     `stream` is made to wait for every one of them before the call returns, so
+ *     stream-order semantics are those of a plain sequence on `stream`;
  *   - return value 0 = success, negative = error; wm_last_error() returns the
  *     message of the last failure on the calling thread;
  *   - weights arrive as one packed fp32 blob per module (layout below), built

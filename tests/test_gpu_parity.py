@@ -476,8 +476,14 @@ def test_losses_vs_oracle_random_and_structured():
     # determinism
     a = wmb200.MultiScaleMelLoss()(s.to(DEV), s_w.to(DEV))
     assert torch.equal(a, wmb200.MultiScaleMelLoss()(s.to(DEV), s_w.to(DEV)))
-    with pytest.raises(NotImplementedError):
-        wmb200.high_freq_penalty(delta.to(DEV).requires_grad_())
+    # under autograd the same call records a graph whose backward is the FFT adjoint kernel (tests/test_autograd_loop.py)
+    dg = delta.to(DEV).requires_grad_()
+    hf = wmb200.high_freq_penalty(dg)
+    assert torch.equal(hf.detach(), wmb200.high_freq_penalty(delta.to(DEV)))
+    hf.backward()
+    assert dg.grad is not None and dg.grad.shape == dg.shape and torch.isfinite(dg.grad).all()
+    with pytest.raises(NotImplementedError):                       # the clean signal is data: no gradient w.r.t. it
+        wmb200.TFLoudnessLoss()(s.to(DEV).requires_grad_(), s_w.to(DEV))
 
 
 def test_bce_heads_vs_torch():

@@ -56,9 +56,11 @@ def test_no_gpu_fails_loudly():
     assert rc != 0 and b"" != L.load().wm_last_error()
 
 
-def test_training_mode_is_refused():
+def test_train_mode_has_no_cpu_fallback_either():
+    """Train-mode forward runs the autograd path on the GPU kernels; on CPU tensors it fails as loudly as eval mode."""
     g = wmb200.Generator(16)
-    with pytest.raises(NotImplementedError):
+    assert g.training
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         g(torch.zeros(1, 1, 16000))
 
 
