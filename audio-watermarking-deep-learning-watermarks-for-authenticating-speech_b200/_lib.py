@@ -12,7 +12,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwmb200.so")
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 # blob offsets (floats) — mirror of the enums in include/wmb200.h
 RB_W1 = 0
@@ -186,6 +186,7 @@ SIGNATURES = {
     "wm_bn_train_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _p, _sz, _p]),
     "wm_conv64_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "wm_conv64_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _sz, _p]),
+    "wm_conv64_train_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _sz, _p]),
     "wm_lstm_train_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "wm_lstm_train_bwd_workspace_bytes": (_sz, [_i, _i]),
     "wm_lstm_train_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _sz, _p]),

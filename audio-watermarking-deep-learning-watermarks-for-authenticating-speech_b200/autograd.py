@@ -39,7 +39,7 @@ class Conv64(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
-        return ops.conv64(x, weight.permute(2, 1, 0).contiguous(), bias, taps=weight.shape[-1])
+        return TR.conv64_train_fwd(x, weight, bias)
 
     @staticmethod
     def backward(ctx, dy):

@@ -22,6 +22,7 @@ void set_error(const char *fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+int math_mode() { return g_math_mode.load(); }
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 int sm_count() {
@@ -734,7 +735,7 @@ int wm_bn_train_bwd(const float *dout, const float *act, const float *z, const f
 
 size_t wm_conv64_bwd_workspace_bytes(int B, int T, int K) {
   if (B <= 0 || T <= 0 || K <= 0) return 0;
-  return (conv_wgrad_scratch_floats(B, T, K) + (size_t)K * 4096 + 64) * sizeof(float);
+  return train_conv64_scratch_floats(B, T, K) * sizeof(float);
 }
 
 int wm_conv64_bwd(const float *x, const float *dy, const float *w, float *dw, float *db, float *dx, int B, int T, int K,
@@ -744,16 +745,18 @@ int wm_conv64_bwd(const float *x, const float *dy, const float *w, float *dw, fl
   WM_CHECK_ARG(K == 1 || K == 3 || K == 7, "conv64_bwd: K must be 1, 3 or 7 (got %d)", K);
   WM_CHECK_ARG(x && dy && dw && db && workspace && (!dx || w), "conv64_bwd: null pointer");
   WM_CHECK_ARG(workspace_bytes >= wm_conv64_bwd_workspace_bytes(B, T, K), "conv64_bwd: workspace too small");
-  cudaStream_t st = as_stream(stream);
-  float *scratch = (float *)workspace;
-  WM_TRY(launch_conv_wgrad(x, dy, dw, db, B, T, K, scratch, st));
-  if (dx) {
-    float *wt = scratch + conv_wgrad_scratch_floats(B, T, K), *zero = wt + (size_t)K * 4096;
-    WM_CHECK_CUDA(cudaMemsetAsync(zero, 0, 64 * sizeof(float), st));
-    WM_TRY(launch_transpose_flip(w, wt, K, st));
-    WM_TRY(launch_conv64_fp32(dy, wt, zero, nullptr, nullptr, dx, B, T, K, 0, st));
-  }
-  return 0;
+  return train_conv64_bwd(x, dy, w, dw, db, dx, B, T, K, (float *)workspace, as_stream(stream));
+}
+
+int wm_conv64_train_fwd(const float *x, const float *w, const float *bias, const float *residual, float *y, int B, int T,
+                        int K, void *workspace, size_t workspace_bytes, void *stream) {
+  WM_ENTRY();
+  WM_CHECK_ARG(B >= 0 && T >= 0, "conv64_train_fwd: negative size");
+  if (B == 0 || T == 0) return 0;
+  WM_CHECK_ARG(K == 1 || K == 3 || K == 7, "conv64_train_fwd: K must be 1, 3 or 7 (got %d)", K);
+  WM_CHECK_ARG(x && w && bias && y && workspace && x != y, "conv64_train_fwd: null pointer or in-place");
+  WM_CHECK_ARG(workspace_bytes >= wm_conv64_bwd_workspace_bytes(B, T, K), "conv64_train_fwd: workspace too small");
+  return train_conv64_fwd(x, w, bias, residual, y, B, T, K, (float *)workspace, as_stream(stream));
 }
 
 int wm_lstm_train_fwd(const float *x, const float *wT_ih, const float *wT_hh, const float *b_ih, const float *b_hh,

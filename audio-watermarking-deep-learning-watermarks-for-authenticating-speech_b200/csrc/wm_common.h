@@ -81,7 +81,7 @@ int launch_head_detect(const float *x, const float *w, const float *b, const int
 
 // tcgen05 path (wm_conv_tc.cu); x / residual / y are planar activations, w_img from launch_pack_conv64_tc
 int launch_conv64_tc(const void *x, const void *w_img, const float *bias, const void *residual, void *y, float *y32,
-                     int B, int T, int taps, int relu, cudaStream_t st);
+                     int B, int T, int taps, int relu, cudaStream_t st, const float *res32 = nullptr);
 int launch_pack_conv64_tc(const float *w, void *img, int taps, cudaStream_t st);
 int launch_to_planar(const float *x, const float *chan_add, void *y, int B, int T, cudaStream_t st);
 int launch_from_planar(const void *x, float *y, int B, int T, cudaStream_t st);
@@ -187,6 +187,18 @@ int launch_resample(const float *x, const float *kern, float *y, int B, int Tin,
                     int width, cudaStream_t st);
 int launch_pcm16(const float *x, short *q, float *xo, long long n, int quantize, float scale, cudaStream_t st);
 int launch_file_metrics(const float *s, const float *sw, const int *valid_len, float *out, int B, int T, cudaStream_t st);
+// wm_wgrad_tc.cu: tcgen05 weight gradient of the 64 -> 64 convolutions (planar operands), bias gradient
+size_t wgrad_tc_scratch_floats(int K);
+int launch_wgrad_tc(const void *xp, const void *dyp, float *dw, int B, int T, int K, float *scratch, cudaStream_t st);
+size_t colsum64_scratch_floats();
+int launch_colsum64(const float *dy, float *db, long long rows, float *scratch, cudaStream_t st);
+int math_mode();   // WM_MATH_FP32 / WM_MATH_BF16X2 (wm_set_math_mode)
+// wm_train.cu: the training step's 64 -> 64 convolution as single operators (tensor cores in the default math mode)
+size_t train_conv64_scratch_floats(int B, int T, int K);
+int train_conv64_fwd(const float *x, const float *w, const float *bias, const float *residual, float *y, int B, int T,
+                     int K, float *scratch, cudaStream_t st);
+int train_conv64_bwd(const float *x, const float *dy, const float *w, float *dw, float *db, float *dx, int B, int T, int K,
+                     float *scratch, cudaStream_t st);
 // wm_eval.cu: second-order IIR (lfilter semantics) + PCM16, detection statistics
 size_t biquad_scratch_bytes(int rows, long long N);
 int launch_biquad(const float *x, float *y, short *q, int rows, long long N, const double *b, const double *a, int clamp,

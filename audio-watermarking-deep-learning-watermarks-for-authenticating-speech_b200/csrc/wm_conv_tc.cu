@@ -59,7 +59,7 @@ template <int TAPS>
 __global__ void __launch_bounds__(576, 1)
     conv64_tc_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ w_img, const float *__restrict__ bias,
                      const uint4 *__restrict__ residual, uint4 *__restrict__ y, float *__restrict__ y32, int B, int T,
-                     int relu) {
+                     int relu, const float *__restrict__ res32) {
   using C = Cfg<TAPS>;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
@@ -200,6 +200,14 @@ __global__ void __launch_bounds__(576, 1)
             for (int c = 0; c < 8; ++c) o[h * 8 + c] += r[c];
           }
         }
+        if (res32 != nullptr && live) {   // fp32 channels-last residual (the training step's gradient accumulation)
+          const float4 *src = reinterpret_cast<const float4 *>(res32 + ((size_t)b * T + t) * 64 + p * 16);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 r = __ldg(src + c);
+            o[4 * c] += r.x; o[4 * c + 1] += r.y; o[4 * c + 2] += r.z; o[4 * c + 3] += r.w;
+          }
+        }
         if (relu) {
 #pragma unroll
           for (int c = 0; c < 16; ++c) o[c] = fmaxf(o[c], 0.0f);
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(576, 1)
 
 template <int TAPS>
 static int launch_conv64_tc_t(const void *x, const void *w_img, const float *bias, const void *residual, void *y,
-                              float *y32, int B, int T, int relu, cudaStream_t st) {
+                              float *y32, int B, int T, int relu, cudaStream_t st, const float *res32) {
   using C = Cfg<TAPS>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -246,17 +254,17 @@ static int launch_conv64_tc_t(const void *x, const void *w_img, const float *bia
   int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
   conv64_tc_kernel<TAPS><<<grid, 576, C::SMEM_BYTES, st>>>(
       reinterpret_cast<const uint4 *>(x), reinterpret_cast<const uint4 *>(w_img), bias,
-      reinterpret_cast<const uint4 *>(residual), reinterpret_cast<uint4 *>(y), y32, B, T, relu);
+      reinterpret_cast<const uint4 *>(residual), reinterpret_cast<uint4 *>(y), y32, B, T, relu, res32);
   WM_CHECK_LAUNCH("conv64_tc");
   return 0;
 }
 
 int launch_conv64_tc(const void *x, const void *w_img, const float *bias, const void *residual, void *y, float *y32,
-                     int B, int T, int taps, int relu, cudaStream_t st) {
+                     int B, int T, int taps, int relu, cudaStream_t st, const float *res32) {
   if (B == 0 || T == 0) return 0;
   switch (taps) {
-    case 3: return launch_conv64_tc_t<3>(x, w_img, bias, residual, y, y32, B, T, relu, st);
-    case 7: return launch_conv64_tc_t<7>(x, w_img, bias, residual, y, y32, B, T, relu, st);
+    case 3: return launch_conv64_tc_t<3>(x, w_img, bias, residual, y, y32, B, T, relu, st, res32);
+    case 7: return launch_conv64_tc_t<7>(x, w_img, bias, residual, y, y32, B, T, relu, st, res32);
     default: set_error("conv64_tc: taps must be 3 or 7 (got %d)", taps); return -1;
   }
 }

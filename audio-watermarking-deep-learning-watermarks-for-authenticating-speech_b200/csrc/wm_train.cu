@@ -5,6 +5,8 @@
 // goes through per-block partial sums added in a fixed order, so a step is deterministic.
 // The generator's backward (LSTM through 16 000 steps, STFT losses) is not built yet: this file is the groundwork of
 // BASELINE config 4 and is exercised against PyTorch autograd in tests/test_train.py.
+#include <stdlib.h>
+
 #include "wm_common.h"
 
 namespace wm {
@@ -603,11 +605,90 @@ int launch_adam(float *p, const float *g, float *m, float *v, long long n, float
   return 0;
 }
 
+// ---- 64 -> 64 convolutions of the training step (forward, data gradient, weight gradient) ---------------------
+// In the library's default math mode (WM_MATH_BF16X2) the channel-heavy convolutions of the training step run on the
+// tensor cores, like the inference path: bf16 hi+lo operand pairs, fp32 accumulation in TMEM.
+//   forward / data gradient: the inference conv kernel (three partial products).  The fp32 channels-last input is
+//     re-laid as hi/lo planes (one HBM pass), the weights -- which change every step -- are re-imaged by a
+//     12 K-element kernel, the output comes back fp32 channels-last with the fp32 residual added in the epilogue;
+//   weight gradient: wm_wgrad_tc.cu (MN-major operands straight from the planes, four partial products).
+// Precision: 2^-17 relative per operand, 64x finer than the TF32 the reference itself trains with
+// (torch.set_float32_matmul_precision('high'), py/main16.py:44, and cuDNN's TF32 default); measured against the fp64
+// oracle next to PyTorch's own step in profiles/r2_train_precision_tc.txt.  WM_MATH_FP32 (wm_set_math_mode) selects the
+// exact-order fp32 FMA kernels, against which the tight operator-level gradient tests run.
+namespace {
+struct TcScratch { void *xp, *yp; float *img, *wg; };
+size_t tc_planar_floats(int B, int T) { return ((size_t)B * ((size_t)T + 2 * WM_PLANAR_PAD) * 64 + 1024 + 63) / 64 * 64; }
+constexpr size_t kTcImgFloats = 7 * 4096;
+size_t tc_scratch_floats(int B, int T) {
+  return 2 * tc_planar_floats(B, T) + kTcImgFloats + wgrad_tc_scratch_floats(7) + colsum64_scratch_floats() + 256;
+}
+bool train_tc_enabled() { return math_mode() == WM_MATH_BF16X2; }
+// y = conv(in) + bias + residual   (w tap-major [K][ci][co])
+int conv64_train(const float *in, const float *w, const float *bias, const float *residual, float *out, int B, int T, int K,
+                 TcScratch tc, cudaStream_t st) {
+  if (!train_tc_enabled() || tc.xp == nullptr || (K != 3 && K != 7))
+    return launch_conv64_fp32(in, w, bias, residual, nullptr, out, B, T, K, 0, st);
+  WM_TRY(launch_to_planar(in, nullptr, tc.xp, B, T, st));
+  WM_TRY(launch_pack_conv64_tc(w, tc.img, K, st));
+  return launch_conv64_tc(tc.xp, tc.img, bias, nullptr, nullptr, out, B, T, K, 0, st, residual);
+}
+// gradients of y = conv(x): dw, db, and dx = conv^T(dy) + dx_residual (dx nullable); wt [K*4096] and zero64 scratch
+int conv64_bwd_train(const float *x, const float *dy, const float *w, float *dw, float *db, float *dx,
+                     const float *dx_residual, int B, int T, int K, TcScratch tc, float *fscratch, float *wt,
+                     const float *zero64, cudaStream_t st) {
+  if (!train_tc_enabled() || tc.xp == nullptr || (K != 3 && K != 7)) {
+    WM_TRY(launch_conv_wgrad(x, dy, dw, db, B, T, K, fscratch, st));
+    if (dx == nullptr) return 0;
+    WM_TRY(launch_transpose_flip(w, wt, K, st));
+    return launch_conv64_fp32(dy, wt, zero64, dx_residual, nullptr, dx, B, T, K, 0, st);
+  }
+  WM_TRY(launch_to_planar(dy, nullptr, tc.yp, B, T, st));
+  WM_TRY(launch_to_planar(x, nullptr, tc.xp, B, T, st));
+  WM_TRY(launch_wgrad_tc(tc.xp, tc.yp, dw, B, T, K, tc.wg, st));
+  WM_TRY(launch_colsum64(dy, db, (long long)B * T, tc.wg + wgrad_tc_scratch_floats(7), st));
+  if (dx == nullptr) return 0;
+  WM_TRY(launch_transpose_flip(w, wt, K, st));
+  WM_TRY(launch_pack_conv64_tc(wt, tc.img, K, st));
+  return launch_conv64_tc(tc.yp, tc.img, zero64, nullptr, nullptr, dx, B, T, K, 0, st, dx_residual);
+}
+TcScratch tc_take(float *base, size_t &off, int B, int T) {   // carve the scratch out of a float workspace (base may be null)
+  TcScratch t;
+  auto take = [&](size_t n) { float *q = base ? base + off : nullptr; off += (n + 63) / 64 * 64; return q; };
+  t.xp = take(tc_planar_floats(B, T));
+  t.yp = take(tc_planar_floats(B, T));
+  t.img = take(kTcImgFloats);
+  t.wg = take(wgrad_tc_scratch_floats(7) + colsum64_scratch_floats() + 64);
+  return t;
+}
+}  // namespace
+
+// single-operator forms behind the C ABI (wm_conv64_train_fwd, wm_conv64_bwd): same code path as inside the step
+size_t train_conv64_scratch_floats(int B, int T, int K) {
+  return tc_scratch_floats(B, T) + conv_wgrad_scratch_floats(B, T, K) + (size_t)K * 4096 + 128;
+}
+int train_conv64_fwd(const float *x, const float *w, const float *bias, const float *residual, float *y, int B, int T,
+                     int K, float *scratch, cudaStream_t st) {
+  size_t off = 0;
+  TcScratch tc = tc_take(scratch, off, B, T);
+  return conv64_train(x, w, bias, residual, y, B, T, K, tc, st);
+}
+int train_conv64_bwd(const float *x, const float *dy, const float *w, float *dw, float *db, float *dx, int B, int T, int K,
+                     float *scratch, cudaStream_t st) {
+  size_t off = 0;
+  TcScratch tc = tc_take(scratch, off, B, T);
+  float *fscratch = scratch + off;
+  float *wt = fscratch + conv_wgrad_scratch_floats(B, T, K), *zero = wt + (size_t)K * 4096;
+  WM_CHECK_CUDA(cudaMemsetAsync(zero, 0, 64 * sizeof(float), st));
+  return conv64_bwd_train(x, dy, w, dw, db, dx, nullptr, B, T, K, tc, fscratch, wt, zero, st);
+}
+
 // ---- the detector's training step ---------------------------------------------------------------------------
 namespace {
 struct DetWs {
   float *x0, *act[2][4] /* z1, u, z2, y */, *logits, *dlog, *g[3], *wt, *stats, *zero64, *fscratch, *losses;
   double *dscratch;
+  TcScratch tc;
   size_t bytes;
 };
 size_t align64(size_t n) { return (n + 63) / 64 * 64; }
@@ -635,6 +716,7 @@ DetWs det_ws(void *base, int B2, int T, int nout) {
   w.losses = take(64);
   w.fscratch = take(fs);
   w.dscratch = (double *)take(2 * train_scratch_doubles((long long)N));
+  w.tc = tc_take(p, off, B2, T);
   w.bytes = off * sizeof(float);
   return w;
 }
@@ -662,10 +744,10 @@ int detector_train_step(float *params, float *grads, float *adam_m, float *adam_
     const float *rb = params + WM_DT_RB0 + k * WM_DT_RB_SIZE;
     float *rs = run_stats + k * 256, *stt = w.stats + k * 256;
     float *z1 = w.act[k][0], *u = w.act[k][1], *z2 = w.act[k][2], *y = w.act[k][3];
-    WM_TRY(launch_conv64_fp32(in, rb + WM_DT_RB_W1, rb + WM_DT_RB_B1, nullptr, nullptr, z1, B2, T, 3, 0, st));
+    WM_TRY(conv64_train(in, rb + WM_DT_RB_W1, rb + WM_DT_RB_B1, nullptr, z1, B2, T, 3, w.tc, st));
     WM_TRY(launch_bn_train_fwd(z1, rb + WM_DT_RB_G1, rb + WM_DT_RB_BE1, nullptr, u, stt, stt + 64, rs, rs + 64, N, 1,
                                w.dscratch, st));
-    WM_TRY(launch_conv64_fp32(u, rb + WM_DT_RB_W2, rb + WM_DT_RB_B2, nullptr, nullptr, z2, B2, T, 3, 0, st));
+    WM_TRY(conv64_train(u, rb + WM_DT_RB_W2, rb + WM_DT_RB_B2, nullptr, z2, B2, T, 3, w.tc, st));
     WM_TRY(launch_bn_train_fwd(z2, rb + WM_DT_RB_G2, rb + WM_DT_RB_BE2, in, y, stt + 128, stt + 192, rs + 128, rs + 192, N,
                                1, w.dscratch, st));
     in = y;
@@ -686,14 +768,12 @@ int detector_train_step(float *params, float *grads, float *adam_m, float *adam_
     const float *z1 = w.act[k][0], *u = w.act[k][1], *z2 = w.act[k][2], *y = w.act[k][3];
     WM_TRY(launch_bn_train_bwd(gA, y, z2, stt + 128, stt + 192, rb + WM_DT_RB_G2, gB, gC, gr + WM_DT_RB_G2,
                                gr + WM_DT_RB_BE2, N, w.dscratch, st));
-    WM_TRY(launch_conv_wgrad(u, gB, gr + WM_DT_RB_W2, gr + WM_DT_RB_B2, B2, T, 3, w.fscratch, st));
-    WM_TRY(launch_transpose_flip(rb + WM_DT_RB_W2, w.wt, 3, st));
-    WM_TRY(launch_conv64_fp32(gB, w.wt, w.zero64, nullptr, nullptr, gA, B2, T, 3, 0, st));
+    WM_TRY(conv64_bwd_train(u, gB, rb + WM_DT_RB_W2, gr + WM_DT_RB_W2, gr + WM_DT_RB_B2, gA, nullptr, B2, T, 3, w.tc,
+                            w.fscratch, w.wt, w.zero64, st));
     WM_TRY(launch_bn_train_bwd(gA, u, z1, stt, stt + 64, rb + WM_DT_RB_G1, gB, nullptr, gr + WM_DT_RB_G1, gr + WM_DT_RB_BE1,
                                N, w.dscratch, st));
-    WM_TRY(launch_conv_wgrad(xin, gB, gr + WM_DT_RB_W1, gr + WM_DT_RB_B1, B2, T, 3, w.fscratch, st));
-    WM_TRY(launch_transpose_flip(rb + WM_DT_RB_W1, w.wt, 3, st));
-    WM_TRY(launch_conv64_fp32(gB, w.wt, w.zero64, gC, nullptr, gA, B2, T, 3, 0, st));
+    WM_TRY(conv64_bwd_train(xin, gB, rb + WM_DT_RB_W1, gr + WM_DT_RB_W1, gr + WM_DT_RB_B1, gA, gC, B2, T, 3, w.tc,
+                            w.fscratch, w.wt, w.zero64, st));
   }
   WM_TRY(launch_conv_in_grads(x, gA, params + WM_DT_IN_W, grads + WM_DT_IN_W, grads + WM_DT_IN_B, d_input, B2, T,
                               w.fscratch, st));
@@ -709,30 +789,29 @@ struct RbActs { float *z1, *u, *z2, *y; };
 
 // relu(x + BN(conv3(relu(BN(conv3(x)))))) in train mode; rb: WM_DT_RB_* block, rs: 256 running stats, stt: 256 batch stats
 int rb_train_fwd(const float *in, const float *rb, float *rs, float *stt, RbActs a, int B, int T, double *dscratch,
-                 cudaStream_t st) {
+                 TcScratch tc, cudaStream_t st) {
   const long long N = (long long)B * T;
-  WM_TRY(launch_conv64_fp32(in, rb + WM_DT_RB_W1, rb + WM_DT_RB_B1, nullptr, nullptr, a.z1, B, T, 3, 0, st));
+  WM_TRY(conv64_train(in, rb + WM_DT_RB_W1, rb + WM_DT_RB_B1, nullptr, a.z1, B, T, 3, tc, st));
   WM_TRY(launch_bn_train_fwd(a.z1, rb + WM_DT_RB_G1, rb + WM_DT_RB_BE1, nullptr, a.u, stt, stt + 64, rs, rs + 64, N, 1,
                              dscratch, st));
-  WM_TRY(launch_conv64_fp32(a.u, rb + WM_DT_RB_W2, rb + WM_DT_RB_B2, nullptr, nullptr, a.z2, B, T, 3, 0, st));
+  WM_TRY(conv64_train(a.u, rb + WM_DT_RB_W2, rb + WM_DT_RB_B2, nullptr, a.z2, B, T, 3, tc, st));
   return launch_bn_train_fwd(a.z2, rb + WM_DT_RB_G2, rb + WM_DT_RB_BE2, in, a.y, stt + 128, stt + 192, rs + 128, rs + 192,
                              N, 1, dscratch, st);
 }
 
 // gA holds dL/dy on entry and dL/dx on exit; gB, gC scratch activations; wt [3*4096], zero64 as in DetWs
 int rb_train_bwd(const float *xin, const float *rb, float *gr, const float *stt, RbActs a, float *gA, float *gB, float *gC,
-                 float *wt, const float *zero64, int B, int T, float *fscratch, double *dscratch, cudaStream_t st) {
+                 float *wt, const float *zero64, int B, int T, float *fscratch, double *dscratch, TcScratch tc,
+                 cudaStream_t st) {
   const long long N = (long long)B * T;
   WM_TRY(launch_bn_train_bwd(gA, a.y, a.z2, stt + 128, stt + 192, rb + WM_DT_RB_G2, gB, gC, gr + WM_DT_RB_G2,
                              gr + WM_DT_RB_BE2, N, dscratch, st));
-  WM_TRY(launch_conv_wgrad(a.u, gB, gr + WM_DT_RB_W2, gr + WM_DT_RB_B2, B, T, 3, fscratch, st));
-  WM_TRY(launch_transpose_flip(rb + WM_DT_RB_W2, wt, 3, st));
-  WM_TRY(launch_conv64_fp32(gB, wt, zero64, nullptr, nullptr, gA, B, T, 3, 0, st));
+  WM_TRY(conv64_bwd_train(a.u, gB, rb + WM_DT_RB_W2, gr + WM_DT_RB_W2, gr + WM_DT_RB_B2, gA, nullptr, B, T, 3, tc, fscratch,
+                          wt, zero64, st));
   WM_TRY(launch_bn_train_bwd(gA, a.u, a.z1, stt, stt + 64, rb + WM_DT_RB_G1, gB, nullptr, gr + WM_DT_RB_G1,
                              gr + WM_DT_RB_BE1, N, dscratch, st));
-  WM_TRY(launch_conv_wgrad(xin, gB, gr + WM_DT_RB_W1, gr + WM_DT_RB_B1, B, T, 3, fscratch, st));
-  WM_TRY(launch_transpose_flip(rb + WM_DT_RB_W1, wt, 3, st));
-  return launch_conv64_fp32(gB, wt, zero64, gC, nullptr, gA, B, T, 3, 0, st);
+  return conv64_bwd_train(xin, gB, rb + WM_DT_RB_W1, gr + WM_DT_RB_W1, gr + WM_DT_RB_B1, gA, gC, B, T, 3, tc, fscratch, wt,
+                          zero64, st);
 }
 
 struct GenWs {
@@ -740,6 +819,7 @@ struct GenWs {
   RbActs rb[3];
   float *draw, *d1, *delta, *xdet /* [2B][T]: s_w then s */, *gsw, *gdraw, *dxdet, *fscratch, *lstm_scratch;
   double *dscratch;
+  TcScratch tc;
   void *det_ws;
   size_t bytes;
 };
@@ -776,6 +856,7 @@ GenWs gen_ws(void *base, int B, int T, int nout) {
   w.fscratch = take(fs);
   w.lstm_scratch = take(lstm_train_bwd_scratch_floats(B, T));
   w.dscratch = (double *)take(2 * train_scratch_doubles((long long)N));
+  w.tc = tc_take(p, off, B, T);
   w.det_ws = p ? (void *)(p + off) : nullptr;
   off += align64(detector_train_workspace_bytes(2 * B, T, nout) / sizeof(float) + 64);
   w.bytes = off * sizeof(float);
@@ -803,14 +884,14 @@ int train_forward_backward(const float *g_params, float *g_grads, float *g_stats
   WM_CHECK_CUDA(cudaMemsetAsync(g_grads, 0, (size_t)WM_GT_SIZE * sizeof(float), st));
   // ---- generator forward (py/main16.py:148-162 in train mode) ----
   WM_TRY(launch_conv_in_k7(s, g_params + WM_GT_IN_W, g_params + WM_GT_IN_B, w.x0, B, T, st));
-  WM_TRY(rb_train_fwd(w.x0, g_params + WM_GT_RB0, g_stats, w.stats, w.rb[0], B, T, w.dscratch, st));
-  WM_TRY(rb_train_fwd(w.rb[0].y, g_params + WM_GT_RB1, g_stats + 256, w.stats + 256, w.rb[1], B, T, w.dscratch, st));
+  WM_TRY(rb_train_fwd(w.x0, g_params + WM_GT_RB0, g_stats, w.stats, w.rb[0], B, T, w.dscratch, w.tc, st));
+  WM_TRY(rb_train_fwd(w.rb[0].y, g_params + WM_GT_RB1, g_stats + 256, w.stats + 256, w.rb[1], B, T, w.dscratch, w.tc, st));
   WM_TRY(launch_lstm_train_fwd(w.rb[1].y, g_params + WM_GT_LSTM_WIH, g_params + WM_GT_LSTM_WHH, g_params + WM_GT_LSTM_BIH,
                                g_params + WM_GT_LSTM_BHH, w.h, w.gates, w.cell, B, T, st));
   add_embedding_kernel<<<grid_for(N * 16, NT), NT, 0, st>>>(w.h, g_params + WM_GT_EMB, msg, w.hE, T, N * 16);
   WM_CHECK_LAUNCH("add_embedding");
-  WM_TRY(launch_conv64_fp32(w.hE, g_params + WM_GT_CT_W, g_params + WM_GT_CT_B, nullptr, nullptr, w.ct, B, T, 7, 0, st));
-  WM_TRY(rb_train_fwd(w.ct, g_params + WM_GT_RB2, g_stats + 512, w.stats + 512, w.rb[2], B, T, w.dscratch, st));
+  WM_TRY(conv64_train(w.hE, g_params + WM_GT_CT_W, g_params + WM_GT_CT_B, nullptr, w.ct, B, T, 7, w.tc, st));
+  WM_TRY(rb_train_fwd(w.ct, g_params + WM_GT_RB2, g_stats + 512, w.stats + 512, w.rb[2], B, T, w.dscratch, w.tc, st));
   WM_TRY(launch_head(w.rb[2].y, g_params + WM_GT_HEAD_W, g_params + WM_GT_HEAD_B, w.draw, B, T, 1, st));
   // ---- post-processing (py/main16.py:245-248): d1 = fir(delta_raw) kept for the backward ----
   WM_TRY(launch_postprocess(w.draw, nullptr, fir, w.d1, nullptr, nullptr, B, T, WM_POST_FIR, 0.02f, 0.005f, 1e-8f, st));
@@ -837,10 +918,9 @@ int train_forward_backward(const float *g_params, float *g_grads, float *g_stats
   WM_TRY(launch_head_bwd(w.gdraw, w.rb[2].y, g_params + WM_GT_HEAD_W, gA, g_grads + WM_GT_HEAD_W, g_grads + WM_GT_HEAD_B, N,
                          1, w.fscratch, st));
   WM_TRY(rb_train_bwd(w.ct, g_params + WM_GT_RB2, g_grads + WM_GT_RB2, w.stats + 512, w.rb[2], gA, gB, gC, w.wt, w.zero64,
-                      B, T, w.fscratch, w.dscratch, st));
-  WM_TRY(launch_conv_wgrad(w.hE, gA, g_grads + WM_GT_CT_W, g_grads + WM_GT_CT_B, B, T, 7, w.fscratch, st));
-  WM_TRY(launch_transpose_flip(g_params + WM_GT_CT_W, w.wt, 7, st));
-  WM_TRY(launch_conv64_fp32(gA, w.wt, w.zero64, nullptr, nullptr, gB, B, T, 7, 0, st));     // gB = dL/d(h + e)
+                      B, T, w.fscratch, w.dscratch, w.tc, st));
+  WM_TRY(conv64_bwd_train(w.hE, gA, g_params + WM_GT_CT_W, g_grads + WM_GT_CT_W, g_grads + WM_GT_CT_B, gB, nullptr, B, T, 7,
+                          w.tc, w.fscratch, w.wt, w.zero64, st));     // gB = dL/d(h + e)
   clip_colsum_kernel<<<B, NT, 0, st>>>(gB, w.colsum, T);
   WM_CHECK_LAUNCH("clip_colsum");
   embedding_scatter_kernel<<<1, 64, 0, st>>>(w.colsum, msg, g_grads + WM_GT_EMB, B);
@@ -851,9 +931,9 @@ int train_forward_backward(const float *g_params, float *g_grads, float *g_stats
   WM_CHECK_CUDA(cudaMemcpyAsync(g_grads + WM_GT_LSTM_BHH, g_grads + WM_GT_LSTM_BIH, 256 * sizeof(float),
                                 cudaMemcpyDeviceToDevice, st));
   WM_TRY(rb_train_bwd(w.rb[0].y, g_params + WM_GT_RB1, g_grads + WM_GT_RB1, w.stats + 256, w.rb[1], gA, gB, gC, w.wt,
-                      w.zero64, B, T, w.fscratch, w.dscratch, st));
+                      w.zero64, B, T, w.fscratch, w.dscratch, w.tc, st));
   WM_TRY(rb_train_bwd(w.x0, g_params + WM_GT_RB0, g_grads + WM_GT_RB0, w.stats, w.rb[0], gA, gB, gC, w.wt, w.zero64, B, T,
-                      w.fscratch, w.dscratch, st));
+                      w.fscratch, w.dscratch, w.tc, st));
   WM_TRY(launch_conv_in_grads(s, gA, g_params + WM_GT_IN_W, g_grads + WM_GT_IN_W, g_grads + WM_GT_IN_B, nullptr, B, T,
                               w.fscratch, st));
   // totals (py/main16.py:273-276)

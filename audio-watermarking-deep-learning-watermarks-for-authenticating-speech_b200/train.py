@@ -82,6 +82,24 @@ def conv64_bwd(x: torch.Tensor, dy: torch.Tensor, weight: torch.Tensor, want_dx:
     return dw.permute(2, 1, 0).contiguous(), db, dx
 
 
+def conv64_train_fwd(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
+                     residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Forward of Conv1d(64,64,K,padding=K//2) as the training step runs it (tensor cores in the default math mode,
+    fp32 FMA under WM_MATH_FP32): channels-last x (B,T,64), `weight` in the reference's (co,ci,K) layout."""
+    lib = L.load()
+    x = _req(x, "x")
+    B, T, _ = x.shape
+    K = weight.shape[-1]
+    w_t = _req(weight, "weight").permute(2, 1, 0).contiguous()          # [k][ci][co]
+    y = torch.empty_like(x)
+    res = _req(residual, "residual") if residual is not None else None
+    n = lib.wm_conv64_bwd_workspace_bytes(B, T, K)
+    ws = _ws(n, x.device)
+    L.check(lib.wm_conv64_train_fwd(L.ptr(x), L.ptr(w_t), L.ptr(_req(bias, "bias")), L.ptr(res), L.ptr(y), B, T, K,
+                                    L.ptr(ws), n, _stream()), "wm_conv64_train_fwd")
+    return y
+
+
 def _gate_t(w: torch.Tensor) -> torch.Tensor:
     """(256,64) PyTorch LSTM weight -> per-gate transposed wT[q][k][r] = W[q*64 + r][k]; its own inverse."""
     return w.reshape(4, 64, 64).permute(0, 2, 1).contiguous()

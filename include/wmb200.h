@@ -40,7 +40,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 16
+#define WM_ABI_VERSION 17
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -450,6 +450,12 @@ int wm_bn_train_bwd(const float *dout, const float *act, const float *z, const f
 /* Gradients of y = Conv1d(64,64,K,padding=K/2)(x) given dy: dw [K][64][64] tap-major, db [64], dx (nullable; needs
  * w, the forward weight in the same layout).  K in {1,3,7}. */
 size_t wm_conv64_bwd_workspace_bytes(int B, int T, int K);
+/* The training step's forward convolution as a single operator: y = conv(x) + bias (+ residual), fp32 channels-last in
+ * and out.  In the default math mode (WM_MATH_BF16X2) forward, data gradient and weight gradient of these
+ * convolutions run on tcgen05 (bf16 hi+lo pairs, fp32 accumulate); WM_MATH_FP32 selects the fp32 FMA kernels.
+ * Workspace: wm_conv64_bwd_workspace_bytes(B, T, K) for both. */
+int wm_conv64_train_fwd(const float *x, const float *w, const float *bias, const float *residual, float *y, int B, int T,
+                        int K, void *workspace, size_t workspace_bytes, void *stream);
 int wm_conv64_bwd(const float *x, const float *dy, const float *w, float *dw, float *db, float *dx, int B, int T, int K,
                   void *workspace, size_t workspace_bytes, void *stream);
 /* Backward of the remaining single operators (each checked against autograd in tests/test_train.py):

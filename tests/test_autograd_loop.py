@@ -102,13 +102,20 @@ def test_reference_loop_body_runs_under_autograd_and_matches_trainer(B, T):
         checked += 1
     assert checked >= 30
 
-    # one Adam step from the same start: parameters agree; BatchNorm running statistics were updated identically
-    for sd_new, sd_ref, sd0 in ((generator.state_dict(), gsd_ref, g0), (detector.state_dict(), dsd_ref, d0)):
+    # one Adam step from the same start.  Adam's first step moves every weight by lr * sign(g): the two paths add the
+    # residual-branch gradient in a different order (conv epilogue vs autograd's accumulation), so an element whose
+    # gradient is round-off noise can take the opposite sign (2 * lr apart); everything else lands on the same value.
+    # BatchNorm running statistics come from the forward pass, which is the same kernels in the same order.
+    for sd_new, sd_ref in ((generator.state_dict(), gsd_ref), (detector.state_dict(), dsd_ref)):
         for k, v in sd_ref.items():
             if k.endswith(("block.0.bias", "block.3.bias", "num_batches_tracked")):
                 continue
-            moved = float((sd0[k].to(device).float() - v.to(device)).abs().max())
-            assert float((sd_new[k].float() - v.to(device)).abs().max()) <= 2e-5 + 0.02 * moved, k
+            dlt = (sd_new[k].float() - v.to(device)).abs()
+            if "running" in k:
+                assert float(dlt.max()) <= 1e-6 * max(1.0, float(v.abs().max())), k
+            else:
+                assert float(dlt.max()) <= 2.1e-3, k
+                assert float(dlt.median()) <= 1e-6, k
     assert int(generator.encoder[1].block[1].num_batches_tracked) == 1
 
     # back to eval: the fused inference path picks up the updated parameters

@@ -17,6 +17,8 @@ distance from the fp64 oracle must stay within 3x the distance of the fp32 oracl
 single operators, which have no such discontinuity at random inputs, are held to 2e-5."""
 import numpy as np
 import pytest
+
+L_MATH_FP32 = 0      # WM_MATH_FP32 (include/wmb200.h)
 import torch
 import torch.nn.functional as F
 
@@ -36,6 +38,24 @@ def rel(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     assert a.shape == b.shape, (a.shape, b.shape)
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+
+@pytest.fixture(autouse=True)
+def _fp32_math_mode(request):
+    """The operator-level checks of this module compare with autograd at fp32 round-off level, so they run the library
+    in WM_MATH_FP32 (exact-order fp32 FMA kernels).  The default mode -- training convolutions on tcgen05 with bf16
+    hi+lo operand pairs -- has its own tests at the end of the module (`tensor_core` in the name) with gates stated
+    relative to PyTorch's own fp32 (TF32) step, and is what tests/test_train_full.py and test_autograd_loop.py run."""
+    if "tensor_core" in request.node.name or not torch.cuda.is_available():
+        yield
+        return
+    from wmb200 import ops
+    prev = ops.set_math_mode(L_MATH_FP32)
+    try:
+        yield
+    finally:
+        ops.set_math_mode(prev)
 
 
 def test_oracle_reproduces_the_reference_training_steps():
@@ -386,3 +406,61 @@ def test_head_bce_and_input_conv_backward_match_autograd():
     Fn.conv1d(s.unsqueeze(1), wi, bi, padding=3).backward(dx.double().permute(0, 2, 1))
     dwi, dbi, ds = TR.conv_in_k7_bwd(s.detach().float(), dx, wi.detach().float())
     assert rel(dwi, wi.grad) < 2e-5 and rel(dbi, bi.grad) < 2e-5 and rel(ds, s.grad) < 2e-5
+
+
+# ---- the default math mode: training convolutions on the tensor cores ---------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,B,T", [(3, 2, 700), (7, 1, 1300), (3, 3, 16000), (7, 2, 16000), (3, 1, 129)])
+def test_tensor_core_conv64_forward_backward(K, B, T):
+    """wm_conv64_train_fwd / wm_conv64_bwd in WM_MATH_BF16X2: forward and data gradient through the tcgen05
+    convolution (3 partial products), weight gradient through the MN-major tcgen05 kernel (4 partial products), against
+    fp64 autograd.  bf16 hi+lo operands carry 16 mantissa bits: 2^-17 relative per product."""
+    from wmb200 import ops
+    from wmb200 import train as TR
+    assert ops.get_math_mode() == 1
+    g = torch.Generator().manual_seed(K * 100 + T)
+    x = torch.randn(B, T, 64, generator=g).cuda()
+    w = (torch.randn(64, 64, K, generator=g) / (8 * K ** 0.5)).cuda()
+    b = torch.randn(64, generator=g).cuda()
+    dy = torch.randn(B, T, 64, generator=g).cuda()
+    xd = x.double().permute(0, 2, 1).requires_grad_()
+    wd, bd = w.double().requires_grad_(), b.double().requires_grad_()
+    yd = torch.nn.functional.conv1d(xd, wd, bd, padding=K // 2)
+    yd.backward(dy.double().permute(0, 2, 1))
+    y = TR.conv64_train_fwd(x, w, b)
+    rel = lambda a, r: float((a.double() - r).abs().max() / r.abs().max())
+    assert rel(y.permute(0, 2, 1), yd.detach()) < 3e-5
+    dw, db, dx = TR.conv64_bwd(x, dy, w)
+    assert rel(dx.permute(0, 2, 1), xd.grad) < 3e-5
+    assert rel(dw, wd.grad) < 3e-5
+    assert rel(db, bd.grad) < 1e-5
+    dw2, db2, _ = TR.conv64_bwd(x, dy, w)                     # deterministic: fixed-order partial sums
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,B2,n_wm,T", [(16, 6, 3, 1000), (16, 5, 2, 2049), (4, 2, 2, 16000)])
+def test_tensor_core_detector_trainer_stays_within_pytorch_fp32(bits, B2, n_wm, T):
+    """Three detector training steps in the default math mode next to the fp64 oracle and to PyTorch's own fp32 step on
+    the same GPU (cuDNN, TF32 allowed -- the reference's setting, py/main16.py:44): losses and every resolved gradient
+    stay within 3x PyTorch's distance to fp64."""
+    import wmb200
+    from wmb200 import train as TR
+    torch.manual_seed(bits + B2)
+    det = wmb200.Detector(message_bits=bits)
+    sd = det.state_dict()
+    tr = TR.DetectorTrainer(det.cuda())
+    o64 = OT.DetectorTrainOracle(sd, dtype=torch.float64, device="cuda")
+    o32 = OT.DetectorTrainOracle(sd, dtype=torch.float32, device="cuda")
+    for step in range(3):
+        x = 0.1 * torch.randn(B2, T, device="cuda")
+        msg = torch.randint(0, 2 ** bits, (n_wm,), device="cuda")
+        want, base = o64.step(x, msg, n_wm), o32.step(x, msg, n_wm)
+        got = tr.step(x, msg, n_wm, want_input_grad=True)
+        for k in ("loc", "bce"):
+            assert abs(float(got[k]) - float(want[k])) < 3 * abs(float(base[k]) - float(want[k])) + 1e-4, (step, k)
+        gd = tr.grad_dict()
+        for k in OT.PARAM_KEYS:
+            if not k.endswith(DEAD):
+                assert rel(gd[k], want["grads"][k]) < 3 * rel(base["grads"][k], want["grads"][k]) + 1e-3, (step, k)
+        assert rel(got["d_input"], want["d_input"]) < 3 * rel(base["d_input"], want["d_input"]) + 1e-3
