@@ -12,7 +12,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwmb200.so")
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 # blob offsets (floats) — mirror of the enums in include/wmb200.h
 RB_W1 = 0
@@ -155,6 +155,14 @@ SIGNATURES = {
     "wm_convtranspose1d_phase_weight_floats": (_sz, [_i, _i, _i]),
     "wm_convtranspose1d_pack": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "wm_convtranspose1d_phase_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "wm_pconv_plane_rows": (_ll, [_i, _i]),
+    "wm_pconv_desc_bytes": (_sz, []),
+    "wm_pconv_weight_bytes": (_sz, [_ll, _i]),
+    "wm_pconv_pack": (_i, [_p, _p, _ll, _i, _p]),
+    "wm_pconv_fwd": (_i, [_p, _p]),
+    "wm_pconv_in_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _ll, _p]),
+    "wm_pconv_to_planar": (_i, [_p, _p, _i, _i, _i, _ll, _p]),
+    "wm_pconv_from_planar": (_i, [_p, _p, _i, _i, _i, _i, _ll, _p]),
     "wm_resample_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "wm_pcm16_quantize_fwd": (_i, [_p, _p, _sz, _p]),
     "wm_pcm16_dequantize_fwd": (_i, [_p, _p, _sz, _f, _p]),

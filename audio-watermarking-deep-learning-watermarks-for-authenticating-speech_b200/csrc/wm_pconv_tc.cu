@@ -1,0 +1,625 @@
+// Convolutions of the main14b_2 residual stack (py/main14b_2.py:83-224, BASELINE config 3) as implicit GEMMs on the
+// 5th-generation tensor cores (sm_100a): strided Conv1d k3, the residual blocks' conv2 with the 1x1 strided skip
+// convolution folded in as extra K, ConvTranspose1d(k = 2s, stride s) as a 2- or 3-tap convolution over s * Cout
+// phase columns, the k7 output convolution.  Channel counts 16..512.
+//
+// GEMM view.  Rows (M) = time steps of ALL clips flattened: clip c, step t sits at row c * (T + GAP) + GAP + t of every
+// plane; the GAP zero rows in front of a clip are the convolution's zero padding, so a tile of 128 consecutive rows
+// may straddle clips.  Columns (N) = output channels (times phases for the transposed convolution) in chunks of
+// NC <= 128.  K = input channels x taps, walked in stages of 16 channels: one stage = one 16-channel slice of one
+// source tile (128 + taps - 1 rows, the taps being descriptor start addresses 16 bytes apart) and its taps' weights.
+//
+// Precision: the bf16-pair scheme of wm_conv_tc.cu (v = hi + lo; hi x [W_hi | W_lo] with N = 2 NC and lo x W_hi with
+// N = NC into the same accumulator; the epilogue adds column n and NC + n).
+//
+// Activations ("planar"): per tensor 2 * C/8 planes of plane_rows rows x 16 B; plane g = bf16 hi of channels
+// 8g..8g+7, plane C/8 + g = bf16 lo.  A plane is the tcgen05 no-swizzle K-major canonical layout, so operand tiles are
+// linear bulk copies.  A producer may write its rows split by phase (row t -> buffer t % s, row t / s): the strided
+// convolution that follows then reads contiguous rows (tap 0: phase s-1 one row up, tap 1: phase 0, tap 2: phase 1;
+// the 1x1 stride-s skip convolution: phase 0).
+#include <cuda_bf16.h>
+
+#include "wm_common.h"
+#include "wm_tc.cuh"
+
+namespace wm {
+
+using namespace tc;
+
+namespace {
+
+constexpr int GAP = WM_PC_GAP;
+constexpr int TILE = 128;
+constexpr int A_PLANE = (TILE + 6) * 16;   // shared-memory pitch of one 8-channel plane of a stage (taps <= 7)
+constexpr int A_BYTES = 4 * A_PLANE;       // hi k8 = 0,1 then lo k8 = 0,1
+constexpr int MAX_STAGE = 8;
+
+struct KSrc {
+  const uint4 *base;
+  int kchunks;     // cin / 16
+  int lo_plane;    // cin / 8: first lo plane
+  int row_off;
+  int taps;
+};
+
+struct KParams {
+  KSrc src[3];
+  int nsrc;
+  long long plane_rows;        // of the sources and the residual
+  int B, T, Tp;                // row geometry
+  long long R;                 // B * Tp + GAP rows
+  const uint8_t *w;
+  long long w_chunk_bytes;     // packed weights of one N chunk
+  const float *bias;
+  int nch;                     // N chunks
+  int n_total;
+  int elu;
+  const uint4 *residual;
+  int mode;
+  void *y;
+  long long out_plane_rows;
+  int out_split;
+  long long out_phase_rows;    // rows (16 B units) between phase buffers of the output
+  int out_Tp;                  // mode 0 split: T / split + GAP; mode 2: out_T + GAP
+  int ct_stride, ct_pad, ct_cout, out_T;
+  int stage_bytes, nstage;
+  signed char chunk_off[64];
+};
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : expm1f(v); }
+
+template <int NC>
+struct Cfg {
+  static constexpr int NSL = NC >= 32 ? 4 : 2;    // column slices of the epilogue
+  static constexpr int CS = NC / NSL;             // channels per slice: 32, 16, 8, 8
+  static constexpr int B_TAP = 2 * NC * 32;       // bytes of one tap's [W_hi | W_lo] x 16 channels
+  static constexpr int TMEM_COLS = 4 * NC < 32 ? 32 : 4 * NC;   // two accumulators of 2 NC columns
+};
+
+// Warps 0..15 epilogue (TMEM lane quadrant = warp % 4, column slice = warp / 4), warp 16 producer, warp 17 MMA issuer.
+template <int NC>
+__global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant__ KParams P) {
+  using C = Cfg<NC>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t s_base = smem_u32(smem);
+  const int NS = P.nstage;
+  const uint32_t bars = s_base + NS * P.stage_bytes;
+  auto full_bar = [&](int s) { return bars + 8 * s; };
+  auto empty_bar = [&](int s) { return bars + 8 * (MAX_STAGE + s); };
+  auto tfull_bar = [&](int a) { return bars + 8 * (2 * MAX_STAGE + a); };
+  auto tempty_bar = [&](int a) { return bars + 8 * (2 * MAX_STAGE + 2 + a); };
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NS * P.stage_bytes + 8 * (2 * MAX_STAGE + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long mtiles = (P.R + TILE - 1) / TILE;
+  const long long ntiles = mtiles * P.nch;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * C::NSL); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 17) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 16) {
+    // ===== producer: per stage 4 plane copies (hi, hi, lo, lo of one 16-channel slice) + the taps' weights =====
+    if (lane == 0) {
+      long long it = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int j = (int)(tile % P.nch);
+        const long long m0 = (tile / P.nch) * TILE;
+        const uint8_t *wj = P.w + (size_t)j * P.w_chunk_bytes;
+        for (int si = 0; si < P.nsrc; ++si) {
+          const KSrc &S = P.src[si];
+          const long long row = m0 + S.row_off + (si == 0 ? (int)P.chunk_off[j] : 0);
+          const uint32_t abytes = (uint32_t)(TILE + S.taps - 1) * 16u;
+          const uint32_t wbytes = (uint32_t)S.taps * C::B_TAP;
+          for (int kc = 0; kc < S.kchunks; ++kc, ++it) {
+            const int s = (int)(it % NS);
+            const uint32_t ph = (uint32_t)(it / NS) & 1u;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            mbar_arrive_expect_tx(full_bar(s), 4 * abytes + wbytes);
+            const uint32_t dst = s_base + s * P.stage_bytes;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int pl = (i >> 1) * S.lo_plane + 2 * kc + (i & 1);
+              bulk_g2s(dst + i * A_PLANE, S.base + ((long long)pl * P.plane_rows + row), abytes, full_bar(s));
+            }
+            bulk_g2s(dst + A_BYTES, wj, wbytes, full_bar(s));
+            wj += wbytes;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 17) {
+    // ===== MMA issuer =====
+    const bool issuer = elect_one();
+    constexpr uint32_t idesc_hi = make_idesc(128, 2 * NC), idesc_lo = make_idesc(128, NC);
+    long long it = 0;
+    int i = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+      const int a = i & 1;
+      const uint32_t aph = (uint32_t)(i >> 1) & 1u;
+      mbar_wait_warp(tempty_bar(a), aph ^ 1);
+      const uint32_t d_tmem = tmem_base + a * (2 * NC);
+      uint32_t accum = 0;
+      for (int si = 0; si < P.nsrc; ++si) {
+        const int taps = P.src[si].taps, kch = P.src[si].kchunks;
+        for (int kc = 0; kc < kch; ++kc, ++it) {
+          const int s = (int)(it % NS);
+          const uint32_t ph = (uint32_t)(it / NS) & 1u;
+          mbar_wait_warp(full_bar(s), ph);
+          tc_fence_after();
+          if (issuer) {
+            const uint32_t st = s_base + s * P.stage_bytes;
+            const uint64_t a0 = smem_desc(st, A_PLANE, 128);
+            const uint64_t b0 = smem_desc(st + A_BYTES, 2 * NC * 16, 128);
+#pragma unroll 1
+            for (int tp = 0; tp < taps; ++tp) {
+              const uint64_t ad = a0 + (uint64_t)tp, bd = b0 + (uint64_t)(tp * (C::B_TAP >> 4));
+              mma_bf16(d_tmem, ad, bd, idesc_hi, accum);
+              mma_bf16(d_tmem, ad + (uint64_t)((2 * A_PLANE) >> 4), bd, idesc_lo, 1u);
+              accum = 1u;
+            }
+            tc_commit(empty_bar(s));
+          }
+          __syncwarp();
+        }
+      }
+      if (issuer) tc_commit(tfull_bar(a));
+      __syncwarp();
+    }
+  } else if ((warp >> 2) < C::NSL) {
+    // ===== epilogue =====
+    const int q = warp & 3, p = warp >> 2;
+    constexpr int CS = C::CS;
+    const int Tp = P.Tp;
+    int i = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+      const int a = i & 1;
+      const uint32_t aph = (uint32_t)(i >> 1) & 1u;
+      const int j = (int)(tile % P.nch);
+      const long long m = (tile / P.nch) * TILE + q * 32 + lane;
+      const int c = (int)(m / Tp);
+      const int r = (int)(m - (long long)c * Tp);
+      const int t = r - GAP;
+      const bool inrange = m < P.R;
+      const int n0 = j * NC + p * CS;        // first GEMM column of this thread's slice
+
+      mbar_wait_warp(tfull_bar(a), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + a * (2 * NC) + ((uint32_t)(q * 32) << 16) + p * CS;
+      float o[CS];
+      {
+        float v2[CS];
+#pragma unroll
+        for (int g = 0; g < CS / 8; ++g) {
+          tmem_ld8(taddr + g * 8, o + g * 8);
+          tmem_ld8(taddr + NC + g * 8, v2 + g * 8);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive_warp(tempty_bar(a));
+#pragma unroll
+        for (int k = 0; k < CS; ++k) o[k] += v2[k];
+      }
+      if (!inrange) continue;
+      {
+        const float4 *bp = reinterpret_cast<const float4 *>(P.bias + n0);
+#pragma unroll
+        for (int k = 0; k < CS / 4; ++k) {
+          const float4 b = __ldg(bp + k);
+          o[4 * k] += b.x; o[4 * k + 1] += b.y; o[4 * k + 2] += b.z; o[4 * k + 3] += b.w;
+        }
+      }
+      const bool real = (c < P.B) && (t >= 0);
+      if (P.residual != nullptr && real) {
+        const int lo0 = P.n_total >> 3;
+#pragma unroll
+        for (int g = 0; g < CS / 8; ++g) {
+          const int pl = (n0 >> 3) + g;
+          const uint4 rh = __ldg(P.residual + ((long long)pl * P.plane_rows + m));
+          const uint4 rl = __ldg(P.residual + ((long long)(lo0 + pl) * P.plane_rows + m));
+          float rr[8];
+          join8(rh, rl, rr);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[g * 8 + k] += rr[k];
+        }
+      }
+      if (P.elu) {
+#pragma unroll
+        for (int k = 0; k < CS; ++k) o[k] = elu1(o[k]);
+      }
+
+      if (P.mode == WM_PC_OUT_PLANAR) {
+        uint4 *y = reinterpret_cast<uint4 *>(P.y);
+        const int lo0 = P.n_total >> 3;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        if (P.out_split <= 1) {
+#pragma unroll
+          for (int g = 0; g < CS / 8; ++g) {
+            const int pl = (n0 >> 3) + g;
+            uint4 hi = z, lo = z;
+            if (real) split8(o + g * 8, hi, lo);
+            y[(long long)pl * P.out_plane_rows + m] = hi;
+            y[(long long)(lo0 + pl) * P.out_plane_rows + m] = lo;
+          }
+        } else {
+          const int sp = P.out_split;
+          if (real) {
+            const int qq = t / sp, phs = t - qq * sp;
+            if (phs <= 1 || phs == sp - 1) {
+              uint4 *yp = y + (long long)phs * P.out_phase_rows;
+              const long long row = (long long)c * P.out_Tp + GAP + qq;
+#pragma unroll
+              for (int g = 0; g < CS / 8; ++g) {
+                const int pl = (n0 >> 3) + g;
+                uint4 hi, lo;
+                split8(o + g * 8, hi, lo);
+                yp[(long long)pl * P.out_plane_rows + row] = hi;
+                yp[(long long)(lo0 + pl) * P.out_plane_rows + row] = lo;
+              }
+            }
+          } else {
+            // gap row r of clip c (or of the closing gap): zero the same gap row of every phase buffer that is read
+            const long long row = (long long)c * P.out_Tp + r;
+            for (int phs = 0; phs < sp; ++phs) {
+              if (!(phs <= 1 || phs == sp - 1)) continue;
+              uint4 *yp = y + (long long)phs * P.out_phase_rows;
+#pragma unroll
+              for (int g = 0; g < CS / 8; ++g) {
+                const int pl = (n0 >> 3) + g;
+                yp[(long long)pl * P.out_plane_rows + row] = z;
+                yp[(long long)(lo0 + pl) * P.out_plane_rows + row] = z;
+              }
+            }
+          }
+        }
+      } else if (P.mode == WM_PC_OUT_CONVT) {
+        // column n = phase * Cout + co; row (c, q = t) -> output step s q + phase of clip c.  The first gap row of a
+        // clip also carries the last outputs of the previous clip when out_T > s * T (odd strides).
+        uint4 *y = reinterpret_cast<uint4 *>(P.y);
+        const int s = P.ct_stride, cout = P.ct_cout, lo0 = cout >> 3;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int g = 0; g < CS / 8; ++g) {
+          const int n = n0 + g * 8;
+          const int phs = n / cout, co = n - phs * cout;
+          const int pl = co >> 3;
+          const int tout = s * t + phs;
+          if (tout >= 0) {
+            if (c < P.B && tout < P.out_T) {
+              uint4 hi, lo;
+              split8(o + g * 8, hi, lo);
+              const long long row = (long long)c * P.out_Tp + GAP + tout;
+              y[(long long)pl * P.out_plane_rows + row] = hi;
+              y[(long long)(lo0 + pl) * P.out_plane_rows + row] = lo;
+            }
+          } else {
+            if (tout >= -GAP) {
+              const long long row = (long long)c * P.out_Tp + GAP + tout;
+              y[(long long)pl * P.out_plane_rows + row] = z;
+              y[(long long)(lo0 + pl) * P.out_plane_rows + row] = z;
+            }
+            if (r == 0 && c >= 1) {
+              const int tout2 = s * P.T + phs;
+              if (tout2 < P.out_T) {
+                uint4 hi, lo;
+                split8(o + g * 8, hi, lo);
+                const long long row = (long long)(c - 1) * P.out_Tp + GAP + tout2;
+                y[(long long)pl * P.out_plane_rows + row] = hi;
+                y[(long long)(lo0 + pl) * P.out_plane_rows + row] = lo;
+              }
+            }
+          }
+        }
+      } else {
+        // fp32 channels-first y[c][ch][t], ch < ct_cout, t < out_T
+        if (real && t < P.out_T) {
+          float *y = reinterpret_cast<float *>(P.y);
+#pragma unroll
+          for (int k = 0; k < CS; ++k) {
+            const int ch = n0 + k;
+            if (ch < P.ct_cout) y[((long long)c * P.ct_cout + ch) * P.out_T + t] = o[k];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
+template <int NC>
+int launch_pconv_t(const KParams &P0, cudaStream_t st) {
+  using C = Cfg<NC>;
+  KParams P = P0;
+  int maxtaps = 1;
+  for (int i = 0; i < P.nsrc; ++i) maxtaps = P.src[i].taps > maxtaps ? P.src[i].taps : maxtaps;
+  P.stage_bytes = (A_BYTES + maxtaps * C::B_TAP + 127) / 128 * 128;
+  const int budget = 200 * 1024;
+  int ns = budget / P.stage_bytes;
+  ns = ns > MAX_STAGE ? MAX_STAGE : ns;
+  WM_CHECK_ARG(ns >= 2, "pconv: a stage of %d bytes does not fit the shared memory twice", P.stage_bytes);
+  P.nstage = ns;
+  const int smem_bytes = ns * P.stage_bytes + 8 * (2 * MAX_STAGE + 4) + 16;
+  static int attr_bytes = 0;
+  if (smem_bytes > attr_bytes) {
+    WM_CHECK_CUDA(cudaFuncSetAttribute(pconv_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_bytes = 227 * 1024;
+  }
+  const long long ntiles = ((P.R + TILE - 1) / TILE) * P.nch;
+  const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  pconv_tc_kernel<NC><<<grid, 576, smem_bytes, st>>>(P);
+  WM_CHECK_LAUNCH("pconv_tc");
+  return 0;
+}
+
+// fp32 Wd[chunk][slice][16][NC] -> bf16 [chunk][slice][k8 = 0,1][n = 0..2NC-1][8]; n < NC: hi of column n, else lo of n - NC
+__global__ void pconv_pack_kernel(const float *__restrict__ wd, __nv_bfloat16 *__restrict__ img, long long nslices, int nc) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per = 32LL * nc;   // elements of one slice: 2 * (2 nc) * 8
+  if (e >= nslices * per) return;
+  const long long sl = e / per;
+  const int w = (int)(e - sl * per);
+  const int i = w & 7, n2 = (w >> 3) % (2 * nc), k8 = w / (16 * nc);
+  const float v = wd[(sl * 16 + k8 * 8 + i) * nc + (n2 % nc)];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  img[e] = n2 < nc ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// Conv1d(1, Cout, K, padding K/2) on the waveform, written planar and split into `split` phases
+// (py/main14b_2.py:123,190 init_conv).  One thread per row of the phase geometry (T / split steps per clip).
+__global__ void __launch_bounds__(256)
+    pconv_in_kernel(const float *__restrict__ s, const float *__restrict__ w, const float *__restrict__ bias,
+                    uint4 *__restrict__ y, int B, int T, int cout, int K, int split, long long plane_rows,
+                    long long phase_rows) {
+  extern __shared__ float ws[];   // [K][cout] then bias[cout]
+  for (int i = threadIdx.x; i < K * cout; i += blockDim.x) ws[i] = w[(i % cout) * K + i / cout];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) ws[K * cout + i] = bias[i];
+  __syncthreads();
+  const int Tq = T / split, Tp = Tq + GAP;
+  const long long R = (long long)B * Tp + GAP;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int phs = blockIdx.y;
+  if (m >= R) return;
+  const int c = (int)(m / Tp), r = (int)(m - (long long)c * Tp), qq = r - GAP;
+  uint4 *yp = y + (long long)phs * phase_rows;
+  const int lo0 = cout >> 3;
+  if (c >= B || qq < 0) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int pl = 0; pl < 2 * lo0; ++pl) yp[(long long)pl * plane_rows + m] = z;
+    return;
+  }
+  const int t = qq * split + phs, P2 = K / 2;
+  float sv[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int tt = t + k - P2;
+    sv[k] = (k < K && tt >= 0 && tt < T) ? __ldg(s + (long long)c * T + tt) : 0.0f;
+  }
+  for (int g = 0; g < lo0; ++g) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float acc = ws[K * cout + g * 8 + i];
+      for (int k = 0; k < K; ++k) acc = fmaf(sv[k], ws[k * cout + g * 8 + i], acc);
+      v[i] = acc;
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    yp[(long long)g * plane_rows + m] = hi;
+    yp[(long long)(lo0 + g) * plane_rows + m] = lo;
+  }
+}
+
+// fp32 channels-first x[b][C][T] -> planar (gap rows zeroed)
+__global__ void __launch_bounds__(256)
+    pconv_to_planar_kernel(const float *__restrict__ x, uint4 *__restrict__ y, int B, int C, int T, long long plane_rows) {
+  const int Tp = T + GAP;
+  const long long R = (long long)B * Tp + GAP;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.y, lo0 = C >> 3;
+  if (m >= R) return;
+  const int c = (int)(m / Tp), t = (int)(m - (long long)c * Tp) - GAP;
+  uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+  if (c < B && t >= 0) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(x + ((long long)c * C + g * 8 + i) * T + t);
+    split8(v, hi, lo);
+  }
+  y[(long long)g * plane_rows + m] = hi;
+  y[(long long)(lo0 + g) * plane_rows + m] = lo;
+}
+
+// planar -> fp32 channels-first y[b][C][Tout] (first Tout steps)
+__global__ void __launch_bounds__(256)
+    pconv_from_planar_kernel(const uint4 *__restrict__ x, float *__restrict__ y, int B, int C, int T, int Tout,
+                             long long plane_rows) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y, c = blockIdx.z, lo0 = C >> 3;
+  if (t >= Tout) return;
+  const long long m = (long long)c * (T + GAP) + GAP + t;
+  const uint4 hi = __ldg(x + (long long)g * plane_rows + m), lo = __ldg(x + (long long)(lo0 + g) * plane_rows + m);
+  float v[8];
+  join8(hi, lo, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) y[((long long)c * C + g * 8 + i) * Tout + t] = v[i];
+}
+
+}  // namespace
+
+}  // namespace wm
+
+using namespace wm;
+
+extern "C" {
+
+long long wm_pconv_plane_rows(int B, int T) {
+  const long long R = (long long)B * (T + WM_PC_GAP) + WM_PC_GAP;
+  return (R + 7) / 8 * 8 + 144;
+}
+
+size_t wm_pconv_desc_bytes(void) { return sizeof(wm_pconv); }
+
+size_t wm_pconv_weight_bytes(long long nslices, int nc) { return (size_t)nslices * 64u * (size_t)nc; }
+
+int wm_pconv_pack(const float *wd, void *img, long long nslices, int nc, void *stream) {
+  if (int rc = require_device()) return rc;
+  WM_CHECK_ARG(wd && img && nslices > 0, "pconv_pack: null pointer or no slices");
+  WM_CHECK_ARG(nc == 16 || nc == 32 || nc == 64 || nc == 128, "pconv_pack: nc must be 16, 32, 64 or 128 (got %d)", nc);
+  const long long n = nslices * 32 * nc;
+  pconv_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(wd, reinterpret_cast<__nv_bfloat16 *>(img),
+                                                                               nslices, nc);
+  WM_CHECK_LAUNCH("pconv_pack");
+  return 0;
+}
+
+int wm_pconv_fwd(const wm_pconv *d, void *stream) {
+  if (int rc = require_device()) return rc;
+  WM_CHECK_ARG(d != nullptr, "pconv: null descriptor");
+  WM_CHECK_ARG(d->B >= 0 && d->T >= 0, "pconv: negative size");
+  if (d->B == 0) return 0;
+  WM_CHECK_ARG(d->nsrc >= 1 && d->nsrc <= 3, "pconv: 1..3 sources (got %d)", d->nsrc);
+  WM_CHECK_ARG(d->nc == 16 || d->nc == 32 || d->nc == 64 || d->nc == 128, "pconv: nc must be 16, 32, 64 or 128 (got %d)",
+               d->nc);
+  WM_CHECK_ARG(d->n_total > 0 && d->n_total % d->nc == 0 && d->n_total / d->nc <= 64,
+               "pconv: n_total %d must be a multiple of nc %d with at most 64 chunks", d->n_total, d->nc);
+  WM_CHECK_ARG(d->w && d->bias && d->y, "pconv: null pointer");
+  WM_CHECK_ARG(d->mode == WM_PC_OUT_PLANAR || d->mode == WM_PC_OUT_CONVT || d->mode == WM_PC_OUT_FP32,
+               "pconv: unknown output mode %d", d->mode);
+  KParams P{};
+  long long slices = 0;
+  for (int i = 0; i < d->nsrc; ++i) {
+    const wm_pconv_src &s = d->src[i];
+    WM_CHECK_ARG(s.base != nullptr, "pconv: source %d is null", i);
+    WM_CHECK_ARG(s.cin >= 16 && s.cin % 16 == 0, "pconv: source %d has %d channels (multiple of 16 required)", i, s.cin);
+    WM_CHECK_ARG(s.taps >= 1 && s.taps <= 7, "pconv: source %d has %d taps (1..7)", i, s.taps);
+    WM_CHECK_ARG(s.row_off >= -WM_PC_GAP && s.row_off + s.taps - 1 <= WM_PC_GAP,
+                 "pconv: source %d reaches beyond the %d gap rows", i, WM_PC_GAP);
+    P.src[i].base = reinterpret_cast<const uint4 *>(s.base);
+    P.src[i].kchunks = s.cin / 16;
+    P.src[i].lo_plane = s.cin / 8;
+    P.src[i].row_off = s.row_off;
+    P.src[i].taps = s.taps;
+    slices += (long long)(s.cin / 16) * s.taps;
+  }
+  P.nsrc = d->nsrc;
+  P.plane_rows = d->plane_rows;
+  P.B = d->B; P.T = d->T; P.Tp = d->T + WM_PC_GAP;
+  P.R = (long long)d->B * P.Tp + WM_PC_GAP;
+  WM_CHECK_ARG(d->plane_rows >= wm_pconv_plane_rows(d->B, d->T), "pconv: plane_rows %lld is below wm_pconv_plane_rows",
+               d->plane_rows);
+  P.w = reinterpret_cast<const uint8_t *>(d->w);
+  P.w_chunk_bytes = slices * 64 * d->nc;
+  P.bias = d->bias;
+  P.nch = d->n_total / d->nc;
+  P.n_total = d->n_total;
+  P.elu = d->elu;
+  P.residual = reinterpret_cast<const uint4 *>(d->residual);
+  P.mode = d->mode;
+  P.y = d->y;
+  P.out_plane_rows = d->out_plane_rows;
+  P.out_split = d->out_split < 1 ? 1 : d->out_split;
+  P.out_phase_rows = d->out_phase_rows;
+  P.ct_stride = d->ct_stride; P.ct_pad = d->ct_pad; P.ct_cout = d->ct_cout; P.out_T = d->out_T;
+  for (int i = 0; i < 64; ++i) P.chunk_off[i] = d->chunk_off[i];
+  if (d->mode == WM_PC_OUT_PLANAR) {
+    WM_CHECK_ARG(d->n_total % 8 == 0, "pconv: planar output needs a multiple of 8 channels");
+    if (P.out_split > 1) {
+      WM_CHECK_ARG(d->T % P.out_split == 0, "pconv: T %d is not a multiple of the output split %d", d->T, P.out_split);
+      WM_CHECK_ARG(d->residual == nullptr || true, "pconv");
+      P.out_Tp = d->T / P.out_split + WM_PC_GAP;
+      WM_CHECK_ARG(d->out_plane_rows >= wm_pconv_plane_rows(d->B, d->T / P.out_split), "pconv: out_plane_rows too small");
+    } else {
+      WM_CHECK_ARG(d->out_plane_rows >= wm_pconv_plane_rows(d->B, d->T), "pconv: out_plane_rows too small");
+    }
+  } else if (d->mode == WM_PC_OUT_CONVT) {
+    WM_CHECK_ARG(d->ct_stride >= 1 && d->ct_cout >= 8 && d->ct_cout % 8 == 0 && d->n_total == d->ct_stride * d->ct_cout,
+                 "pconv: transposed output needs n_total == stride * cout, cout a multiple of 8");
+    WM_CHECK_ARG(d->out_T >= d->ct_stride * d->T - d->ct_stride && d->out_T <= d->ct_stride * (d->T + 1),
+                 "pconv: transposed output length %d does not fit stride %d x %d rows", d->out_T, d->ct_stride, d->T);
+    WM_CHECK_ARG(d->residual == nullptr, "pconv: no residual on the transposed output");
+    P.out_Tp = d->out_T + WM_PC_GAP;
+    WM_CHECK_ARG(d->out_plane_rows >= wm_pconv_plane_rows(d->B, d->out_T), "pconv: out_plane_rows too small");
+  } else {
+    WM_CHECK_ARG(d->ct_cout >= 1 && d->ct_cout <= d->n_total && d->out_T >= 0 && d->out_T <= d->T,
+                 "pconv: fp32 output needs 1 <= channels <= n_total and out_T <= T");
+  }
+  cudaStream_t st = as_stream(stream);
+  switch (d->nc) {
+    case 16: return launch_pconv_t<16>(P, st);
+    case 32: return launch_pconv_t<32>(P, st);
+    case 64: return launch_pconv_t<64>(P, st);
+    default: return launch_pconv_t<128>(P, st);
+  }
+}
+
+int wm_pconv_in_fwd(const float *s, const float *w, const float *bias, void *y, int B, int T, int cout, int K, int split,
+                    long long plane_rows, void *stream) {
+  if (int rc = require_device()) return rc;
+  WM_CHECK_ARG(B >= 0 && T >= 0, "pconv_in: negative size");
+  if (B == 0) return 0;
+  WM_CHECK_ARG(s && w && bias && y, "pconv_in: null pointer");
+  WM_CHECK_ARG(cout >= 8 && cout % 8 == 0 && cout <= 128, "pconv_in: cout %d must be a multiple of 8, at most 128", cout);
+  WM_CHECK_ARG(K >= 1 && K <= 7 && (K & 1), "pconv_in: K %d must be odd, at most 7", K);
+  WM_CHECK_ARG(split >= 1 && T % split == 0, "pconv_in: T %d is not a multiple of split %d", T, split);
+  WM_CHECK_ARG(plane_rows >= wm_pconv_plane_rows(B, T / split), "pconv_in: plane_rows too small");
+  const long long R = (long long)B * (T / split + WM_PC_GAP) + WM_PC_GAP;
+  dim3 grid((unsigned)((R + 255) / 256), split);
+  pconv_in_kernel<<<grid, 256, (K + 1) * cout * sizeof(float), as_stream(stream)>>>(
+      s, w, bias, reinterpret_cast<uint4 *>(y), B, T, cout, K, split, plane_rows, 2LL * (cout / 8) * plane_rows);
+  WM_CHECK_LAUNCH("pconv_in");
+  return 0;
+}
+
+int wm_pconv_to_planar(const float *x, void *y, int B, int C, int T, long long plane_rows, void *stream) {
+  if (int rc = require_device()) return rc;
+  WM_CHECK_ARG(B >= 0 && T >= 0 && C >= 8 && C % 8 == 0, "pconv_to_planar: bad size");
+  if (B == 0) return 0;
+  WM_CHECK_ARG(x && y, "pconv_to_planar: null pointer");
+  WM_CHECK_ARG(plane_rows >= wm_pconv_plane_rows(B, T), "pconv_to_planar: plane_rows too small");
+  const long long R = (long long)B * (T + WM_PC_GAP) + WM_PC_GAP;
+  dim3 grid((unsigned)((R + 255) / 256), C / 8);
+  pconv_to_planar_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, reinterpret_cast<uint4 *>(y), B, C, T, plane_rows);
+  WM_CHECK_LAUNCH("pconv_to_planar");
+  return 0;
+}
+
+int wm_pconv_from_planar(const void *x, float *y, int B, int C, int T, int Tout, long long plane_rows, void *stream) {
+  if (int rc = require_device()) return rc;
+  WM_CHECK_ARG(B >= 0 && T >= 0 && C >= 8 && C % 8 == 0 && Tout >= 0 && Tout <= T, "pconv_from_planar: bad size");
+  if (B == 0 || Tout == 0) return 0;
+  WM_CHECK_ARG(x && y, "pconv_from_planar: null pointer");
+  WM_CHECK_ARG(B <= 65535, "pconv_from_planar: at most 65535 clips per call");
+  dim3 grid((Tout + 255) / 256, C / 8, B);
+  pconv_from_planar_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4 *>(x), y, B, C, T, Tout,
+                                                               plane_rows);
+  WM_CHECK_LAUNCH("pconv_from_planar");
+  return 0;
+}
+
+}  // extern "C"

@@ -14,7 +14,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .ops import _req, _stream
+from . import pconv
+from .ops import _req, _stream, get_math_mode
 
 HIDDEN_DIM = 32            # py/main14b_2.py:40
 NUM_BITS = 16              # :41
@@ -22,6 +23,13 @@ CHANNELS = 32              # :42
 OUTPUT_CH = 128            # :43
 STRIDES = [2, 4, 5, 8]     # :44
 LSTM_LAYERS = 2            # :45
+
+
+def _tensor_core_path(mod, x) -> bool:
+    """The whole-model tcgen05 walk (pconv.py) in the default math mode when the layer pattern fits it; otherwise —
+    and always under WM_MATH_FP32 — the layer-by-layer fp32 CUDA operators below (the exact-order cross-check)."""
+    _req(x, "input")
+    return get_math_mode() == L.MATH_BF16X2 and pconv.supported(mod, x.shape[-1])
 
 
 def conv1d(x, conv: nn.Conv1d, act: bool = False, residual=None, chan_add=None) -> torch.Tensor:
@@ -165,6 +173,8 @@ class Generator(nn.Module):
         if s.dim() != 3:
             raise ValueError(f"s: expected (B, C, T), got {tuple(s.shape)}")
         B, _, T = s.shape
+        if _tensor_core_path(self, s):
+            return pconv.generator_forward(self, _req(s, "s"), message)
         x = conv1d(s, self.init_conv)
         for blk in self.encoder_blocks:
             x = blk(x)
@@ -216,6 +226,8 @@ class Detector(nn.Module):
         if x.dim() != 3:
             raise ValueError(f"x: expected (B, C, T), got {tuple(x.shape)}")
         T = x.shape[-1]
+        if _tensor_core_path(self, x):
+            return pconv.detector_forward(self, _req(x, "x"))
         x = conv1d(x, self.init_conv)
         for blk in self.encoder_blocks:
             x = blk(x)

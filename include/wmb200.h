@@ -40,7 +40,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 17
+#define WM_ABI_VERSION 18
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -375,6 +375,67 @@ int wm_convtranspose1d_phase_fwd(const float *x, const float *packed, float *y, 
  * [layers][4H][H], bias [layers][4H] = b_ih + b_hh; zero initial state; H <= 64, layers <= 4. */
 int wm_lstm_small_fwd(const float *x, const float *w_ih, const float *w_hh, const float *bias, float *y, int B, int H,
                       int T, int layers, void *stream);
+
+/* ---- the same stack on the tensor cores: planar bf16-pair activations, tcgen05 implicit GEMMs ----
+ * (py/main14b_2.py:86-103 ResidualBlock incl. the strided conv1 and the 1x1 skip_conv, :146,201 ConvTranspose1d,
+ * :149,205 the k7 output convolutions.)  A planar tensor of C channels (C % 8 == 0) for B clips of T steps is
+ * 2 * C/8 planes of wm_pconv_plane_rows(B, T) rows x 16 bytes: plane g = bf16 hi of channels 8g..8g+7, plane
+ * C/8 + g = bf16 lo (value = hi + lo); clip c, step t is row c * (T + WM_PC_GAP) + WM_PC_GAP + t, the gap rows are
+ * zero (they are the convolutions' padding) and every producer below rewrites them.  The caller allocates
+ * planes * plane_rows * 16 bytes with at least 128 readable bytes in front of the first plane.
+ * One call computes, for every row m and output column n,
+ *     acc[m][n] = bias[n] + sum over sources s, channels ci, taps j of  src_s[ci][m + row_off_s + j] * W
+ * (chunk_off[n / nc] is added to the row offset of source 0), adds `residual` (planar, same geometry), applies ELU
+ * when `elu`, and stores by `mode`:
+ *   WM_PC_OUT_PLANAR  planar, same geometry; out_split = s > 1 writes step t to phase buffer t % s at step t / s
+ *                     (buffers out_phase_rows rows apart, geometry (B, T / s); only phases 0, 1 and s - 1, the ones a
+ *                     k3 stride-s convolution reads, are written);
+ *   WM_PC_OUT_CONVT   column n = phase * ct_cout + co of row (c, q) is step ct_stride * q + phase of clip c in a planar
+ *                     tensor of geometry (B, out_T);
+ *   WM_PC_OUT_FP32    fp32 channels-first y[c][ch][t] for ch < ct_cout, t < out_T.
+ * Weights come from wm_pconv_pack: fp32 wd[chunk][slice][16][nc] (slice = source-major, then 16-channel group, then
+ * tap) -> bf16 hi | lo operand tiles. */
+#define WM_PC_GAP 4
+#define WM_PC_OUT_PLANAR 0
+#define WM_PC_OUT_CONVT 2
+#define WM_PC_OUT_FP32 3
+typedef struct wm_pconv_src {
+  const void *base;   /* first plane of the source (phase buffer) */
+  int cin;            /* channels, multiple of 16 */
+  int row_off;        /* source row of tap 0 relative to the output row */
+  int taps;           /* taps on consecutive rows, 1..7 */
+  int reserved;
+} wm_pconv_src;
+typedef struct wm_pconv {
+  wm_pconv_src src[3];
+  int nsrc;
+  int B, T;                     /* row geometry shared by the sources, the residual and the GEMM rows */
+  long long plane_rows;         /* rows per plane of the sources and the residual */
+  const void *w;                /* wm_pconv_pack image */
+  const float *bias;            /* [n_total] */
+  int n_total, nc;              /* GEMM columns, columns per chunk (16, 32, 64, 128) */
+  signed char chunk_off[64];
+  int elu;
+  int mode;
+  const void *residual;         /* nullable */
+  void *y;
+  long long out_plane_rows;
+  long long out_phase_rows;     /* WM_PC_OUT_PLANAR with out_split > 1: rows between phase buffers */
+  int out_split;
+  int ct_stride, ct_pad, ct_cout;
+  int out_T;
+} wm_pconv;
+long long wm_pconv_plane_rows(int B, int T);
+size_t wm_pconv_desc_bytes(void);   /* sizeof(wm_pconv), for bindings that mirror the struct */
+size_t wm_pconv_weight_bytes(long long nslices, int nc);
+int wm_pconv_pack(const float *wd, void *img, long long nslices, int nc, void *stream);
+int wm_pconv_fwd(const wm_pconv *desc, void *stream);
+/* Conv1d(1, cout, K, padding K/2) on waveforms s[B][T] (py/main14b_2.py:123,190) -> planar, split into `split` phases */
+int wm_pconv_in_fwd(const float *s, const float *w, const float *bias, void *y, int B, int T, int cout, int K, int split,
+                    long long plane_rows, void *stream);
+/* fp32 channels-first x[B][C][T] <-> planar */
+int wm_pconv_to_planar(const float *x, void *y, int B, int C, int T, long long plane_rows, void *stream);
+int wm_pconv_from_planar(const void *x, float *y, int B, int C, int T, int Tout, long long plane_rows, void *stream);
 
 /* ---- audio formats either side of the path ----
  * torchaudio.transforms.Resample(orig, new)(x) (py/main16.py:985,1121): `kern` [K][up] is torchaudio's windowed-sinc
