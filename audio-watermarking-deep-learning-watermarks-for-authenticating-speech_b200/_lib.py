@@ -161,6 +161,7 @@ SIGNATURES = {
     "wm_pconv_pack": (_i, [_p, _p, _ll, _i, _p]),
     "wm_pconv_fwd": (_i, [_p, _p]),
     "wm_pconv_in_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _ll, _p]),
+    "wm_m14_tail8_fwd": (_i, [_p, _ll, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
     "wm_pconv_to_planar": (_i, [_p, _p, _i, _i, _i, _ll, _p]),
     "wm_pconv_from_planar": (_i, [_p, _p, _i, _i, _i, _i, _ll, _p]),
     "wm_resample_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),

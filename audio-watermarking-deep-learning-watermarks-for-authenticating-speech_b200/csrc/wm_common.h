@@ -182,6 +182,9 @@ int launch_convtranspose1d_generic(const float *x, const float *w, const float *
                                    int Cout, int K, int stride, int pad, cudaStream_t st);
 int launch_lstm_small(const float *x, const float *w_ih, const float *w_hh, const float *bias, float *y, int B, int H,
                       int T, int L, cudaStream_t st);
+// wm_m14_small.cu: 0 = done, 1 = shape not handled there (caller uses the generic kernel), < 0 error
+int launch_lstm_small_reg(const float *x, const float *w_ih, const float *w_hh, const float *bias, float *y, int B, int H,
+                          int T, int L, cudaStream_t st);
 // audio formats either side of the path (wm_audio.cu)
 int launch_resample(const float *x, const float *kern, float *y, int B, int Tin, int Tout, int down, int up, int K,
                     int width, cudaStream_t st);

@@ -526,6 +526,10 @@ int launch_lstm_small(const float *x, const float *w_ih, const float *w_hh, cons
     set_error("lstm_small: hidden size %d / layers %d outside the supported range (<= 64 / <= 4)", H, L);
     return -1;
   }
+  {
+    const int rc = launch_lstm_small_reg(x, w_ih, w_hh, bias, y, B, H, T, L, st);   // H = 32, L <= 2: weights in registers
+    if (rc <= 0) return rc;
+  }
   const size_t smem = (size_t)(2 * L * H + 4 * H + H) * sizeof(float);
   lstm_small_kernel<<<B, 4 * H, smem, st>>>(x, w_ih, w_hh, bias, y, H, T, L);
   WM_CHECK_LAUNCH("lstm_small");

@@ -75,7 +75,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : expm1f(v); }
+// ELU for the epilogue: exp(v) - 1 through ex2.approx (absolute error ~1e-7, the rounding of exp(v) itself).  expm1f costs
+// ~40 instructions per element and made every layer with a short K loop epilogue-issue bound (128 x NC elements per tile).
+__device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : ex2_approx(v * 1.4426950408889634f) - 1.0f; }
 
 template <int NC>
 struct Cfg {
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(256)
     pconv_in_kernel(const float *__restrict__ s, const float *__restrict__ w, const float *__restrict__ bias,
                     uint4 *__restrict__ y, int B, int T, int cout, int K, int split, long long plane_rows,
                     long long phase_rows) {
-  extern __shared__ float ws[];   // [K][cout] then bias[cout]
+  extern __shared__ __align__(16) float ws[];   // [K][cout] then bias[cout]
   for (int i = threadIdx.x; i < K * cout; i += blockDim.x) ws[i] = w[(i % cout) * K + i / cout];
   for (int i = threadIdx.x; i < cout; i += blockDim.x) ws[K * cout + i] = bias[i];
   __syncthreads();
@@ -423,11 +425,20 @@ __global__ void __launch_bounds__(256)
   }
   for (int g = 0; g < lo0; ++g) {
     float v[8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4 *>(ws + K * cout + g * 8);
+      const float4 b1 = *reinterpret_cast<const float4 *>(ws + K * cout + g * 8 + 4);
+      v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
+    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float acc = ws[K * cout + g * 8 + i];
-      for (int k = 0; k < K; ++k) acc = fmaf(sv[k], ws[k * cout + g * 8 + i], acc);
-      v[i] = acc;
+    for (int k = 0; k < 7; ++k) {
+      if (k < K) {
+        const float4 w0 = *reinterpret_cast<const float4 *>(ws + k * cout + g * 8);
+        const float4 w1 = *reinterpret_cast<const float4 *>(ws + k * cout + g * 8 + 4);
+        v[0] = fmaf(sv[k], w0.x, v[0]); v[1] = fmaf(sv[k], w0.y, v[1]); v[2] = fmaf(sv[k], w0.z, v[2]);
+        v[3] = fmaf(sv[k], w0.w, v[3]); v[4] = fmaf(sv[k], w1.x, v[4]); v[5] = fmaf(sv[k], w1.y, v[5]);
+        v[6] = fmaf(sv[k], w1.z, v[6]); v[7] = fmaf(sv[k], w1.w, v[7]);
+      }
     }
     uint4 hi, lo;
     split8(v, hi, lo);

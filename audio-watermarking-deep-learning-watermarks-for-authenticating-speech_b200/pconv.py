@@ -208,6 +208,16 @@ class CudaBackend:
                 "wm_pconv_from_planar")
         return y
 
+    def tail8(self, x: Planar, rb, final: nn.Conv1d, T: int):
+        from . import _lib as L
+        from .ops import _stream
+        y = torch.empty(x.B, 1, T, device=x.store.device, dtype=torch.float32)
+        p = [t.detach().contiguous() for t in (rb.conv1.weight, rb.conv1.bias, rb.conv2.weight, rb.conv2.bias,
+                                               final.weight, final.bias)]
+        L.check(L.load().wm_m14_tail8_fwd(x.ptr(), x.RP, x.B, x.T, *[t.data_ptr() for t in p], y.data_ptr(), T, _stream()),
+                "wm_m14_tail8_fwd")
+        return y
+
     def run(self, g: Gemm, srcs: Sequence[Tuple[Planar, int]], B, T, elu, residual, mode, out, out_split=1, ct=None,
             out_T=0, cout=0):
         from . import _lib as L
@@ -372,6 +382,14 @@ def detector_forward(mod, x):
     return M._fit_length(M.conv1d(h, mod.final_conv), T)
 
 
+def _tail8_fits(rest, final: nn.Conv1d, cur) -> bool:
+    if len(rest) != 1 or isinstance(rest[0], nn.ConvTranspose1d) or cur.C != 8:
+        return False
+    rb = rest[0]
+    return (not rb.downsample and rb.conv1.in_channels == 8 and rb.conv1.kernel_size[0] == 3 and rb.conv2.kernel_size[0] == 3
+            and (final.in_channels, final.out_channels, final.kernel_size[0], final.padding[0], final.stride[0]) == (8, 1, 7, 3, 1))
+
+
 def generator_forward(mod, s, message=None):
     """Generator.forward (py/main14b_2.py:150-182): delta (B, 1, T)."""
     from . import main14b_2 as M
@@ -387,6 +405,9 @@ def generator_forward(mod, s, message=None):
         cur = be.planar(x.shape[1], B, t, 1, s.device)
         be.to_planar(x, cur)
         cur, t = _decoder(plan, cur, t)
+        if _tail8_fits(plan["dec_rest"], mod.final_conv_dec, cur):
+            # ResidualBlock(8, 8) + final_conv_dec + crop in one kernel on the planar tensor (py/main14b_2.py:147-149,173-177)
+            return be.tail8(cur, plan["dec_rest"][0], mod.final_conv_dec, T)
         x = be.from_planar(cur, t)
     for blk in plan["dec_rest"]:
         x = M.conv_transpose1d(x, blk) if isinstance(blk, nn.ConvTranspose1d) else blk(x)

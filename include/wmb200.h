@@ -433,6 +433,11 @@ int wm_pconv_fwd(const wm_pconv *desc, void *stream);
 /* Conv1d(1, cout, K, padding K/2) on waveforms s[B][T] (py/main14b_2.py:123,190) -> planar, split into `split` phases */
 int wm_pconv_in_fwd(const float *s, const float *w, const float *bias, void *y, int B, int T, int cout, int K, int split,
                     long long plane_rows, void *stream);
+/* The Generator's last ResidualBlock(8, 8) + final_conv_dec Conv1d(8, 1, 7, padding 3) + crop to T
+ * (py/main14b_2.py:97-105,149,173-177) in one kernel: x planar (8 channels, geometry (B, Tx)), reference weight layouts
+ * w1, w2 (8,8,3), wf (1,8,7) -> delta[B][T] (zero beyond Tx). */
+int wm_m14_tail8_fwd(const void *x, long long plane_rows, int B, int Tx, const float *w1, const float *b1, const float *w2,
+                     const float *b2, const float *wf, const float *bf, float *delta, int T, void *stream);
 /* fp32 channels-first x[B][C][T] <-> planar */
 int wm_pconv_to_planar(const float *x, void *y, int B, int C, int T, long long plane_rows, void *stream);
 int wm_pconv_from_planar(const void *x, float *y, int B, int C, int T, int Tout, long long plane_rows, void *stream);

@@ -156,3 +156,25 @@ def test_whole_models_match_the_fp32_operators():
     assert relerr(d_tc, d_32) < 1e-4, relerr(d_tc, d_32)
     assert float((l_tc - l_32).abs().max()) < 2e-4, float((l_tc - l_32).abs().max())
     assert n_tc < 120                       # incl. one weight pack per layer on first use
+
+
+def test_generator_tail_kernel():
+    """ResidualBlock(8, 8) + Conv1d(8, 1, 7) + crop (wm_m14_tail8_fwd) against torch, clip edges and a ragged last block"""
+    torch.manual_seed(11)
+    B, Tx, T = 3, 1000, 993
+    rb, fin = M.ResidualBlock(8, 8).to(DEV), nn.Conv1d(8, 1, 7, padding=3).to(DEV)
+    x = torch.randn(B, 8, Tx, device=DEV)
+    with torch.no_grad():
+        want = fin(F.elu(rb.conv2(F.elu(rb.conv1(x))) + x))[:, :, :T]
+    got = BE.tail8(planar_from(x), rb, fin, T)
+    assert got.shape == want.shape and relerr(got, want) < 2e-5, relerr(got, want)
+
+
+@pytest.mark.parametrize("B,T,L", [(3, 50, 2), (2, 130, 1)])
+def test_register_lstm(B, T, L):
+    torch.manual_seed(T)
+    lstm = nn.LSTM(32, 32, num_layers=L, batch_first=True).to(DEV)
+    x = torch.randn(B, 32, T, device=DEV)
+    with torch.no_grad():
+        want = lstm(x.transpose(1, 2))[0].transpose(1, 2)
+    assert relerr(M.lstm_small(x, lstm), want) < 1e-5
