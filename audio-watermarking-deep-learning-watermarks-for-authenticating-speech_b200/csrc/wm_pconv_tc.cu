@@ -123,32 +123,36 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
 
   if (warp == 16) {
     // ===== producer: per stage 4 plane copies (hi, hi, lo, lo of one 16-channel slice) + the taps' weights =====
-    if (lane == 0) {
-      long long it = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int j = (int)(tile % P.nch);
-        const long long m0 = (tile / P.nch) * TILE;
-        const uint8_t *wj = P.w + (size_t)j * P.w_chunk_bytes;
-        for (int si = 0; si < P.nsrc; ++si) {
-          const KSrc &S = P.src[si];
-          const long long row = m0 + S.row_off + (si == 0 ? (int)P.chunk_off[j] : 0);
-          const uint32_t abytes = (uint32_t)(TILE + S.taps - 1) * 16u;
-          const uint32_t wbytes = (uint32_t)S.taps * C::B_TAP;
-          for (int kc = 0; kc < S.kchunks; ++kc, ++it) {
-            const int s = (int)(it % NS);
-            const uint32_t ph = (uint32_t)(it / NS) & 1u;
-            mbar_wait(empty_bar(s), ph ^ 1);
-            mbar_arrive_expect_tx(full_bar(s), 4 * abytes + wbytes);
-            const uint32_t dst = s_base + s * P.stage_bytes;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int pl = (i >> 1) * S.lo_plane + 2 * kc + (i & 1);
-              bulk_g2s(dst + i * A_PLANE, S.base + ((long long)pl * P.plane_rows + row), abytes, full_bar(s));
-            }
-            bulk_g2s(dst + A_BYTES, wj, wbytes, full_bar(s));
-            wj += wbytes;
-          }
+    // Lane i < 4 issues plane copy i, lane 4 the weights: a stage costs each lane a handful of instructions (one thread
+    // doing all of it, with 64-bit index arithmetic, made EVERY stage ~1000 cycles whatever it held).
+    uint32_t s = 0, ph = 0;
+    const uint32_t nch = (uint32_t)P.nch;
+    for (uint32_t tile = blockIdx.x; tile < (uint32_t)ntiles; tile += gridDim.x) {
+      const uint32_t mt = tile / nch, j = tile - mt * nch;
+      const long long m0 = (long long)mt * TILE;
+      const uint8_t *wj = P.w + (size_t)j * P.w_chunk_bytes;
+      for (int si = 0; si < P.nsrc; ++si) {
+        const KSrc &S = P.src[si];
+        const long long row = m0 + S.row_off + (si == 0 ? (int)P.chunk_off[j] : 0);
+        const uint32_t abytes = (uint32_t)(TILE + S.taps - 1) * 16u;
+        const uint32_t wbytes = (uint32_t)S.taps * C::B_TAP;
+        // this lane's source pointer for 16-channel slice 0 and its step per slice
+        const uint8_t *src = lane < 4 ? reinterpret_cast<const uint8_t *>(
+                                            S.base + ((long long)((lane >> 1) * S.lo_plane + (lane & 1)) * P.plane_rows + row))
+                                      : wj;
+        const size_t step = lane < 4 ? (size_t)(2 * P.plane_rows) * 16u : (size_t)wbytes;
+        const uint32_t bytes = lane < 4 ? abytes : wbytes;
+        const uint32_t doff = lane < 4 ? (uint32_t)lane * A_PLANE : (uint32_t)A_BYTES;
+        const int kch = S.kchunks;
+        for (int kc = 0; kc < kch; ++kc) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          if (lane == 0) mbar_arrive_expect_tx(full_bar(s), 4 * abytes + wbytes);
+          __syncwarp();
+          if (lane < 5) bulk_g2s(s_base + s * P.stage_bytes + doff, src, bytes, full_bar(s));
+          src += step;
+          if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
         }
+        wj += (size_t)kch * wbytes;
       }
     }
     __syncwarp();
@@ -156,19 +160,14 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
     // ===== MMA issuer =====
     const bool issuer = elect_one();
     constexpr uint32_t idesc_hi = make_idesc(128, 2 * NC), idesc_lo = make_idesc(128, NC);
-    long long it = 0;
-    int i = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
-      const int a = i & 1;
-      const uint32_t aph = (uint32_t)(i >> 1) & 1u;
+    uint32_t s = 0, ph = 0, a = 0, aph = 0;
+    for (uint32_t tile = blockIdx.x; tile < (uint32_t)ntiles; tile += gridDim.x) {
       mbar_wait_warp(tempty_bar(a), aph ^ 1);
       const uint32_t d_tmem = tmem_base + a * (2 * NC);
       uint32_t accum = 0;
       for (int si = 0; si < P.nsrc; ++si) {
         const int taps = P.src[si].taps, kch = P.src[si].kchunks;
-        for (int kc = 0; kc < kch; ++kc, ++it) {
-          const int s = (int)(it % NS);
-          const uint32_t ph = (uint32_t)(it / NS) & 1u;
+        for (int kc = 0; kc < kch; ++kc) {
           mbar_wait_warp(full_bar(s), ph);
           tc_fence_after();
           if (issuer) {
@@ -185,23 +184,28 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
             tc_commit(empty_bar(s));
           }
           __syncwarp();
+          if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
         }
       }
       if (issuer) tc_commit(tfull_bar(a));
       __syncwarp();
+      a ^= 1;
+      if (a == 0) aph ^= 1;
     }
   } else if ((warp >> 2) < C::NSL) {
     // ===== epilogue =====
     const int q = warp & 3, p = warp >> 2;
     constexpr int CS = C::CS;
     const int Tp = P.Tp;
-    int i = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
-      const int a = i & 1;
-      const uint32_t aph = (uint32_t)(i >> 1) & 1u;
-      const int j = (int)(tile % P.nch);
-      const long long m = (tile / P.nch) * TILE + q * 32 + lane;
-      const int c = (int)(m / Tp);
+    uint32_t i = 0;
+    const uint32_t nch = (uint32_t)P.nch;
+    for (uint32_t tile = blockIdx.x; tile < (uint32_t)ntiles; tile += gridDim.x, ++i) {
+      const uint32_t a = i & 1u;
+      const uint32_t aph = (i >> 1) & 1u;
+      const uint32_t mt = tile / nch;
+      const int j = (int)(tile - mt * nch);
+      const long long m = (long long)mt * TILE + q * 32 + lane;
+      const int c = (int)((uint32_t)m / (uint32_t)Tp);
       const int r = (int)(m - (long long)c * Tp);
       const int t = r - GAP;
       const bool inrange = m < P.R;
@@ -374,6 +378,8 @@ int launch_pconv_t(const KParams &P0, cudaStream_t st) {
     attr_bytes = 227 * 1024;
   }
   const long long ntiles = ((P.R + TILE - 1) / TILE) * P.nch;
+  WM_CHECK_ARG(P.R < (1LL << 31) && ntiles < (1LL << 31), "pconv: %lld rows x %d chunks exceed the 32-bit tile index", P.R,
+               P.nch);
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
   pconv_tc_kernel<NC><<<grid, 576, smem_bytes, st>>>(P);
   WM_CHECK_LAUNCH("pconv_tc");
