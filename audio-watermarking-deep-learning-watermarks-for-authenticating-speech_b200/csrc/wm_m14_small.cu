@@ -14,7 +14,8 @@ namespace {
 constexpr int GAP = WM_PC_GAP;
 constexpr int TT = 256;   // outputs per block of the tail kernel
 
-__device__ __forceinline__ float elu_f(float v) { return v > 0.0f ? v : expm1f(v); }
+// exp(v) - 1 through ex2.approx: absolute error ~1e-7 (expm1f is ~40 instructions, 16 of them per output sample here)
+__device__ __forceinline__ float elu_f(float v) { return v > 0.0f ? v : ex2_approx(v * 1.4426950408889634f) - 1.0f; }
 
 // x planar (8 channels: plane 0 = hi, plane 1 = lo; geometry (B, Tx)) ->
 //   u = elu(conv1(x)), z = elu(conv2(u) + x)   (ResidualBlock, py/main14b_2.py:97-105; k3, padding 1)

@@ -296,14 +296,30 @@ def measure_main14b2(dev, world, rank, steps, warmup, B=1024):
     def step():
         with torch.no_grad():
             return D(s + G(s, msg))
+    # parity gate (outside the timed region): the tensor-core walk against the layer-by-layer fp32 CUDA operators
+    with torch.no_grad():
+        d_tc, l_tc = G(s[:4], msg[:4]), D(s[:4])
+        old = ops.set_math_mode(0)
+        try:
+            d_32, l_32 = G(s[:4], msg[:4]), D(s[:4])
+        finally:
+            ops.set_math_mode(old)
+    parity = {"clips": 4, "against": "the fp32 CUDA operators of the same layers (WM_MATH_FP32), pinned on the reference's goldens by tests/test_main14b2.py",
+              "delta_rel_err": float((d_tc - d_32).abs().max() / d_32.abs().max().clamp_min(1e-12)),
+              "logit_abs_err": float((l_tc - l_32).abs().max()), "tolerances": {"delta_rel_err": 1e-4, "logit_abs_err": 2e-4}}
+    tc = ops.get_math_mode() != 0
     n0 = ops.launch_count()
     ms = _event_ms(step, steps, max(warmup, 3), world, dev)
     return {"metric": "clip-seconds/sec embed+detect (main14b_2 stack)", "value": world * B * 1000.0 / ms,
             "unit": "clip-s/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x2 (fp32 accumulate)" if tc else "f32", "data": "synthetic",
             "config": {"workload": "main14b_2 Generator+Detector, %d clips x 1 s @ 16 kHz per GPU (BASELINE configs[2])" % B,
-                       "parallelism": "dp%d" % world},
-            "gpu_launches": int(ops.launch_count() - n0), "algorithmic_tflops": 4.540e9 * world * B / ms * 1e3 / 1e12}
+                       "parallelism": "dp%d" % world,
+                       "kernels": "tcgen05 implicit GEMMs over planar bf16-pair activations (pconv_tc_kernel)" if tc
+                       else "fp32 CUDA-core operators"},
+            "gpu_launches": int(ops.launch_count() - n0) // (steps + max(warmup, 3)),
+            "algorithmic_tflops": 4.540e9 * world * B / ms * 1e3 / 1e12, "parity": parity}
 
 
 def measure_train(dev, world, rank, steps, warmup, B=16):
