@@ -64,6 +64,11 @@ struct KParams {
   int ct_stride, ct_pad, ct_cout, out_T;
   int stage_bytes, nstage;
   signed char chunk_off[64];
+  // fused residual block (pconv_rb_kernel): second GEMM on the first one's output kept in shared memory
+  const uint8_t *w2;           // packed conv2 weights: 16-channel group major, 3 taps each; then the skip source's slices
+  const float *bias2;
+  KSrc skip;                   // kchunks == 0: none
+  int u_off, w2_bytes;         // shared-memory offsets / sizes set by the launcher
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
@@ -78,6 +83,56 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
 // ELU for the epilogue: exp(v) - 1 through ex2.approx (absolute error ~1e-7, the rounding of exp(v) itself).  expm1f costs
 // ~40 instructions per element and made every layer with a short K loop epilogue-issue bound (128 x NC elements per tile).
 __device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : ex2_approx(v * 1.4426950408889634f) - 1.0f; }
+
+// Planar store of CS channels (first GEMM column n0) of row m = (clip c, gap-relative row r, step t): same geometry, or
+// split by phase for a strided consumer.  Gap rows are written as zeros (they are the next convolution's padding).
+template <int CS>
+__device__ __forceinline__ void store_planar(const KParams &P, const float *o, int n0, long long m, int c, int r, int t,
+                                             bool real) {
+  uint4 *y = reinterpret_cast<uint4 *>(P.y);
+  const int lo0 = P.n_total >> 3;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  if (P.out_split <= 1) {
+#pragma unroll
+    for (int g = 0; g < CS / 8; ++g) {
+      const int pl = (n0 >> 3) + g;
+      uint4 hi = z, lo = z;
+      if (real) split8(o + g * 8, hi, lo);
+      y[(long long)pl * P.out_plane_rows + m] = hi;
+      y[(long long)(lo0 + pl) * P.out_plane_rows + m] = lo;
+    }
+  } else {
+    const int sp = P.out_split;
+    if (real) {
+      const int qq = t / sp, phs = t - qq * sp;
+      if (phs <= 1 || phs == sp - 1) {
+        uint4 *yp = y + (long long)phs * P.out_phase_rows;
+        const long long row = (long long)c * P.out_Tp + GAP + qq;
+#pragma unroll
+        for (int g = 0; g < CS / 8; ++g) {
+          const int pl = (n0 >> 3) + g;
+          uint4 hi, lo;
+          split8(o + g * 8, hi, lo);
+          yp[(long long)pl * P.out_plane_rows + row] = hi;
+          yp[(long long)(lo0 + pl) * P.out_plane_rows + row] = lo;
+        }
+      }
+    } else {
+      // gap row r of clip c (or of the closing gap): zero the same gap row of every phase buffer that is read
+      const long long row = (long long)c * P.out_Tp + r;
+      for (int phs = 0; phs < sp; ++phs) {
+        if (!(phs <= 1 || phs == sp - 1)) continue;
+        uint4 *yp = y + (long long)phs * P.out_phase_rows;
+#pragma unroll
+        for (int g = 0; g < CS / 8; ++g) {
+          const int pl = (n0 >> 3) + g;
+          yp[(long long)pl * P.out_plane_rows + row] = z;
+          yp[(long long)(lo0 + pl) * P.out_plane_rows + row] = z;
+        }
+      }
+    }
+  }
+}
 
 template <int NC>
 struct Cfg {
@@ -257,49 +312,7 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
       }
 
       if (P.mode == WM_PC_OUT_PLANAR) {
-        uint4 *y = reinterpret_cast<uint4 *>(P.y);
-        const int lo0 = P.n_total >> 3;
-        const uint4 z = make_uint4(0, 0, 0, 0);
-        if (P.out_split <= 1) {
-#pragma unroll
-          for (int g = 0; g < CS / 8; ++g) {
-            const int pl = (n0 >> 3) + g;
-            uint4 hi = z, lo = z;
-            if (real) split8(o + g * 8, hi, lo);
-            y[(long long)pl * P.out_plane_rows + m] = hi;
-            y[(long long)(lo0 + pl) * P.out_plane_rows + m] = lo;
-          }
-        } else {
-          const int sp = P.out_split;
-          if (real) {
-            const int qq = t / sp, phs = t - qq * sp;
-            if (phs <= 1 || phs == sp - 1) {
-              uint4 *yp = y + (long long)phs * P.out_phase_rows;
-              const long long row = (long long)c * P.out_Tp + GAP + qq;
-#pragma unroll
-              for (int g = 0; g < CS / 8; ++g) {
-                const int pl = (n0 >> 3) + g;
-                uint4 hi, lo;
-                split8(o + g * 8, hi, lo);
-                yp[(long long)pl * P.out_plane_rows + row] = hi;
-                yp[(long long)(lo0 + pl) * P.out_plane_rows + row] = lo;
-              }
-            }
-          } else {
-            // gap row r of clip c (or of the closing gap): zero the same gap row of every phase buffer that is read
-            const long long row = (long long)c * P.out_Tp + r;
-            for (int phs = 0; phs < sp; ++phs) {
-              if (!(phs <= 1 || phs == sp - 1)) continue;
-              uint4 *yp = y + (long long)phs * P.out_phase_rows;
-#pragma unroll
-              for (int g = 0; g < CS / 8; ++g) {
-                const int pl = (n0 >> 3) + g;
-                yp[(long long)pl * P.out_plane_rows + row] = z;
-                yp[(long long)(lo0 + pl) * P.out_plane_rows + row] = z;
-              }
-            }
-          }
-        }
+        store_planar<CS>(P, o, n0, m, c, r, t, real);
       } else if (P.mode == WM_PC_OUT_CONVT) {
         // column n = phase * Cout + co; row (c, q = t) -> output step s q + phase of clip c.  The first gap row of a
         // clip also carries the last outputs of the previous clip when out_T > s * T (odd strides).
@@ -383,6 +396,358 @@ int launch_pconv_t(const KParams &P0, cudaStream_t st) {
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
   pconv_tc_kernel<NC><<<grid, 576, smem_bytes, st>>>(P);
   WM_CHECK_LAUNCH("pconv_tc");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused ResidualBlock (py/main14b_2.py:97-105) for blocks of up to 64 output channels, the ones that run at
+// T = 2000..16000 and are bound by HBM when conv1's output makes a round trip:
+//     u = elu(conv1(x) + b1)  ->  bf16-pair tile in SHARED MEMORY  ->  y = elu(conv2(u) + b2 + skip(x) | x)
+// GEMM 1 is the stage pipeline of pconv_tc_kernel (any source list: plain k3, or the three phase sources of a strided
+// conv1); its epilogue writes the 128-row u tile in the canonical operand layout; GEMM 2 reads it with three row-shifted
+// descriptors against conv2's weights RESIDENT in shared memory, optionally followed by streamed stages of the 1x1
+// skip convolution (phase 0 of x).  A tile yields 126 output rows (u rows u0 .. u0 + 127 -> y rows u0 + 1 .. u0 + 126).
+// The identity residual is read from global memory in the second epilogue (an L2 hit: the same rows were just loaded).
+// Warps 0..7 epilogue 1, 8..15 epilogue 2 (quadrant = warp % 4, half of the channels = (warp / 4) % 2), 16 producer,
+// 17 MMA issuer.  The issuer runs GEMM 1 of tile i + 1 before GEMM 2 of tile i, so epilogue 1 overlaps tensor work.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RB_ROWS = 126;
+constexpr int U_PLANE = 136 * 16;
+
+template <int NC>
+__global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant__ KParams P) {
+  using C = Cfg<NC>;
+  constexpr int CS = NC / 2;                 // channels per epilogue thread
+  constexpr int U_BYTES = 2 * (NC / 8) * U_PLANE;
+  constexpr int KC2 = NC / 16;               // 16-channel groups of u
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t s_base = smem_u32(smem);
+  const int NS = P.nstage;
+  const uint32_t w2_smem = s_base + NS * P.stage_bytes;
+  const uint32_t u_smem = s_base + P.u_off;
+  const uint32_t bars = u_smem + 2 * U_BYTES;
+  auto full_bar = [&](int s) { return bars + 8 * s; };
+  auto empty_bar = [&](int s) { return bars + 8 * (MAX_STAGE + s); };
+  const uint32_t xb = bars + 8 * 2 * MAX_STAGE;
+  auto t1_full = [&](int a) { return xb + 8 * a; };
+  auto t1_empty = [&](int a) { return xb + 8 * (2 + a); };
+  auto u_full = [&](int a) { return xb + 8 * (4 + a); };
+  auto u_empty = [&](int a) { return xb + 8 * (6 + a); };
+  auto t2_full = [&](int a) { return xb + 8 * (8 + a); };
+  auto t2_empty = [&](int a) { return xb + 8 * (10 + a); };
+  const uint32_t w2bar = xb + 8 * 12;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + P.u_off + 2 * U_BYTES + 8 * (2 * MAX_STAGE + 13));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ntiles = (uint32_t)((P.R + RB_ROWS - 1) / RB_ROWS);
+  const uint32_t nmine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(t1_full(a), 1); mbar_init(t1_empty(a), 8);
+      mbar_init(u_full(a), 8); mbar_init(u_empty(a), 1);
+      mbar_init(t2_full(a), 1); mbar_init(t2_empty(a), 8);
+    }
+    mbar_init(w2bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 17) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(8 * NC)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc1 = tmem_base, acc2 = tmem_base + 4 * NC;
+
+  if (warp == 16) {
+    // ===== producer =====
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w2bar, (uint32_t)P.w2_bytes);
+      for (int off = 0; off < P.w2_bytes; off += C::B_TAP) bulk_g2s(w2_smem + off, P.w2 + off, C::B_TAP, w2bar);
+    }
+    uint32_t s = 0, ph = 0;
+    const uint8_t *wsk = P.w2 + P.w2_bytes;      // skip slices follow conv2's
+    for (uint32_t i = 0; i <= nmine; ++i) {
+      if (i < nmine) {
+        const long long u0 = (long long)(blockIdx.x + i * gridDim.x) * RB_ROWS - 1;
+        const uint8_t *wj = P.w;
+        for (int si = 0; si < P.nsrc; ++si) {
+          const KSrc &S = P.src[si];
+          const long long row = u0 + S.row_off;
+          const uint32_t abytes = (uint32_t)(TILE + S.taps - 1) * 16u;
+          const uint32_t wbytes = (uint32_t)S.taps * C::B_TAP;
+          const uint8_t *src = lane < 4 ? reinterpret_cast<const uint8_t *>(
+                                              S.base + ((long long)((lane >> 1) * S.lo_plane + (lane & 1)) * P.plane_rows + row))
+                                        : wj;
+          const size_t step = lane < 4 ? (size_t)(2 * P.plane_rows) * 16u : (size_t)wbytes;
+          const uint32_t bytes = lane < 4 ? abytes : wbytes;
+          const uint32_t doff = lane < 4 ? (uint32_t)lane * A_PLANE : (uint32_t)A_BYTES;
+          const int kch = S.kchunks;
+          for (int kc = 0; kc < kch; ++kc) {
+            mbar_wait(empty_bar(s), ph ^ 1);
+            if (lane == 0) mbar_arrive_expect_tx(full_bar(s), 4 * abytes + wbytes);
+            __syncwarp();
+            if (lane < 5) bulk_g2s(s_base + s * P.stage_bytes + doff, src, bytes, full_bar(s));
+            src += step;
+            if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
+          }
+          wj += (size_t)kch * wbytes;
+        }
+      }
+      if (i >= 1 && P.skip.kchunks > 0) {
+        // skip stages of tile i - 1: phase-0 rows of x under the tile's OUTPUT rows (u0 + 1 ..)
+        const KSrc &S = P.skip;
+        const long long row = (long long)(blockIdx.x + (i - 1) * gridDim.x) * RB_ROWS + S.row_off;
+        const uint32_t abytes = (uint32_t)TILE * 16u, wbytes = (uint32_t)C::B_TAP;
+        const uint8_t *src = lane < 4 ? reinterpret_cast<const uint8_t *>(
+                                            S.base + ((long long)((lane >> 1) * S.lo_plane + (lane & 1)) * P.plane_rows + row))
+                                      : wsk;
+        const size_t step = lane < 4 ? (size_t)(2 * P.plane_rows) * 16u : (size_t)wbytes;
+        const uint32_t bytes = lane < 4 ? abytes : wbytes;
+        const uint32_t doff = lane < 4 ? (uint32_t)lane * A_PLANE : (uint32_t)A_BYTES;
+        for (int kc = 0; kc < S.kchunks; ++kc) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          if (lane == 0) mbar_arrive_expect_tx(full_bar(s), 4 * abytes + wbytes);
+          __syncwarp();
+          if (lane < 5) bulk_g2s(s_base + s * P.stage_bytes + doff, src, bytes, full_bar(s));
+          src += step;
+          if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 17) {
+    // ===== MMA issuer =====
+    const bool issuer = elect_one();
+    constexpr uint32_t idesc_hi = make_idesc(128, 2 * NC), idesc_lo = make_idesc(128, NC);
+    uint32_t s = 0, ph = 0;
+    mbar_wait_warp(w2bar, 0);
+    for (uint32_t i = 0; i <= nmine; ++i) {
+      if (i < nmine) {
+        const uint32_t a = i & 1u, aph = (i >> 1) & 1u;
+        mbar_wait_warp(t1_empty(a), aph ^ 1);
+        const uint32_t d_tmem = acc1 + a * (2 * NC);
+        uint32_t accum = 0;
+        for (int si = 0; si < P.nsrc; ++si) {
+          const int taps = P.src[si].taps, kch = P.src[si].kchunks;
+          for (int kc = 0; kc < kch; ++kc) {
+            mbar_wait_warp(full_bar(s), ph);
+            tc_fence_after();
+            if (issuer) {
+              const uint32_t st = s_base + s * P.stage_bytes;
+              const uint64_t a0 = smem_desc(st, A_PLANE, 128);
+              const uint64_t b0 = smem_desc(st + A_BYTES, 2 * NC * 16, 128);
+#pragma unroll 1
+              for (int tp = 0; tp < taps; ++tp) {
+                const uint64_t ad = a0 + (uint64_t)tp, bd = b0 + (uint64_t)(tp * (C::B_TAP >> 4));
+                mma_bf16(d_tmem, ad, bd, idesc_hi, accum);
+                mma_bf16(d_tmem, ad + (uint64_t)((2 * A_PLANE) >> 4), bd, idesc_lo, 1u);
+                accum = 1u;
+              }
+              tc_commit(empty_bar(s));
+            }
+            __syncwarp();
+            if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
+          }
+        }
+        if (issuer) tc_commit(t1_full(a));
+        __syncwarp();
+      }
+      if (i >= 1) {
+        const uint32_t j = i - 1, a = j & 1u, aph = (j >> 1) & 1u;
+        mbar_wait_warp(u_full(a), aph);
+        mbar_wait_warp(t2_empty(a), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = acc2 + a * (2 * NC);
+        if (issuer) {
+          const uint64_t a0 = smem_desc(u_smem + a * U_BYTES, U_PLANE, 128);
+          const uint64_t b0 = smem_desc(w2_smem, 2 * NC * 16, 128);
+          uint32_t accum = 0;
+#pragma unroll 1
+          for (int kc = 0; kc < KC2; ++kc) {
+#pragma unroll
+            for (int tp = 0; tp < 3; ++tp) {
+              const uint64_t ad = a0 + (uint64_t)((2 * kc * U_PLANE) >> 4) + (uint64_t)tp;
+              const uint64_t bd = b0 + (uint64_t)(((kc * 3 + tp) * C::B_TAP) >> 4);
+              mma_bf16(d_tmem, ad, bd, idesc_hi, accum);
+              mma_bf16(d_tmem, ad + (uint64_t)(((NC / 8) * U_PLANE) >> 4), bd, idesc_lo, 1u);
+              accum = 1u;
+            }
+          }
+        }
+        __syncwarp();
+        for (int kc = 0; kc < P.skip.kchunks; ++kc) {
+          mbar_wait_warp(full_bar(s), ph);
+          tc_fence_after();
+          if (issuer) {
+            const uint32_t st = s_base + s * P.stage_bytes;
+            const uint64_t ad = smem_desc(st, A_PLANE, 128), bd = smem_desc(st + A_BYTES, 2 * NC * 16, 128);
+            mma_bf16(d_tmem, ad, bd, idesc_hi, 1u);
+            mma_bf16(d_tmem, ad + (uint64_t)((2 * A_PLANE) >> 4), bd, idesc_lo, 1u);
+            tc_commit(empty_bar(s));
+          }
+          __syncwarp();
+          if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
+        }
+        if (issuer) {
+          tc_commit(u_empty(a));
+          tc_commit(t2_full(a));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 8) {
+    // ===== epilogue 1: accumulator -> elu -> bf16 pair -> u tile in shared memory =====
+    const int q = warp & 3, p = warp >> 2;
+    const int n0 = p * CS;
+    const int Tp = P.Tp;
+    for (uint32_t i = 0; i < nmine; ++i) {
+      const uint32_t a = i & 1u, aph = (i >> 1) & 1u;
+      const long long mu = (long long)(blockIdx.x + i * gridDim.x) * RB_ROWS - 1 + q * 32 + lane;
+      bool real = false;
+      if (mu >= 0 && mu < P.R) {
+        const int c = (int)((uint32_t)mu / (uint32_t)Tp);
+        real = c < P.B && (int)(mu - (long long)c * Tp) >= GAP;
+      }
+      mbar_wait_warp(t1_full(a), aph);
+      tc_fence_after();
+      const uint32_t taddr = acc1 + a * (2 * NC) + ((uint32_t)(q * 32) << 16) + n0;
+      float o[CS];
+      {
+        float v2[CS];
+#pragma unroll
+        for (int g = 0; g < CS / 8; ++g) {
+          tmem_ld8(taddr + g * 8, o + g * 8);
+          tmem_ld8(taddr + NC + g * 8, v2 + g * 8);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive_warp(t1_empty(a));
+#pragma unroll
+        for (int k = 0; k < CS; ++k) o[k] += v2[k];
+      }
+      {
+        const float4 *bp = reinterpret_cast<const float4 *>(P.bias + n0);
+#pragma unroll
+        for (int k = 0; k < CS / 4; ++k) {
+          const float4 b = __ldg(bp + k);
+          o[4 * k] += b.x; o[4 * k + 1] += b.y; o[4 * k + 2] += b.z; o[4 * k + 3] += b.w;
+        }
+      }
+      mbar_wait_warp(u_empty(a), aph ^ 1);        // GEMM 2 of tile i - 2 has read this buffer
+      uint8_t *ub = smem + P.u_off + a * U_BYTES + (q * 32 + lane) * 16;
+#pragma unroll
+      for (int g = 0; g < CS / 8; ++g) {
+        uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+        if (real) {
+          float e[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) e[k] = elu1(o[g * 8 + k]);
+          split8(e, hi, lo);
+        }
+        const int pl = (n0 >> 3) + g;
+        *reinterpret_cast<uint4 *>(ub + pl * U_PLANE) = hi;
+        *reinterpret_cast<uint4 *>(ub + (NC / 8 + pl) * U_PLANE) = lo;
+      }
+      fence_async_smem();                          // generic-proxy stores -> the MMA's operand reads
+      mbar_arrive_warp(u_full(a));
+    }
+  } else if (warp < 16) {
+    // ===== epilogue 2: accumulator + bias (+ residual) -> elu -> planar output =====
+    const int q = warp & 3, p = (warp >> 2) & 1;
+    const int n0 = p * CS;
+    const int Tp = P.Tp;
+    for (uint32_t i = 0; i < nmine; ++i) {
+      const uint32_t a = i & 1u, aph = (i >> 1) & 1u;
+      const int ri = q * 32 + lane;
+      const long long m = (long long)(blockIdx.x + i * gridDim.x) * RB_ROWS + ri;
+      const int c = (int)((uint32_t)m / (uint32_t)Tp);
+      const int r = (int)(m - (long long)c * Tp);
+      const int t = r - GAP;
+      mbar_wait_warp(t2_full(a), aph);
+      tc_fence_after();
+      const uint32_t taddr = acc2 + a * (2 * NC) + ((uint32_t)(q * 32) << 16) + n0;
+      float o[CS];
+      {
+        float v2[CS];
+#pragma unroll
+        for (int g = 0; g < CS / 8; ++g) {
+          tmem_ld8(taddr + g * 8, o + g * 8);
+          tmem_ld8(taddr + NC + g * 8, v2 + g * 8);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive_warp(t2_empty(a));
+#pragma unroll
+        for (int k = 0; k < CS; ++k) o[k] += v2[k];
+      }
+      if (ri >= RB_ROWS || m >= P.R) continue;
+      {
+        const float4 *bp = reinterpret_cast<const float4 *>(P.bias2 + n0);
+#pragma unroll
+        for (int k = 0; k < CS / 4; ++k) {
+          const float4 b = __ldg(bp + k);
+          o[4 * k] += b.x; o[4 * k + 1] += b.y; o[4 * k + 2] += b.z; o[4 * k + 3] += b.w;
+        }
+      }
+      const bool real = (c < P.B) && (t >= 0);
+      if (P.residual != nullptr && real) {
+        const int lo0 = P.n_total >> 3;
+#pragma unroll
+        for (int g = 0; g < CS / 8; ++g) {
+          const int pl = (n0 >> 3) + g;
+          const uint4 rh = __ldg(P.residual + ((long long)pl * P.plane_rows + m));
+          const uint4 rl = __ldg(P.residual + ((long long)(lo0 + pl) * P.plane_rows + m));
+          float rr[8];
+          join8(rh, rl, rr);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[g * 8 + k] += rr[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < CS; ++k) o[k] = elu1(o[k]);
+      store_planar<CS>(P, o, n0, m, c, r, t, real);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(8 * NC) : "memory");
+  }
+}
+
+template <int NC>
+int launch_pconv_rb_t(const KParams &P0, cudaStream_t st) {
+  using C = Cfg<NC>;
+  KParams P = P0;
+  int maxtaps = 1;
+  for (int i = 0; i < P.nsrc; ++i) maxtaps = P.src[i].taps > maxtaps ? P.src[i].taps : maxtaps;
+  P.stage_bytes = (A_BYTES + maxtaps * C::B_TAP + 127) / 128 * 128;
+  P.w2_bytes = (NC / 16) * 3 * C::B_TAP;
+  const int u_bytes = 2 * 2 * (NC / 8) * U_PLANE;
+  const int fixed = (P.w2_bytes + 127) / 128 * 128 + u_bytes + 8 * (2 * MAX_STAGE + 13) + 16;
+  int ns = (225 * 1024 - fixed) / P.stage_bytes;
+  ns = ns > MAX_STAGE ? MAX_STAGE : ns;
+  WM_CHECK_ARG(ns >= 2, "pconv_rb: stages of %d bytes do not fit the shared memory", P.stage_bytes);
+  P.nstage = ns;
+  P.u_off = ns * P.stage_bytes + (P.w2_bytes + 127) / 128 * 128;
+  const int smem_bytes = P.u_off + u_bytes + 8 * (2 * MAX_STAGE + 13) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WM_CHECK_CUDA(cudaFuncSetAttribute(pconv_rb_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const long long ntiles = (P.R + RB_ROWS - 1) / RB_ROWS;
+  WM_CHECK_ARG(P.R < (1LL << 31), "pconv_rb: %lld rows exceed the 32-bit tile index", P.R);
+  const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  pconv_rb_kernel<NC><<<grid, 576, smem_bytes, st>>>(P);
+  WM_CHECK_LAUNCH("pconv_rb");
   return 0;
 }
 
@@ -587,6 +952,28 @@ int wm_pconv_fwd(const wm_pconv *d, void *stream) {
                  "pconv: fp32 output needs 1 <= channels <= n_total and out_T <= T");
   }
   cudaStream_t st = as_stream(stream);
+  if (d->fused) {
+    WM_CHECK_ARG(d->mode == WM_PC_OUT_PLANAR && d->n_total == d->nc && d->nc <= 64,
+                 "pconv: the fused residual block needs planar output and one chunk of at most 64 columns");
+    WM_CHECK_ARG(d->w2 && d->bias2, "pconv: the fused residual block needs w2 and bias2");
+    WM_CHECK_ARG(d->chunk_off[0] == 0, "pconv: no chunk offset in the fused residual block");
+    P.w2 = reinterpret_cast<const uint8_t *>(d->w2);
+    P.bias2 = d->bias2;
+    if (d->skip.base != nullptr) {
+      WM_CHECK_ARG(d->skip.cin >= 16 && d->skip.cin % 16 == 0 && d->skip.taps == 1 && d->skip.row_off == 0,
+                   "pconv: the skip source is one tap at row offset 0 over a multiple of 16 channels");
+      P.skip.base = reinterpret_cast<const uint4 *>(d->skip.base);
+      P.skip.kchunks = d->skip.cin / 16;
+      P.skip.lo_plane = d->skip.cin / 8;
+      P.skip.row_off = 0;
+      P.skip.taps = 1;
+    }
+    switch (d->nc) {
+      case 16: return launch_pconv_rb_t<16>(P, st);
+      case 32: return launch_pconv_rb_t<32>(P, st);
+      default: return launch_pconv_rb_t<64>(P, st);
+    }
+  }
   switch (d->nc) {
     case 16: return launch_pconv_t<16>(P, st);
     case 32: return launch_pconv_t<32>(P, st);

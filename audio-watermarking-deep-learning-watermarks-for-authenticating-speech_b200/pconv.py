@@ -141,7 +141,8 @@ class _Desc(C.Structure):
                 ("chunk_off", C.c_byte * 64), ("elu", C.c_int), ("mode", C.c_int), ("residual", C.c_void_p),
                 ("y", C.c_void_p), ("out_plane_rows", C.c_longlong), ("out_phase_rows", C.c_longlong),
                 ("out_split", C.c_int), ("ct_stride", C.c_int), ("ct_pad", C.c_int), ("ct_cout", C.c_int),
-                ("out_T", C.c_int)]
+                ("out_T", C.c_int), ("fused", C.c_int), ("reserved2", C.c_int), ("w2", C.c_void_p), ("bias2", C.c_void_p),
+                ("skip", _Src)]
 
 
 class Planar:
@@ -219,7 +220,9 @@ class CudaBackend:
         return y
 
     def run(self, g: Gemm, srcs: Sequence[Tuple[Planar, int]], B, T, elu, residual, mode, out, out_split=1, ct=None,
-            out_T=0, cout=0):
+            out_T=0, cout=0, g2: Optional[Gemm] = None, skip=None):
+        """One wm_pconv_fwd call; with `g2` the fused residual block: g = conv1 (u stays in shared memory), g2 = conv2
+        (+ the skip source `skip` = (planar, phase) when g2 carries its slices), residual / elu / out apply to g2."""
         from . import _lib as L
         from .ops import _stream
         dev = srcs[0][0].store.device
@@ -244,10 +247,21 @@ class CudaBackend:
             d.y, d.out_plane_rows, d.out_phase_rows = out.ptr(), out.RP, out.phase_rows
             if mode == OUT_CONVT:
                 d.ct_stride, d.ct_pad, d.ct_cout, d.out_T = ct[0], ct[1], ct[2], out_T
+        if g2 is not None:
+            self.pack(g2, dev)
+            d.fused, d.w2, d.bias2 = 1, g2.img.data_ptr(), g2.dbias.data_ptr()
+            if skip is not None:
+                d.skip.base, d.skip.cin, d.skip.row_off, d.skip.taps = skip[0].ptr(skip[1]), skip[0].C, 0, 1
         L.check(L.load().wm_pconv_fwd(C.byref(d), _stream()), "wm_pconv_fwd")
 
 
 _BACKEND = CudaBackend()
+
+
+def fusable(g1: Gemm, g2: Gemm) -> bool:
+    """conv1 + conv2 of a ResidualBlock run as ONE kernel (conv1's output stays in shared memory) when the block has at
+    most 64 output channels in one chunk — the layers at T = 2000..16000, which a round trip of u makes HBM-bound."""
+    return g1.n_total == g1.nc == g2.n_total == g2.nc and g1.nc <= 64 and g1.cout == g1.n_total and g2.srcs[0][1] == g1.n_total
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -327,9 +341,16 @@ def _encoder(mod, s, plan, last_fp32: bool):
     t = T
     for i, (st, g1, g2) in enumerate(plan["enc"]):
         to = t // st
+        last = i + 1 == len(strides)
+        if fusable(g1, g2) and not (last and last_fp32):
+            nsp = 1 if last else strides[i + 1]
+            nxt = be.planar(g2.cout, B, to // nsp, nsp, dev)
+            be.run(g1, [(cur, st - 1), (cur, 0), (cur, 1)], B, to, True, None, OUT_PLANAR, nxt, out_split=nsp, g2=g2,
+                   skip=(cur, 0))
+            cur, t = nxt, to
+            continue
         u = be.planar(g1.cout, B, to, 1, dev)
         be.run(g1, [(cur, st - 1), (cur, 0), (cur, 1)], B, to, True, None, OUT_PLANAR, u)
-        last = i + 1 == len(strides)
         if last and last_fp32:
             y = be.fp32((B, g2.cout, to), dev)
             be.run(g2, [(u, 0), (cur, 0)], B, to, True, None, OUT_FP32, y, out_T=to, cout=g2.cout)
@@ -355,10 +376,13 @@ def _decoder(plan, cur, t):
             cur, t = y, to
         else:
             _, blk, g1, g2 = item
-            u = be.planar(g1.cout, B, t, 1, dev)
-            be.run(g1, [(cur, 0)], B, t, True, None, OUT_PLANAR, u)
             y = be.planar(g2.cout, B, t, 1, dev)
-            be.run(g2, [(u, 0)], B, t, True, cur, OUT_PLANAR, y)
+            if fusable(g1, g2):
+                be.run(g1, [(cur, 0)], B, t, True, cur, OUT_PLANAR, y, g2=g2)
+            else:
+                u = be.planar(g1.cout, B, t, 1, dev)
+                be.run(g1, [(cur, 0)], B, t, True, None, OUT_PLANAR, u)
+                be.run(g2, [(u, 0)], B, t, True, cur, OUT_PLANAR, y)
             cur = y
     return cur, t
 

@@ -40,7 +40,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 18
+#define WM_ABI_VERSION 19
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -424,6 +424,15 @@ typedef struct wm_pconv {
   int out_split;
   int ct_stride, ct_pad, ct_cout;
   int out_T;
+  /* fused ResidualBlock (py/main14b_2.py:97-105), n_total == nc <= 64, WM_PC_OUT_PLANAR: the call above is conv1
+   * (its result u = elu(acc) stays in shared memory), followed by
+   *     y = elu( bias2 + sum over u's channels and 3 taps of u[m - 1 + j] * W2 + skip[ci][m] * Wskip + residual )
+   * with w2 = wm_pconv_pack image of conv2's slices (16-channel group major, 3 taps) followed by the skip source's. */
+  int fused;
+  int reserved2;
+  const void *w2;
+  const float *bias2;
+  wm_pconv_src skip;            /* base == NULL: none (one tap, row offset 0: phase 0 of the block input) */
 } wm_pconv;
 long long wm_pconv_plane_rows(int B, int T);
 size_t wm_pconv_desc_bytes(void);   /* sizeof(wm_pconv), for bindings that mirror the struct */

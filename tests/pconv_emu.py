@@ -58,7 +58,16 @@ class EmuBackend:
             d = final(z)
         return d[:, :, :T] if d.shape[-1] >= T else F.pad(d, (0, T - d.shape[-1]))
 
-    def run(self, g, srcs, B, T, elu, residual, mode, out, out_split=1, ct=None, out_T=0, cout=0):
+    def run(self, g, srcs, B, T, elu, residual, mode, out, out_split=1, ct=None, out_T=0, cout=0, g2=None, skip=None):
+        if g2 is not None:
+            # contract of the fused residual block = the two calls it replaces
+            assert mode == PC.OUT_PLANAR and PC.fusable(g, g2) and elu
+            u = EmuPlanar(g.n_total, B, T)
+            self.run(g, srcs, B, T, True, None, PC.OUT_PLANAR, u)
+            self.calls[-1] = self.calls[-1] + ("fused",)
+            s2 = [(u, 0)] + ([skip] if skip is not None else [])
+            assert len(s2) == len(g2.srcs)
+            return self.run(g2, s2, B, T, True, residual, PC.OUT_PLANAR, out, out_split=out_split)
         self.calls.append((mode, g.n_total, g.nc, [s[1:] for s in g.srcs]))
         Tp = T + GAP
         R = B * Tp + GAP

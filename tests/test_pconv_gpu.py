@@ -178,3 +178,44 @@ def test_register_lstm(B, T, L):
     with torch.no_grad():
         want = lstm(x.transpose(1, 2))[0].transpose(1, 2)
     assert relerr(M.lstm_small(x, lstm), want) < 5e-5      # cuDNN vs expf/tanhf round-off over 130 steps
+
+
+@pytest.mark.parametrize("C,B,T", [(16, 3, 300), (32, 2, 1000), (64, 3, 517), (64, 1, 126), (32, 5, 125)])
+def test_fused_residual_block(C, B, T):
+    """conv1 -> shared memory -> conv2 + identity residual in one kernel, tiles of 126 rows straddling clips"""
+    torch.manual_seed(C + T)
+    blk = M.ResidualBlock(C, C).to(DEV)
+    x = torch.randn(B, C, T, device=DEV)
+    with torch.no_grad():
+        want = F.elu(blk.conv2(F.elu(blk.conv1(x))) + x)
+    g1, g2 = PC.gemm_conv_s1(blk.conv1.weight, blk.conv1.bias), PC.gemm_conv_s1(blk.conv2.weight, blk.conv2.bias)
+    assert PC.fusable(g1, g2)
+    xin, out = planar_from(x), fresh(C, B, T)
+    BE.run(g1, [(xin, 0)], B, T, True, xin, PC.OUT_PLANAR, out, g2=g2)
+    got = BE.from_planar(out, T)
+    assert relerr(got, want) < 3e-5, relerr(got, want)
+    assert gap_rows_zero(out)
+
+
+@pytest.mark.parametrize("s,cin,cout,nsp", [(2, 32, 64, 4), (4, 16, 32, 1), (5, 32, 64, 5)])
+def test_fused_strided_block(s, cin, cout, nsp):
+    """strided conv1 from phase buffers -> shared memory -> conv2 + folded skip, phase-split output"""
+    torch.manual_seed(s + cout)
+    B = 3
+    T = s * nsp * 53
+    blk = M.ResidualBlock(cin, cout, stride=s).to(DEV)
+    x = torch.randn(B, cin, T, device=DEV)
+    with torch.no_grad():
+        y_ref = F.elu(blk.conv2(F.elu(blk.conv1(x))) + blk.skip_conv(x))
+    xin = planar_from(x, s)
+    g1 = PC.gemm_conv_strided(blk.conv1.weight, blk.conv1.bias, s)
+    g2 = PC.gemm_conv2_skip(blk.conv2.weight, blk.conv2.bias, blk.skip_conv.weight, blk.skip_conv.bias)
+    assert PC.fusable(g1, g2)
+    To = T // s
+    y = fresh(cout, B, To // nsp, nsp)
+    BE.run(g1, [(xin, s - 1), (xin, 0), (xin, 1)], B, To, True, None, PC.OUT_PLANAR, y, out_split=nsp, g2=g2, skip=(xin, 0))
+    phases = sorted({0, 1 % nsp, nsp - 1})
+    for ph in phases:
+        got = BE.from_planar(y, To // nsp, ph)
+        assert relerr(got, y_ref[:, :, ph::nsp]) < 3e-5, (ph, relerr(got, y_ref[:, :, ph::nsp]))
+    assert gap_rows_zero(y, phases)

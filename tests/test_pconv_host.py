@@ -155,6 +155,8 @@ def test_whole_models_against_the_oracle(monkeypatch, B, T):
     assert float((got_l.float() - want_l).abs().max()) < 1e-4
     # generator: 8 encoder GEMMs + 4 transposed + 3 residual blocks on the tensor-core path; detector: 8 + 4 + 8 + final
     assert n_g == 8 + 4 + 6 and len(be.calls) - n_g == 8 + 4 + 8 + 1
+    # blocks of <= 64 channels are fused: encoder block 1 (both models), generator RB64/32/16, detector RB64/32
+    assert sum(1 for c in be.calls if c[-1] == "fused") == 2 + 3 + 2
     assert sum(1 for c in be.calls if c[0] == PC.OUT_CONVT and len(c[3]) == 1 and c[3][0][2] == 2) >= 5   # 2-tap form used
 
 
