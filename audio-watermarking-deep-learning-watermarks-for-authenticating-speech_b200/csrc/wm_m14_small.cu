@@ -13,21 +13,46 @@ namespace {
 
 constexpr int GAP = WM_PC_GAP;
 constexpr int TT = 256;   // outputs per block of the tail kernel
+constexpr int TN = TT / 4;  // threads: four consecutive time steps each
 
 // exp(v) - 1 through ex2.approx: absolute error ~1e-7 (expm1f is ~40 instructions, 16 of them per output sample here)
 __device__ __forceinline__ float elu_f(float v) { return v > 0.0f ? v : ex2_approx(v * 1.4426950408889634f) - 1.0f; }
 
+// a[pos][co] += sum over ci, k of in[ci][4 j + pos + k] * w[k][ci][co] for four consecutive positions: every weight
+// vector and input value is fetched from shared memory once per FOUR outputs (one position per thread made the kernel
+// LSU-bound: 72 shared loads per 192 FMAs)
+template <int W>
+__device__ __forceinline__ void conv8k3x4(const float (*in)[W], const float (*w)[8][8], int j, float (&a)[4][8]) {
+#pragma unroll 2
+  for (int ci = 0; ci < 8; ++ci) {
+    const float4 v = *reinterpret_cast<const float4 *>(&in[ci][4 * j]);
+    const float2 v2 = *reinterpret_cast<const float2 *>(&in[ci][4 * j + 4]);
+    const float xin[6] = {v.x, v.y, v.z, v.w, v2.x, v2.y};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float4 wa = *reinterpret_cast<const float4 *>(&w[k][ci][0]), wb = *reinterpret_cast<const float4 *>(&w[k][ci][4]);
+      const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int pos = 0; pos < 4; ++pos)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[pos][c] = fmaf(xin[pos + k], wv[c], a[pos][c]);
+    }
+  }
+}
+
 // x planar (8 channels: plane 0 = hi, plane 1 = lo; geometry (B, Tx)) ->
 //   u = elu(conv1(x)), z = elu(conv2(u) + x)   (ResidualBlock, py/main14b_2.py:97-105; k3, padding 1)
 //   delta[b][t] = final(z)[t] for t < T         (Conv1d(8, 1, 7, padding 3), :149,173; crop :175-177)
-__global__ void __launch_bounds__(TT, 3)
+// shared arrays: xs[i] = x at t0 - 5 + i, us[i] = u at t0 - 4 + i, zs[i] = z at t0 - 3 + i
+__global__ void __launch_bounds__(TN)
     m14_tail8_kernel(const uint4 *__restrict__ x, long long plane_rows, int Tx, const float *__restrict__ w1,
                      const float *__restrict__ b1, const float *__restrict__ w2, const float *__restrict__ b2,
                      const float *__restrict__ wf, const float *__restrict__ bf, float *__restrict__ delta, int T) {
-  __shared__ float xs[8][TT + 10], us[8][TT + 8], zs[8][TT + 6];
+  constexpr int WX = TT + 16, WU = TT + 12, WZ = TT + 8;
+  __shared__ __align__(16) float xs[8][WX], us[8][WU], zs[8][WZ];
   __shared__ __align__(16) float w1s[3][8][8], w2s[3][8][8], wfs[7][8], bs[2][8];   // [tap][ci][co]
   const int b = blockIdx.y, t0 = blockIdx.x * TT, tid = threadIdx.x;
-  for (int i = tid; i < 192; i += TT) {
+  for (int i = tid; i < 192; i += TN) {
     const int co = i & 7, ci = (i >> 3) & 7, k = i >> 6;
     w1s[k][ci][co] = w1[(co * 8 + ci) * 3 + k];
     w2s[k][ci][co] = w2[(co * 8 + ci) * 3 + k];
@@ -35,7 +60,7 @@ __global__ void __launch_bounds__(TT, 3)
   if (tid < 56) wfs[tid >> 3][tid & 7] = wf[(tid & 7) * 7 + (tid >> 3)];
   if (tid < 8) { bs[0][tid] = b1[tid]; bs[1][tid] = b2[tid]; }
   const long long row0 = (long long)b * (Tx + GAP) + GAP;
-  for (int i = tid; i < TT + 10; i += TT) {
+  for (int i = tid; i < WX; i += TN) {
     const int t = t0 - 5 + i;
     float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (t >= 0 && t < Tx) {
@@ -46,55 +71,72 @@ __global__ void __launch_bounds__(TT, 3)
     for (int c = 0; c < 8; ++c) xs[c][i] = v[c];
   }
   __syncthreads();
-  for (int i = tid; i < TT + 8; i += TT) {      // u at t0 - 4 + i
-    const int t = t0 - 4 + i;
-    float a[8];
+  for (int j = tid; j < WU / 4; j += TN) {       // u at indices 4j .. 4j+3
+    float a[4][8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) a[c] = bs[0][c];
-#pragma unroll 1
-    for (int k = 0; k < 3; ++k)
+    for (int pos = 0; pos < 4; ++pos)
 #pragma unroll
-      for (int ci = 0; ci < 8; ++ci) {
-        const float xv = xs[ci][i + k];
-        const float4 wa = *reinterpret_cast<const float4 *>(&w1s[k][ci][0]), wb = *reinterpret_cast<const float4 *>(&w1s[k][ci][4]);
-        a[0] = fmaf(xv, wa.x, a[0]); a[1] = fmaf(xv, wa.y, a[1]); a[2] = fmaf(xv, wa.z, a[2]); a[3] = fmaf(xv, wa.w, a[3]);
-        a[4] = fmaf(xv, wb.x, a[4]); a[5] = fmaf(xv, wb.y, a[5]); a[6] = fmaf(xv, wb.z, a[6]); a[7] = fmaf(xv, wb.w, a[7]);
+      for (int c = 0; c < 8; ++c) a[pos][c] = bs[0][c];
+    conv8k3x4<WX>(xs, w1s, j, a);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float4 o;
+      float *op = &o.x;
+#pragma unroll
+      for (int pos = 0; pos < 4; ++pos) {
+        const int t = t0 - 4 + 4 * j + pos;
+        op[pos] = (t >= 0 && t < Tx) ? elu_f(a[pos][c]) : 0.0f;
       }
-    const bool in = t >= 0 && t < Tx;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) us[c][i] = in ? elu_f(a[c]) : 0.0f;
-  }
-  __syncthreads();
-  for (int i = tid; i < TT + 6; i += TT) {      // z at t0 - 3 + i
-    const int t = t0 - 3 + i;
-    float a[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) a[c] = bs[1][c];
-#pragma unroll 1
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-      for (int ci = 0; ci < 8; ++ci) {
-        const float uv = us[ci][i + k];
-        const float4 wa = *reinterpret_cast<const float4 *>(&w2s[k][ci][0]), wb = *reinterpret_cast<const float4 *>(&w2s[k][ci][4]);
-        a[0] = fmaf(uv, wa.x, a[0]); a[1] = fmaf(uv, wa.y, a[1]); a[2] = fmaf(uv, wa.z, a[2]); a[3] = fmaf(uv, wa.w, a[3]);
-        a[4] = fmaf(uv, wb.x, a[4]); a[5] = fmaf(uv, wb.y, a[5]); a[6] = fmaf(uv, wb.z, a[6]); a[7] = fmaf(uv, wb.w, a[7]);
-      }
-    const bool in = t >= 0 && t < Tx;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) zs[c][i] = in ? elu_f(a[c] + xs[c][i + 2]) : 0.0f;
-  }
-  __syncthreads();
-  const int t = t0 + tid;
-  if (t < T) {
-    float a = 0.0f;
-    if (t < Tx) {
-      a = bf[0];
-#pragma unroll
-      for (int ci = 0; ci < 8; ++ci)
-#pragma unroll
-        for (int k = 0; k < 7; ++k) a = fmaf(zs[ci][tid + k], wfs[k][ci], a);
+      *reinterpret_cast<float4 *>(&us[c][4 * j]) = o;
     }
-    delta[(long long)b * T + t] = a;
+  }
+  __syncthreads();
+  for (int j = tid; j < WZ / 4; j += TN) {       // z at indices 4j .. 4j+3
+    float a[4][8];
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[pos][c] = bs[1][c];
+    conv8k3x4<WU>(us, w2s, j, a);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float4 o;
+      float *op = &o.x;
+#pragma unroll
+      for (int pos = 0; pos < 4; ++pos) {
+        const int t = t0 - 3 + 4 * j + pos;
+        op[pos] = (t >= 0 && t < Tx) ? elu_f(a[pos][c] + xs[c][4 * j + pos + 2]) : 0.0f;
+      }
+      *reinterpret_cast<float4 *>(&zs[c][4 * j]) = o;
+    }
+  }
+  __syncthreads();
+  {
+    float acc[4];
+    const float bfv = bf[0];
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos) acc[pos] = bfv;
+#pragma unroll
+    for (int ci = 0; ci < 8; ++ci) {
+      const float4 va = *reinterpret_cast<const float4 *>(&zs[ci][4 * tid]), vb = *reinterpret_cast<const float4 *>(&zs[ci][4 * tid + 4]);
+      const float2 vc = *reinterpret_cast<const float2 *>(&zs[ci][4 * tid + 8]);
+      const float zin[10] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y};
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const float wv = wfs[k][ci];
+#pragma unroll
+        for (int pos = 0; pos < 4; ++pos) acc[pos] = fmaf(zin[pos + k], wv, acc[pos]);
+      }
+    }
+    const int t = t0 + 4 * tid;
+    float *dst = delta + (long long)b * T + t;
+    if (t + 3 < T && t + 3 < Tx && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+      *reinterpret_cast<float4 *>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
+#pragma unroll
+      for (int pos = 0; pos < 4; ++pos)
+        if (t + pos < T) dst[pos] = t + pos < Tx ? acc[pos] : 0.0f;
+    }
   }
 }
 
@@ -184,7 +226,7 @@ extern "C" int wm_m14_tail8_fwd(const void *x, long long plane_rows, int B, int 
   WM_CHECK_ARG(plane_rows >= wm_pconv_plane_rows(B, Tx), "m14_tail8: plane_rows too small");
   WM_CHECK_ARG(B <= 65535, "m14_tail8: at most 65535 clips per call");
   dim3 grid((T + TT - 1) / TT, B);
-  m14_tail8_kernel<<<grid, TT, 0, as_stream(stream)>>>(reinterpret_cast<const uint4 *>(x), plane_rows, Tx, w1, b1, w2, b2,
+  m14_tail8_kernel<<<grid, TN, 0, as_stream(stream)>>>(reinterpret_cast<const uint4 *>(x), plane_rows, Tx, w1, b1, w2, b2,
                                                        wf, bf, delta, T);
   WM_CHECK_LAUNCH("m14_tail8");
   return 0;

@@ -71,6 +71,8 @@ struct KParams {
   int u_off, w2_bytes;         // shared-memory offsets / sizes set by the launcher
 };
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -265,6 +267,15 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
       const int t = r - GAP;
       const bool inrange = m < P.R;
       const int n0 = j * NC + p * CS;        // first GEMM column of this thread's slice
+      if (P.residual != nullptr && inrange && c < P.B && t >= 0) {
+        const int lo0 = P.n_total >> 3;      // residual rows towards L1 while the accumulator is still being computed
+#pragma unroll
+        for (int g = 0; g < CS / 8; ++g) {
+          const int pl = (n0 >> 3) + g;
+          prefetch_l1(P.residual + ((long long)pl * P.plane_rows + m));
+          prefetch_l1(P.residual + ((long long)(lo0 + pl) * P.plane_rows + m));
+        }
+      }
 
       mbar_wait_warp(tfull_bar(a), aph);
       tc_fence_after();
@@ -669,6 +680,17 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
       const int c = (int)((uint32_t)m / (uint32_t)Tp);
       const int r = (int)(m - (long long)c * Tp);
       const int t = r - GAP;
+      const bool real = (c < P.B) && (t >= 0) && ri < RB_ROWS;
+      if (P.residual != nullptr && real) {
+        // start the residual rows towards L1 now: their latency then overlaps the wait for the accumulator
+        const int lo0 = P.n_total >> 3;
+#pragma unroll
+        for (int g = 0; g < CS / 8; ++g) {
+          const int pl = (n0 >> 3) + g;
+          prefetch_l1(P.residual + ((long long)pl * P.plane_rows + m));
+          prefetch_l1(P.residual + ((long long)(lo0 + pl) * P.plane_rows + m));
+        }
+      }
       mbar_wait_warp(t2_full(a), aph);
       tc_fence_after();
       const uint32_t taddr = acc2 + a * (2 * NC) + ((uint32_t)(q * 32) << 16) + n0;
@@ -695,7 +717,6 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
           o[4 * k] += b.x; o[4 * k + 1] += b.y; o[4 * k + 2] += b.z; o[4 * k + 3] += b.w;
         }
       }
-      const bool real = (c < P.B) && (t >= 0);
       if (P.residual != nullptr && real) {
         const int lo0 = P.n_total >> 3;
 #pragma unroll
