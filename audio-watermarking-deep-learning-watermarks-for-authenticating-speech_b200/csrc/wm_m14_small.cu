@@ -12,30 +12,33 @@ using namespace tc;
 namespace {
 
 constexpr int GAP = WM_PC_GAP;
-constexpr int TT = 256;   // outputs per block of the tail kernel
-constexpr int TN = TT / 4;  // threads: four consecutive time steps each
+constexpr int TT = 240;   // outputs per block of the tail kernel: with their halos u (TT + 8) and z (TT + 6) fit 64 x 4
+constexpr int TN = 64;    // threads: four consecutive time steps each
 
 // exp(v) - 1 through ex2.approx: absolute error ~1e-7 (expm1f is ~40 instructions, 16 of them per output sample here)
 __device__ __forceinline__ float elu_f(float v) { return v > 0.0f ? v : ex2_approx(v * 1.4426950408889634f) - 1.0f; }
 
-// a[pos][co] += sum over ci, k of in[ci][4 j + pos + k] * w[k][ci][co] for four consecutive positions: every weight
+// a[pos][co pair] += sum over ci, k of in[ci][4 j + pos + k] * w[k][ci][co] for four consecutive positions: every weight
 // vector and input value is fetched from shared memory once per FOUR outputs (one position per thread made the kernel
-// LSU-bound: 72 shared loads per 192 FMAs)
+// LSU-bound: 72 shared loads per 192 FMAs), and the FMAs are packed f32x2 (two output channels per instruction).
 template <int W>
-__device__ __forceinline__ void conv8k3x4(const float (*in)[W], const float (*w)[8][8], int j, float (&a)[4][8]) {
+__device__ __forceinline__ void conv8k3x4(const float (*in)[W], const float (*w)[8][8], int j, f32x2 (&a)[4][4]) {
 #pragma unroll 2
   for (int ci = 0; ci < 8; ++ci) {
     const float4 v = *reinterpret_cast<const float4 *>(&in[ci][4 * j]);
     const float2 v2 = *reinterpret_cast<const float2 *>(&in[ci][4 * j + 4]);
-    const float xin[6] = {v.x, v.y, v.z, v.w, v2.x, v2.y};
+    const f32x2 xin[6] = {pk2(v.x, v.x), pk2(v.y, v.y), pk2(v.z, v.z), pk2(v.w, v.w), pk2(v2.x, v2.x), pk2(v2.y, v2.y)};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const float4 wa = *reinterpret_cast<const float4 *>(&w[k][ci][0]), wb = *reinterpret_cast<const float4 *>(&w[k][ci][4]);
-      const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+      const ulonglong2 wa = *reinterpret_cast<const ulonglong2 *>(&w[k][ci][0]);
+      const ulonglong2 wb = *reinterpret_cast<const ulonglong2 *>(&w[k][ci][4]);
 #pragma unroll
-      for (int pos = 0; pos < 4; ++pos)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) a[pos][c] = fmaf(xin[pos + k], wv[c], a[pos][c]);
+      for (int pos = 0; pos < 4; ++pos) {
+        a[pos][0] = fma2(xin[pos + k], wa.x, a[pos][0]);
+        a[pos][1] = fma2(xin[pos + k], wa.y, a[pos][1]);
+        a[pos][2] = fma2(xin[pos + k], wb.x, a[pos][2]);
+        a[pos][3] = fma2(xin[pos + k], wb.y, a[pos][3]);
+      }
     }
   }
 }
@@ -48,7 +51,7 @@ __global__ void __launch_bounds__(TN)
     m14_tail8_kernel(const uint4 *__restrict__ x, long long plane_rows, int Tx, const float *__restrict__ w1,
                      const float *__restrict__ b1, const float *__restrict__ w2, const float *__restrict__ b2,
                      const float *__restrict__ wf, const float *__restrict__ bf, float *__restrict__ delta, int T) {
-  constexpr int WX = TT + 16, WU = TT + 12, WZ = TT + 8;
+  constexpr int WX = 4 * TN + 8, WU = 4 * TN + 8, WZ = 4 * TN + 8;   // 264: every thread reads 4 j .. 4 j + 9 at most
   __shared__ __align__(16) float xs[8][WX], us[8][WU], zs[8][WZ];
   __shared__ __align__(16) float w1s[3][8][8], w2s[3][8][8], wfs[7][8], bs[2][8];   // [tap][ci][co]
   const int b = blockIdx.y, t0 = blockIdx.x * TT, tid = threadIdx.x;
@@ -71,43 +74,53 @@ __global__ void __launch_bounds__(TN)
     for (int c = 0; c < 8; ++c) xs[c][i] = v[c];
   }
   __syncthreads();
-  for (int j = tid; j < WU / 4; j += TN) {       // u at indices 4j .. 4j+3
-    float a[4][8];
+  {                                               // u at indices 4 tid .. 4 tid + 3 (TT + 8 needed)
+    const int j = tid;
+    f32x2 a2[4][4];
+    const ulonglong2 ba = *reinterpret_cast<const ulonglong2 *>(&bs[0][0]), bb = *reinterpret_cast<const ulonglong2 *>(&bs[0][4]);
 #pragma unroll
-    for (int pos = 0; pos < 4; ++pos)
+    for (int pos = 0; pos < 4; ++pos) { a2[pos][0] = ba.x; a2[pos][1] = ba.y; a2[pos][2] = bb.x; a2[pos][3] = bb.y; }
+    conv8k3x4<WX>(xs, w1s, j, a2);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) a[pos][c] = bs[0][c];
-    conv8k3x4<WX>(xs, w1s, j, a);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float4 o;
-      float *op = &o.x;
+    for (int c2 = 0; c2 < 4; ++c2) {
+      float4 o0, o1;
+      float *p0 = &o0.x, *p1 = &o1.x;
 #pragma unroll
       for (int pos = 0; pos < 4; ++pos) {
         const int t = t0 - 4 + 4 * j + pos;
-        op[pos] = (t >= 0 && t < Tx) ? elu_f(a[pos][c]) : 0.0f;
+        const bool in = t >= 0 && t < Tx;
+        float e0, e1;
+        upk2(a2[pos][c2], e0, e1);
+        p0[pos] = in ? elu_f(e0) : 0.0f;
+        p1[pos] = in ? elu_f(e1) : 0.0f;
       }
-      *reinterpret_cast<float4 *>(&us[c][4 * j]) = o;
+      *reinterpret_cast<float4 *>(&us[2 * c2][4 * j]) = o0;
+      *reinterpret_cast<float4 *>(&us[2 * c2 + 1][4 * j]) = o1;
     }
   }
   __syncthreads();
-  for (int j = tid; j < WZ / 4; j += TN) {       // z at indices 4j .. 4j+3
-    float a[4][8];
+  {                                               // z at indices 4 tid .. 4 tid + 3 (TT + 6 needed)
+    const int j = tid;
+    f32x2 a2[4][4];
+    const ulonglong2 ba = *reinterpret_cast<const ulonglong2 *>(&bs[1][0]), bb = *reinterpret_cast<const ulonglong2 *>(&bs[1][4]);
 #pragma unroll
-    for (int pos = 0; pos < 4; ++pos)
+    for (int pos = 0; pos < 4; ++pos) { a2[pos][0] = ba.x; a2[pos][1] = ba.y; a2[pos][2] = bb.x; a2[pos][3] = bb.y; }
+    conv8k3x4<WU>(us, w2s, j, a2);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) a[pos][c] = bs[1][c];
-    conv8k3x4<WU>(us, w2s, j, a);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float4 o;
-      float *op = &o.x;
+    for (int c2 = 0; c2 < 4; ++c2) {
+      float4 o0, o1;
+      float *p0 = &o0.x, *p1 = &o1.x;
 #pragma unroll
       for (int pos = 0; pos < 4; ++pos) {
         const int t = t0 - 3 + 4 * j + pos;
-        op[pos] = (t >= 0 && t < Tx) ? elu_f(a[pos][c] + xs[c][4 * j + pos + 2]) : 0.0f;
+        const bool in = t >= 0 && t < Tx;
+        float e0, e1;
+        upk2(a2[pos][c2], e0, e1);
+        p0[pos] = in ? elu_f(e0 + xs[2 * c2][4 * j + pos + 2]) : 0.0f;
+        p1[pos] = in ? elu_f(e1 + xs[2 * c2 + 1][4 * j + pos + 2]) : 0.0f;
       }
-      *reinterpret_cast<float4 *>(&zs[c][4 * j]) = o;
+      *reinterpret_cast<float4 *>(&zs[2 * c2][4 * j]) = o0;
+      *reinterpret_cast<float4 *>(&zs[2 * c2 + 1][4 * j]) = o1;
     }
   }
   __syncthreads();
@@ -130,7 +143,8 @@ __global__ void __launch_bounds__(TN)
     }
     const int t = t0 + 4 * tid;
     float *dst = delta + (long long)b * T + t;
-    if (t + 3 < T && t + 3 < Tx && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+    if (4 * tid >= TT) {
+    } else if (t + 3 < T && t + 3 < Tx && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
       *reinterpret_cast<float4 *>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     } else {
 #pragma unroll

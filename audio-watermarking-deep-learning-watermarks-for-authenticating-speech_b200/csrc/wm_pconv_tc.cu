@@ -32,7 +32,7 @@ constexpr int GAP = WM_PC_GAP;
 constexpr int TILE = 128;
 constexpr int A_PLANE = (TILE + 6) * 16;   // shared-memory pitch of one 8-channel plane of a stage (taps <= 7)
 constexpr int A_BYTES = 4 * A_PLANE;       // hi k8 = 0,1 then lo k8 = 0,1
-constexpr int MAX_STAGE = 8;
+constexpr int MAX_STAGE = 16;
 
 struct KSrc {
   const uint4 *base;
@@ -68,7 +68,7 @@ struct KParams {
   const uint8_t *w2;           // packed conv2 weights: 16-channel group major, 3 taps each; then the skip source's slices
   const float *bias2;
   KSrc skip;                   // kchunks == 0: none
-  int u_off, w2_bytes;         // shared-memory offsets / sizes set by the launcher
+  int u_off, w1_bytes, w2_bytes;   // shared-memory offsets / sizes set by the launcher (w2_bytes includes the skip slices)
 };
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -434,8 +434,9 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
   const int NS = P.nstage;
-  const uint32_t w2_smem = s_base + NS * P.stage_bytes;
-  const uint32_t u_smem = s_base + P.u_off;
+  const uint32_t w1_smem = s_base + NS * P.stage_bytes;     // BOTH convolutions' weights stay in shared memory: streaming
+  const uint32_t w2_smem = w1_smem + P.w1_bytes;            // conv1's with every stage cost more L2 traffic than the
+  const uint32_t u_smem = s_base + P.u_off;                 // activations and left room for only 5 stages of prefetch
   const uint32_t bars = u_smem + 2 * U_BYTES;
   auto full_bar = [&](int s) { return bars + 8 * s; };
   auto empty_bar = [&](int s) { return bars + 8 * (MAX_STAGE + s); };
@@ -478,54 +479,45 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
   if (warp == 16) {
     // ===== producer =====
     if (lane == 0) {
-      mbar_arrive_expect_tx(w2bar, (uint32_t)P.w2_bytes);
+      mbar_arrive_expect_tx(w2bar, (uint32_t)(P.w1_bytes + P.w2_bytes));
+      for (int off = 0; off < P.w1_bytes; off += C::B_TAP) bulk_g2s(w1_smem + off, P.w + off, C::B_TAP, w2bar);
       for (int off = 0; off < P.w2_bytes; off += C::B_TAP) bulk_g2s(w2_smem + off, P.w2 + off, C::B_TAP, w2bar);
     }
     uint32_t s = 0, ph = 0;
-    const uint8_t *wsk = P.w2 + P.w2_bytes;      // skip slices follow conv2's
     for (uint32_t i = 0; i <= nmine; ++i) {
       if (i < nmine) {
         const long long u0 = (long long)(blockIdx.x + i * gridDim.x) * RB_ROWS - 1;
-        const uint8_t *wj = P.w;
         for (int si = 0; si < P.nsrc; ++si) {
           const KSrc &S = P.src[si];
           const long long row = u0 + S.row_off;
           const uint32_t abytes = (uint32_t)(TILE + S.taps - 1) * 16u;
-          const uint32_t wbytes = (uint32_t)S.taps * C::B_TAP;
-          const uint8_t *src = lane < 4 ? reinterpret_cast<const uint8_t *>(
-                                              S.base + ((long long)((lane >> 1) * S.lo_plane + (lane & 1)) * P.plane_rows + row))
-                                        : wj;
-          const size_t step = lane < 4 ? (size_t)(2 * P.plane_rows) * 16u : (size_t)wbytes;
-          const uint32_t bytes = lane < 4 ? abytes : wbytes;
-          const uint32_t doff = lane < 4 ? (uint32_t)lane * A_PLANE : (uint32_t)A_BYTES;
+          const uint8_t *src = reinterpret_cast<const uint8_t *>(
+              S.base + ((long long)(((lane >> 1) & 1) * S.lo_plane + (lane & 1)) * P.plane_rows + row));
+          const size_t step = (size_t)(2 * P.plane_rows) * 16u;
           const int kch = S.kchunks;
           for (int kc = 0; kc < kch; ++kc) {
             mbar_wait(empty_bar(s), ph ^ 1);
-            if (lane == 0) mbar_arrive_expect_tx(full_bar(s), 4 * abytes + wbytes);
+            if (lane == 0) mbar_arrive_expect_tx(full_bar(s), 4 * abytes);
             __syncwarp();
-            if (lane < 5) bulk_g2s(s_base + s * P.stage_bytes + doff, src, bytes, full_bar(s));
+            if (lane < 4) bulk_g2s(s_base + s * P.stage_bytes + (uint32_t)lane * A_PLANE, src, abytes, full_bar(s));
             src += step;
             if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
           }
-          wj += (size_t)kch * wbytes;
         }
       }
       if (i >= 1 && P.skip.kchunks > 0) {
         // skip stages of tile i - 1: phase-0 rows of x under the tile's OUTPUT rows (u0 + 1 ..)
         const KSrc &S = P.skip;
         const long long row = (long long)(blockIdx.x + (i - 1) * gridDim.x) * RB_ROWS + S.row_off;
-        const uint32_t abytes = (uint32_t)TILE * 16u, wbytes = (uint32_t)C::B_TAP;
-        const uint8_t *src = lane < 4 ? reinterpret_cast<const uint8_t *>(
-                                            S.base + ((long long)((lane >> 1) * S.lo_plane + (lane & 1)) * P.plane_rows + row))
-                                      : wsk;
-        const size_t step = lane < 4 ? (size_t)(2 * P.plane_rows) * 16u : (size_t)wbytes;
-        const uint32_t bytes = lane < 4 ? abytes : wbytes;
-        const uint32_t doff = lane < 4 ? (uint32_t)lane * A_PLANE : (uint32_t)A_BYTES;
+        const uint32_t abytes = (uint32_t)TILE * 16u;
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(
+            S.base + ((long long)(((lane >> 1) & 1) * S.lo_plane + (lane & 1)) * P.plane_rows + row));
+        const size_t step = (size_t)(2 * P.plane_rows) * 16u;
         for (int kc = 0; kc < S.kchunks; ++kc) {
           mbar_wait(empty_bar(s), ph ^ 1);
-          if (lane == 0) mbar_arrive_expect_tx(full_bar(s), 4 * abytes + wbytes);
+          if (lane == 0) mbar_arrive_expect_tx(full_bar(s), 4 * abytes);
           __syncwarp();
-          if (lane < 5) bulk_g2s(s_base + s * P.stage_bytes + doff, src, bytes, full_bar(s));
+          if (lane < 4) bulk_g2s(s_base + s * P.stage_bytes + (uint32_t)lane * A_PLANE, src, abytes, full_bar(s));
           src += step;
           if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
         }
@@ -544,20 +536,20 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
         mbar_wait_warp(t1_empty(a), aph ^ 1);
         const uint32_t d_tmem = acc1 + a * (2 * NC);
         uint32_t accum = 0;
+        uint64_t bd = smem_desc(w1_smem, 2 * NC * 16, 128);     // walks conv1's resident slices in stage order
         for (int si = 0; si < P.nsrc; ++si) {
           const int taps = P.src[si].taps, kch = P.src[si].kchunks;
           for (int kc = 0; kc < kch; ++kc) {
             mbar_wait_warp(full_bar(s), ph);
             tc_fence_after();
             if (issuer) {
-              const uint32_t st = s_base + s * P.stage_bytes;
-              const uint64_t a0 = smem_desc(st, A_PLANE, 128);
-              const uint64_t b0 = smem_desc(st + A_BYTES, 2 * NC * 16, 128);
+              const uint64_t a0 = smem_desc(s_base + s * P.stage_bytes, A_PLANE, 128);
 #pragma unroll 1
               for (int tp = 0; tp < taps; ++tp) {
-                const uint64_t ad = a0 + (uint64_t)tp, bd = b0 + (uint64_t)(tp * (C::B_TAP >> 4));
+                const uint64_t ad = a0 + (uint64_t)tp;
                 mma_bf16(d_tmem, ad, bd, idesc_hi, accum);
                 mma_bf16(d_tmem, ad + (uint64_t)((2 * A_PLANE) >> 4), bd, idesc_lo, 1u);
+                bd += (uint64_t)(C::B_TAP >> 4);
                 accum = 1u;
               }
               tc_commit(empty_bar(s));
@@ -596,8 +588,8 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
           mbar_wait_warp(full_bar(s), ph);
           tc_fence_after();
           if (issuer) {
-            const uint32_t st = s_base + s * P.stage_bytes;
-            const uint64_t ad = smem_desc(st, A_PLANE, 128), bd = smem_desc(st + A_BYTES, 2 * NC * 16, 128);
+            const uint64_t ad = smem_desc(s_base + s * P.stage_bytes, A_PLANE, 128);
+            const uint64_t bd = smem_desc(w2_smem + (KC2 * 3 + kc) * C::B_TAP, 2 * NC * 16, 128);
             mma_bf16(d_tmem, ad, bd, idesc_hi, 1u);
             mma_bf16(d_tmem, ad + (uint64_t)((2 * A_PLANE) >> 4), bd, idesc_lo, 1u);
             tc_commit(empty_bar(s));
@@ -749,15 +741,19 @@ int launch_pconv_rb_t(const KParams &P0, cudaStream_t st) {
   KParams P = P0;
   int maxtaps = 1;
   for (int i = 0; i < P.nsrc; ++i) maxtaps = P.src[i].taps > maxtaps ? P.src[i].taps : maxtaps;
-  P.stage_bytes = (A_BYTES + maxtaps * C::B_TAP + 127) / 128 * 128;
-  P.w2_bytes = (NC / 16) * 3 * C::B_TAP;
+  (void)maxtaps;
+  P.stage_bytes = A_BYTES;                       // activations only: the weights are resident
+  int slices1 = 0;
+  for (int i = 0; i < P.nsrc; ++i) slices1 += P.src[i].kchunks * P.src[i].taps;
+  P.w1_bytes = slices1 * C::B_TAP;
+  P.w2_bytes = ((NC / 16) * 3 + P.skip.kchunks) * C::B_TAP;
   const int u_bytes = 2 * 2 * (NC / 8) * U_PLANE;
-  const int fixed = (P.w2_bytes + 127) / 128 * 128 + u_bytes + 8 * (2 * MAX_STAGE + 13) + 16;
-  int ns = (225 * 1024 - fixed) / P.stage_bytes;
+  const int fixed = P.w1_bytes + P.w2_bytes + u_bytes + 8 * (2 * MAX_STAGE + 13) + 16;
+  int ns = (226 * 1024 - fixed) / P.stage_bytes;
   ns = ns > MAX_STAGE ? MAX_STAGE : ns;
-  WM_CHECK_ARG(ns >= 2, "pconv_rb: stages of %d bytes do not fit the shared memory", P.stage_bytes);
+  WM_CHECK_ARG(ns >= 3, "pconv_rb: %d bytes of resident weights leave no room for the activation stages", P.w1_bytes + P.w2_bytes);
   P.nstage = ns;
-  P.u_off = ns * P.stage_bytes + (P.w2_bytes + 127) / 128 * 128;
+  P.u_off = ns * P.stage_bytes + P.w1_bytes + P.w2_bytes;
   const int smem_bytes = P.u_off + u_bytes + 8 * (2 * MAX_STAGE + 13) + 16;
   static bool attr_set = false;
   if (!attr_set) {
