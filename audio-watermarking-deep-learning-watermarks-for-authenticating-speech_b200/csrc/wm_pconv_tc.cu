@@ -144,6 +144,31 @@ struct Cfg {
   static constexpr int TMEM_COLS = 4 * NC < 32 ? 32 : 4 * NC;   // two accumulators of 2 NC columns
 };
 
+// MMAs of one stage: TAPS row-shifted A descriptors against TAPS consecutive weight tiles, all offsets compile-time.
+// (A rolled tap loop with run-time descriptor arithmetic cost ~30 uniform-datapath instructions per tap on the single
+// issuing thread — more than the 88..112 tensor cycles a tap of a 32/64-column chunk takes: the layers with few
+// channels were bound by MMA ISSUE, tensor pipe 42 % busy and never waiting on a barrier.)
+template <int TAPS, int NC>
+__device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint64_t a0, uint64_t b0, uint32_t accum) {
+  constexpr uint32_t idesc_hi = make_idesc(128, 2 * NC), idesc_lo = make_idesc(128, NC);
+#pragma unroll
+  for (int tp = 0; tp < TAPS; ++tp) {
+    mma_bf16(d_tmem, a0 + (uint64_t)tp, b0 + (uint64_t)(tp * ((2 * NC * 32) >> 4)), idesc_hi, tp == 0 ? accum : 1u);
+    mma_bf16(d_tmem, a0 + (uint64_t)(tp + ((2 * A_PLANE) >> 4)), b0 + (uint64_t)(tp * ((2 * NC * 32) >> 4)), idesc_lo, 1u);
+  }
+}
+template <int NC>
+__device__ __forceinline__ void issue_stage(int taps, uint32_t d_tmem, uint64_t a0, uint64_t b0, uint32_t accum) {
+  switch (taps) {
+    case 1: issue_taps<1, NC>(d_tmem, a0, b0, accum); break;
+    case 2: issue_taps<2, NC>(d_tmem, a0, b0, accum); break;
+    case 3: issue_taps<3, NC>(d_tmem, a0, b0, accum); break;
+    case 7: issue_taps<7, NC>(d_tmem, a0, b0, accum); break;
+    default:
+      for (int tp = 0; tp < taps; ++tp) issue_taps<1, NC>(d_tmem, a0 + (uint64_t)tp, b0 + (uint64_t)(tp * ((2 * NC * 32) >> 4)), tp == 0 ? accum : 1u);
+  }
+}
+
 // Warps 0..15 epilogue (TMEM lane quadrant = warp % 4, column slice = warp / 4), warp 16 producer, warp 17 MMA issuer.
 template <int NC>
 __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant__ KParams P) {
@@ -216,8 +241,12 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
   } else if (warp == 17) {
     // ===== MMA issuer =====
     const bool issuer = elect_one();
-    constexpr uint32_t idesc_hi = make_idesc(128, 2 * NC), idesc_lo = make_idesc(128, NC);
     uint32_t s = 0, ph = 0, a = 0, aph = 0;
+    // running descriptors of the current stage: A tile, and its weights (a compile-time distance behind it)
+    const uint64_t a_base = smem_desc(s_base, A_PLANE, 128);
+    const uint64_t b_delta = smem_desc(A_BYTES, 2 * NC * 16, 128) - smem_desc(0, A_PLANE, 128);
+    const uint64_t st_step = (uint64_t)(P.stage_bytes >> 4);
+    uint64_t a_cur = a_base;
     for (uint32_t tile = blockIdx.x; tile < (uint32_t)ntiles; tile += gridDim.x) {
       mbar_wait_warp(tempty_bar(a), aph ^ 1);
       const uint32_t d_tmem = tmem_base + a * (2 * NC);
@@ -228,20 +257,13 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
           mbar_wait_warp(full_bar(s), ph);
           tc_fence_after();
           if (issuer) {
-            const uint32_t st = s_base + s * P.stage_bytes;
-            const uint64_t a0 = smem_desc(st, A_PLANE, 128);
-            const uint64_t b0 = smem_desc(st + A_BYTES, 2 * NC * 16, 128);
-#pragma unroll 1
-            for (int tp = 0; tp < taps; ++tp) {
-              const uint64_t ad = a0 + (uint64_t)tp, bd = b0 + (uint64_t)(tp * (C::B_TAP >> 4));
-              mma_bf16(d_tmem, ad, bd, idesc_hi, accum);
-              mma_bf16(d_tmem, ad + (uint64_t)((2 * A_PLANE) >> 4), bd, idesc_lo, 1u);
-              accum = 1u;
-            }
+            issue_stage<NC>(taps, d_tmem, a_cur, a_cur + b_delta, accum);
             tc_commit(empty_bar(s));
           }
+          accum = 1u;
           __syncwarp();
-          if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
+          a_cur += st_step;
+          if (++s == (uint32_t)NS) { s = 0; ph ^= 1; a_cur = a_base; }
         }
       }
       if (issuer) tc_commit(tfull_bar(a));
@@ -529,6 +551,10 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
     const bool issuer = elect_one();
     constexpr uint32_t idesc_hi = make_idesc(128, 2 * NC), idesc_lo = make_idesc(128, NC);
     uint32_t s = 0, ph = 0;
+    const uint64_t a_base = smem_desc(s_base, A_PLANE, 128), st_step = (uint64_t)(P.stage_bytes >> 4);
+    const uint64_t w1_desc = smem_desc(w1_smem, 2 * NC * 16, 128), w2_desc = smem_desc(w2_smem, 2 * NC * 16, 128);
+    const uint64_t u_desc = smem_desc(u_smem, U_PLANE, 128);
+    uint64_t a_cur = a_base;
     mbar_wait_warp(w2bar, 0);
     for (uint32_t i = 0; i <= nmine; ++i) {
       if (i < nmine) {
@@ -536,26 +562,21 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
         mbar_wait_warp(t1_empty(a), aph ^ 1);
         const uint32_t d_tmem = acc1 + a * (2 * NC);
         uint32_t accum = 0;
-        uint64_t bd = smem_desc(w1_smem, 2 * NC * 16, 128);     // walks conv1's resident slices in stage order
+        uint64_t bd = w1_desc;                                   // walks conv1's resident slices in stage order
         for (int si = 0; si < P.nsrc; ++si) {
           const int taps = P.src[si].taps, kch = P.src[si].kchunks;
           for (int kc = 0; kc < kch; ++kc) {
             mbar_wait_warp(full_bar(s), ph);
             tc_fence_after();
             if (issuer) {
-              const uint64_t a0 = smem_desc(s_base + s * P.stage_bytes, A_PLANE, 128);
-#pragma unroll 1
-              for (int tp = 0; tp < taps; ++tp) {
-                const uint64_t ad = a0 + (uint64_t)tp;
-                mma_bf16(d_tmem, ad, bd, idesc_hi, accum);
-                mma_bf16(d_tmem, ad + (uint64_t)((2 * A_PLANE) >> 4), bd, idesc_lo, 1u);
-                bd += (uint64_t)(C::B_TAP >> 4);
-                accum = 1u;
-              }
+              issue_stage<NC>(taps, d_tmem, a_cur, bd, accum);
               tc_commit(empty_bar(s));
             }
+            accum = 1u;
+            bd += (uint64_t)(taps * (C::B_TAP >> 4));
             __syncwarp();
-            if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
+            a_cur += st_step;
+            if (++s == (uint32_t)NS) { s = 0; ph ^= 1; a_cur = a_base; }
           }
         }
         if (issuer) tc_commit(t1_full(a));
@@ -568,18 +589,15 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = acc2 + a * (2 * NC);
         if (issuer) {
-          const uint64_t a0 = smem_desc(u_smem + a * U_BYTES, U_PLANE, 128);
-          const uint64_t b0 = smem_desc(w2_smem, 2 * NC * 16, 128);
-          uint32_t accum = 0;
-#pragma unroll 1
+          const uint64_t a0 = u_desc + (uint64_t)(a * (U_BYTES >> 4));
+#pragma unroll
           for (int kc = 0; kc < KC2; ++kc) {
 #pragma unroll
             for (int tp = 0; tp < 3; ++tp) {
-              const uint64_t ad = a0 + (uint64_t)((2 * kc * U_PLANE) >> 4) + (uint64_t)tp;
-              const uint64_t bd = b0 + (uint64_t)(((kc * 3 + tp) * C::B_TAP) >> 4);
-              mma_bf16(d_tmem, ad, bd, idesc_hi, accum);
+              const uint64_t ad = a0 + (uint64_t)(((2 * kc * U_PLANE) >> 4) + tp);
+              const uint64_t bd = w2_desc + (uint64_t)(((kc * 3 + tp) * C::B_TAP) >> 4);
+              mma_bf16(d_tmem, ad, bd, idesc_hi, (kc | tp) == 0 ? 0u : 1u);
               mma_bf16(d_tmem, ad + (uint64_t)(((NC / 8) * U_PLANE) >> 4), bd, idesc_lo, 1u);
-              accum = 1u;
             }
           }
         }
@@ -588,14 +606,12 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
           mbar_wait_warp(full_bar(s), ph);
           tc_fence_after();
           if (issuer) {
-            const uint64_t ad = smem_desc(s_base + s * P.stage_bytes, A_PLANE, 128);
-            const uint64_t bd = smem_desc(w2_smem + (KC2 * 3 + kc) * C::B_TAP, 2 * NC * 16, 128);
-            mma_bf16(d_tmem, ad, bd, idesc_hi, 1u);
-            mma_bf16(d_tmem, ad + (uint64_t)((2 * A_PLANE) >> 4), bd, idesc_lo, 1u);
+            issue_taps<1, NC>(d_tmem, a_cur, w2_desc + (uint64_t)(((KC2 * 3 + kc) * C::B_TAP) >> 4), 1u);
             tc_commit(empty_bar(s));
           }
           __syncwarp();
-          if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
+          a_cur += st_step;
+          if (++s == (uint32_t)NS) { s = 0; ph ^= 1; a_cur = a_base; }
         }
         if (issuer) {
           tc_commit(u_empty(a));
