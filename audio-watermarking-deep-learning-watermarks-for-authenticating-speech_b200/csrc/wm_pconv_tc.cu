@@ -68,6 +68,7 @@ struct KParams {
   const uint8_t *w2;           // packed conv2 weights: 16-channel group major, 3 taps each; then the skip source's slices
   const float *bias2;
   KSrc skip;                   // kchunks == 0: none
+  long long *prof;             // developer hook (wm_debug_lstm_profile buffer): per-role cycle sums of block 0, or null
   int u_off, w1_bytes, w2_bytes;   // shared-memory offsets / sizes set by the launcher (w2_bytes includes the skip slices)
 };
 
@@ -444,6 +445,7 @@ int launch_pconv_t(const KParams &P0, cudaStream_t st) {
 // Warps 0..7 epilogue 1, 8..15 epilogue 2 (quadrant = warp % 4, half of the channels = (warp / 4) % 2), 16 producer,
 // 17 MMA issuer.  The issuer runs GEMM 1 of tile i + 1 before GEMM 2 of tile i, so epilogue 1 overlaps tensor work.
 // ---------------------------------------------------------------------------------------------------------------
+#define RB_TICK(k) do { if (pf) { const long long now_ = clock64(); pa[k] += now_ - last_; last_ = now_; } } while (0)
 constexpr int RB_ROWS = 126;
 constexpr int U_PLANE = 136 * 16;
 
@@ -506,6 +508,8 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
       for (int off = 0; off < P.w2_bytes; off += C::B_TAP) bulk_g2s(w2_smem + off, P.w2 + off, C::B_TAP, w2bar);
     }
     uint32_t s = 0, ph = 0;
+    const bool pf = P.prof != nullptr && blockIdx.x == 0 && lane == 0;
+    long long pa[2] = {0, 0}, last_ = pf ? clock64() : 0;
     for (uint32_t i = 0; i <= nmine; ++i) {
       if (i < nmine) {
         const long long u0 = (long long)(blockIdx.x + i * gridDim.x) * RB_ROWS - 1;
@@ -518,7 +522,9 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
           const size_t step = (size_t)(2 * P.plane_rows) * 16u;
           const int kch = S.kchunks;
           for (int kc = 0; kc < kch; ++kc) {
+            RB_TICK(1);
             mbar_wait(empty_bar(s), ph ^ 1);
+            RB_TICK(0);
             if (lane == 0) mbar_arrive_expect_tx(full_bar(s), 4 * abytes);
             __syncwarp();
             if (lane < 4) bulk_g2s(s_base + s * P.stage_bytes + (uint32_t)lane * A_PLANE, src, abytes, full_bar(s));
@@ -545,12 +551,15 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
         }
       }
     }
+    if (pf) { P.prof[0] = pa[0]; P.prof[1] = pa[1]; P.prof[31] = nmine; }
     __syncwarp();
   } else if (warp == 17) {
     // ===== MMA issuer =====
     const bool issuer = elect_one();
     constexpr uint32_t idesc_hi = make_idesc(128, 2 * NC), idesc_lo = make_idesc(128, NC);
     uint32_t s = 0, ph = 0;
+    const bool pf = P.prof != nullptr && blockIdx.x == 0 && issuer;
+    long long pa[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last_ = pf ? clock64() : 0;
     const uint64_t a_base = smem_desc(s_base, A_PLANE, 128), st_step = (uint64_t)(P.stage_bytes >> 4);
     const uint64_t w1_desc = smem_desc(w1_smem, 2 * NC * 16, 128), w2_desc = smem_desc(w2_smem, 2 * NC * 16, 128);
     const uint64_t u_desc = smem_desc(u_smem, U_PLANE, 128);
@@ -559,19 +568,24 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
     for (uint32_t i = 0; i <= nmine; ++i) {
       if (i < nmine) {
         const uint32_t a = i & 1u, aph = (i >> 1) & 1u;
+        RB_TICK(7);
         mbar_wait_warp(t1_empty(a), aph ^ 1);
+        RB_TICK(0);
         const uint32_t d_tmem = acc1 + a * (2 * NC);
         uint32_t accum = 0;
         uint64_t bd = w1_desc;                                   // walks conv1's resident slices in stage order
         for (int si = 0; si < P.nsrc; ++si) {
           const int taps = P.src[si].taps, kch = P.src[si].kchunks;
           for (int kc = 0; kc < kch; ++kc) {
+            RB_TICK(7);
             mbar_wait_warp(full_bar(s), ph);
+            RB_TICK(1);
             tc_fence_after();
             if (issuer) {
               issue_stage<NC>(taps, d_tmem, a_cur, bd, accum);
               tc_commit(empty_bar(s));
             }
+            RB_TICK(2);
             accum = 1u;
             bd += (uint64_t)(taps * (C::B_TAP >> 4));
             __syncwarp();
@@ -584,8 +598,11 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
       }
       if (i >= 1) {
         const uint32_t j = i - 1, a = j & 1u, aph = (j >> 1) & 1u;
+        RB_TICK(7);
         mbar_wait_warp(u_full(a), aph);
+        RB_TICK(3);
         mbar_wait_warp(t2_empty(a), aph ^ 1);
+        RB_TICK(4);
         tc_fence_after();
         const uint32_t d_tmem = acc2 + a * (2 * NC);
         if (issuer) {
@@ -617,14 +634,18 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
           tc_commit(u_empty(a));
           tc_commit(t2_full(a));
         }
+        RB_TICK(5);
         __syncwarp();
       }
     }
+    if (pf) { for (int k = 0; k < 8; ++k) P.prof[8 + k] = pa[k]; }
   } else if (warp < 8) {
     // ===== epilogue 1: accumulator -> elu -> bf16 pair -> u tile in shared memory =====
     const int q = warp & 3, p = warp >> 2;
     const int n0 = p * CS;
     const int Tp = P.Tp;
+    const bool pf = P.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long pa[6] = {0, 0, 0, 0, 0, 0}, last_ = pf ? clock64() : 0;
     for (uint32_t i = 0; i < nmine; ++i) {
       const uint32_t a = i & 1u, aph = (i >> 1) & 1u;
       const long long mu = (long long)(blockIdx.x + i * gridDim.x) * RB_ROWS - 1 + q * 32 + lane;
@@ -633,7 +654,9 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
         const int c = (int)((uint32_t)mu / (uint32_t)Tp);
         real = c < P.B && (int)(mu - (long long)c * Tp) >= GAP;
       }
+      RB_TICK(5);
       mbar_wait_warp(t1_full(a), aph);
+      RB_TICK(0);
       tc_fence_after();
       const uint32_t taddr = acc1 + a * (2 * NC) + ((uint32_t)(q * 32) << 16) + n0;
       float o[CS];
@@ -658,7 +681,9 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
           o[4 * k] += b.x; o[4 * k + 1] += b.y; o[4 * k + 2] += b.z; o[4 * k + 3] += b.w;
         }
       }
+      RB_TICK(1);
       mbar_wait_warp(u_empty(a), aph ^ 1);        // GEMM 2 of tile i - 2 has read this buffer
+      RB_TICK(2);
       uint8_t *ub = smem + P.u_off + a * U_BYTES + (q * 32 + lane) * 16;
 #pragma unroll
       for (int g = 0; g < CS / 8; ++g) {
@@ -673,14 +698,19 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
         *reinterpret_cast<uint4 *>(ub + pl * U_PLANE) = hi;
         *reinterpret_cast<uint4 *>(ub + (NC / 8 + pl) * U_PLANE) = lo;
       }
+      RB_TICK(3);
       fence_async_smem();                          // generic-proxy stores -> the MMA's operand reads
       mbar_arrive_warp(u_full(a));
+      RB_TICK(4);
     }
+    if (pf) { for (int k = 0; k < 6; ++k) P.prof[16 + k] = pa[k]; }
   } else if (warp < 16) {
     // ===== epilogue 2: accumulator + bias (+ residual) -> elu -> planar output =====
     const int q = warp & 3, p = (warp >> 2) & 1;
     const int n0 = p * CS;
     const int Tp = P.Tp;
+    const bool pf = P.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 256;
+    long long pa[4] = {0, 0, 0, 0}, last_ = pf ? clock64() : 0;
     for (uint32_t i = 0; i < nmine; ++i) {
       const uint32_t a = i & 1u, aph = (i >> 1) & 1u;
       const int ri = q * 32 + lane;
@@ -699,7 +729,9 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
           prefetch_l1(P.residual + ((long long)(lo0 + pl) * P.plane_rows + m));
         }
       }
+      RB_TICK(3);
       mbar_wait_warp(t2_full(a), aph);
+      RB_TICK(0);
       tc_fence_after();
       const uint32_t taddr = acc2 + a * (2 * NC) + ((uint32_t)(q * 32) << 16) + n0;
       float o[CS];
@@ -716,6 +748,7 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
 #pragma unroll
         for (int k = 0; k < CS; ++k) o[k] += v2[k];
       }
+      RB_TICK(1);
       if (ri >= RB_ROWS || m >= P.R) continue;
       {
         const float4 *bp = reinterpret_cast<const float4 *>(P.bias2 + n0);
@@ -741,7 +774,9 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
 #pragma unroll
       for (int k = 0; k < CS; ++k) o[k] = elu1(o[k]);
       store_planar<CS>(P, o, n0, m, c, r, t, real);
+      RB_TICK(2);
     }
+    if (pf) { for (int k = 0; k < 4; ++k) P.prof[24 + k] = pa[k]; }
   }
   tc_fence_before();
   __syncthreads();
@@ -992,6 +1027,7 @@ int wm_pconv_fwd(const wm_pconv *d, void *stream) {
     WM_CHECK_ARG(d->chunk_off[0] == 0, "pconv: no chunk offset in the fused residual block");
     P.w2 = reinterpret_cast<const uint8_t *>(d->w2);
     P.bias2 = d->bias2;
+    P.prof = get_profile_buffer();
     if (d->skip.base != nullptr) {
       WM_CHECK_ARG(d->skip.cin >= 16 && d->skip.cin % 16 == 0 && d->skip.taps == 1 && d->skip.row_off == 0,
                    "pconv: the skip source is one tap at row offset 0 over a multiple of 16 channels");
