@@ -86,6 +86,20 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
 // ELU for the epilogue: exp(v) - 1 through ex2.approx (absolute error ~1e-7, the rounding of exp(v) itself).  expm1f costs
 // ~40 instructions per element and made every layer with a short K loop epilogue-issue bound (128 x NC elements per tile).
 __device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : ex2_approx(v * 1.4426950408889634f) - 1.0f; }
+// the same on N values with the multiply and the subtraction packed two per instruction
+template <int N>
+__device__ __forceinline__ void elu_packed(float *o) {
+  const f32x2 l2e = pk2(1.4426950408889634f, 1.4426950408889634f), m1 = pk2(-1.0f, -1.0f);
+#pragma unroll
+  for (int k = 0; k < N; k += 2) {
+    float ta, tb;
+    upk2(mul2(pk2(o[k], o[k + 1]), l2e), ta, tb);
+    float ea, eb;
+    upk2(add2(pk2(ex2_approx(ta), ex2_approx(tb)), m1), ea, eb);
+    o[k] = o[k] > 0.0f ? o[k] : ea;
+    o[k + 1] = o[k + 1] > 0.0f ? o[k + 1] : eb;
+  }
+}
 
 // Planar store of CS channels (first GEMM column n0) of row m = (clip c, gap-relative row r, step t): same geometry, or
 // split by phase for a strided consumer.  Gap rows are written as zeros (they are the next convolution's padding).
@@ -314,8 +328,7 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive_warp(tempty_bar(a));
-#pragma unroll
-        for (int k = 0; k < CS; ++k) o[k] += v2[k];
+        add_packed<CS>(o, v2);
       }
       if (!inrange) continue;
       {
@@ -323,7 +336,7 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
 #pragma unroll
         for (int k = 0; k < CS / 4; ++k) {
           const float4 b = __ldg(bp + k);
-          o[4 * k] += b.x; o[4 * k + 1] += b.y; o[4 * k + 2] += b.z; o[4 * k + 3] += b.w;
+          add_packed<4>(o + 4 * k, &b.x);
         }
       }
       const bool real = (c < P.B) && (t >= 0);
@@ -336,14 +349,10 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
           const uint4 rl = __ldg(P.residual + ((long long)(lo0 + pl) * P.plane_rows + m));
           float rr[8];
           join8(rh, rl, rr);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o[g * 8 + k] += rr[k];
+          add_packed<8>(o + g * 8, rr);
         }
       }
-      if (P.elu) {
-#pragma unroll
-        for (int k = 0; k < CS; ++k) o[k] = elu1(o[k]);
-      }
+      if (P.elu) elu_packed<CS>(o);
 
       if (P.mode == WM_PC_OUT_PLANAR) {
         store_planar<CS>(P, o, n0, m, c, r, t, real);
@@ -670,15 +679,14 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive_warp(t1_empty(a));
-#pragma unroll
-        for (int k = 0; k < CS; ++k) o[k] += v2[k];
+        add_packed<CS>(o, v2);
       }
       {
         const float4 *bp = reinterpret_cast<const float4 *>(P.bias + n0);
 #pragma unroll
         for (int k = 0; k < CS / 4; ++k) {
           const float4 b = __ldg(bp + k);
-          o[4 * k] += b.x; o[4 * k + 1] += b.y; o[4 * k + 2] += b.z; o[4 * k + 3] += b.w;
+          add_packed<4>(o + 4 * k, &b.x);
         }
       }
       RB_TICK(1);
@@ -689,10 +697,8 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
       for (int g = 0; g < CS / 8; ++g) {
         uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
         if (real) {
-          float e[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) e[k] = elu1(o[g * 8 + k]);
-          split8(e, hi, lo);
+          elu_packed<8>(o + g * 8);
+          split8(o + g * 8, hi, lo);
         }
         const int pl = (n0 >> 3) + g;
         *reinterpret_cast<uint4 *>(ub + pl * U_PLANE) = hi;
@@ -745,8 +751,7 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive_warp(t2_empty(a));
-#pragma unroll
-        for (int k = 0; k < CS; ++k) o[k] += v2[k];
+        add_packed<CS>(o, v2);
       }
       RB_TICK(1);
       if (ri >= RB_ROWS || m >= P.R) continue;
@@ -755,7 +760,7 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
 #pragma unroll
         for (int k = 0; k < CS / 4; ++k) {
           const float4 b = __ldg(bp + k);
-          o[4 * k] += b.x; o[4 * k + 1] += b.y; o[4 * k + 2] += b.z; o[4 * k + 3] += b.w;
+          add_packed<4>(o + 4 * k, &b.x);
         }
       }
       if (P.residual != nullptr && real) {
@@ -767,12 +772,10 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
           const uint4 rl = __ldg(P.residual + ((long long)(lo0 + pl) * P.plane_rows + m));
           float rr[8];
           join8(rh, rl, rr);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o[g * 8 + k] += rr[k];
+          add_packed<8>(o + g * 8, rr);
         }
       }
-#pragma unroll
-      for (int k = 0; k < CS; ++k) o[k] = elu1(o[k]);
+      elu_packed<CS>(o);
       store_planar<CS>(P, o, n0, m, c, r, t, real);
       RB_TICK(2);
     }

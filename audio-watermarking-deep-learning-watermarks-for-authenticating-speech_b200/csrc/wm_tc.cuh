@@ -87,6 +87,30 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100): one issue slot for two lanes of arithmetic
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t *>(&h);
@@ -95,7 +119,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // pipe) and integer unpacking: the scalar cvt.rn.bf16.f32 runs on the 16-lane XU pipe.
 __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
   hi = pack_bf16x2(a, b);
-  lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
+  // a - hi_a and b - hi_b are exact in fp32; one packed FMA computes both (bit-identical to two subtractions)
+  float ra, rb;
+  upk2(fma2(pk2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u)), pk2(-1.0f, -1.0f), pk2(a, b)), ra, rb);
+  lo = pack_bf16x2(ra, rb);
 }
 __device__ __forceinline__ void split8(const float *v, uint4 &hi, uint4 &lo) {
   uint32_t h[4], l[4];
@@ -112,10 +139,16 @@ __device__ __forceinline__ void join8(const uint4 &hi, const uint4 &lo, float *v
   const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    // bf16 -> fp32 is a 16-bit shift
-    v[2 * i] = __uint_as_float(h[i] << 16) + __uint_as_float(l[i] << 16);
-    v[2 * i + 1] = __uint_as_float(h[i] & 0xFFFF0000u) + __uint_as_float(l[i] & 0xFFFF0000u);
+    // bf16 -> fp32 is a 16-bit shift; the two additions of a word as one packed add
+    upk2(add2(pk2(__uint_as_float(h[i] << 16), __uint_as_float(h[i] & 0xFFFF0000u)),
+              pk2(__uint_as_float(l[i] << 16), __uint_as_float(l[i] & 0xFFFF0000u))), v[2 * i], v[2 * i + 1]);
   }
+}
+// o[0..N) += v[0..N) as packed adds
+template <int N>
+__device__ __forceinline__ void add_packed(float *o, const float *v) {
+#pragma unroll
+  for (int k = 0; k < N; k += 2) upk2(add2(pk2(o[k], o[k + 1]), pk2(v[k], v[k + 1])), o[k], o[k + 1]);
 }
 
 
@@ -237,30 +270,6 @@ __device__ __forceinline__ void tc_commit_cta2(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-// packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100): one issue slot for two lanes of arithmetic
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float a, float b) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void upk2(f32x2 v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
 
 }  // namespace tc
 }  // namespace wm
