@@ -47,6 +47,13 @@ def relerr(a, b):
 
 
 def gap_rows_zero(p, phases=(0,)):
+    # the 128 guard bytes in front of the first plane and behind the last one still hold the fill pattern
+    # (compute-sanitizer is closed on this pool: this is the out-of-bounds-write check the tests can make themselves)
+    assert int(p.store[:128].min()) == 0xFF and int(p.store[-128:].min()) == 0xFF, "write outside the planar tensor"
+    rows_used = p.B * (p.T + GAP) + GAP
+    for ph in phases:
+        raw = p.store[128 + ph * p.phase_rows * 16: 128 + (ph + 1) * p.phase_rows * 16].view(2 * (p.C // 8), p.RP, 16)
+        assert int(raw[:, rows_used:].min()) == 0xFF, "write behind the last row of a plane"
     Tp = p.T + GAP
     for ph in phases:
         raw = p.store[128 + ph * p.phase_rows * 16: 128 + (ph + 1) * p.phase_rows * 16].view(2 * (p.C // 8), p.RP, 16)

@@ -23,6 +23,7 @@ with torch.no_grad():
     for _ in range(reps):
         y = D(s + G(s, msg))
     e1.record()
+    t_issue = time.perf_counter() - t0
     torch.cuda.synchronize()
-    print("B", B, "ms/step", e0.elapsed_time(e1) / reps, "host ms", (time.perf_counter() - t0) * 1e3 / reps,
+    print("B", B, "ms/step", e0.elapsed_time(e1) / reps, "host issue ms", t_issue * 1e3 / reps, "host ms", (time.perf_counter() - t0) * 1e3 / reps,
           "clip-s/s", B * 1e3 * reps / e0.elapsed_time(e1), "finite", bool(torch.isfinite(y).all()))
