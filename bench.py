@@ -553,7 +553,7 @@ def run_ours(args):
                           "what": "the same step with delta RMS and the fused majority-vote bit fractions "
                                   "(evaluate_model, py/main16.py:385-398)"}}
     if not args.no_aux:
-        for name, fn in (("config3_main14b2", lambda: measure_main14b2(dev, world, rank, 3, 3)),
+        for name, fn in (("config3_main14b2", lambda: measure_main14b2(dev, world, rank, 5, 6)),
                          ("config4_train", lambda: measure_train(dev, world, rank, 5, 3, args.train_batch)),
                          ("config5_stream_10h", lambda: measure_stream(gen, det, dev, world, rank, args.stream_hours))):
             try:

@@ -560,9 +560,17 @@ int wm_adam_step(float *p, const float *g, float *m, float *v, long long n, floa
                  float eps, int step, void *stream);
 
 /* Same unit with HOST (pinned) buffers: H2D of s and message, the device pipeline in
- * micro-batches of `chunk` clips, D2H of s_w, probs, clip_prob and msg_logits, all on
- * `stream`.  This is what the file-level API and bench.py's e2e leg call.  The device
- * staging area lives in the caller's workspace (wm_embed_detect_host_workspace_bytes). */
+ * micro-batches of `chunk` clips, D2H of s_w, probs, clip_prob and msg_logits.  This is what
+ * the file-level API and bench.py's e2e leg call.  The device staging area lives in the
+ * caller's workspace (wm_embed_detect_host_workspace_bytes).
+ * Stream contract: the kernels run on `stream`; the copies run on two copy streams (in / out)
+ * that the LIBRARY owns per host thread (created on first use, never destroyed) so that they
+ * overlap the kernels — a deviation from "the caller owns everything", made because the
+ * overlap needs three streams and the reference-facing call has one.  The call orders them
+ * with events: the copy-in stream waits for everything queued on `stream` before the call,
+ * and before returning `stream` is made to wait for every copy of this call, so work the
+ * caller queues on `stream` afterwards sees the results and may reuse the buffers.  The call
+ * itself does not block the host. */
 size_t wm_embed_detect_host_workspace_bytes(int chunk, int T, int nout);
 int wm_embed_detect_host(const float *g_blob, const float *embedding, int64_t emb_rows,
                          const float *d_blob, const float *fir,
