@@ -73,6 +73,7 @@ def postprocess_delta(delta: torch.Tensor, s: Optional[torch.Tensor] = None):
 
 
 @torch.no_grad()
+@ops.nvtx("embed_detect")
 def embed_detect(generator, detector, s: torch.Tensor, message: Optional[torch.Tensor],
                  postprocess: bool = True, want_delta: bool = True, want_probs: bool = True,
                  want_votes: bool = True, want_rms: bool = False) -> dict:

@@ -48,6 +48,28 @@ def launch_count() -> int:
     return int(L.load().wm_launch_count())
 
 
+_NVTX = os.environ.get("WMB200_NVTX", "0") == "1"
+
+
+def nvtx(name: str):
+    """Decorator: an NVTX range around the call when WMB200_NVTX=1 (ncu --nvtx --nvtx-include "wmb200.<name>/" selects the
+    kernels of one API call; SURVEY.md section 5's tracing row).  A no-op otherwise."""
+    def wrap(fn):
+        if not _NVTX:
+            return fn
+        import functools
+
+        @functools.wraps(fn)
+        def inner(*a, **k):
+            torch.cuda.nvtx.range_push("wmb200." + name)
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return inner
+    return wrap
+
+
 def max_chunk() -> int:
     """Clips per device pass (workspace ~12.4 MB per clip in the fp32 layout)."""
     return int(os.environ.get("WMB200_MAX_CLIPS", "4736"))

@@ -387,6 +387,12 @@ def _decoder(plan, cur, t):
     return cur, t
 
 
+def _nvtx(name):
+    from .ops import nvtx
+    return nvtx(name)
+
+
+@_nvtx("main14b_2.detector")
 def detector_forward(mod, x):
     """Detector.forward (py/main14b_2.py:207-224): logits (B, 1 + bits, T)."""
     from . import main14b_2 as M
@@ -414,6 +420,7 @@ def _tail8_fits(rest, final: nn.Conv1d, cur) -> bool:
             and (final.in_channels, final.out_channels, final.kernel_size[0], final.padding[0], final.stride[0]) == (8, 1, 7, 3, 1))
 
 
+@_nvtx("main14b_2.generator")
 def generator_forward(mod, s, message=None):
     """Generator.forward (py/main14b_2.py:150-182): delta (B, 1, T)."""
     from . import main14b_2 as M

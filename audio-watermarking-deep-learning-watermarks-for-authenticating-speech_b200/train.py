@@ -17,6 +17,7 @@ import torch
 
 from . import _lib as L
 from .ops import _req, _stream, _ws
+from .ops import nvtx as ops_nvtx
 
 LR = 1e-3            # py/main16.py:33
 LAMBDA_L1 = 1.0      # py/main16.py:38
@@ -606,6 +607,7 @@ class Trainer:
         adam_step(self.g_params, self.g_grads, self.g_m, self.g_v, self.steps, self.lr, self.betas, self.eps)
         adam_step(self.d_params, self.d_grads, self.d_m, self.d_v, self.steps, self.lr, self.betas, self.eps)
 
+    @ops_nvtx("train_step")
     def step(self, s: torch.Tensor, message: torch.Tensor) -> Dict[str, torch.Tensor]:
         out = self.forward_backward(s, message)
         self.all_reduce_gradients()
