@@ -213,6 +213,7 @@ int launch_roc_points(const float *clean, long long n0, const float *wm, long lo
 int launch_auc_pairs(const float *clean, long long n0, const float *wm, long long n1, unsigned long long *out, cudaStream_t st);
 void set_lstm_profile_buffer(long long *p);
 void set_lstm_opts(int opts);
+int get_debug_opts();   // developer A/B switches (wm_debug_lstm_opts): bit 8 = pconv without stores, bit 9 = pconv without MMAs
 long long *get_profile_buffer();
 int launch_pack_lstm_tc(const float *w_ih, const float *w_hh, const float *bias, void *wpk, float *bias_p,
                         cudaStream_t st);

@@ -371,6 +371,7 @@ static long long *g_lstm_prof = nullptr;
 constexpr int kLstmDefaultOpts = 0;
 static int g_lstm_opts = kLstmDefaultOpts;
 void set_lstm_opts(int o) { g_lstm_opts = o < 0 ? kLstmDefaultOpts : o; }
+int get_debug_opts() { return g_lstm_opts; }
 void set_lstm_profile_buffer(long long *p) { g_lstm_prof = p; }
 long long *get_profile_buffer() { return g_lstm_prof; }
 
