@@ -17,9 +17,7 @@
 // linear bulk copies.  A producer may write its rows split by phase (row t -> buffer t % s, row t / s): the strided
 // convolution that follows then reads contiguous rows (tap 0: phase s-1 one row up, tap 1: phase 0, tap 2: phase 1;
 // the 1x1 stride-s skip convolution: phase 0).
-#include <cuda.h>
 #include <cuda_bf16.h>
-#include <cudaTypedefs.h>
 
 #include "wm_common.h"
 #include "wm_tc.cuh"
@@ -45,8 +43,6 @@ struct KSrc {
 };
 
 struct KParams {
-  CUtensorMap amap[4];         // one 4-d tensor map per source (index 3: the fused block's skip source): {16 B row, rows,
-                               // planes of a half, hi / lo}; a stage's operand tile is ONE box {16 B, 134 rows, 2, 2}
   KSrc src[3];
   int nsrc;
   long long plane_rows;        // of the sources and the residual
@@ -76,17 +72,6 @@ struct KParams {
   long long *prof;             // developer hook (wm_debug_lstm_profile buffer): per-role cycle sums of block 0, or null
   int u_off, w1_bytes, w2_bytes;   // shared-memory offsets / sizes set by the launcher (w2_bytes includes the skip slices)
 };
-
-// One stage's activation tile by TMA (cp.async.bulk.tensor, SASS UTMALDG): rows row .. row + 133 of planes 2 kc, 2 kc + 1
-// of both halves land as [hi, hi, lo, lo][134 rows][16 B] = the A_PLANE layout the descriptors expect.  Rows outside the
-// tensor are zero-filled.  (Four linear bulk copies per stage, each behind its own operand-uniformising loop, made the
-// producer warp the bottleneck of every layer with short stages: ~550 cycles per stage, measured.)
-__device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap *map, uint32_t bar, int row, int plane) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(0), "r"(row), "r"(plane), "r"(0)
-      : "memory");
-}
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -240,28 +225,32 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
     // doing all of it, with 64-bit index arithmetic, made EVERY stage ~1000 cycles whatever it held).
     uint32_t s = 0, ph = 0;
     const uint32_t nch = (uint32_t)P.nch;
-    const bool leader = elect_one();
     for (uint32_t tile = blockIdx.x; tile < (uint32_t)ntiles; tile += gridDim.x) {
       const uint32_t mt = tile / nch, j = tile - mt * nch;
-      const int m0 = (int)(mt * TILE);
+      const long long m0 = (long long)mt * TILE;
       const uint8_t *wj = P.w + (size_t)j * P.w_chunk_bytes;
       for (int si = 0; si < P.nsrc; ++si) {
         const KSrc &S = P.src[si];
-        const int row = m0 + S.row_off + (si == 0 ? (int)P.chunk_off[j] : 0);
+        const long long row = m0 + S.row_off + (si == 0 ? (int)P.chunk_off[j] : 0);
+        const uint32_t abytes = (uint32_t)(TILE + S.taps - 1) * 16u;
         const uint32_t wbytes = (uint32_t)S.taps * C::B_TAP;
+        // this lane's source pointer for 16-channel slice 0 and its step per slice
+        const uint8_t *src = lane < 4 ? reinterpret_cast<const uint8_t *>(
+                                            S.base + ((long long)((lane >> 1) * S.lo_plane + (lane & 1)) * P.plane_rows + row))
+                                      : wj;
+        const size_t step = lane < 4 ? (size_t)(2 * P.plane_rows) * 16u : (size_t)wbytes;
+        const uint32_t bytes = lane < 4 ? abytes : wbytes;
+        const uint32_t doff = lane < 4 ? (uint32_t)lane * A_PLANE : (uint32_t)A_BYTES;
         const int kch = S.kchunks;
         for (int kc = 0; kc < kch; ++kc) {
           mbar_wait(empty_bar(s), ph ^ 1);
-          if (leader) {
-            const uint32_t dst = s_base + s * P.stage_bytes;
-            mbar_arrive_expect_tx(full_bar(s), A_BYTES + wbytes);
-            tma_load_tile(dst, &P.amap[si], full_bar(s), row, 2 * kc);
-            bulk_g2s(dst + A_BYTES, wj, wbytes, full_bar(s));
-          }
+          if (lane == 0) mbar_arrive_expect_tx(full_bar(s), 4 * abytes + wbytes);
           __syncwarp();
-          wj += wbytes;
+          if (lane < 5) bulk_g2s(s_base + s * P.stage_bytes + doff, src, bytes, full_bar(s));
+          src += step;
           if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
         }
+        wj += (size_t)kch * wbytes;
       }
     }
     __syncwarp();
@@ -536,39 +525,45 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
       for (int off = 0; off < P.w2_bytes; off += C::B_TAP) bulk_g2s(w2_smem + off, P.w2 + off, C::B_TAP, w2bar);
     }
     uint32_t s = 0, ph = 0;
-    const bool leader = elect_one();
-    const bool pf = P.prof != nullptr && blockIdx.x == 0 && leader;
+    const bool pf = P.prof != nullptr && blockIdx.x == 0 && lane == 0;
     long long pa[2] = {0, 0}, last_ = pf ? clock64() : 0;
     for (uint32_t i = 0; i <= nmine; ++i) {
       if (i < nmine) {
-        const int u0 = (int)((blockIdx.x + i * gridDim.x) * RB_ROWS) - 1;
+        const long long u0 = (long long)(blockIdx.x + i * gridDim.x) * RB_ROWS - 1;
         for (int si = 0; si < P.nsrc; ++si) {
           const KSrc &S = P.src[si];
-          const int row = u0 + S.row_off;
+          const long long row = u0 + S.row_off;
+          const uint32_t abytes = (uint32_t)(TILE + S.taps - 1) * 16u;
+          const uint8_t *src = reinterpret_cast<const uint8_t *>(
+              S.base + ((long long)(((lane >> 1) & 1) * S.lo_plane + (lane & 1)) * P.plane_rows + row));
+          const size_t step = (size_t)(2 * P.plane_rows) * 16u;
           const int kch = S.kchunks;
           for (int kc = 0; kc < kch; ++kc) {
             RB_TICK(1);
             mbar_wait(empty_bar(s), ph ^ 1);
             RB_TICK(0);
-            if (leader) {
-              mbar_arrive_expect_tx(full_bar(s), A_BYTES);
-              tma_load_tile(s_base + s * P.stage_bytes, &P.amap[si], full_bar(s), row, 2 * kc);
-            }
+            if (lane == 0) mbar_arrive_expect_tx(full_bar(s), 4 * abytes);
             __syncwarp();
+            if (lane < 4) bulk_g2s(s_base + s * P.stage_bytes + (uint32_t)lane * A_PLANE, src, abytes, full_bar(s));
+            src += step;
             if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
           }
         }
       }
       if (i >= 1 && P.skip.kchunks > 0) {
         // skip stages of tile i - 1: phase-0 rows of x under the tile's OUTPUT rows (u0 + 1 ..)
-        const int row = (int)((blockIdx.x + (i - 1) * gridDim.x) * RB_ROWS) + P.skip.row_off;
-        for (int kc = 0; kc < P.skip.kchunks; ++kc) {
+        const KSrc &S = P.skip;
+        const long long row = (long long)(blockIdx.x + (i - 1) * gridDim.x) * RB_ROWS + S.row_off;
+        const uint32_t abytes = (uint32_t)TILE * 16u;
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(
+            S.base + ((long long)(((lane >> 1) & 1) * S.lo_plane + (lane & 1)) * P.plane_rows + row));
+        const size_t step = (size_t)(2 * P.plane_rows) * 16u;
+        for (int kc = 0; kc < S.kchunks; ++kc) {
           mbar_wait(empty_bar(s), ph ^ 1);
-          if (leader) {
-            mbar_arrive_expect_tx(full_bar(s), A_BYTES);
-            tma_load_tile(s_base + s * P.stage_bytes, &P.amap[3], full_bar(s), row, 2 * kc);
-          }
+          if (lane == 0) mbar_arrive_expect_tx(full_bar(s), 4 * abytes);
           __syncwarp();
+          if (lane < 4) bulk_g2s(s_base + s * P.stage_bytes + (uint32_t)lane * A_PLANE, src, abytes, full_bar(s));
+          src += step;
           if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
         }
       }
@@ -936,35 +931,6 @@ __global__ void __launch_bounds__(256)
   for (int i = 0; i < 8; ++i) y[((long long)c * C + g * 8 + i) * Tout + t] = v[i];
 }
 
-// The planar tensor of one source as a 4-d tensor of 32-bit words {4 words = one 16-byte row, rows, planes of a half,
-// hi / lo}; box = one stage's operand tile.
-static int make_plane_map(CUtensorMap *map, const void *base, int cin, long long plane_rows) {
-  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
-  if (encode == nullptr) {
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    WM_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
-      set_error("cuTensorMapEncodeTiled is not available in this driver");
-      return -3;
-    }
-    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-  }
-  const cuuint64_t planes = (cuuint64_t)(cin / 8);
-  const cuuint64_t dims[4] = {4, (cuuint64_t)plane_rows, planes, 2};
-  const cuuint64_t strides[3] = {16, (cuuint64_t)plane_rows * 16, planes * (cuuint64_t)plane_rows * 16};
-  const cuuint32_t box[4] = {4, TILE + 6, 2, 2};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void *>(base), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) for a planar tensor of %d channels x %lld rows", (int)r, cin, plane_rows);
-    return -3;
-  }
-  return 0;
-}
-
 }  // namespace
 
 }  // namespace wm
@@ -1021,7 +987,6 @@ int wm_pconv_fwd(const wm_pconv *d, void *stream) {
     P.src[i].row_off = s.row_off;
     P.src[i].taps = s.taps;
     slices += (long long)(s.cin / 16) * s.taps;
-    WM_TRY(make_plane_map(&P.amap[i], s.base, s.cin, d->plane_rows));
   }
   P.nsrc = d->nsrc;
   P.plane_rows = d->plane_rows;
@@ -1083,7 +1048,6 @@ int wm_pconv_fwd(const wm_pconv *d, void *stream) {
       P.skip.lo_plane = d->skip.cin / 8;
       P.skip.row_off = 0;
       P.skip.taps = 1;
-      WM_TRY(make_plane_map(&P.amap[3], d->skip.base, d->skip.cin, d->plane_rows));
     }
     switch (d->nc) {
       case 16: return launch_pconv_rb_t<16>(P, st);
