@@ -223,34 +223,43 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
     // ===== producer: per stage 4 plane copies (hi, hi, lo, lo of one 16-channel slice) + the taps' weights =====
     // Lane i < 4 issues plane copy i, lane 4 the weights: a stage costs each lane a handful of instructions (one thread
     // doing all of it, with 64-bit index arithmetic, made EVERY stage ~1000 cycles whatever it held).
+    // ONE ELECTED lane issues the five copies of a stage.  (elect.sync tells ptxas that exactly one lane is active, so
+    // the copies take their operands from uniform registers directly; under `lane == 0` / `lane < 5` every
+    // cp.async.bulk sat in its own operand-uniformising loop and a stage cost ~550 cycles of producer time — the bound
+    // of every layer with short stages, measured with the MMAs and the stores switched off.  One TMA tensor load per
+    // stage was tried instead and is slower: a box with a 16-byte inner dimension moves 16 bytes per request.)
     uint32_t s = 0, ph = 0;
     const uint32_t nch = (uint32_t)P.nch;
+    const bool leader = elect_one();
+    const long long prow = P.plane_rows;
     for (uint32_t tile = blockIdx.x; tile < (uint32_t)ntiles; tile += gridDim.x) {
       const uint32_t mt = tile / nch, j = tile - mt * nch;
       const long long m0 = (long long)mt * TILE;
       const uint8_t *wj = P.w + (size_t)j * P.w_chunk_bytes;
       for (int si = 0; si < P.nsrc; ++si) {
         const KSrc &S = P.src[si];
-        const long long row = m0 + S.row_off + (si == 0 ? (int)P.chunk_off[j] : 0);
         const uint32_t abytes = (uint32_t)(TILE + S.taps - 1) * 16u;
         const uint32_t wbytes = (uint32_t)S.taps * C::B_TAP;
-        // this lane's source pointer for 16-channel slice 0 and its step per slice
-        const uint8_t *src = lane < 4 ? reinterpret_cast<const uint8_t *>(
-                                            S.base + ((long long)((lane >> 1) * S.lo_plane + (lane & 1)) * P.plane_rows + row))
-                                      : wj;
-        const size_t step = lane < 4 ? (size_t)(2 * P.plane_rows) * 16u : (size_t)wbytes;
-        const uint32_t bytes = lane < 4 ? abytes : wbytes;
-        const uint32_t doff = lane < 4 ? (uint32_t)lane * A_PLANE : (uint32_t)A_BYTES;
+        const uint4 *hi = S.base + (m0 + S.row_off + (si == 0 ? (int)P.chunk_off[j] : 0));
+        const uint4 *lo = hi + (long long)S.lo_plane * prow;
         const int kch = S.kchunks;
         for (int kc = 0; kc < kch; ++kc) {
           mbar_wait(empty_bar(s), ph ^ 1);
-          if (lane == 0) mbar_arrive_expect_tx(full_bar(s), 4 * abytes + wbytes);
+          if (leader) {
+            const uint32_t dst = s_base + s * P.stage_bytes, fb = full_bar(s);
+            mbar_arrive_expect_tx(fb, 4 * abytes + wbytes);
+            bulk_g2s(dst, hi, abytes, fb);
+            bulk_g2s(dst + A_PLANE, hi + prow, abytes, fb);
+            bulk_g2s(dst + 2 * A_PLANE, lo, abytes, fb);
+            bulk_g2s(dst + 3 * A_PLANE, lo + prow, abytes, fb);
+            bulk_g2s(dst + A_BYTES, wj, wbytes, fb);
+          }
           __syncwarp();
-          if (lane < 5) bulk_g2s(s_base + s * P.stage_bytes + doff, src, bytes, full_bar(s));
-          src += step;
+          hi += 2 * prow;
+          lo += 2 * prow;
+          wj += wbytes;
           if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
         }
-        wj += (size_t)kch * wbytes;
       }
     }
     __syncwarp();
@@ -525,27 +534,34 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
       for (int off = 0; off < P.w2_bytes; off += C::B_TAP) bulk_g2s(w2_smem + off, P.w2 + off, C::B_TAP, w2bar);
     }
     uint32_t s = 0, ph = 0;
-    const bool pf = P.prof != nullptr && blockIdx.x == 0 && lane == 0;
+    const bool leader = elect_one();
+    const bool pf = P.prof != nullptr && blockIdx.x == 0 && leader;
     long long pa[2] = {0, 0}, last_ = pf ? clock64() : 0;
+    const long long prow = P.plane_rows;
     for (uint32_t i = 0; i <= nmine; ++i) {
       if (i < nmine) {
         const long long u0 = (long long)(blockIdx.x + i * gridDim.x) * RB_ROWS - 1;
         for (int si = 0; si < P.nsrc; ++si) {
           const KSrc &S = P.src[si];
-          const long long row = u0 + S.row_off;
           const uint32_t abytes = (uint32_t)(TILE + S.taps - 1) * 16u;
-          const uint8_t *src = reinterpret_cast<const uint8_t *>(
-              S.base + ((long long)(((lane >> 1) & 1) * S.lo_plane + (lane & 1)) * P.plane_rows + row));
-          const size_t step = (size_t)(2 * P.plane_rows) * 16u;
+          const uint4 *hi = S.base + (u0 + S.row_off);
+          const uint4 *lo = hi + (long long)S.lo_plane * prow;
           const int kch = S.kchunks;
           for (int kc = 0; kc < kch; ++kc) {
             RB_TICK(1);
             mbar_wait(empty_bar(s), ph ^ 1);
             RB_TICK(0);
-            if (lane == 0) mbar_arrive_expect_tx(full_bar(s), 4 * abytes);
+            if (leader) {
+              const uint32_t dst = s_base + s * P.stage_bytes, fb = full_bar(s);
+              mbar_arrive_expect_tx(fb, 4 * abytes);
+              bulk_g2s(dst, hi, abytes, fb);
+              bulk_g2s(dst + A_PLANE, hi + prow, abytes, fb);
+              bulk_g2s(dst + 2 * A_PLANE, lo, abytes, fb);
+              bulk_g2s(dst + 3 * A_PLANE, lo + prow, abytes, fb);
+            }
             __syncwarp();
-            if (lane < 4) bulk_g2s(s_base + s * P.stage_bytes + (uint32_t)lane * A_PLANE, src, abytes, full_bar(s));
-            src += step;
+            hi += 2 * prow;
+            lo += 2 * prow;
             if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
           }
         }
@@ -553,17 +569,22 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
       if (i >= 1 && P.skip.kchunks > 0) {
         // skip stages of tile i - 1: phase-0 rows of x under the tile's OUTPUT rows (u0 + 1 ..)
         const KSrc &S = P.skip;
-        const long long row = (long long)(blockIdx.x + (i - 1) * gridDim.x) * RB_ROWS + S.row_off;
         const uint32_t abytes = (uint32_t)TILE * 16u;
-        const uint8_t *src = reinterpret_cast<const uint8_t *>(
-            S.base + ((long long)(((lane >> 1) & 1) * S.lo_plane + (lane & 1)) * P.plane_rows + row));
-        const size_t step = (size_t)(2 * P.plane_rows) * 16u;
+        const uint4 *hi = S.base + ((long long)(blockIdx.x + (i - 1) * gridDim.x) * RB_ROWS + S.row_off);
+        const uint4 *lo = hi + (long long)S.lo_plane * prow;
         for (int kc = 0; kc < S.kchunks; ++kc) {
           mbar_wait(empty_bar(s), ph ^ 1);
-          if (lane == 0) mbar_arrive_expect_tx(full_bar(s), 4 * abytes);
+          if (leader) {
+            const uint32_t dst = s_base + s * P.stage_bytes, fb = full_bar(s);
+            mbar_arrive_expect_tx(fb, 4 * abytes);
+            bulk_g2s(dst, hi, abytes, fb);
+            bulk_g2s(dst + A_PLANE, hi + prow, abytes, fb);
+            bulk_g2s(dst + 2 * A_PLANE, lo, abytes, fb);
+            bulk_g2s(dst + 3 * A_PLANE, lo + prow, abytes, fb);
+          }
           __syncwarp();
-          if (lane < 4) bulk_g2s(s_base + s * P.stage_bytes + (uint32_t)lane * A_PLANE, src, abytes, full_bar(s));
-          src += step;
+          hi += 2 * prow;
+          lo += 2 * prow;
           if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
         }
       }
