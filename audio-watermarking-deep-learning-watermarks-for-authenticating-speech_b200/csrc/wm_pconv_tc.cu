@@ -187,7 +187,7 @@ __device__ __forceinline__ void issue_stage(int taps, uint32_t d_tmem, uint64_t 
 
 // Warps 0..15 epilogue (TMEM lane quadrant = warp % 4, column slice = warp / 4), warp 16 producer, warp 17 MMA issuer.
 template <int NC>
-__global__ void __launch_bounds__(608, 1) pconv_tc_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant__ KParams P) {
   using C = Cfg<NC>;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
@@ -219,11 +219,8 @@ __global__ void __launch_bounds__(608, 1) pconv_tc_kernel(const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 16 || warp == 18) {
-    // ===== producers: per stage 4 plane copies (hi, hi, lo, lo of one 16-channel slice) + the taps' weights =====
-    // Warp 16 issues the hi planes and announces the stage's bytes, warp 18 the lo planes and the weights: a bulk copy
-    // costs its issuing thread ~90 cycles, and with all five on one thread a stage took ~450 cycles of producer time.
-    const bool second = warp == 18;
+  if (warp == 16) {
+    // ===== producer: per stage 4 plane copies (hi, hi, lo, lo of one 16-channel slice) + the taps' weights =====
     // Lane i < 4 issues plane copy i, lane 4 the weights: a stage costs each lane a handful of instructions (one thread
     // doing all of it, with 64-bit index arithmetic, made EVERY stage ~1000 cycles whatever it held).
     // ONE ELECTED lane issues the five copies of a stage.  (elect.sync tells ptxas that exactly one lane is active, so
@@ -250,15 +247,12 @@ __global__ void __launch_bounds__(608, 1) pconv_tc_kernel(const __grid_constant_
           mbar_wait(empty_bar(s), ph ^ 1);
           if (leader) {
             const uint32_t dst = s_base + s * P.stage_bytes, fb = full_bar(s);
-            if (!second) {
-              mbar_arrive_expect_tx(fb, 4 * abytes + wbytes);
-              bulk_g2s(dst, hi, abytes, fb);
-              bulk_g2s(dst + A_PLANE, hi + prow, abytes, fb);
-            } else {
-              bulk_g2s(dst + 2 * A_PLANE, lo, abytes, fb);
-              bulk_g2s(dst + 3 * A_PLANE, lo + prow, abytes, fb);
-              bulk_g2s(dst + A_BYTES, wj, wbytes, fb);
-            }
+            mbar_arrive_expect_tx(fb, 4 * abytes + wbytes);
+            bulk_g2s(dst, hi, abytes, fb);
+            bulk_g2s(dst + A_PLANE, hi + prow, abytes, fb);
+            bulk_g2s(dst + 2 * A_PLANE, lo, abytes, fb);
+            bulk_g2s(dst + 3 * A_PLANE, lo + prow, abytes, fb);
+            bulk_g2s(dst + A_BYTES, wj, wbytes, fb);
           }
           __syncwarp();
           hi += 2 * prow;
@@ -460,7 +454,7 @@ int launch_pconv_t(const KParams &P0, cudaStream_t st) {
   WM_CHECK_ARG(P.R < (1LL << 31) && ntiles < (1LL << 31), "pconv: %lld rows x %d chunks exceed the 32-bit tile index", P.R,
                P.nch);
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-  pconv_tc_kernel<NC><<<grid, 608, smem_bytes, st>>>(P);
+  pconv_tc_kernel<NC><<<grid, 576, smem_bytes, st>>>(P);
   WM_CHECK_LAUNCH("pconv_tc");
   return 0;
 }
@@ -482,7 +476,7 @@ constexpr int RB_ROWS = 126;
 constexpr int U_PLANE = 136 * 16;
 
 template <int NC>
-__global__ void __launch_bounds__(608, 1) pconv_rb_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant__ KParams P) {
   using C = Cfg<NC>;
   constexpr int CS = NC / 2;                 // channels per epilogue thread
   constexpr int U_BYTES = 2 * (NC / 8) * U_PLANE;
@@ -532,17 +526,16 @@ __global__ void __launch_bounds__(608, 1) pconv_rb_kernel(const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc1 = tmem_base, acc2 = tmem_base + 4 * NC;
 
-  if (warp == 16 || warp == 18) {
-    // ===== producers (warp 16: hi planes + byte count, warp 18: lo planes) =====
-    const bool second = warp == 18;
-    if (lane == 0 && !second) {
+  if (warp == 16) {
+    // ===== producer =====
+    if (lane == 0) {
       mbar_arrive_expect_tx(w2bar, (uint32_t)(P.w1_bytes + P.w2_bytes));
       for (int off = 0; off < P.w1_bytes; off += C::B_TAP) bulk_g2s(w1_smem + off, P.w + off, C::B_TAP, w2bar);
       for (int off = 0; off < P.w2_bytes; off += C::B_TAP) bulk_g2s(w2_smem + off, P.w2 + off, C::B_TAP, w2bar);
     }
     uint32_t s = 0, ph = 0;
     const bool leader = elect_one();
-    const bool pf = P.prof != nullptr && blockIdx.x == 0 && leader && !second;
+    const bool pf = P.prof != nullptr && blockIdx.x == 0 && leader;
     long long pa[2] = {0, 0}, last_ = pf ? clock64() : 0;
     const long long prow = P.plane_rows;
     for (uint32_t i = 0; i <= nmine; ++i) {
@@ -560,14 +553,11 @@ __global__ void __launch_bounds__(608, 1) pconv_rb_kernel(const __grid_constant_
             RB_TICK(0);
             if (leader) {
               const uint32_t dst = s_base + s * P.stage_bytes, fb = full_bar(s);
-              if (!second) {
-                mbar_arrive_expect_tx(fb, 4 * abytes);
-                bulk_g2s(dst, hi, abytes, fb);
-                bulk_g2s(dst + A_PLANE, hi + prow, abytes, fb);
-              } else {
-                bulk_g2s(dst + 2 * A_PLANE, lo, abytes, fb);
-                bulk_g2s(dst + 3 * A_PLANE, lo + prow, abytes, fb);
-              }
+              mbar_arrive_expect_tx(fb, 4 * abytes);
+              bulk_g2s(dst, hi, abytes, fb);
+              bulk_g2s(dst + A_PLANE, hi + prow, abytes, fb);
+              bulk_g2s(dst + 2 * A_PLANE, lo, abytes, fb);
+              bulk_g2s(dst + 3 * A_PLANE, lo + prow, abytes, fb);
             }
             __syncwarp();
             hi += 2 * prow;
@@ -586,14 +576,11 @@ __global__ void __launch_bounds__(608, 1) pconv_rb_kernel(const __grid_constant_
           mbar_wait(empty_bar(s), ph ^ 1);
           if (leader) {
             const uint32_t dst = s_base + s * P.stage_bytes, fb = full_bar(s);
-            if (!second) {
-              mbar_arrive_expect_tx(fb, 4 * abytes);
-              bulk_g2s(dst, hi, abytes, fb);
-              bulk_g2s(dst + A_PLANE, hi + prow, abytes, fb);
-            } else {
-              bulk_g2s(dst + 2 * A_PLANE, lo, abytes, fb);
-              bulk_g2s(dst + 3 * A_PLANE, lo + prow, abytes, fb);
-            }
+            mbar_arrive_expect_tx(fb, 4 * abytes);
+            bulk_g2s(dst, hi, abytes, fb);
+            bulk_g2s(dst + A_PLANE, hi + prow, abytes, fb);
+            bulk_g2s(dst + 2 * A_PLANE, lo, abytes, fb);
+            bulk_g2s(dst + 3 * A_PLANE, lo + prow, abytes, fb);
           }
           __syncwarp();
           hi += 2 * prow;
@@ -859,7 +846,7 @@ int launch_pconv_rb_t(const KParams &P0, cudaStream_t st) {
   const long long ntiles = (P.R + RB_ROWS - 1) / RB_ROWS;
   WM_CHECK_ARG(P.R < (1LL << 31), "pconv_rb: %lld rows exceed the 32-bit tile index", P.R);
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-  pconv_rb_kernel<NC><<<grid, 608, smem_bytes, st>>>(P);
+  pconv_rb_kernel<NC><<<grid, 576, smem_bytes, st>>>(P);
   WM_CHECK_LAUNCH("pconv_rb");
   return 0;
 }
