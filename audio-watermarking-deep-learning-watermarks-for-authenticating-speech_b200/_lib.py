@@ -12,7 +12,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwmb200.so")
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 # blob offsets (floats) — mirror of the enums in include/wmb200.h
 RB_W1 = 0
@@ -203,6 +203,8 @@ SIGNATURES = {
     "wm_embed_detect_host_workspace_bytes": (_sz, [_i, _i, _i]),
     "wm_embed_detect_host": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
                                   _i, _i, _i, _i, _i, _p]),
+    "wm_embed_detect_host_ragged": (_i, [_p, _p, _i64, _p, _p, _p, _p, _ll, _p, _p, _p, _p, _p, _sz,
+                                         _i, _i, _i, _i, _i, _p]),
 }
 
 

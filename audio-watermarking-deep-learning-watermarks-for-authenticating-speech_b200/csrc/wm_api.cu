@@ -970,13 +970,36 @@ thread_local HostPipe g_pipe;
 // latency-bound LSTM runs once over the whole pass.  Staging buffers alternate between passes, so pass c+1's
 // input copy and pass c-1's output copy also overlap pass c.  On return, `stream` has been made to wait for
 // every copy: stream-order semantics are those of a plain sequence of copies and kernels on `stream`.
+// H2D of `n` floats of clip data starting `off` floats into the caller's buffer, of which only the first `valid` floats
+// exist: the rest is zero on the device (a ragged last segment read straight out of the caller's pinned recording).
+static int copy_in_ragged(float *dst, const float *host_s, long long off, long long n, long long valid, cudaStream_t st) {
+  long long have = valid - off;
+  have = have < 0 ? 0 : (have > n ? n : have);
+  if (have > 0) WM_CHECK_CUDA(cudaMemcpyAsync(dst, host_s + off, (size_t)have * 4, cudaMemcpyHostToDevice, st));
+  if (have < n) WM_CHECK_CUDA(cudaMemsetAsync(dst + have, 0, (size_t)(n - have) * 4, st));
+  return 0;
+}
+
 int wm_embed_detect_host(const float *g_blob, const float *embedding, int64_t emb_rows,
                          const float *d_blob, const float *fir, const int64_t *host_message,
                          const float *host_s, float *host_s_w, float *host_probs,
                          float *host_clip_prob, float *host_msg_logits, void *workspace,
                          size_t workspace_bytes, int B, int T, int nout, int chunk, int post_mode,
                          void *stream) {
+  return wm_embed_detect_host_ragged(g_blob, embedding, emb_rows, d_blob, fir, host_message, host_s, (long long)B * T,
+                                     host_s_w, host_probs, host_clip_prob, host_msg_logits, workspace, workspace_bytes, B,
+                                     T, nout, chunk, post_mode, stream);
+}
+
+int wm_embed_detect_host_ragged(const float *g_blob, const float *embedding, int64_t emb_rows,
+                                const float *d_blob, const float *fir, const int64_t *host_message,
+                                const float *host_s, long long host_s_floats, float *host_s_w, float *host_probs,
+                                float *host_clip_prob, float *host_msg_logits, void *workspace,
+                                size_t workspace_bytes, int B, int T, int nout, int chunk, int post_mode,
+                                void *stream) {
   WM_ENTRY();
+  WM_CHECK_ARG(host_s_floats >= 0 && host_s_floats <= (long long)B * T,
+               "embed_detect_host: host_s_floats %lld outside [0, B * T]", host_s_floats);
   WM_CHECK_ARG(B >= 0 && T >= 0 && chunk > 0, "embed_detect_host: bad size");
   WM_CHECK_ARG(nout >= 1 && nout <= WM_MAX_HEAD, "embed_detect_host: nout must be in [1,%d]", WM_MAX_HEAD);
   if (B == 0 || T == 0) return 0;
@@ -1001,7 +1024,7 @@ int wm_embed_detect_host(const float *g_blob, const float *embedding, int64_t em
   if (g_math_mode.load() != WM_MATH_BF16X2) {   // fp32 cross-check mode: plain sequence on `stream`
     for (int b0 = 0; b0 < B; b0 += chunk) {
       int nb = B - b0 < chunk ? B - b0 : chunk;
-      WM_CHECK_CUDA(cudaMemcpyAsync(d_s[0], host_s + (size_t)b0 * T, (size_t)nb * T * 4, cudaMemcpyHostToDevice, st));
+      WM_TRY(copy_in_ragged(d_s[0], host_s, (long long)b0 * T, (long long)nb * T, host_s_floats, st));
       if (host_message)
         WM_CHECK_CUDA(cudaMemcpyAsync(d_msg[0], host_message + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, st));
       WM_TRY(wm_embed_detect_fwd(g_blob, embedding, emb_rows, d_blob, fir, host_message ? d_msg[0] : nullptr, d_s[0],
@@ -1046,8 +1069,8 @@ int wm_embed_detect_host(const float *g_blob, const float *embedding, int64_t em
     for (int k = 0; k < ns; ++k) {
       const int k0 = k * sb, kn = nb - k0 < sb ? nb - k0 : sb;
       if (kn <= 0) { WM_CHECK_CUDA(cudaEventRecord(hp.in_done[p][k], hp.in)); continue; }
-      WM_CHECK_CUDA(cudaMemcpyAsync(d_s[p] + (size_t)k0 * T, host_s + ((size_t)b0 + k0) * T, (size_t)kn * T * 4,
-                                    cudaMemcpyHostToDevice, hp.in));
+      WM_TRY(copy_in_ragged(d_s[p] + (size_t)k0 * T, host_s, ((long long)b0 + k0) * T, (long long)kn * T, host_s_floats,
+                            hp.in));
       WM_CHECK_CUDA(cudaEventRecord(hp.in_done[p][k], hp.in));
     }
     // ---- encoder per sub-batch, LSTM over the pass ----

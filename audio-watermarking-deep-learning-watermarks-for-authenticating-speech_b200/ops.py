@@ -334,17 +334,22 @@ class HostPipeline:
 
     def __call__(self, host_s, host_message, host_s_w, host_probs=None, host_clip_prob=None,
                  host_msg_logits=None):
+        """host_s: (B, T), or a flat tensor of fewer than B * T samples (B taken from host_s_w): the missing tail of
+        the last clip is zero on the device (wm_embed_detect_host_ragged)."""
         for name, t in (("host_s", host_s), ("host_s_w", host_s_w), ("host_probs", host_probs)):
             if t is not None and (t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32):
                 raise ValueError(f"{name}: expected a contiguous fp32 host tensor")
-        B, T = host_s.shape
+        B, T = host_s_w.shape
         assert T == self.T
+        n = host_s.numel()
+        if n > B * T or n <= (B - 1) * T:
+            raise ValueError(f"host_s holds {n} samples, expected more than {(B - 1) * T} and at most {B * T}")
         emb = self.embedding
-        L.check(self.lib.wm_embed_detect_host(
+        L.check(self.lib.wm_embed_detect_host_ragged(
             L.ptr(self.g_blob), L.ptr(emb), emb.shape[0] if emb is not None else 0, L.ptr(self.d_blob),
-            L.ptr(self.fir), L.ptr(host_message), L.ptr(host_s), L.ptr(host_s_w), L.ptr(host_probs),
+            L.ptr(self.fir), L.ptr(host_message), L.ptr(host_s), n, L.ptr(host_s_w), L.ptr(host_probs),
             L.ptr(host_clip_prob), L.ptr(host_msg_logits), L.ptr(self.ws), self.nbytes, B, T, self.nout,
-            self.chunk, self.post_mode, _stream()), "wm_embed_detect_host")
+            self.chunk, self.post_mode, _stream()), "wm_embed_detect_host_ragged")
 
 
 # ---- training-loss forward (py/main16.py:74-81, 192-217, 255-266) ----------------------------

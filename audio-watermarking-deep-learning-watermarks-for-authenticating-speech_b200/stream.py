@@ -94,10 +94,13 @@ def embed_detect_stream(generator, detector, waveform: torch.Tensor, messages: O
     else:
         # host staging: the input buffer is cached between calls (pinning gigabytes costs more than the GPU pass);
         # result buffers are the caller's — fresh pinned tensors unless `buffers` hands reusable ones in
-        hs = _staging("hs", (nb, SEG), torch.float32)
-        hs.view(-1)[:s1 - s0] = x[s0:s1]
-        if s1 - s0 < nb * SEG:
-            hs.view(-1)[s1 - s0:] = 0.0
+        if x.is_pinned() and x.is_contiguous():
+            hs = x[s0:s1]                     # straight out of the caller's pinned recording: the ragged tail of the last
+        else:                                 # segment is zero-filled on the device (wm_embed_detect_host_ragged)
+            hs = _staging("hs", (nb, SEG), torch.float32)
+            hs.view(-1)[:s1 - s0] = x[s0:s1]
+            if s1 - s0 < nb * SEG:
+                hs.view(-1)[s1 - s0:] = 0.0
         hm = _staging("hm", (nb,), torch.int64)
         hm.copy_(messages[lo:hi])
         buffers = buffers if buffers is not None else {}

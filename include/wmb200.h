@@ -40,7 +40,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 19
+#define WM_ABI_VERSION 20
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -578,6 +578,15 @@ int wm_embed_detect_host(const float *g_blob, const float *embedding, int64_t em
                          float *host_s_w, float *host_probs, float *host_clip_prob,
                          float *host_msg_logits, void *workspace, size_t workspace_bytes,
                          int B, int T, int nout, int chunk, int post_mode, void *stream);
+/* The same call on a caller's buffer that holds only `host_s_floats` <= B * T samples: the missing tail of the last
+ * clip(s) is zero on the device (py/main16.py:1011-1026 right-zero-pads the last partial segment).  Lets the long-form
+ * drivers run a ragged recording straight out of its own pinned memory, with no staging copy. */
+int wm_embed_detect_host_ragged(const float *g_blob, const float *embedding, int64_t emb_rows,
+                                const float *d_blob, const float *fir,
+                                const int64_t *host_message, const float *host_s, long long host_s_floats,
+                                float *host_s_w, float *host_probs, float *host_clip_prob,
+                                float *host_msg_logits, void *workspace, size_t workspace_bytes,
+                                int B, int T, int nout, int chunk, int post_mode, void *stream);
 
 #ifdef __cplusplus
 }

@@ -583,6 +583,14 @@ def test_long_form_stream_sharded_matches_batched(gen_B, det):
     assert maxerr(torch.cat([p["probs"] for p in parts]), full["probs"]) < 1e-4
     tot = sum(float(p["probs"].double().sum()) for p in parts) / N
     assert abs(tot - full["mean_probability"]) < 1e-6
+    # a pinned recording is read in place (no staging copy; the ragged tail is zero-filled on the device): same results,
+    # in one piece and as the last shard of three
+    pinned = wav.pin_memory()
+    zc = wmb200.embed_detect_stream(gen_B, det, pinned, msg, chunk=64)
+    for k in ("watermarked", "probs", "clip_prob", "msg_logits"):
+        assert torch.equal(zc[k], full[k]), k
+    last = wmb200.embed_detect_stream(gen_B, det, pinned, msg, chunk=64, rank=2, world=3, reduce=False)
+    assert torch.equal(last["watermarked"], parts[2]["watermarked"]) and torch.equal(last["probs"], parts[2]["probs"])
 
 
 def test_folder_driver_matches_per_file_api(tmp_path, gen_B, det):
