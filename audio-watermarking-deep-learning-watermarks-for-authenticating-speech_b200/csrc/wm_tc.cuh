@@ -33,6 +33,7 @@ __device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  long long t0 = 0;
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n.reg .pred p;\n"
@@ -41,7 +42,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity), "r"((uint32_t)WM_WAIT_HINT_NS)
         : "memory");
-    if (!done && spin > (1u << 20)) __trap();
+    if (!done && (spin & 255) == 255) {      // a wait of more than ~4 s of SM clocks is a protocol error
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) __trap();
+    }
   }
 }
 // Converged-warp wait.  Every lane polls: measured on B200, one polling lane + __syncwarp made
