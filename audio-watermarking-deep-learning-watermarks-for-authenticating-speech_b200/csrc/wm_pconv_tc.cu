@@ -198,6 +198,9 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
   auto tfull_bar = [&](int a) { return bars + 8 * (2 * MAX_STAGE + a); };
   auto tempty_bar = [&](int a) { return bars + 8 * (2 * MAX_STAGE + 2 + a); };
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NS * P.stage_bytes + 8 * (2 * MAX_STAGE + 4));
+  // the layer's biases, staged once (per-tile __ldg of 8 float4 sat on the epilogue warps' critical path)
+  float *bias_s = reinterpret_cast<float *>(smem + NS * P.stage_bytes + 8 * (2 * MAX_STAGE + 4) + 16);
+  for (int i = threadIdx.x; i < P.n_total; i += blockDim.x) bias_s[i] = P.bias[i];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long mtiles = (P.R + TILE - 1) / TILE;
@@ -342,10 +345,10 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
       }
       if (!inrange) continue;
       {
-        const float4 *bp = reinterpret_cast<const float4 *>(P.bias + n0);
+        const float4 *bp = reinterpret_cast<const float4 *>(bias_s + n0);
 #pragma unroll
         for (int k = 0; k < CS / 4; ++k) {
-          const float4 b = __ldg(bp + k);
+          const float4 b = bp[k];
           add_packed<4>(o + 4 * k, &b.x);
         }
       }
@@ -439,12 +442,12 @@ int launch_pconv_t(const KParams &P0, cudaStream_t st) {
   int maxtaps = 1;
   for (int i = 0; i < P.nsrc; ++i) maxtaps = P.src[i].taps > maxtaps ? P.src[i].taps : maxtaps;
   P.stage_bytes = (A_BYTES + maxtaps * C::B_TAP + 127) / 128 * 128;
-  const int budget = 200 * 1024;
+  const int budget = 200 * 1024;   // + barriers and up to 8 KB of biases
   int ns = budget / P.stage_bytes;
   ns = ns > MAX_STAGE ? MAX_STAGE : ns;
   WM_CHECK_ARG(ns >= 2, "pconv: a stage of %d bytes does not fit the shared memory twice", P.stage_bytes);
   P.nstage = ns;
-  const int smem_bytes = ns * P.stage_bytes + 8 * (2 * MAX_STAGE + 4) + 16;
+  const int smem_bytes = ns * P.stage_bytes + 8 * (2 * MAX_STAGE + 4) + 16 + P.n_total * 4;
   static int attr_bytes = 0;
   if (smem_bytes > attr_bytes) {
     WM_CHECK_CUDA(cudaFuncSetAttribute(pconv_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -499,6 +502,8 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
   auto t2_empty = [&](int a) { return xb + 8 * (10 + a); };
   const uint32_t w2bar = xb + 8 * 12;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + P.u_off + 2 * U_BYTES + 8 * (2 * MAX_STAGE + 13));
+  float *bias_s = reinterpret_cast<float *>(smem + P.u_off + 2 * U_BYTES + 8 * (2 * MAX_STAGE + 13) + 24);   // b1 then b2 (16-byte aligned)
+  if (threadIdx.x < 2 * NC) bias_s[threadIdx.x] = threadIdx.x < NC ? P.bias[threadIdx.x] : P.bias2[threadIdx.x - NC];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ntiles = (uint32_t)((P.R + RB_ROWS - 1) / RB_ROWS);
@@ -711,10 +716,10 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
         add_packed<CS>(o, v2);
       }
       {
-        const float4 *bp = reinterpret_cast<const float4 *>(P.bias + n0);
+        const float4 *bp = reinterpret_cast<const float4 *>(bias_s + n0);
 #pragma unroll
         for (int k = 0; k < CS / 4; ++k) {
-          const float4 b = __ldg(bp + k);
+          const float4 b = bp[k];
           add_packed<4>(o + 4 * k, &b.x);
         }
       }
@@ -785,10 +790,10 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
       RB_TICK(1);
       if (ri >= RB_ROWS || m >= P.R) continue;
       {
-        const float4 *bp = reinterpret_cast<const float4 *>(P.bias2 + n0);
+        const float4 *bp = reinterpret_cast<const float4 *>(bias_s + NC + n0);
 #pragma unroll
         for (int k = 0; k < CS / 4; ++k) {
-          const float4 b = __ldg(bp + k);
+          const float4 b = bp[k];
           add_packed<4>(o + 4 * k, &b.x);
         }
       }
@@ -831,13 +836,13 @@ int launch_pconv_rb_t(const KParams &P0, cudaStream_t st) {
   P.w1_bytes = slices1 * C::B_TAP;
   P.w2_bytes = ((NC / 16) * 3 + P.skip.kchunks) * C::B_TAP;
   const int u_bytes = 2 * 2 * (NC / 8) * U_PLANE;
-  const int fixed = P.w1_bytes + P.w2_bytes + u_bytes + 8 * (2 * MAX_STAGE + 13) + 16;
+  const int fixed = P.w1_bytes + P.w2_bytes + u_bytes + 8 * (2 * MAX_STAGE + 13) + 24 + 2 * NC * 4;
   int ns = (226 * 1024 - fixed) / P.stage_bytes;
   ns = ns > MAX_STAGE ? MAX_STAGE : ns;
   WM_CHECK_ARG(ns >= 3, "pconv_rb: %d bytes of resident weights leave no room for the activation stages", P.w1_bytes + P.w2_bytes);
   P.nstage = ns;
   P.u_off = ns * P.stage_bytes + P.w1_bytes + P.w2_bytes;
-  const int smem_bytes = P.u_off + u_bytes + 8 * (2 * MAX_STAGE + 13) + 16;
+  const int smem_bytes = P.u_off + u_bytes + 8 * (2 * MAX_STAGE + 13) + 24 + 2 * NC * 4;
   static bool attr_set = false;
   if (!attr_set) {
     WM_CHECK_CUDA(cudaFuncSetAttribute(pconv_rb_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
