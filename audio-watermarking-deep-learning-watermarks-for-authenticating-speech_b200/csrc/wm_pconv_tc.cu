@@ -827,9 +827,6 @@ template <int NC>
 int launch_pconv_rb_t(const KParams &P0, cudaStream_t st) {
   using C = Cfg<NC>;
   KParams P = P0;
-  int maxtaps = 1;
-  for (int i = 0; i < P.nsrc; ++i) maxtaps = P.src[i].taps > maxtaps ? P.src[i].taps : maxtaps;
-  (void)maxtaps;
   P.stage_bytes = A_BYTES;                       // activations only: the weights are resident
   int slices1 = 0;
   for (int i = 0; i < P.nsrc; ++i) slices1 += P.src[i].kchunks * P.src[i].taps;
@@ -1039,7 +1036,6 @@ int wm_pconv_fwd(const wm_pconv *d, void *stream) {
     WM_CHECK_ARG(d->n_total % 8 == 0, "pconv: planar output needs a multiple of 8 channels");
     if (P.out_split > 1) {
       WM_CHECK_ARG(d->T % P.out_split == 0, "pconv: T %d is not a multiple of the output split %d", d->T, P.out_split);
-      WM_CHECK_ARG(d->residual == nullptr || true, "pconv");
       P.out_Tp = d->T / P.out_split + WM_PC_GAP;
       WM_CHECK_ARG(d->out_plane_rows >= wm_pconv_plane_rows(d->B, d->T / P.out_split), "pconv: out_plane_rows too small");
     } else {

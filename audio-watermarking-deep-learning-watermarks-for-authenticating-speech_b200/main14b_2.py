@@ -1,10 +1,12 @@
-"""main14b_2's configurable residual stack (py/main14b_2.py:83-224, BASELINE config 3) on libwmb200's generic
-fp32 operators: `ResidualBlock`, `Generator`, `Detector` with the reference's constructor arguments, attribute
-and state-dict names (so its checkpoints load unchanged and a seeded construction draws identical weights).
+"""main14b_2's configurable residual stack (py/main14b_2.py:83-224, BASELINE config 3): `ResidualBlock`, `Generator`,
+`Detector` with the reference's constructor arguments, attribute and state-dict names (so its checkpoints load unchanged
+and a seeded construction draws identical weights).
 
-The torch sub-modules only own the parameters; `forward` hands their raw pointers to the C ABI
-(`wm_conv1d_fwd`, `wm_convtranspose1d_fwd`, `wm_lstm_small_fwd`), layer by layer, channels-first fp32 exactly
-as the reference holds its tensors.  Inference only (this model has no BatchNorm, so eval == train forward).
+The torch sub-modules only own the parameters.  `Generator.forward` / `Detector.forward` run the whole model through
+the tensor-core layer walk of `pconv.py` (tcgen05 implicit GEMMs over planar bf16-pair activations, `wm_pconv_fwd`) when
+the layer pattern fits it and the math mode is the default; otherwise — other shapes, `WM_MATH_FP32` — layer by layer
+through the fp32 CUDA operators below (`wm_conv1d_fwd`, `wm_convtranspose1d_fwd`, `wm_lstm_small_fwd`), channels-first
+fp32 exactly as the reference holds its tensors.  Inference only (this model has no BatchNorm, so eval == train forward).
 """
 from __future__ import annotations
 
