@@ -226,3 +226,18 @@ def test_fused_strided_block(s, cin, cout, nsp):
         got = BE.from_planar(y, To // nsp, ph)
         assert relerr(got, y_ref[:, :, ph::nsp]) < 3e-5, (ph, relerr(got, y_ref[:, :, ph::nsp]))
     assert gap_rows_zero(y, phases)
+
+
+def test_rows_are_independent_of_batch_composition():
+    """The flattened-row GEMM lets a 128-row tile straddle clips; a clip's result must not depend on its neighbours or on
+    where the tile boundaries fall: the same clip alone, in a batch of 37 and at the end of a batch of 300 gives
+    bit-identical logits and deltas (size-independent property, checked at a batch whose T = 50 layers span 127 tiles)."""
+    torch.manual_seed(21)
+    G, D = M.Generator().to(DEV).eval(), M.Detector().to(DEV).eval()
+    s = (0.1 * torch.randn(300, 1, 16000, device=DEV)).clamp(-0.99, 0.99)
+    msg = torch.randint(0, 65536, (300,), device=DEV)
+    d_all, l_all = G(s, msg), D(s)
+    for idx in ([0], [299], list(range(100, 137))):
+        d_sub, l_sub = G(s[idx], msg[idx]), D(s[idx])
+        assert torch.equal(d_sub, d_all[idx]), idx[0]
+        assert torch.equal(l_sub, l_all[idx]), idx[0]
