@@ -26,6 +26,7 @@ from wmb200 import stream as ST
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--hours", type=float, default=10.0)
+    ap.add_argument("--unpinned", action="store_true", help="pageable source: the driver stages it through its cached pinned buffer")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -36,7 +37,7 @@ def main():
     d = wmb200.Detector(message_bits=16).cuda().eval()
     n = int(a.hours * 3600 * 16000) - 4321                      # a ragged tail segment
     gen = torch.Generator().manual_seed(7)
-    x = torch.empty(n)
+    x = torch.empty(n, pin_memory=not a.unpinned)      # host-pinned source (read in place)
     for i in range(0, n, 16_000_000):                            # 0.1 * randn in slabs (host RAM friendly)
         x[i:i + 16_000_000] = 0.1 * torch.randn(min(16_000_000, n - i), generator=gen)
     times, bufs = [], {}
