@@ -37,18 +37,14 @@ __global__ void bias_sum_kernel(const float *__restrict__ a, const float *__rest
 
 // The input half of the gates, W_ih x_t + b, does not depend on the recurrence: it is computed for all steps by four
 // 1-tap convolutions into the gate planes, and this kernel walks the chain with only the 64-term W_hh h_{t-1} dot
-// per thread, overwriting each pre-activation with the activated gate.
-// Thread (j, q) = (tid / 4, tid % 4) owns gate q of hidden unit j, so the four gates of a unit sit in four adjacent
-// lanes: they meet through warp shuffles, every lane of the quad carries the unit's cell state, and a step needs ONE
-// block barrier (h_t visible to all) instead of two plus a shared-memory round trip of the gates.  h is double buffered
-// so that the writes of step t + 1 cannot overtake a slow warp's reads of step t.
-constexpr int GP = 72;   // shared-memory pitch of one gate's 64 values: 8 q + j spreads a quad's four rows over the banks
+// per thread, overwriting each pre-activation with the activated gate.  thread (q, j) owns gate row q*64 + j.
 __global__ void __launch_bounds__(256, 1)
     lstm_train_fwd_kernel(float *__restrict__ gates, const float *__restrict__ wT_hh, float *__restrict__ h_out,
                           float *__restrict__ cell, long long plane, int T) {
-  __shared__ __align__(16) float xs[2][TC][4 * GP];
-  __shared__ __align__(16) float hs[2][64];
-  const int tid = threadIdx.x, q = tid & 3, j = tid >> 2, b = blockIdx.x, qbase = (tid & 31) & ~3;
+  __shared__ __align__(16) float xs[2][TC][256];
+  __shared__ __align__(16) float hs[64];
+  __shared__ float gs[256];
+  const int tid = threadIdx.x, q = tid >> 6, j = tid & 63, b = blockIdx.x;
   float wh[64];
 #pragma unroll
   for (int k = 0; k < 64; ++k) wh[k] = wT_hh[(q * 64 + k) * 64 + j];
@@ -59,11 +55,11 @@ __global__ void __launch_bounds__(256, 1)
     const int t0 = chunk * TC;
     for (int i = tid; i < TC * 64; i += 256) {
       const int tt = i >> 6, qq = (i >> 4) & 3, c4 = (i & 15) * 4;
-      if (t0 + tt < T) cp_async16(&xs[buf][tt][qq * GP + c4], gb + (size_t)qq * plane + (size_t)(t0 + tt) * 64 + c4);
+      if (t0 + tt < T) cp_async16(&xs[buf][tt][qq * 64 + c4], gb + (size_t)qq * plane + (size_t)(t0 + tt) * 64 + c4);
     }
     cp_async_commit();
   };
-  if (tid < 128) (&hs[0][0])[tid] = 0.0f;
+  if (tid < 64) hs[tid] = 0.0f;
   float c_prev = 0.0f;
   const int nchunks = (T + TC - 1) / TC;
   stage(0, 0);
@@ -73,44 +69,42 @@ __global__ void __launch_bounds__(256, 1)
     __syncthreads();
     const int tend = min(TC, T - ch * TC);
     for (int tt = 0; tt < tend; ++tt) {
-      const int t = ch * TC + tt, cur = t & 1;
-      float a0 = xs[buf][tt][q * GP + j], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+      const int t = ch * TC + tt;
+      float a0 = xs[buf][tt][tid], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll
       for (int k = 0; k < 64; k += 4) {
-        const float4 hv = *reinterpret_cast<const float4 *>(&hs[cur][k]);
+        const float4 hv = *reinterpret_cast<const float4 *>(&hs[k]);
         a0 = fmaf(wh[k], hv.x, a0); a1 = fmaf(wh[k + 1], hv.y, a1);
         a2 = fmaf(wh[k + 2], hv.z, a2); a3 = fmaf(wh[k + 3], hv.w, a3);
       }
       const float a = (a0 + a1) + (a2 + a3);
       const float g = q == 2 ? tanhx(a) : sigm(a);
+      gs[tid] = g;
       gq[(size_t)t * 64 + j] = g;
-      const float gi = __shfl_sync(0xffffffffu, g, qbase), gf = __shfl_sync(0xffffffffu, g, qbase + 1);
-      const float gg = __shfl_sync(0xffffffffu, g, qbase + 2), go = __shfl_sync(0xffffffffu, g, qbase + 3);
-      const float c = fmaf(gf, c_prev, gi * gg);
-      c_prev = c;
-      const float h = go * tanhx(c);
-      if (q == 0) {
-        hs[cur ^ 1][j] = h;
-        hb[(size_t)t * 64 + j] = h;
-        cb[(size_t)t * 64 + j] = c;
+      __syncthreads();
+      if (tid < 64) {
+        const float c = fmaf(gs[64 + tid], c_prev, gs[tid] * gs[128 + tid]);
+        c_prev = c;
+        const float h = gs[192 + tid] * tanhx(c);
+        hs[tid] = h;
+        hb[(size_t)t * 64 + tid] = h;
+        cb[(size_t)t * 64 + tid] = c;
       }
       __syncthreads();
     }
   }
 }
 
-// Thread (j, q) = (tid / 4, tid % 4): phase A makes da of gate q of unit j for step t; phase B makes the partial of
-// W_hh^T da over gate q's 64 rows for hidden unit j (W_hh[q*64 + rr][j], rr = 0..63, in registers).  The four partials of
-// a unit sit in adjacent lanes and are summed by shuffles (same association as a sum over a shared array), da is double
-// buffered in shared memory: one block barrier per step.  Operands of TC steps are staged by cp.async, chunks walked
-// from the last to the first.
+// thread (q, j): phase A makes da[q*64 + j] of step t; phase B makes the partial of W_hh^T da over gate q's 64 rows
+// for hidden unit j (W_hh[q*64 + rr][j], rr = 0..63, in registers).  Operands of TC steps are staged by cp.async,
+// chunks walked from the last to the first.
 constexpr int BWD_BUF = TC * 256 + (TC + 1) * 64 + TC * 64;   // floats per staging buffer
 __global__ void __launch_bounds__(256, 1)
     lstm_train_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ wT_hh, const float *__restrict__ gates,
                           const float *__restrict__ cell, float *__restrict__ da, long long plane, int T) {
   extern __shared__ __align__(16) float bsm[];
-  __shared__ __align__(16) float das[2][4 * GP];
-  const int tid = threadIdx.x, q = tid & 3, j = tid >> 2, b = blockIdx.x, qbase = (tid & 31) & ~3;
+  __shared__ __align__(16) float das[256], part[4][64];
+  const int tid = threadIdx.x, q = tid >> 6, j = tid & 63, b = blockIdx.x;
   float w[64];   // w[rr] = W_hh[q*64 + rr][j] = wT_hh[q][j][rr]
 #pragma unroll
   for (int rr = 0; rr < 64; rr += 4) {
@@ -137,9 +131,8 @@ __global__ void __launch_bounds__(256, 1)
     }
     cp_async_commit();
   };
-  float part = 0.0f;        // this thread's partial of W_hh^T da_{t+1} for unit j (gate q's rows)
+  part[q][j] = 0.0f;
   float dc_carry = 0.0f;
-  int cur = 0;
   const int nchunks = (T + TC - 1) / TC;
   stage(nchunks - 1, 0);
   for (int ci = 0; ci < nchunks; ++ci) {
@@ -148,15 +141,12 @@ __global__ void __launch_bounds__(256, 1)
     __syncthreads();
     const float *gsm = bsm + buf * BWD_BUF, *csm = gsm + TC * 256, *dsm = csm + (TC + 1) * 64;
     const int tend = min(TC, T - ch * TC);
-    for (int tt = tend - 1; tt >= 0; --tt, cur ^= 1) {
+    for (int tt = tend - 1; tt >= 0; --tt) {
       const int t = ch * TC + tt;
       const float gi = gsm[tt * 256 + j], gf = gsm[tt * 256 + 64 + j], gg = gsm[tt * 256 + 128 + j],
                   go = gsm[tt * 256 + 192 + j];
       const float ct = csm[(tt + 1) * 64 + j], cp = csm[tt * 64 + j];
-      // dh = dy + (part_0 + part_1) + (part_2 + part_3), the pair sums by one butterfly step
-      const float pair = part + __shfl_xor_sync(0xffffffffu, part, 1);
-      const float s01 = __shfl_sync(0xffffffffu, pair, qbase), s23 = __shfl_sync(0xffffffffu, pair, qbase + 2);
-      const float dh = dsm[tt * 64 + j] + s01 + s23;
+      const float dh = dsm[tt * 64 + j] + (part[0][j] + part[1][j]) + (part[2][j] + part[3][j]);
       const float th = tanhx(ct);
       const float dc = fmaf(dh * go, 1.0f - th * th, dc_carry);
       dc_carry = dc * gf;
@@ -165,17 +155,18 @@ __global__ void __launch_bounds__(256, 1)
       else if (q == 1) d = dc * cp * gf * (1.0f - gf);
       else if (q == 2) d = dc * gi * (1.0f - gg * gg);
       else d = dh * th * go * (1.0f - go);
-      das[cur][q * GP + j] = d;
+      das[tid] = d;
       dab[(size_t)t * 64 + j] = d;
       __syncthreads();
       float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
 #pragma unroll
       for (int rr = 0; rr < 64; rr += 4) {
-        const float4 v = *reinterpret_cast<const float4 *>(&das[cur][q * GP + rr]);
+        const float4 v = *reinterpret_cast<const float4 *>(&das[q * 64 + rr]);
         p0 = fmaf(w[rr], v.x, p0); p1 = fmaf(w[rr + 1], v.y, p1);
         p2 = fmaf(w[rr + 2], v.z, p2); p3 = fmaf(w[rr + 3], v.w, p3);
       }
-      part = (p0 + p1) + (p2 + p3);
+      part[q][j] = (p0 + p1) + (p2 + p3);
+      __syncthreads();
     }
   }
 }
