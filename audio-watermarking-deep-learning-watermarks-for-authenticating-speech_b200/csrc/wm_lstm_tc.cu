@@ -98,7 +98,10 @@ __global__ void __launch_bounds__(THREADS, 1)
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t s_base = smem_u32(smem);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 2 * 64);
-  (void)opts;   // reserved for A/B switches (wm_debug_lstm_opts); none at present
+  // A/B switch (wm_debug_lstm_opts bit 0): the epilogue warps wait on the accumulator's mbarrier themselves (a
+  // try_wait with a suspend hint sleeps until the tcgen05.commit arrives) instead of being released by the MMA thread
+  // through a named barrier after ITS wait
+  const bool direct_acc = (opts & 1) != 0;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t RP = (size_t)T + 2 * PAD;
@@ -190,7 +193,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       long long c0 = pf ? clock64() : 0;
-      bar_sync(BAR_ACC + g, N_EPI + 32);                    // the MMA thread saw this step's accumulator complete
+      if (direct_acc) mbar_wait(acc_full0 + 8 * buf, (uint32_t)((t >> 1) & 1));
+      else bar_sync(BAR_ACC + g, N_EPI + 32);               // the MMA thread saw this step's accumulator complete
       tc_fence_after();
       long long c1 = pf ? clock64() : 0;
       uint32_t r[32];
@@ -324,10 +328,12 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
       __syncwarp();
       long long m2 = pf ? clock64() : 0;
-      if (issuer) mbar_wait(acc_full0 + 8 * buf, (uint32_t)((t >> 1) & 1));
-      __syncwarp();
-      tc_fence_before();
-      bar_arrive(BAR_ACC + g, N_EPI + 32);                  // release the epilogue warps
+      if (!direct_acc) {
+        if (issuer) mbar_wait(acc_full0 + 8 * buf, (uint32_t)((t >> 1) & 1));
+        __syncwarp();
+        tc_fence_before();
+        bar_arrive(BAR_ACC + g, N_EPI + 32);                // release the epilogue warps
+      }
       long long m3 = pf ? clock64() : 0;
       const int t1 = t + 1;
       if (t1 < T) {
