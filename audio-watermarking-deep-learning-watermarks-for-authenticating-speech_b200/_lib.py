@@ -12,7 +12,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwmb200.so")
-ABI_VERSION = 20
+ABI_VERSION = 21
 
 # blob offsets (floats) — mirror of the enums in include/wmb200.h
 RB_W1 = 0

@@ -62,6 +62,7 @@ struct KParams {
   long long out_phase_rows;    // rows (16 B units) between phase buffers of the output
   int out_Tp;                  // mode 0 split: T / split + GAP; mode 2: out_T + GAP
   int ct_stride, ct_pad, ct_cout, out_T;
+  int ct_pk;                   // phases interleaved per 8-channel group (>= 1)
   int stage_bytes, nstage;
   signed char chunk_off[64];
   // fused residual block (pconv_rb_kernel): second GEMM on the first one's output kept in shared memory
@@ -72,6 +73,13 @@ struct KParams {
   long long *prof;             // developer hook (wm_debug_lstm_profile buffer): per-role cycle sums of block 0, or null
   int u_off, w1_bytes, w2_bytes;   // shared-memory offsets / sizes set by the launcher (w2_bytes includes the skip slices)
 };
+
+// two adjacent 16-byte rows as one 256-bit store (sm_100: STG.256)
+__device__ __forceinline__ void st_global_256(uint4 *p, const uint4 &a, const uint4 &b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -377,16 +385,19 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
       if (P.mode == WM_PC_OUT_PLANAR) {
         store_planar<CS>(P, o, n0, m, c, r, t, real);
       } else if (P.mode == WM_PC_OUT_CONVT) {
-        // column n = phase * Cout + co; row (c, q = t) -> output step s q + phase of clip c.  The first gap row of a
-        // clip also carries the last outputs of the previous clip when out_T > s * T (odd strides).
+        // column n = (phase, co) (see wm_pconv.ct_interleave); row (c, q = t) -> output step s q + phase of clip c.  The
+        // first gap row of a clip also carries the last outputs of the previous clip when out_T > s * T (odd strides).
         uint4 *y = reinterpret_cast<uint4 *>(P.y);
-        const int s = P.ct_stride, cout = P.ct_cout, lo0 = cout >> 3;
+        const int s = P.ct_stride, cout = P.ct_cout, lo0 = cout >> 3, pk = P.ct_pk;
         const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int g = 0; g < CS / 8; ++g) {
-          const int n = n0 + g * 8;
-          const int phs = n / cout, co = n - phs * cout;
-          const int pl = co >> 3;
+        auto decode = [&](int n, int &phs, int &pl) {      // 8-column group starting at n -> phase, 8-channel plane
+          const int blk = cout * pk, kb = n / blk, rem = n - kb * blk, gg = rem / (8 * pk);
+          phs = kb * pk + ((rem - gg * 8 * pk) >> 3);
+          pl = gg;
+        };
+        auto store_one = [&](int g) {
+          int phs, pl;
+          decode(n0 + g * 8, phs, pl);
           const int tout = s * t + phs;
           if (tout >= 0) {
             if (c < P.B && tout < P.out_T) {
@@ -413,6 +424,31 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
               }
             }
           }
+        };
+        if constexpr (CS >= 16) {
+          // with an even interleave two consecutive 8-column groups of a thread are phases ph, ph + 1 of the same 8
+          // channels = two adjacent 16-byte rows: ONE 32-byte store each for hi and lo.  (Rows a stride apart made every
+          // 16-byte store its own half-empty sector: 4096 sector writes per tile, the stride-4 layer's bottleneck.)
+#pragma unroll
+          for (int g = 0; g < CS / 8; g += 2) {
+            int phs, pl;
+            decode(n0 + g * 8, phs, pl);
+            const int tout = s * t + phs;
+            const long long row = (long long)c * P.out_Tp + GAP + tout;
+            if ((pk & 1) == 0 && (phs & 1) == 0 && c < P.B && tout >= 0 && tout + 1 < P.out_T && (row & 1) == 0) {
+              uint4 h0, l0, h1, l1;
+              split8(o + g * 8, h0, l0);
+              split8(o + g * 8 + 8, h1, l1);
+              st_global_256(y + ((long long)pl * P.out_plane_rows + row), h0, h1);
+              st_global_256(y + ((long long)(lo0 + pl) * P.out_plane_rows + row), l0, l1);
+            } else {
+              store_one(g);
+              store_one(g + 1);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < CS / 8; ++g) store_one(g);
         }
       } else {
         // fp32 channels-first y[c][ch][t], ch < ct_cout, t < out_T
@@ -1030,6 +1066,7 @@ int wm_pconv_fwd(const wm_pconv *d, void *stream) {
   P.out_split = d->out_split < 1 ? 1 : d->out_split;
   P.out_phase_rows = d->out_phase_rows;
   P.ct_stride = d->ct_stride; P.ct_pad = d->ct_pad; P.ct_cout = d->ct_cout; P.out_T = d->out_T;
+  P.ct_pk = d->ct_interleave < 1 ? 1 : d->ct_interleave;
   P.dbg = (get_debug_opts() >> 8) & 3;
   for (int i = 0; i < 64; ++i) P.chunk_off[i] = d->chunk_off[i];
   if (d->mode == WM_PC_OUT_PLANAR) {
@@ -1047,6 +1084,7 @@ int wm_pconv_fwd(const wm_pconv *d, void *stream) {
     WM_CHECK_ARG(d->out_T >= d->ct_stride * d->T - d->ct_stride && d->out_T <= d->ct_stride * (d->T + 1),
                  "pconv: transposed output length %d does not fit stride %d x %d rows", d->out_T, d->ct_stride, d->T);
     WM_CHECK_ARG(d->residual == nullptr, "pconv: no residual on the transposed output");
+    WM_CHECK_ARG(d->ct_stride % P.ct_pk == 0, "pconv: ct_interleave %d does not divide the stride %d", P.ct_pk, d->ct_stride);
     P.out_Tp = d->out_T + WM_PC_GAP;
     WM_CHECK_ARG(d->out_plane_rows >= wm_pconv_plane_rows(d->B, d->out_T), "pconv: out_plane_rows too small");
   } else {

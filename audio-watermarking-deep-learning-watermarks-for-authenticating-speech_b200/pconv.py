@@ -48,6 +48,8 @@ class Gemm:
     cout: int = 0            # real output channels (before padding to a multiple of 16)
     img: Optional[torch.Tensor] = None     # packed on the device by the backend
     dbias: Optional[torch.Tensor] = None
+    interleave: int = 1      # transposed convolutions: phases interleaved per 8-channel group (convt_columns)
+    cols: Optional[list] = None
 
 
 def _nc_for(n: int) -> int:
@@ -98,8 +100,27 @@ def gemm_conv2_skip(w2, b2, ws, bs) -> Gemm:
                 [0] * (n // nc), cout)
 
 
+def convt_columns(s: int, cout: int, pk: int) -> List[Tuple[int, int]]:
+    """(phase, channel) of every GEMM column of a transposed convolution laid out with `pk` phases interleaved per
+    8-channel group: n = kb * (cout * pk) + g * (8 * pk) + phl * 8 + c  <->  phase kb * pk + phl, channel 8 g + c.
+    pk = 1 is phase-major (n = phase * cout + co).  With pk >= 2 a thread of the epilogue holds consecutive phases of the
+    same 8 channels, i.e. consecutive output rows: it stores them 32 bytes at a time."""
+    assert s % pk == 0 and cout % 8 == 0
+    return [(kb * pk + phl, g * 8 + c) for kb in range(s // pk) for g in range(cout // 8) for phl in range(pk)
+            for c in range(8)]
+
+
+def convt_decode(n: int, cout: int, pk: int) -> Tuple[int, int]:
+    """the kernel's decoding of column n (csrc/wm_pconv_tc.cu, WM_PC_OUT_CONVT)"""
+    blk = cout * pk
+    kb, rem = divmod(n, blk)
+    g, r2 = divmod(rem, 8 * pk)
+    return kb * pk + r2 // 8, g * 8 + r2 % 8
+
+
 def gemm_convT(w: torch.Tensor, b: torch.Tensor, s: int, p: int) -> Gemm:
-    """ConvTranspose1d(Cin, Cout, 2s, stride s, padding p); w (Cin, Cout, 2s).  Column n = phase * Cout + co."""
+    """ConvTranspose1d(Cin, Cout, 2s, stride s, padding p); w (Cin, Cout, 2s).  Columns = (phase, channel) pairs in the
+    order of convt_columns(s, Cout, interleave)."""
     w, b = w.detach().float(), b.detach().float()
     cin, cout, K = w.shape
     assert K == 2 * s and 0 <= p < s and cout % 8 == 0
@@ -112,20 +133,32 @@ def gemm_convT(w: torch.Tensor, b: torch.Tensor, s: int, p: int) -> Gemm:
     n = s * cout
     nc = _nc_for(n)
     nch = n // nc
-    wconv = w3.permute(2, 3, 1, 0).reshape(n, cin, 3)
+
+    def kinds_of(cols):
+        return [{ph + p >= s for ph, _ in cols[j * nc:(j + 1) * nc]} for j in range(nch)]
+
+    # candidates: phases of one kind (same pair of input rows) interleaved per 8 channels, phase-major, fully interleaved
+    choice = None
+    for pk in ([s // 2] if s % 2 == 0 and s >= 4 else []) + [1]:
+        cols = convt_columns(s, cout, pk)
+        kinds = kinds_of(cols)
+        if all(len(k) == 1 for k in kinds):
+            choice = (pk, cols, [1 if True in k else 0 for k in kinds], 2)
+            break
+    if choice is None:
+        pk = s if s % 2 == 0 else 1
+        choice = (pk, convt_columns(s, cout, pk), [0] * nch, 3)
+    pk, cols, offs, taps = choice
+    ph_idx = torch.tensor([c[0] for c in cols])
+    co_idx = torch.tensor([c[1] for c in cols])
+    wconv = w3[:, :, ph_idx, co_idx].permute(2, 1, 0)                            # (n, cin, 3)
     wd5 = wconv.reshape(nch, nc, cin // 16, 16, 3).permute(0, 2, 4, 3, 1)       # chunk, kc, tap, 16, nc
-    kinds = []
-    for j in range(nch):
-        phs = range(j * nc // cout, ((j + 1) * nc - 1) // cout + 1)
-        kinds.append({ph + p >= s for ph in phs})
-    if all(len(k) == 1 for k in kinds):
-        offs = [1 if True in k else 0 for k in kinds]
-        wd = torch.stack([wd5[j, :, offs[j]:offs[j] + 2] for j in range(nch)])
-        taps = 2
-    else:
-        offs, wd, taps = [0] * nch, wd5, 3
-    wd = wd.reshape(nch, (cin // 16) * taps, 16, nc).contiguous()
-    return Gemm([(0, cin, -1, taps)], wd, b.repeat(s), nc, n, offs, cout)
+    if taps == 2:
+        wd5 = torch.stack([wd5[j, :, offs[j]:offs[j] + 2] for j in range(nch)])
+    wd = wd5.reshape(nch, (cin // 16) * taps, 16, nc).contiguous()
+    g = Gemm([(0, cin, -1, taps)], wd, b[co_idx], nc, n, offs, cout)
+    g.interleave, g.cols = pk, cols
+    return g
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -141,7 +174,7 @@ class _Desc(C.Structure):
                 ("chunk_off", C.c_byte * 64), ("elu", C.c_int), ("mode", C.c_int), ("residual", C.c_void_p),
                 ("y", C.c_void_p), ("out_plane_rows", C.c_longlong), ("out_phase_rows", C.c_longlong),
                 ("out_split", C.c_int), ("ct_stride", C.c_int), ("ct_pad", C.c_int), ("ct_cout", C.c_int),
-                ("out_T", C.c_int), ("fused", C.c_int), ("reserved2", C.c_int), ("w2", C.c_void_p), ("bias2", C.c_void_p),
+                ("out_T", C.c_int), ("fused", C.c_int), ("ct_interleave", C.c_int), ("w2", C.c_void_p), ("bias2", C.c_void_p),
                 ("skip", _Src)]
 
 
@@ -246,7 +279,7 @@ class CudaBackend:
         else:
             d.y, d.out_plane_rows, d.out_phase_rows = out.ptr(), out.RP, out.phase_rows
             if mode == OUT_CONVT:
-                d.ct_stride, d.ct_pad, d.ct_cout, d.out_T = ct[0], ct[1], ct[2], out_T
+                d.ct_stride, d.ct_pad, d.ct_cout, d.out_T, d.ct_interleave = ct[0], ct[1], ct[2], out_T, g.interleave
         if g2 is not None:
             self.pack(g2, dev)
             d.fused, d.w2, d.bias2 = 1, g2.img.data_ptr(), g2.dbias.data_ptr()

@@ -40,7 +40,7 @@ extern "C" {
 #define WM_C 64            /* channels of every hidden activation (py/main16.py:134) */
 #define WM_FIR_TAPS 101    /* py/main16.py:53 */
 #define WM_MAX_HEAD 32     /* max outputs of the 1x1 head (1 + message_bits)        */
-#define WM_ABI_VERSION 20
+#define WM_ABI_VERSION 21
 #define WM_PLANAR_PAD 4      /* zero rows before / after every plane of the planar layout */
 #define WM_POST_FIR 1
 #define WM_POST_CLAMP 2
@@ -390,8 +390,9 @@ int wm_lstm_small_fwd(const float *x, const float *w_ih, const float *w_hh, cons
  *   WM_PC_OUT_PLANAR  planar, same geometry; out_split = s > 1 writes step t to phase buffer t % s at step t / s
  *                     (buffers out_phase_rows rows apart, geometry (B, T / s); only phases 0, 1 and s - 1, the ones a
  *                     k3 stride-s convolution reads, are written);
- *   WM_PC_OUT_CONVT   column n = phase * ct_cout + co of row (c, q) is step ct_stride * q + phase of clip c in a planar
- *                     tensor of geometry (B, out_T);
+ *   WM_PC_OUT_CONVT   column n = (phase, co) of row (c, q) is step ct_stride * q + phase of clip c in a planar tensor of
+ *                     geometry (B, out_T); phase-major columns, or ct_interleave phases interleaved per 8 channels so that
+ *                     a thread holds consecutive rows and stores them 32 bytes at a time;
  *   WM_PC_OUT_FP32    fp32 channels-first y[c][ch][t] for ch < ct_cout, t < out_T.
  * Weights come from wm_pconv_pack: fp32 wd[chunk][slice][16][nc] (slice = source-major, then 16-channel group, then
  * tap) -> bf16 hi | lo operand tiles. */
@@ -429,7 +430,8 @@ typedef struct wm_pconv {
    *     y = elu( bias2 + sum over u's channels and 3 taps of u[m - 1 + j] * W2 + skip[ci][m] * Wskip + residual )
    * with w2 = wm_pconv_pack image of conv2's slices (16-channel group major, 3 taps) followed by the skip source's. */
   int fused;
-  int reserved2;
+  int ct_interleave;            /* WM_PC_OUT_CONVT: column n = kb * (ct_cout * k) + g * (8 k) + phl * 8 + c is phase kb * k + phl of
+                                 * channel 8 g + c (k = ct_interleave, a divisor of ct_stride; 0 or 1: n = phase * ct_cout + co) */
   const void *w2;
   const float *bias2;
   wm_pconv_src skip;            /* base == NULL: none (one tap, row offset 0: phase 0 of the block input) */

@@ -117,8 +117,15 @@ class EmuBackend:
             s, p, co_n = ct
             assert g.n_total == s * co_n and out.C == co_n and out.T == out_T and out.B == B
             oTp = out_T + GAP
+            layout = g.cols if g.cols is not None else PC.convt_columns(s, co_n, 1)
+            assert [PC.convt_decode(n, co_n, g.interleave) for n in range(g.n_total)] == layout   # the kernel's decoding
+            ph_of = torch.tensor([c_[0] for c_ in layout])
+            co_of = torch.tensor([c_[1] for c_ in layout])
             for ph in range(s):
-                cols = acc[:, ph * co_n:(ph + 1) * co_n]
+                sel_cols = (ph_of == ph).nonzero().flatten()
+                assert torch.equal(co_of[sel_cols].sort().values, torch.arange(co_n))
+                cols = torch.empty(R, co_n, dtype=acc.dtype)
+                cols[:, co_of[sel_cols]] = acc[:, sel_cols]
                 tout = s * t + ph
                 v = (tout >= 0) & (c < B) & (tout < out_T)
                 out.store[0][:, (c * oTp + GAP + tout)[v]] = cols[v].T
