@@ -236,3 +236,37 @@ class Detector(nn.Module):
         for blk in self.upsample_blocks:
             x = conv_transpose1d(x, blk) if isinstance(blk, nn.ConvTranspose1d) else blk(x)
         return _fit_length(conv1d(x, self.final_conv), T)
+
+
+class GraphedEmbedDetect:
+    """`logits = D(s + G(s, message))` for a FIXED batch shape as one CUDA graph: the ~46 kernel launches of the layer walk
+    are captured once and replayed, so a call costs the host one launch (the eager walk costs ~2 ms of Python per pass,
+    which is what bounds small batches — and large ones on a slow host).  Inputs are copied into static buffers; the
+    returned tensors are static too and are OVERWRITTEN by the next call (clone what must survive).  Inference only;
+    rebuild after changing parameters."""
+
+    def __init__(self, generator: "Generator", detector: "Detector", B: int, T: int = 16000, device=None):
+        dev = torch.device(device) if device is not None else next(generator.parameters()).device
+        self.G, self.D = generator.eval(), detector.eval()
+        self.s = torch.zeros(B, 1, T, device=dev)
+        self.message = torch.zeros(B, dtype=torch.int64, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):                      # weight packing, function attributes, allocator warm-up
+                self._walk()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.delta, self.logits = self._walk()
+
+    def _walk(self):
+        delta = self.G(self.s, self.message)
+        return delta, self.D(self.s + delta)
+
+    def __call__(self, s: torch.Tensor, message: torch.Tensor):
+        """-> (delta (B,1,T), logits (B,1+bits,T)), both static buffers"""
+        self.s.copy_(s, non_blocking=True)
+        self.message.copy_(message, non_blocking=True)
+        self.graph.replay()
+        return self.delta, self.logits

@@ -310,6 +310,24 @@ def measure_main14b2(dev, world, rank, steps, warmup, B=1024):
     tc = ops.get_math_mode() != 0
     n0 = ops.launch_count()
     ms = _event_ms(step, steps, max(warmup, 3), world, dev)
+    launches = int(ops.launch_count() - n0) // (steps + max(warmup, 3))
+    graphed = None
+    if tc:
+        # the same pass captured once as a CUDA graph and replayed (static shapes): host cost of a pass = one launch
+        try:
+            ge = M.GraphedEmbedDetect(G, D, B, 16000, dev)
+            out = {}
+
+            def gstep():
+                out["r"] = ge(s, msg)
+            gms = _event_ms(gstep, steps, max(warmup, 3), world, dev)
+            with torch.no_grad():
+                same = bool(torch.equal(out["r"][1][:2], D(s[:2] + G(s[:2], msg[:2]))))
+            graphed = {"value": world * B * 1000.0 / gms, "unit": "clip-s/s", "ms_per_step": gms,
+                       "bit_identical_to_eager": same, "what": "main14b_2.GraphedEmbedDetect: one CUDA-graph replay per pass"}
+            del ge, out
+        except Exception as e:                                   # informational leg: never fail the line
+            graphed = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     return {"metric": "clip-seconds/sec embed+detect (main14b_2 stack)", "value": world * B * 1000.0 / ms,
             "unit": "clip-s/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -318,7 +336,7 @@ def measure_main14b2(dev, world, rank, steps, warmup, B=1024):
                        "parallelism": "dp%d" % world,
                        "kernels": "tcgen05 implicit GEMMs over planar bf16-pair activations (pconv_tc_kernel)" if tc
                        else "fp32 CUDA-core operators"},
-            "gpu_launches": int(ops.launch_count() - n0) // (steps + max(warmup, 3)),
+            "gpu_launches": launches, "graphed": graphed,
             "algorithmic_tflops": 4.540e9 * world * B / ms * 1e3 / 1e12, "parity": parity}
 
 

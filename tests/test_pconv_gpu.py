@@ -241,3 +241,17 @@ def test_rows_are_independent_of_batch_composition():
         d_sub, l_sub = G(s[idx], msg[idx]), D(s[idx])
         assert torch.equal(d_sub, d_all[idx]), idx[0]
         assert torch.equal(l_sub, l_all[idx]), idx[0]
+
+
+def test_graph_replay_matches_the_eager_walk():
+    """main14b_2.GraphedEmbedDetect: the captured layer walk replayed on new inputs gives the eager walk's bits"""
+    torch.manual_seed(4)
+    G, D = M.Generator().to(DEV).eval(), M.Detector().to(DEV).eval()
+    ge = M.GraphedEmbedDetect(G, D, 3, 640)
+    for seed in (1, 2):
+        g = torch.Generator(device=DEV).manual_seed(seed)
+        s = 0.1 * torch.randn(3, 1, 640, device=DEV, generator=g)
+        msg = torch.randint(0, 65536, (3,), device=DEV, generator=g)
+        delta, logits = ge(s, msg)
+        want_d = G(s, msg)
+        assert torch.equal(delta, want_d) and torch.equal(logits, D(s + want_d))
