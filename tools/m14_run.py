@@ -27,3 +27,17 @@ with torch.no_grad():
     torch.cuda.synchronize()
     print("B", B, "ms/step", e0.elapsed_time(e1) / reps, "host issue ms", t_issue * 1e3 / reps, "host ms", (time.perf_counter() - t0) * 1e3 / reps,
           "clip-s/s", B * 1e3 * reps / e0.elapsed_time(e1), "finite", bool(torch.isfinite(y).all()))
+    if len(sys.argv) > 3 and sys.argv[3] == "graph":
+        ge = M.GraphedEmbedDetect(G, D, B, 16000)
+        for _ in range(2):
+            ge(s, msg)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(reps):
+            ge(s, msg)
+        e1.record()
+        t_issue = time.perf_counter() - t0
+        torch.cuda.synchronize()
+        print("B", B, "graph replay ms/step", e0.elapsed_time(e1) / reps, "host issue ms", t_issue * 1e3 / reps,
+              "clip-s/s", B * 1e3 * reps / e0.elapsed_time(e1))
