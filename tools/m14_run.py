@@ -27,6 +27,24 @@ with torch.no_grad():
     torch.cuda.synchronize()
     print("B", B, "ms/step", e0.elapsed_time(e1) / reps, "host issue ms", t_issue * 1e3 / reps, "host ms", (time.perf_counter() - t0) * 1e3 / reps,
           "clip-s/s", B * 1e3 * reps / e0.elapsed_time(e1), "finite", bool(torch.isfinite(y).all()))
+    if len(sys.argv) > 3 and sys.argv[3] == "torch":
+        # stock PyTorch eager (cuDNN) on the same GPU through the oracle's functional restatement of the reference
+        # (informational: TF32 as the reference sets it, and off)
+        from oracle import wm_oracle_14b2 as O
+        gsd, dsd = G.state_dict(), D.state_dict()
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            for _ in range(2):
+                yt = O.detector_forward(dsd, s + O.generator_forward(gsd, s, msg))
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                yt = O.detector_forward(dsd, s + O.generator_forward(gsd, s, msg))
+            e1.record()
+            torch.cuda.synchronize()
+            print("B", B, "torch eager tf32=%s ms/step" % tf32, e0.elapsed_time(e1) / reps, "clip-s/s",
+                  B * 1e3 * reps / e0.elapsed_time(e1), "max |logit diff| vs wmb200", float((yt - y).abs().max()))
     if len(sys.argv) > 3 and sys.argv[3] == "graph":
         ge = M.GraphedEmbedDetect(G, D, B, 16000)
         for _ in range(2):
