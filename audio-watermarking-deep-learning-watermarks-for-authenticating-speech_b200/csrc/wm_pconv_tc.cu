@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
     // ===== producer: per stage 4 plane copies (hi, hi, lo, lo of one 16-channel slice) + the taps' weights =====
     // Lane i < 4 issues plane copy i, lane 4 the weights: a stage costs each lane a handful of instructions (one thread
     // doing all of it, with 64-bit index arithmetic, made EVERY stage ~1000 cycles whatever it held).
-    // ONE ELECTED lane issues the five copies of a stage.  (elect.sync tells ptxas that exactly one lane is active, so
+    // ONE ELECTED lane walks the pipeline and issues the five copies of a stage (the other lanes of the warp idle).  (elect.sync tells ptxas that exactly one lane is active, so
     // the copies take their operands from uniform registers directly; under `lane == 0` / `lane < 5` every
     // cp.async.bulk sat in its own operand-uniformising loop and a stage cost ~550 cycles of producer time — the bound
     // of every layer with short stages, measured with the MMAs and the stores switched off.  One TMA tensor load per
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
     const uint32_t nch = (uint32_t)P.nch;
     const bool leader = elect_one();
     const long long prow = P.plane_rows;
-    for (uint32_t tile = blockIdx.x; tile < (uint32_t)ntiles; tile += gridDim.x) {
+    for (uint32_t tile = blockIdx.x; leader && tile < (uint32_t)ntiles; tile += gridDim.x) {
       const uint32_t mt = tile / nch, j = tile - mt * nch;
       const long long m0 = (long long)mt * TILE;
       const uint8_t *wj = P.w + (size_t)j * P.w_chunk_bytes;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
         const int kch = S.kchunks;
         for (int kc = 0; kc < kch; ++kc) {
           mbar_wait(empty_bar(s), ph ^ 1);
-          if (leader) {
+          {
             const uint32_t dst = s_base + s * P.stage_bytes, fb = full_bar(s);
             mbar_arrive_expect_tx(fb, 4 * abytes + wbytes);
             bulk_g2s(dst, hi, abytes, fb);
@@ -265,7 +265,6 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
             bulk_g2s(dst + 3 * A_PLANE, lo + prow, abytes, fb);
             bulk_g2s(dst + A_BYTES, wj, wbytes, fb);
           }
-          __syncwarp();
           hi += 2 * prow;
           lo += 2 * prow;
           wj += wbytes;
@@ -579,7 +578,7 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
     const bool pf = P.prof != nullptr && blockIdx.x == 0 && leader;
     long long pa[2] = {0, 0}, last_ = pf ? clock64() : 0;
     const long long prow = P.plane_rows;
-    for (uint32_t i = 0; i <= nmine; ++i) {
+    for (uint32_t i = 0; leader && i <= nmine; ++i) {      // only the elected lane walks the pipeline
       if (i < nmine) {
         const long long u0 = (long long)(blockIdx.x + i * gridDim.x) * RB_ROWS - 1;
         for (int si = 0; si < P.nsrc; ++si) {
@@ -592,7 +591,7 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
             RB_TICK(1);
             mbar_wait(empty_bar(s), ph ^ 1);
             RB_TICK(0);
-            if (leader) {
+            {
               const uint32_t dst = s_base + s * P.stage_bytes, fb = full_bar(s);
               mbar_arrive_expect_tx(fb, 4 * abytes);
               bulk_g2s(dst, hi, abytes, fb);
@@ -600,7 +599,6 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
               bulk_g2s(dst + 2 * A_PLANE, lo, abytes, fb);
               bulk_g2s(dst + 3 * A_PLANE, lo + prow, abytes, fb);
             }
-            __syncwarp();
             hi += 2 * prow;
             lo += 2 * prow;
             if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
@@ -615,7 +613,7 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
         const uint4 *lo = hi + (long long)S.lo_plane * prow;
         for (int kc = 0; kc < S.kchunks; ++kc) {
           mbar_wait(empty_bar(s), ph ^ 1);
-          if (leader) {
+          {
             const uint32_t dst = s_base + s * P.stage_bytes, fb = full_bar(s);
             mbar_arrive_expect_tx(fb, 4 * abytes);
             bulk_g2s(dst, hi, abytes, fb);
@@ -623,7 +621,6 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
             bulk_g2s(dst + 2 * A_PLANE, lo, abytes, fb);
             bulk_g2s(dst + 3 * A_PLANE, lo + prow, abytes, fb);
           }
-          __syncwarp();
           hi += 2 * prow;
           lo += 2 * prow;
           if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
