@@ -71,6 +71,7 @@ struct KParams {
   KSrc skip;                   // kchunks == 0: none
   int dbg;                     // developer A/B switches (timing experiments only): 1 = no global stores, 2 = no MMAs
   long long *prof;             // developer hook (wm_debug_lstm_profile buffer): per-role cycle sums of block 0, or null
+  int kps;                     // fused block: 16-channel slices per stage (2 when every source has an even number)
   int u_off, w1_bytes, w2_bytes;   // shared-memory offsets / sizes set by the launcher (w2_bytes includes the skip slices)
 };
 
@@ -587,20 +588,21 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
           const uint4 *hi = S.base + (u0 + S.row_off);
           const uint4 *lo = hi + (long long)S.lo_plane * prow;
           const int kch = S.kchunks;
-          for (int kc = 0; kc < kch; ++kc) {
+          for (int kc = 0; kc < kch; kc += P.kps) {
             RB_TICK(1);
             mbar_wait(empty_bar(s), ph ^ 1);
             RB_TICK(0);
-            {
-              const uint32_t dst = s_base + s * P.stage_bytes, fb = full_bar(s);
-              mbar_arrive_expect_tx(fb, 4 * abytes);
+            const uint32_t fb = full_bar(s);
+            mbar_arrive_expect_tx(fb, (uint32_t)P.kps * 4 * abytes);
+            for (int q2 = 0; q2 < P.kps; ++q2) {
+              const uint32_t dst = s_base + s * P.stage_bytes + q2 * A_BYTES;
               bulk_g2s(dst, hi, abytes, fb);
               bulk_g2s(dst + A_PLANE, hi + prow, abytes, fb);
               bulk_g2s(dst + 2 * A_PLANE, lo, abytes, fb);
               bulk_g2s(dst + 3 * A_PLANE, lo + prow, abytes, fb);
+              hi += 2 * prow;
+              lo += 2 * prow;
             }
-            hi += 2 * prow;
-            lo += 2 * prow;
             if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
           }
         }
@@ -611,18 +613,19 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
         const uint32_t abytes = (uint32_t)TILE * 16u;
         const uint4 *hi = S.base + ((long long)(blockIdx.x + (i - 1) * gridDim.x) * RB_ROWS + S.row_off);
         const uint4 *lo = hi + (long long)S.lo_plane * prow;
-        for (int kc = 0; kc < S.kchunks; ++kc) {
+        for (int kc = 0; kc < S.kchunks; kc += P.kps) {
           mbar_wait(empty_bar(s), ph ^ 1);
-          {
-            const uint32_t dst = s_base + s * P.stage_bytes, fb = full_bar(s);
-            mbar_arrive_expect_tx(fb, 4 * abytes);
+          const uint32_t fb = full_bar(s);
+          mbar_arrive_expect_tx(fb, (uint32_t)P.kps * 4 * abytes);
+          for (int q2 = 0; q2 < P.kps; ++q2) {
+            const uint32_t dst = s_base + s * P.stage_bytes + q2 * A_BYTES;
             bulk_g2s(dst, hi, abytes, fb);
             bulk_g2s(dst + A_PLANE, hi + prow, abytes, fb);
             bulk_g2s(dst + 2 * A_PLANE, lo, abytes, fb);
             bulk_g2s(dst + 3 * A_PLANE, lo + prow, abytes, fb);
+            hi += 2 * prow;
+            lo += 2 * prow;
           }
-          hi += 2 * prow;
-          lo += 2 * prow;
           if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
         }
       }
@@ -652,18 +655,20 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
         uint64_t bd = w1_desc;                                   // walks conv1's resident slices in stage order
         for (int si = 0; si < P.nsrc; ++si) {
           const int taps = P.src[si].taps, kch = P.src[si].kchunks;
-          for (int kc = 0; kc < kch; ++kc) {
+          for (int kc = 0; kc < kch; kc += P.kps) {
             RB_TICK(7);
             mbar_wait_warp(full_bar(s), ph);
             RB_TICK(1);
             tc_fence_after();
             if (issuer) {
               issue_stage<NC>(taps, d_tmem, a_cur, bd, accum);
+              if (P.kps == 2)
+                issue_stage<NC>(taps, d_tmem, a_cur + (uint64_t)(A_BYTES >> 4), bd + (uint64_t)(taps * (C::B_TAP >> 4)), 1u);
               tc_commit(empty_bar(s));
             }
             RB_TICK(2);
             accum = 1u;
-            bd += (uint64_t)(taps * (C::B_TAP >> 4));
+            bd += (uint64_t)(P.kps * taps * (C::B_TAP >> 4));
             __syncwarp();
             a_cur += st_step;
             if (++s == (uint32_t)NS) { s = 0; ph ^= 1; a_cur = a_base; }
@@ -695,11 +700,13 @@ __global__ void __launch_bounds__(576, 1) pconv_rb_kernel(const __grid_constant_
           }
         }
         __syncwarp();
-        for (int kc = 0; kc < P.skip.kchunks; ++kc) {
+        for (int kc = 0; kc < P.skip.kchunks; kc += P.kps) {
           mbar_wait_warp(full_bar(s), ph);
           tc_fence_after();
           if (issuer) {
             issue_taps<1, NC>(d_tmem, a_cur, w2_desc + (uint64_t)(((KC2 * 3 + kc) * C::B_TAP) >> 4), 1u);
+            if (P.kps == 2)
+              issue_taps<1, NC>(d_tmem, a_cur + (uint64_t)(A_BYTES >> 4), w2_desc + (uint64_t)(((KC2 * 3 + kc + 1) * C::B_TAP) >> 4), 1u);
             tc_commit(empty_bar(s));
           }
           __syncwarp();
@@ -860,7 +867,10 @@ template <int NC>
 int launch_pconv_rb_t(const KParams &P0, cudaStream_t st) {
   using C = Cfg<NC>;
   KParams P = P0;
-  P.stage_bytes = A_BYTES;                       // activations only: the weights are resident
+  P.kps = (P.skip.kchunks % 2 == 0) ? 2 : 1;     // two 16-channel slices per stage when every source allows it: half the
+  for (int i = 0; i < P.nsrc; ++i)               // barrier waits and commits on the MMA thread, which paces this kernel
+    if (P.src[i].kchunks % 2) P.kps = 1;
+  P.stage_bytes = P.kps * A_BYTES;               // activations only: the weights are resident
   int slices1 = 0;
   for (int i = 0; i < P.nsrc; ++i) slices1 += P.src[i].kchunks * P.src[i].taps;
   P.w1_bytes = slices1 * C::B_TAP;
