@@ -255,3 +255,11 @@ def test_graph_replay_matches_the_eager_walk():
         delta, logits = ge(s, msg)
         want_d = G(s, msg)
         assert torch.equal(delta, want_d) and torch.equal(logits, D(s + want_d))
+
+
+def test_empty_batch():
+    """B = 0 goes through the whole walk without a launch error and returns empty tensors of the right shape"""
+    G, D = M.Generator().to(DEV).eval(), M.Detector().to(DEV).eval()
+    s = torch.zeros(0, 1, 16000, device=DEV)
+    assert G(s, torch.zeros(0, dtype=torch.int64, device=DEV)).shape == (0, 1, 16000)
+    assert D(s).shape == (0, 17, 16000)
