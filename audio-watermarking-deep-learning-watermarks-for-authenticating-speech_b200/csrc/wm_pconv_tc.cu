@@ -233,13 +233,12 @@ __global__ void __launch_bounds__(576, 1) pconv_tc_kernel(const __grid_constant_
 
   if (warp == 16) {
     // ===== producer: per stage 4 plane copies (hi, hi, lo, lo of one 16-channel slice) + the taps' weights =====
-    // Lane i < 4 issues plane copy i, lane 4 the weights: a stage costs each lane a handful of instructions (one thread
-    // doing all of it, with 64-bit index arithmetic, made EVERY stage ~1000 cycles whatever it held).
-    // ONE ELECTED lane walks the pipeline and issues the five copies of a stage (the other lanes of the warp idle).  (elect.sync tells ptxas that exactly one lane is active, so
-    // the copies take their operands from uniform registers directly; under `lane == 0` / `lane < 5` every
-    // cp.async.bulk sat in its own operand-uniformising loop and a stage cost ~550 cycles of producer time — the bound
-    // of every layer with short stages, measured with the MMAs and the stores switched off.  One TMA tensor load per
-    // stage was tried instead and is slower: a box with a 16-byte inner dimension moves 16 bytes per request.)
+    // ONE ELECTED lane walks the pipeline and issues the five copies of a stage; the other lanes of the warp idle.
+    // History of this role (cycles of producer time per stage, whatever the stage held): one thread under `lane == 0`
+    // with 64-bit index arithmetic ~1000; one copy per lane under `lane < 5` ~550 (every cp.async.bulk sat in its own
+    // operand-uniformising loop); an elected lane ~400 (elect.sync tells ptxas exactly one lane is active: the copies
+    // take their operands from uniform registers) and ~270 once the other lanes stopped polling along.  One TMA tensor
+    // load per stage was tried instead and is slower: a box with a 16-byte inner dimension moves 16 bytes per request.
     uint32_t s = 0, ph = 0;
     const uint32_t nch = (uint32_t)P.nch;
     const bool leader = elect_one();
