@@ -188,18 +188,12 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
       };
       auto conv2 = [&](uint32_t a_tile, uint32_t d_tmem) {   // accumulates on the residual stored by group 1
         const uint64_t a0 = smem_desc(a_tile, PLANE_B, 128), b0 = smem_desc(w_smem, 2048, 128);
-        // The very first product is issued as two N = 64 halves: A_hi x W_hi accumulates on the residual that group 1
-        // stored in columns 0..63, A_hi x W_lo OVERWRITES columns 64..127 — so group 1 does not have to zero them with
-        // a second tcgen05.st per tile (it is the stage that paces this kernel).
-        mma_bf16(d_tmem, a0, b0, kIdescLo, 1u);
-        mma_bf16(d_tmem + 64, a0, b0 + (uint64_t)((64 * 16) >> 4), kIdescLo, 0u);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-              if (j == 0 && kk == 0 && half == 0) continue;
               mma_bf16(d_tmem, a0 + (uint64_t)(((half * 8 + 2 * kk) * PLANE_B + j * 16) >> 4),
                        b0 + (uint64_t)((j * W_TAP_B + (2 * kk) * 2048) >> 4), half ? kIdescLo : kIdesc, 1u);
             }
@@ -294,7 +288,7 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
           *reinterpret_cast<uint4 *>(us + ch * PLANE_B) = hi;
           *reinterpret_cast<uint4 *>(us + (8 + ch) * PLANE_B) = lo;
         }
-        // residual x0 + b_in + b2 -> conv2's accumulator (columns of the hi product);
+        // residual x0 + b_in + b2 -> conv2's accumulator (columns of the hi product; the lo-product columns start at 0);
         // waited for as late as possible: the epilogue of tile i-2 must have drained D2[a]
         g3c = clk();
         if (i >= 2) {
@@ -302,7 +296,10 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
           tc_fence_after();
         }
         g4c = clk();
-        tmem_st16(t2 + p * 16, xr);        // columns 64..127 are overwritten by conv2's first lo-weight product
+        tmem_st16(t2 + p * 16, xr);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) xr[c] = 0.0f;
+        tmem_st16(t2 + 64 + p * 16, xr);
       }
       tmem_st_wait();
       tc_fence_before();
