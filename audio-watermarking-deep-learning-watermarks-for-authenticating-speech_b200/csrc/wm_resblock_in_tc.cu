@@ -262,6 +262,19 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 16; ++c) { u[c] += bias_s[p * 16 + c]; xr[c] += bias_s[64 + p * 16 + c]; }
+        // residual x0 + b_in + b2 -> conv2's accumulator (columns of the hi product; the lo-product columns start at 0).
+        // Issued BEFORE the u part so that the tensor-memory store's latency (tcgen05.wait::st below took ~900 cycles
+        // on this group's critical path) overlaps the ReLU / split / shared-memory stores of the intermediate tile.
+        g3c = clk();
+        if (i >= 2) {
+          mbar_wait_warp(bar(D2_EMPTY + a), (uint32_t)(((i >> 1) - 1) & 1));   // tile i-2's epilogue has drained D2[a]
+          tc_fence_after();
+        }
+        g4c = clk();
+        tmem_st16(t2 + p * 16, xr);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) xr[c] = 0.0f;
+        tmem_st16(t2 + 64 + p * 16, xr);
         if (edge) {   // first / last sample of the clip: take back conv1's tap that fell on the zero padding of x0
           const float *sb = s + (size_t)b * T;
           const bool drop0 = tu == 0, drop2 = tu == T - 1;
@@ -288,18 +301,6 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
           *reinterpret_cast<uint4 *>(us + ch * PLANE_B) = hi;
           *reinterpret_cast<uint4 *>(us + (8 + ch) * PLANE_B) = lo;
         }
-        // residual x0 + b_in + b2 -> conv2's accumulator (columns of the hi product; the lo-product columns start at 0);
-        // waited for as late as possible: the epilogue of tile i-2 must have drained D2[a]
-        g3c = clk();
-        if (i >= 2) {
-          mbar_wait_warp(bar(D2_EMPTY + a), (uint32_t)(((i >> 1) - 1) & 1));
-          tc_fence_after();
-        }
-        g4c = clk();
-        tmem_st16(t2 + p * 16, xr);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) xr[c] = 0.0f;
-        tmem_st16(t2 + 64 + p * 16, xr);
       }
       tmem_st_wait();
       tc_fence_before();
