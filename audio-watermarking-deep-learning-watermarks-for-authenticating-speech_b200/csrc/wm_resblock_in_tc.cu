@@ -227,7 +227,6 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
         tc_fence_after();
         conv2(u_smem + a * TILE_B, tmem + 256 + a * 128);
         tc_commit(bar(D2_FULL + a));
-        tc_commit(bar(U_EMPTY + a));
         if (pf0) { prof[2] += m1 - m0; prof[3] += m2 - m1; prof[4] += m3 - m2; prof[5] += clk() - m3; prof[15] = my_tiles; }
       }
     }
@@ -250,7 +249,8 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
       const long long g0 = clk();
       mbar_wait_warp(bar(D1_FULL + a), (uint32_t)((i >> 1) & 1));
       const long long g1c = clk();
-      if (i >= 2) mbar_wait_warp(bar(U_EMPTY + a), (uint32_t)(((i >> 1) - 1) & 1));   // conv2(i-2) has finished reading U[a]
+      // (no separate wait for "conv2(i-2) has finished reading U[a]": the D2_EMPTY wait below, made before the first
+      // store into U[a], implies it — tile i-2's epilogue drains D2[a] only after those MMAs completed)
       const long long g2c = clk();
       long long g3c = g2c, g4c = g2c;
       tc_fence_after();
