@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwmb200.so")
+LIB_PATH = os.environ.get("WMB200_LIB") or os.path.join(HERE, "libwmb200.so")   # WMB200_LIB: developer A/B builds
 ABI_VERSION = 21
 
 # blob offsets (floats) — mirror of the enums in include/wmb200.h

@@ -75,9 +75,48 @@ static_assert(RB_SMEM <= 232448, "shared memory budget");
 template <int NW>
 struct RbParams {
   float b1[64], b2[64];   // folded BatchNorm biases of conv1 / conv2 (used when BIASP)
-  float w[NW * 64];       // 1x1 head rows [out][64]
+  float w[NW * 64];       // 1x1 head: row 0 as [64]; rows 1.. (NW > 1, the vote epilogue) transposed to [channel][NW - 1]
   float b[NW];
 };
+// The message-head FMAs of the fused vote epilogue for the 16-channel slice P.  Compile-time weight indices: the
+// weights are uniform-register operands fetched by LDCU.128 (message rows are stored [channel][bit] in the kernel
+// parameter, so a channel's 16 weights are one 64-byte run), and two bits share one packed FFMA2 (fma.rn.f32x2: the
+// activation is the broadcast scalar operand, the weight pair a uniform-register pair) — 512 FFMA2 + 256 LDCU.128 per
+// row.  With a run-time slice index the same FMAs needed an indexed LDC.64 per two weights and this epilogue, not the
+// tensor pipe, paced the kernel.  Detector pass with votes, 4096 clips: 28 ms -> 19.0 (scalar FFMA, WM_VOTE_F32X2=0)
+// -> 18.0 ms; 15.0 ms without votes.  Each lane of the packed FMA is an ordinary fp32 FMA and per bit the channels are
+// accumulated in ascending order, so the vote counts are those of the scalar form.
+#ifndef WM_VOTE_F32X2
+#define WM_VOTE_F32X2 1
+#endif
+constexpr int NVOTE = WM_FUSED_VOTE_MAX - 1;
+template <int P>
+__device__ __forceinline__ void vote_fma(const float (&o)[16], float (&lacc)[NVOTE], const float *w) {
+#if WM_VOTE_F32X2
+  unsigned long long acc2[NVOTE / 2];
+#pragma unroll
+  for (int jp = 0; jp < NVOTE / 2; ++jp) asm("mov.b64 %0, {%1, %2};" : "=l"(acc2[jp]) : "f"(lacc[2 * jp]), "f"(lacc[2 * jp + 1]));
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    unsigned long long ov;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ov) : "f"(o[c]));
+#pragma unroll
+    for (int jp = 0; jp < NVOTE / 2; ++jp) {
+      const unsigned long long wv = *reinterpret_cast<const unsigned long long *>(&w[64 + (P * 16 + c) * NVOTE + 2 * jp]);
+      asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[jp]) : "l"(ov), "l"(wv));
+    }
+  }
+#pragma unroll
+  for (int jp = 0; jp < NVOTE / 2; ++jp) asm("mov.b64 {%0, %1}, %2;" : "=f"(lacc[2 * jp]), "=f"(lacc[2 * jp + 1]) : "l"(acc2[jp]));
+#else
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+#pragma unroll
+    for (int j = 0; j < NVOTE; ++j) lacc[j] = fmaf(o[c], w[64 + (P * 16 + c) * NVOTE + j], lacc[j]);
+  }
+#endif
+}
+
 template <int NHEAD>
 struct RbParamsFor { using type = RbParams<NHEAD == 3 ? WM_FUSED_VOTE_MAX : 1>; };
 
@@ -451,11 +490,12 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
           for (int c = 0; c < 16; ++c) hacc = fmaf(o[c], hp.w[p * 16 + c], hacc);
         }
         if constexpr (NHEAD == 3) {
-          // per-sample message logits: rows 1.. of the head, weights as constant-bank operands
-#pragma unroll
-          for (int j = 0; j < WM_FUSED_VOTE_MAX - 1; ++j) {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) lacc[j] = fmaf(o[c], hp.w[(1 + j) * 64 + p * 16 + c], lacc[j]);
+          // per-sample message logits (rows 1.. of the head): one specialisation per channel slice, see vote_fma
+          switch (p) {
+            case 0: vote_fma<0>(o, lacc, hp.w); break;
+            case 1: vote_fma<1>(o, lacc, hp.w); break;
+            case 2: vote_fma<2>(o, lacc, hp.w); break;
+            default: vote_fma<3>(o, lacc, hp.w); break;
           }
         }
         if constexpr (NHEAD >= 2) {
@@ -547,6 +587,11 @@ static int launch_rb(const void *x, const void *w_img, const float *b1, const fl
   memset(&hp, 0, sizeof(hp));
   if (NHEAD > 0) {
     memcpy(hp.w, host_head, sizeof(float) * 64 * nw);
+    if (NHEAD == 3) {   // message rows transposed to [channel][bit]: a channel's 16 weights are one 64-byte run
+      memset(hp.w + 64, 0, sizeof(float) * 64 * (WM_FUSED_VOTE_MAX - 1));
+      for (int j = 1; j < nw; ++j)
+        for (int c = 0; c < 64; ++c) hp.w[64 + c * (WM_FUSED_VOTE_MAX - 1) + (j - 1)] = host_head[j * 64 + c];
+    }
     memcpy(hp.b, host_head + 64 * nw, sizeof(float) * nw);
   }
   const bool biasp = host_b12 != nullptr;
