@@ -22,6 +22,18 @@ __device__ __forceinline__ float tanhx(float x) { return __fdividef(2.0f, 1.0f +
 
 constexpr int TC = 16;   // time steps staged per cp.async chunk
 
+// Packed fp32 FMA (fma.rn.f32x2, SASS FFMA2): two independent IEEE fp32 FMAs per instruction.  The 64-term dots of
+// the recurrence are four interleaved partial sums; packing them two by two halves the FMA instructions on the
+// step's critical path without changing a bit of the result.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void ffma2(f32x2 &d, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
@@ -45,9 +57,9 @@ __global__ void __launch_bounds__(256, 1)
   __shared__ __align__(16) float hs[64];
   __shared__ float gs[256];
   const int tid = threadIdx.x, q = tid >> 6, j = tid & 63, b = blockIdx.x;
-  float wh[64];
+  f32x2 wh[32];   // (W[k], W[k + 1]) pairs
 #pragma unroll
-  for (int k = 0; k < 64; ++k) wh[k] = wT_hh[(q * 64 + k) * 64 + j];
+  for (int k = 0; k < 64; k += 2) wh[k >> 1] = pk2(wT_hh[(q * 64 + k) * 64 + j], wT_hh[(q * 64 + k + 1) * 64 + j]);
   float *gq = gates + (size_t)q * plane + (size_t)b * T * 64;
   const float *gb = gates + (size_t)b * T * 64;
   float *hb = h_out + (size_t)b * T * 64, *cb = cell + (size_t)b * T * 64;
@@ -70,13 +82,16 @@ __global__ void __launch_bounds__(256, 1)
     const int tend = min(TC, T - ch * TC);
     for (int tt = 0; tt < tend; ++tt) {
       const int t = ch * TC + tt;
-      float a0 = xs[buf][tt][tid], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+      f32x2 a01 = pk2(xs[buf][tt][tid], 0.0f), a23 = pk2(0.0f, 0.0f);
 #pragma unroll
       for (int k = 0; k < 64; k += 4) {
-        const float4 hv = *reinterpret_cast<const float4 *>(&hs[k]);
-        a0 = fmaf(wh[k], hv.x, a0); a1 = fmaf(wh[k + 1], hv.y, a1);
-        a2 = fmaf(wh[k + 2], hv.z, a2); a3 = fmaf(wh[k + 3], hv.w, a3);
+        const ulonglong2 hv = *reinterpret_cast<const ulonglong2 *>(&hs[k]);   // (h[k], h[k+1]), (h[k+2], h[k+3])
+        ffma2(a01, wh[k >> 1], hv.x);
+        ffma2(a23, wh[(k >> 1) + 1], hv.y);
       }
+      float a0, a1, a2, a3;
+      upk2(a01, a0, a1);
+      upk2(a23, a2, a3);
       const float a = (a0 + a1) + (a2 + a3);
       const float g = q == 2 ? tanhx(a) : sigm(a);
       gs[tid] = g;
@@ -105,11 +120,11 @@ __global__ void __launch_bounds__(256, 1)
   extern __shared__ __align__(16) float bsm[];
   __shared__ __align__(16) float das[256], part[4][64];
   const int tid = threadIdx.x, q = tid >> 6, j = tid & 63, b = blockIdx.x;
-  float w[64];   // w[rr] = W_hh[q*64 + rr][j] = wT_hh[q][j][rr]
+  f32x2 w[32];   // pairs of w[rr] = W_hh[q*64 + rr][j] = wT_hh[q][j][rr]
 #pragma unroll
   for (int rr = 0; rr < 64; rr += 4) {
-    const float4 v = *reinterpret_cast<const float4 *>(&wT_hh[(q * 64 + j) * 64 + rr]);
-    w[rr] = v.x; w[rr + 1] = v.y; w[rr + 2] = v.z; w[rr + 3] = v.w;
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&wT_hh[(q * 64 + j) * 64 + rr]);
+    w[rr >> 1] = v.x; w[(rr >> 1) + 1] = v.y;
   }
   const float *dyb = dy + (size_t)b * T * 64, *gb = gates + (size_t)b * T * 64, *cb = cell + (size_t)b * T * 64;
   float *dab = da + (size_t)q * plane + (size_t)b * T * 64;
@@ -158,13 +173,16 @@ __global__ void __launch_bounds__(256, 1)
       das[tid] = d;
       dab[(size_t)t * 64 + j] = d;
       __syncthreads();
-      float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+      f32x2 p01 = pk2(0.0f, 0.0f), p23 = p01;
 #pragma unroll
       for (int rr = 0; rr < 64; rr += 4) {
-        const float4 v = *reinterpret_cast<const float4 *>(&das[q * 64 + rr]);
-        p0 = fmaf(w[rr], v.x, p0); p1 = fmaf(w[rr + 1], v.y, p1);
-        p2 = fmaf(w[rr + 2], v.z, p2); p3 = fmaf(w[rr + 3], v.w, p3);
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&das[q * 64 + rr]);
+        ffma2(p01, w[rr >> 1], v.x);
+        ffma2(p23, w[(rr >> 1) + 1], v.y);
       }
+      float p0, p1, p2, p3;
+      upk2(p01, p0, p1);
+      upk2(p23, p2, p3);
       part[q][j] = (p0 + p1) + (p2 + p3);
       __syncthreads();
     }
