@@ -84,6 +84,18 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
   const int ntile_t = (T + TO - 1) / TO;
   const long long ntiles = (long long)B * ntile_t;
   const long long my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // (clip, time tile) of a role's current tile, advanced by a fixed stride per iteration: no division in the tile loops
+  struct TileWalk {
+    int b, tt, sb, st, nt;
+    __device__ __forceinline__ TileWalk(long long first, long long stride, int ntile_t)
+        : b((int)(first / ntile_t)), tt((int)(first % ntile_t)), sb((int)(stride / ntile_t)), st((int)(stride % ntile_t)),
+          nt(ntile_t) {}
+    __device__ __forceinline__ void next() {
+      b += sb;
+      tt += st;
+      if (tt >= nt) { tt -= nt; ++b; }
+    }
+  };
   const size_t RP = (size_t)T + 2 * PAD;
 
   if (threadIdx.x == 0) {
@@ -134,23 +146,24 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
     // rows are cut from that window (measured: 36 dependent global loads per lane made this warp pace the kernel).
     float *swin = reinterpret_cast<float *>(smem + OFF_WIN);
     float wreg[5];
-    auto fetch_window = [&](long long i) {
-      const long long tile = blockIdx.x + i * gridDim.x;
-      const float *sb = s + (size_t)(tile / ntile_t) * T;
-      const int ts0 = (int)(tile % ntile_t) * TO - 5;
+    TileWalk wk(blockIdx.x, gridDim.x, ntile_t);
+    auto fetch_window = [&]() {   // the window of the walk's current tile; advances the walk
+      const float *sb = s + (size_t)wk.b * T;
+      const int ts0 = wk.tt * TO - 5;
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
         const int ts = ts0 + lane + 32 * k;
         wreg[k] = (ts >= 0 && ts < T) ? __ldg(sb + ts) : 0.0f;
       }
+      wk.next();
     };
-    if (my_tiles > 0) fetch_window(0);
+    if (my_tiles > 0) fetch_window();
     for (long long i = 0; i < my_tiles; ++i) {
       const int st = (int)(i & 1);
 #pragma unroll
       for (int k = 0; k < 5; ++k) swin[lane + 32 * k] = wreg[k];
       __syncwarp();
-      if (i + 1 < my_tiles) fetch_window(i + 1);
+      if (i + 1 < my_tiles) fetch_window();
       const long long p0 = clk();
       if (i >= 2) mbar_wait_warp(bar(A_EMPTY + st), (uint32_t)(((i >> 1) - 1) & 1));
       const long long p1 = clk();
@@ -237,10 +250,10 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
     const int q = warp & 3, p = warp >> 2;             // TMEM lane quadrant, 16-channel slice
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    for (long long i = 0; i < my_tiles; ++i) {
-      const long long tile = blockIdx.x + i * gridDim.x;
-      const long long b = tile / ntile_t;
-      const int t0 = (int)(tile % ntile_t) * TO;
+    TileWalk wk(blockIdx.x, gridDim.x, ntile_t);
+    for (long long i = 0; i < my_tiles; ++i, wk.next()) {
+      const long long b = wk.b;
+      const int t0 = wk.tt * TO;
       const int a = (int)(i & 1);
       const int tu = t0 - 1 + row;
       const bool inside = tu >= 0 && tu < T;     // conv2 zero-pads the intermediate feature map
@@ -316,10 +329,10 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
     const int q = w2 & 3, g = w2 >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    for (long long i = g; i < my_tiles; i += 2) {
-      const long long tile = blockIdx.x + i * gridDim.x;
-      const long long b = tile / ntile_t;
-      const int t0 = (int)(tile % ntile_t) * TO;
+    TileWalk wk(blockIdx.x + (long long)g * gridDim.x, 2LL * gridDim.x, ntile_t);
+    for (long long i = g; i < my_tiles; i += 2, wk.next()) {
+      const long long b = wk.b;
+      const int t0 = wk.tt * TO;
       const int t = t0 + row;
       const bool live = row < TO && t < T;
       const size_t prow = (size_t)t + PAD;
