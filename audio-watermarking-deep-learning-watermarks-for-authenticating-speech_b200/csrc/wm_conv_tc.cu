@@ -105,13 +105,14 @@ __global__ void __launch_bounds__(576, 1)
         bulk_g2s(w_smem + j * C::W_TAP_BYTES, reinterpret_cast<const uint8_t *>(w_img) + (size_t)j * C::W_TAP_BYTES,
                  C::W_TAP_BYTES, wbar);
       int i = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+      TileWalk wk(blockIdx.x, gridDim.x, ntile_t);
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i, wk.next()) {
         const int s = i % C::NSTAGE;
         const uint32_t ph = (i / C::NSTAGE) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
         mbar_arrive_expect_tx(full_bar(s), C::A_STAGE_BYTES);
-        const long long b = tile / ntile_t;
-        const int t0 = (int)(tile % ntile_t) * TILE;
+        const long long b = wk.b;
+        const int t0 = wk.tt * TILE;
         const size_t row0 = (size_t)(t0 + PAD - C::P);
 #pragma unroll 4
         for (int p = 0; p < 16; ++p)
@@ -159,11 +160,12 @@ __global__ void __launch_bounds__(576, 1)
     // ===== epilogue =====
     const int q = warp & 3, p = warp >> 2;
     int i = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+    TileWalk wk(blockIdx.x, gridDim.x, ntile_t);
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i, wk.next()) {
       const int a = i & 1;
       const uint32_t aph = (i >> 1) & 1;
-      const long long b = tile / ntile_t;
-      const int t0 = (int)(tile % ntile_t) * TILE;
+      const long long b = wk.b;
+      const int t0 = wk.tt * TILE;
       const int t = t0 + q * 32 + lane;
       const bool live = t < T;
       if (y != nullptr && warp == 0 && lane < 2 * PAD) {

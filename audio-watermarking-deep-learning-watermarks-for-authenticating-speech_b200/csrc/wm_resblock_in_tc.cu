@@ -84,18 +84,6 @@ __global__ void __launch_bounds__(RBI_THREADS, 1)
   const int ntile_t = (T + TO - 1) / TO;
   const long long ntiles = (long long)B * ntile_t;
   const long long my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  // (clip, time tile) of a role's current tile, advanced by a fixed stride per iteration: no division in the tile loops
-  struct TileWalk {
-    int b, tt, sb, st, nt;
-    __device__ __forceinline__ TileWalk(long long first, long long stride, int ntile_t)
-        : b((int)(first / ntile_t)), tt((int)(first % ntile_t)), sb((int)(stride / ntile_t)), st((int)(stride % ntile_t)),
-          nt(ntile_t) {}
-    __device__ __forceinline__ void next() {
-      b += sb;
-      tt += st;
-      if (tt >= nt) { tt -= nt; ++b; }
-    }
-  };
   const size_t RP = (size_t)T + 2 * PAD;
 
   if (threadIdx.x == 0) {

@@ -212,13 +212,18 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
         for (int j = 0; j < 6; ++j)
           bulk_g2s(w_smem + j * W_TAP_B, reinterpret_cast<const uint8_t *>(w_img) + (size_t)j * W_TAP_B, W_TAP_B, bar(WBAR));
       }
-      for (long long i = 0; i < my_tiles; ++i) {
-        const long long tile = tile_of(i);
+      TileWalk wk(first_t, stride_t, ntile_t);       // single-CTA mode: tile_raw(i) < ntiles for every i < my_tiles
+      for (long long i = 0; i < my_tiles; ++i, wk.next()) {
         const int s = (int)(i % NST);
         mbar_wait(bar(EMPTY + s), (uint32_t)(((i / NST) & 1) ^ 1));
         mbar_arrive_expect_tx(bar(FULL + s), TILE_B);
-        const long long b = tile / ntile_t;
-        const int t0 = (int)(tile % ntile_t) * TO;
+        long long b = wk.b;
+        int t0 = wk.tt * TO;
+        if constexpr (CTA2) {
+          const long long tile = tile_of(i);
+          b = tile / ntile_t;
+          t0 = (int)(tile % ntile_t) * TO;
+        }
         const size_t row0 = (size_t)(t0 + PAD - 2);
 #pragma unroll 4
         for (int p = 0; p < 16; ++p)
@@ -344,9 +349,10 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
     // "no instruction" and the kernel ran 37 % longer (profiles/r2_resblock_icache.md).  With BIASP the biases are
     // indexed constant-bank loads (LDC), which do not touch the shared-memory pipeline the MMAs are bound by.
     const int half = warp >> 2;
-    for (long long i = 0; i < my_tiles; ++i) {
-      const long long tile = tile_of(i);
-      const int t0 = (int)(tile % ntile_t) * TO;
+    TileWalk wk(first_t, stride_t, ntile_t);
+    for (long long i = 0; i < my_tiles; ++i, wk.next()) {
+      int t0 = wk.tt * TO;
+      if constexpr (CTA2) t0 = (int)(tile_of(i) % ntile_t) * TO;
       const int a = (int)(i & 1);
       const int tu = t0 - 1 + row;
       const bool inside = tu >= 0 && tu < T;     // conv2 zero-pads the intermediate feature map
@@ -399,11 +405,17 @@ __global__ void __launch_bounds__(RB_THREADS, 1)
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const bool pfe = prof != nullptr && blockIdx.x == 0 && lane == 0 && w2 == 0;
     long long pe[3] = {0, 0, 0};
-    for (long long i = g; i < my_tiles; i += 2) {
-      const long long tile = tile_of(i);
-      const bool real_tile = tile_raw(i) < ntiles;     // a pair's second tile may not exist: compute, do not store
-      const long long b = tile / ntile_t;
-      const int tt = (int)(tile % ntile_t);
+    TileWalk wk(first_t + g * stride_t, 2 * stride_t, ntile_t);
+    for (long long i = g; i < my_tiles; i += 2, wk.next()) {
+      bool real_tile = true;
+      long long b = wk.b;
+      int tt = wk.tt;
+      if constexpr (CTA2) {
+        const long long tile = tile_of(i);
+        real_tile = tile_raw(i) < ntiles;               // a pair's second tile may not exist: compute, do not store
+        b = tile / ntile_t;
+        tt = (int)(tile % ntile_t);
+      }
       const int t0 = tt * TO;
       const int t = t0 + row;
       const bool live = real_tile && row < TO && t < T;
